@@ -1,0 +1,345 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU oracle for the RBEPWT encode -> threshold -> decode path.
+ *
+ * Plain-C restatement of the reference's algorithm (nareto/rbepwt, rbepwt.py) on flat
+ * arrays.  It is the checker for the CUDA product in rbepwt_b200/csrc and the "port" CPU
+ * baseline of bench.py; the product never links, imports or calls it.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may.
+ *
+ * Pinned against the reference itself: the .npz files under tests/golden/ are produced by executing
+ * the unmodified /root/reference/rbepwt.py (oracle/ref_harness.py, tests/golden/make_golden.py)
+ * and tests/test_oracle_golden.py requires this file to reproduce them -- paths,
+ * permutations and kept indices bit for bit, coefficients/pixels to 1e-9 relative.
+ * The wavelet arithmetic (PyWavelets, absent from /root/reference and from this image)
+ * is restated from its published algorithm: PARITY UNPINNED for that part, see
+ * oracle/pywt_port.py.
+ *
+ * Reference map (file:line in /root/reference/rbepwt.py):
+ *   build_regions      Segmentation.compute_label_dict            840-848
+ *   easy_path          Region.easy_path, neighborhood, rotate     1273-1347, 84-104, 78-82
+ *                      start point = lexicographic min (row,col)  1020-1036
+ *   reduce (in encode) RegionCollection.reduce/Region.reduce_points 1563-1584, 1349-1375
+ *   dwt_per/idwt_per   pywt.dwt/idwt 'periodization' call sites   2041, 2067
+ *   rbo_encode         Rbepwt.encode                              1996-2053
+ *   rbo_threshold      Rbepwt.threshold_coefs                     2081-2112
+ *   rbo_decode         Rbepwt.decode, RegionCollection.expand,    2055-2079, 1586-1613,
+ *                      Image.decode_rbepwt                        307-317
+ *   rbo_psnr           psnr                                       156-162
+ *
+ * Build: see oracle/Makefile (-O2 -ffp-contract=off: the reference's tie-break uses one
+ * explicit FMA -- numpy's ddot tail -- and nothing else may be contracted).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define RBO_MODE_EUCLID 0 /* path_type='easypath', euclidean_distance=True  (rbepwt.py:1304) */
+#define RBO_MODE_CHEB 1   /* path_type='easypath', euclidean_distance=False (rbepwt.py:1306) */
+#define RBO_MODE_EPWT 2   /* path_type='epwt-easypath'                      (rbepwt.py:1302) */
+
+/* ------------------------------------------------------------------ label dict ---- */
+
+/* Region id = rank of first appearance of the label in a row-major scan; pixels inside a
+ * region in row-major order (rbepwt.py:840-848).  rid[] gets the region id of every pixel.
+ * Returns R. */
+static int build_region_ids(const int32_t *labels, int n, int32_t *rid) {
+  int cap = 1;
+  while (cap < 2 * n + 2) cap <<= 1;
+  int32_t *keys = (int32_t *)malloc(sizeof(int32_t) * cap);
+  int32_t *vals = (int32_t *)malloc(sizeof(int32_t) * cap);
+  memset(vals, 0xff, sizeof(int32_t) * cap); /* -1 = empty */
+  int R = 0;
+  for (int p = 0; p < n; p++) {
+    uint32_t h = ((uint32_t)labels[p] * 2654435761u) & (uint32_t)(cap - 1);
+    while (vals[h] != -1 && keys[h] != labels[p]) h = (h + 1) & (uint32_t)(cap - 1);
+    if (vals[h] == -1) {
+      keys[h] = labels[p];
+      vals[h] = R++;
+    }
+    rid[p] = vals[h];
+  }
+  free(keys);
+  free(vals);
+  return R;
+}
+
+int rbo_count_regions(const int32_t *labels, int H, int W) {
+  int n = H * W;
+  int32_t *rid = (int32_t *)malloc(sizeof(int32_t) * n);
+  int R = build_region_ids(labels, n, rid);
+  free(rid);
+  return R;
+}
+
+/* ------------------------------------------------------------------ wavelet ------- */
+
+/* cA[o] = sum_j dec_lo[j] x[(2o + F/2 - j) mod n], ascending j, mul then add, from 0. */
+static void dwt_per(const double *x, int n, int flen, const double *dec_lo,
+                    const double *dec_hi, double *ca, double *cd) {
+  int half = n / 2;
+  for (int o = 0; o < half; o++) {
+    double a = 0.0, d = 0.0;
+    for (int j = 0; j < flen; j++) {
+      long idx = ((long)2 * o + flen / 2 - j) % n;
+      if (idx < 0) idx += n;
+      double xv = x[idx];
+      a = a + dec_lo[j] * xv;
+      d = d + dec_hi[j] * xv;
+    }
+    ca[o] = a;
+    cd[o] = d;
+  }
+}
+
+/* x[t] = S_lo + S_hi; taps m ascending with (t + F/2 - 1 - m) even, o = that / 2 mod n/2. */
+static void idwt_per(const double *ca, const double *cd, int n, int flen,
+                     const double *rec_lo, const double *rec_hi, double *x) {
+  int half = n / 2;
+  for (int t = 0; t < n; t++) {
+    double slo = 0.0, shi = 0.0;
+    int base = t + flen / 2 - 1;
+    for (int m = base & 1; m < flen; m += 2) {
+      long o = ((long)(base - m) / 2) % half; /* base-m even; may be negative */
+      if (o < 0) o += half;
+      slo = slo + rec_lo[m] * ca[o];
+      shi = shi + rec_hi[m] * cd[o];
+    }
+    x[t] = slo + shi;
+  }
+}
+
+/* ------------------------------------------------------------------ easy path ----- */
+
+typedef struct {
+  int H, W;
+  int32_t *owner;  /* per pixel: region id if the pixel is an unvisited point of the level, else -1 */
+  int32_t *idxmap; /* per pixel: index of the point in its region's incoming order */
+  const double *valmap; /* per pixel value at this level (EPWT mode only) */
+} path_ctx;
+
+/* One region's path.  pix[0..n) are the region's points (pixel ids) in incoming order.
+ * Writes perm[t] (index into the incoming order) and path_pix[t]. */
+static void easy_path(path_ctx *c, int r, const int32_t *pix, int n, int mode, int u8wrap,
+                      int32_t *perm, int32_t *path_pix) {
+  if (n == 0) return;
+  if (n == 1) { /* rbepwt.py:1275-1277 */
+    perm[0] = 0;
+    path_pix[0] = pix[0];
+    return;
+  }
+  const int W = c->W, H = c->H;
+  int start = 0, rmin = H, rmax = -1, cmin = W, cmax = -1;
+  for (int i = 0; i < n; i++) {
+    c->owner[pix[i]] = r;
+    c->idxmap[pix[i]] = i;
+    if (pix[i] < pix[start]) start = i; /* row-major id order == (row, col) lexicographic order */
+    int rr = pix[i] / W, cc = pix[i] % W;
+    if (rr < rmin) rmin = rr;
+    if (rr > rmax) rmax = rr;
+    if (cc < cmin) cmin = cc;
+    if (cc > cmax) cmax = cc;
+  }
+  int ci = pix[start] / W, cj = pix[start] % W;
+  c->owner[pix[start]] = -1;
+  perm[0] = start;
+  path_pix[0] = pix[start];
+  long p0 = 0, p1 = 1; /* prefered_direc = (0,1), rbepwt.py:1290 */
+  for (int t = 1; t < n; t++) {
+    int found = 0, bi = 0, bj = 0;
+    double bdist = 0.0, bsp1 = 0.0;
+    long bcross = 0, bd2 = 0;
+    double curval = (mode == RBO_MODE_EPWT) ? c->valmap[ci * W + cj] : 0.0;
+    for (int rad = 1; !found; rad <<= 1) { /* half-width 2^(k-1), k = 1,2,..  rbepwt.py:1296-1299, 90-92 */
+      int i0 = ci - rad < rmin ? rmin : ci - rad, i1 = ci + rad > rmax ? rmax : ci + rad;
+      int j0 = cj - rad < cmin ? cmin : cj - rad, j1 = cj + rad > cmax ? cmax : cj + rad;
+      for (int i = i0; i <= i1; i++) {
+        for (int j = j0; j <= j1; j++) {
+          if (c->owner[i * W + j] != r) continue;
+          long di = i - ci, dj = j - cj;
+          long d2 = di * di + dj * dj;
+          double dist;
+          if (mode == RBO_MODE_EPWT) {
+            double dv = curval - c->valmap[i * W + j];
+            if (u8wrap) dist = dv < 0 ? dv + 256.0 : dv; /* uint8 wrap, rbepwt.py:1302 on a uint8 image */
+            else dist = fabs(dv);
+          } else if (mode == RBO_MODE_EUCLID) {
+            dist = (double)d2; /* norm compares like d2 */
+          } else {
+            long a = di < 0 ? -di : di, b = dj < 0 ? -dj : dj;
+            dist = (double)(a > b ? a : b);
+          }
+          if (found && dist > bdist) continue;
+          /* v = off/||off||; sp1 = np.dot(v, pref) = fma(v1, p1, v0*p0) (OpenBLAS ddot tail) */
+          double nrm = sqrt((double)d2);
+          double v0 = (double)di / nrm, v1 = (double)dj / nrm;
+          double sp1 = fma(v1, (double)p1, v0 * (double)p0);
+          long cross = di * p1 - dj * p0; /* orders like v . rotate(pref,-pi/2), rbepwt.py:1320-1322 */
+          int better;
+          if (!found || dist < bdist) better = 1;
+          else if (sp1 != bsp1) better = sp1 > bsp1;
+          else if (cross != bcross) better = cross > bcross;
+          else better = d2 < bd2; /* complete tie (EPWT, collinear, equal |dv|): unpinned in the
+                                     reference (CPython set order); our rule: nearer first */
+          if (better) {
+            found = 1; bi = i; bj = j; bdist = dist; bsp1 = sp1; bcross = cross; bd2 = d2;
+          }
+        }
+      }
+    }
+    int pid = bi * W + bj;
+    c->owner[pid] = -1;
+    perm[t] = c->idxmap[pid];
+    path_pix[t] = pid;
+    p0 = bi - ci; p1 = bj - cj; /* rbepwt.py:1331: integer vector, not normalised */
+    ci = bi; cj = bj;
+  }
+}
+
+/* ------------------------------------------------------------------ encode -------- */
+
+static long level_len(long n, int lev) { return n >> (lev - 1); } /* lev = 1.. */
+
+/* Offsets of level `lev` (1-based) inside the per-level concatenated buffers. */
+long rbo_level_offset(long n, int lev) {
+  long off = 0;
+  for (int l = 1; l < lev; l++) off += level_len(n, l);
+  return off;
+}
+
+/*
+ * Outputs (caller-allocated), with N = H*W, N_l = N >> (l-1), lo(l) = rbo_level_offset(N, l):
+ *   roff    [(levels+1) * (R+1)]   region offsets at level l = 1..levels+1 (row l-1)
+ *   inc_pix [lo(levels+2)]         pixel ids in INCOMING order at level l = 1..levels+1
+ *   path_pix[lo(levels+1)]         pixel ids in PATH order at level l = 1..levels
+ *   perm    [lo(levels+1)]         per-region local permutation at level l (Region.permutation)
+ *   coefs   [N]                    details[1] | ... | details[levels] | approx
+ * labels == NULL  <=>  one region holding every pixel (EPWT).
+ */
+int rbo_encode(const double *img, const int32_t *labels, int H, int W, int levels, int flen,
+               const double *dec_lo, const double *dec_hi, int mode, int u8wrap, int R,
+               int32_t *roff, int32_t *inc_pix, int32_t *path_pix, int32_t *perm,
+               double *coefs) {
+  const int N = H * W;
+  if (N <= 0 || (N & (N - 1))) return -1;       /* rbepwt.py:301-302 */
+  if (levels < 1 || levels > 30 || ((long)1 << levels) > N) return -2; /* rbepwt.py:1977-1978 */
+  int32_t *rid = (int32_t *)malloc(sizeof(int32_t) * N);
+  if (labels) {
+    int R2 = build_region_ids(labels, N, rid);
+    if (R2 != R) { free(rid); return -3; }
+  } else {
+    if (R != 1) { free(rid); return -3; }
+    memset(rid, 0, sizeof(int32_t) * N);
+  }
+  /* level-1 incoming order: regions by first appearance, pixels row-major (counting sort) */
+  int32_t *off = roff;
+  memset(off, 0, sizeof(int32_t) * (R + 1));
+  for (int p = 0; p < N; p++) off[rid[p] + 1]++;
+  for (int r = 0; r < R; r++) off[r + 1] += off[r];
+  int32_t *fill = (int32_t *)malloc(sizeof(int32_t) * (R + 1));
+  memcpy(fill, off, sizeof(int32_t) * (R + 1));
+  for (int p = 0; p < N; p++) inc_pix[fill[rid[p]]++] = p;
+  free(fill);
+  free(rid);
+
+  path_ctx c;
+  c.H = H; c.W = W;
+  c.owner = (int32_t *)malloc(sizeof(int32_t) * N);
+  c.idxmap = (int32_t *)malloc(sizeof(int32_t) * N);
+  double *valmap = (double *)malloc(sizeof(double) * N);
+  c.valmap = valmap;
+  memset(c.owner, 0xff, sizeof(int32_t) * N);
+  double *val = (double *)malloc(sizeof(double) * N); /* values in incoming order */
+  double *sig = (double *)malloc(sizeof(double) * N); /* values in path order */
+  double *ca = (double *)malloc(sizeof(double) * N);
+  for (int i = 0; i < N; i++) val[i] = img[inc_pix[i]];
+
+  long coef_off = 0;
+  for (int lev = 1; lev <= levels; lev++) {
+    const long nl = level_len(N, lev), lo = rbo_level_offset(N, lev);
+    const int32_t *cur_off = roff + (long)(lev - 1) * (R + 1);
+    int32_t *nxt_off = roff + (long)lev * (R + 1);
+    const int32_t *ipix = inc_pix + lo;
+    int32_t *ppix = path_pix + lo, *pm = perm + lo;
+    if (mode == RBO_MODE_EPWT)
+      for (long i = 0; i < nl; i++) valmap[ipix[i]] = val[i];
+    for (int r = 0; r < R; r++) {
+      int a = cur_off[r], n = cur_off[r + 1] - a;
+      easy_path(&c, r, ipix + a, n, mode, u8wrap && lev == 1, pm + a, ppix + a);
+      for (int t = 0; t < n; t++) sig[a + t] = val[a + pm[a + t]];
+    }
+    dwt_per(sig, (int)nl, flen, dec_lo, dec_hi, ca, coefs + coef_off);
+    coef_off += nl / 2;
+    /* reduce: keep the points at even global position g; they carry cA[g/2] (rbepwt.py:1563-1584) */
+    int32_t *npix = inc_pix + rbo_level_offset(N, lev + 1);
+    for (int r = 0; r <= R; r++) nxt_off[r] = (cur_off[r] + 1) / 2;
+    for (long g = 0; g < nl; g += 2) {
+      npix[g / 2] = ppix[g];
+      val[g / 2] = ca[g / 2];
+    }
+  }
+  memcpy(coefs + coef_off, val, sizeof(double) * level_len(N, levels + 1));
+  free(c.owner); free(c.idxmap); free(valmap); free(val); free(sig); free(ca);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ threshold ----- */
+
+typedef struct { double mag; int64_t idx; } mag_idx;
+static int cmp_mag_desc(const void *a, const void *b) {
+  const mag_idx *x = (const mag_idx *)a, *y = (const mag_idx *)b;
+  if (x->mag != y->mag) return x->mag > y->mag ? -1 : 1;
+  return x->idx > y->idx ? -1 : (x->idx < y->idx ? 1 : 0); /* ties: highest flat index first */
+}
+
+/* Keep the k largest |coef|, zero the rest, in place (rbepwt.py:2081-2112).  k <= 0 or k >= n
+ * keeps everything (the reference's `counter == ncoefs` test never fires).  Ties at the k-th
+ * magnitude are unpinned in the reference (unstable argsort); rule here: highest index first. */
+int rbo_threshold(double *coefs, int64_t n, int64_t k) {
+  if (k <= 0 || k >= n) return 0;
+  mag_idx *v = (mag_idx *)malloc(sizeof(mag_idx) * n);
+  for (int64_t i = 0; i < n; i++) { v[i].mag = fabs(coefs[i]); v[i].idx = i; }
+  qsort(v, n, sizeof(mag_idx), cmp_mag_desc);
+  for (int64_t i = k; i < n; i++) coefs[v[i].idx] = 0.0;
+  free(v);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ decode -------- */
+
+int rbo_decode(const double *coefs, int H, int W, int levels, int flen, const double *rec_lo,
+               const double *rec_hi, int R, const int32_t *roff, const int32_t *inc_pix1,
+               const int32_t *perm, double *out_img) {
+  const int N = H * W;
+  double *x = (double *)malloc(sizeof(double) * N);
+  double *s = (double *)malloc(sizeof(double) * N);
+  long coef_off = N - level_len(N, levels + 1);
+  memcpy(x, coefs + coef_off, sizeof(double) * level_len(N, levels + 1));
+  for (int lev = levels; lev >= 1; lev--) {
+    const long nl = level_len(N, lev), lo = rbo_level_offset(N, lev);
+    coef_off -= nl / 2;
+    idwt_per(x, coefs + coef_off, (int)nl, flen, rec_lo, rec_hi, s);
+    const int32_t *cur_off = roff + (long)(lev - 1) * (R + 1);
+    for (int r = 0; r < R; r++) { /* expand: undo the region's permutation (rbepwt.py:1600-1608) */
+      int a = cur_off[r], n = cur_off[r + 1] - a;
+      for (int t = 0; t < n; t++) x[a + perm[lo + a + t]] = s[a + t];
+    }
+  }
+  for (int i = 0; i < N; i++) { /* rbepwt.py:309-314: no rounding, clip to [0,255] */
+    double v = x[i];
+    if (v > 255.0) v = 255.0;
+    if (v < 0.0) v = 0.0;
+    out_img[inc_pix1[i]] = v;
+  }
+  free(x); free(s);
+  return 0;
+}
+
+/* psnr (rbepwt.py:156-162): -1 when the images are identical. */
+double rbo_psnr(const double *a, const double *b, int64_t n) {
+  double mse = 0.0;
+  for (int64_t i = 0; i < n; i++) { double d = a[i] - b[i]; mse += d * d; }
+  if (mse == 0.0) return -1.0;
+  mse /= (double)n;
+  return 20.0 * log10(255.0 / sqrt(mse));
+}

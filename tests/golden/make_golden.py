@@ -1,0 +1,102 @@
+"""Generate the golden fixtures by executing the UNMODIFIED reference (/root/reference/rbepwt.py).
+
+Run in the build container only (the reference does not exist on the GPU box):
+
+    python tests/golden/make_golden.py [--only NAME ...] [--big]
+
+Each fixture tests/golden/<name>.npz holds the inputs (img, labels) and what the reference
+produced for encode_rbepwt -> threshold_coefs -> decode_rbepwt -> psnr, in the flat layout of
+oracle/ref_harness.run_reference.  The only non-reference arithmetic involved is the
+pywt.dwt/idwt restatement (oracle/pywt_port.py) -- PyWavelets is not installed here.
+`--big` adds the 256x256 BASELINE.json config-1 case (about 4 minutes of reference time).
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
+
+from oracle import ref_harness  # noqa: E402
+from rbepwt_b200 import synth  # noqa: E402
+
+
+def noise_labels(h, w, nlab, seed):
+    """Salt-and-pepper labels: every region is a sparse, disconnected point set, so almost
+    every step is a jump (r >= 2) with an arbitrary preferred direction -- the tie-break stress."""
+    return np.random.default_rng(seed).integers(0, nlab, size=(h, w)).astype(np.int32) * 7 - 3
+
+
+def cases(big):
+    c = []
+    img = np.array([[10, 12, 50, 52], [11, 49, 51, 53], [13, 14, 15, 54], [90, 91, 16, 55]], dtype=np.float64)
+    lab = np.array([[5, 5, 2, 2], [5, 2, 2, 2], [5, 5, 5, 2], [7, 7, 5, 2]], dtype=np.int32)
+    c.append(("survey11_4x4_haar", img, lab, 4, "haar", "easypath", True, 4))
+    for s in range(6):  # tie-break stress, euclid + chebyshev
+        lab = noise_labels(32, 32, 5 + 3 * s, 100 + s)
+        img = synth.noise_image(32, 32, seed=200 + s)
+        c.append(("noise32_euclid_s%d" % s, img, lab, 10, "bior4.4" if s % 2 else "haar", "easypath", True, 64))
+        c.append(("noise32_cheb_s%d" % s, img, lab, 10, "db2", "easypath", False, 100))
+    lab = synth.voronoi_labels(32, 32, 23, seed=1)
+    img = synth.piecewise_smooth_image(lab, seed=1)
+    c.append(("vor32_euclid_bior44", img, lab, 10, "bior4.4", "easypath", True, 37))
+    c.append(("vor32_cheb_haar", img, lab, 10, "haar", "easypath", False, 37))
+    c.append(("vor32_euclid_db3_L3", img, lab, 3, "db3", "easypath", True, 200))
+    c.append(("vor32_u8img_db4", np.round(img).astype(np.uint8), lab, 10, "db4", "easypath", True, 50))
+    c.append(("one_label32_euclid", img, np.zeros((32, 32), np.int32), 10, "bior4.4", "easypath", True, 64))
+    lab = synth.voronoi_labels(32, 64, 30, seed=2)  # H*W power of two, H != W (rbepwt.py:301)
+    c.append(("vor32x64_euclid_bior44", synth.piecewise_smooth_image(lab, seed=2), lab, 11, "bior4.4", "easypath", True, 128))
+    lab = (np.arange(64)[:, None] // 3 + 0 * np.arange(64)[None, :]).astype(np.int32)  # stripes
+    c.append(("stripes64_euclid_haar", synth.noise_image(64, 64, seed=3), lab, 12, "haar", "easypath", True, 256))
+    lab = synth.voronoi_labels(64, 64, 40, seed=4)
+    img = synth.piecewise_smooth_image(lab, seed=4)
+    c.append(("vor64_euclid_bior44", img, lab, 12, "bior4.4", "easypath", True, 256))
+    c.append(("vor64_k0_keeps_all", img, lab, 12, "bior4.4", "easypath", True, 0))
+    c.append(("epwt16_bior44", synth.noise_image(16, 16, seed=5), None, 8, "bior4.4", "epwt-easypath", True, 32))
+    c.append(("epwt32_smooth_haar", synth.smooth_field_image(32, 32, seed=6, sigma=2.0), None, 10, "haar", "epwt-easypath", True, 64))
+    c.append(("epwt64_noise_bior44", synth.noise_image(64, 64, seed=7), None, 12, "bior4.4", "epwt-easypath", True, 256))
+    c.append(("epwt64_smooth_db2", synth.smooth_field_image(64, 64, seed=8, sigma=3.0), None, 12, "db2", "epwt-easypath", True, 256))
+    lab = synth.voronoi_labels(128, 128, 96, seed=9)
+    c.append(("vor128_euclid_bior44", synth.piecewise_smooth_image(lab, seed=9), lab, 14, "bior4.4", "easypath", True, 512))
+    c.append(("epwt128_smooth_bior44", synth.smooth_field_image(128, 128, seed=10, sigma=4.0), None, 14, "bior4.4", "epwt-easypath", True, 512))
+    if big:
+        img, lab = synth.config_inputs("cameraman256")  # BASELINE.json configs[0]
+        c.append(("config1_cameraman256", img, lab, 16, "bior4.4", "easypath", True, 512))
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", nargs="*")
+    ap.add_argument("--big", action="store_true")
+    ap.add_argument("--force", action="store_true")
+    args = ap.parse_args()
+    for name, img, lab, levels, wav, ptype, euclid, k in cases(args.big):
+        if args.only and name not in args.only:
+            continue
+        path = os.path.join(HERE, name + ".npz")
+        if os.path.exists(path) and not args.force:
+            continue
+        t0 = time.perf_counter()
+        out = ref_harness.run_reference(img, lab, levels, wav, ptype, euclid, ncoefs=k)
+        dt = time.perf_counter() - t0
+        np.savez_compressed(
+            path,
+            img=img,
+            labels=(lab if lab is not None else np.zeros((0, 0), np.int32)),
+            levels=levels, wavelet=wav, path_type=ptype, euclidean_distance=euclid, ncoefs=k,
+            perm=np.concatenate([out["perm"][l] for l in range(1, levels + 1)]).astype(np.int32),
+            roff=np.stack([out["roff"][l] for l in range(1, levels + 2)]).astype(np.int32),
+            points=np.concatenate([out["points"][l] for l in range(1, levels + 2)]).astype(np.int16),
+            coefs=out["coefs"], thresholded=out["thresholded"], kept=out["kept"],
+            decoded=out["decoded"], psnr=out["psnr"], nonzero_coefs=out["nonzero_coefs"],
+            reference_seconds=dt,
+        )
+        print("%-28s %6.1fs  %d KB" % (name, dt, os.path.getsize(path) // 1024), flush=True)
+
+
+if __name__ == "__main__":
+    main()

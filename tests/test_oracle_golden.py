@@ -1,0 +1,38 @@
+"""The C oracle (oracle/rbepwt_oracle.c) must reproduce what the unmodified reference produced
+(tests/golden/*.npz): paths, permutations, kept indices bit-exact; coefficients, pixels 1e-9."""
+import numpy as np
+import pytest
+
+from conftest import assert_matches_golden, golden_names, load_golden
+from oracle import c_oracle
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_c_oracle_reproduces_reference(name):
+    g = load_golden(name)
+    out = c_oracle.run(g["img"], g["labels"], g["levels"], g["wavelet"], g["path_type"],
+                       g["euclidean_distance"], ncoefs=g["ncoefs"])
+    assert_matches_golden(out, g)
+
+
+def test_golden_set_is_present():
+    names = golden_names()
+    assert "survey11_4x4_haar" in names and len(names) >= 25
+
+
+def test_oracle_guards():
+    img = np.zeros((6, 8))
+    lab = np.zeros((6, 8), np.int32)
+    with pytest.raises(Exception, match="power of 2"):
+        c_oracle.encode(img, lab, 2, "haar", c_oracle.MODE_EUCLID)
+    with pytest.raises(Exception, match="levels"):
+        c_oracle.encode(np.zeros((4, 4)), np.zeros((4, 4), np.int32), 5, "haar", c_oracle.MODE_EUCLID)
+
+
+def test_threshold_quirks():
+    x = np.array([3.0, -5.0, 1.0, 5.0, 0.5])
+    np.testing.assert_array_equal(c_oracle.threshold(x, 0), x)       # k=0 keeps everything
+    np.testing.assert_array_equal(c_oracle.threshold(x, 5), x)
+    np.testing.assert_array_equal(c_oracle.threshold(x, 99), x)
+    np.testing.assert_array_equal(c_oracle.threshold(x, 1), [0, 0, 0, 5.0, 0])  # tie: highest index
+    np.testing.assert_array_equal(c_oracle.threshold(x, 3), [3.0, -5.0, 0, 5.0, 0])
