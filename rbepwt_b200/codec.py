@@ -1,0 +1,244 @@
+"""Batched host-side driver of the CUDA path: thin Python over the C ABI (include/rbepwt_b200.h).
+
+`BatchCodec` is what a throughput user calls: B images of one shape in, coefficients / decoded
+images out, everything resident on one GPU between the three calls.  Inputs may be numpy arrays
+(host path: the library copies host<->device inside the call) or torch CUDA tensors (device path:
+raw data_ptr()s are passed, no copy).  The reference-shaped single-image facade is image.py.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from .wavelets import filter_bank
+
+PATH_MODES = {("easypath", True): _capi.PATH_EUCLID, ("easypath", False): _capi.PATH_CHEB}
+
+
+def path_mode(path_type, euclidean_distance=True):
+    """Reference arguments -> C-ABI path mode (rbepwt.py:2026-2031, 1301-1306)."""
+    if path_type == "epwt-easypath":
+        return _capi.PATH_EPWT  # euclidean_distance is ignored by the reference in this mode
+    if path_type == "easypath":
+        return PATH_MODES[("easypath", bool(euclidean_distance))]
+    if path_type == "gradpath":
+        raise NotImplementedError(
+            "path_type='gradpath' is outside the B200 hot path: its exact abs-dot ties are resolved by "
+            "CPython set iteration order in the reference and cannot be reproduced bit-exactly")
+    raise ValueError("unknown path_type %r" % (path_type,))
+
+
+def _is_torch_cuda(x):
+    return type(x).__module__.startswith("torch") and getattr(x, "is_cuda", False)
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data_as(ctypes.c_void_p)
+    return ctypes.c_void_p(x.data_ptr())
+
+
+class BatchCodec:
+    """One GPU context: encode -> threshold -> decode for a batch of same-shape images."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = _capi.lib()
+        self._ctx = ctypes.c_void_p()
+        sp = ctypes.c_void_p(int(stream)) if stream else None
+        _capi.check(self._lib.rbepwt_create(int(device), sp, ctypes.byref(self._ctx)))
+        self.device = int(device)
+        self.shape = None       # (B, H, W)
+        self.levels = None
+        self.wavelet = None
+        self._keep = []         # keeps device inputs alive while the library references them
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.rbepwt_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # -- configuration -----------------------------------------------------------------
+    def set_wavelet(self, wavelet):
+        dl, dh, rl, rh = filter_bank(wavelet)
+        _capi.check(self._lib.rbepwt_set_wavelet(self._ctx, dl.size, _ptr(dl), _ptr(dh), _ptr(rl), _ptr(rh)))
+        self.wavelet = wavelet
+
+    def enable_timing(self, on=True):
+        _capi.check(self._lib.rbepwt_enable_timing(self._ctx, int(bool(on))))
+
+    def timings(self):
+        """{stage: ms} of the calls since the last encode (CUDA events on the context's stream)."""
+        ms = (ctypes.c_float * 7)()
+        self._lib.rbepwt_get_timings(self._ctx, ms, 7)
+        return dict(zip(_capi.T_NAMES, [float(v) for v in ms]))
+
+    def launch_count(self):
+        return int(self._lib.rbepwt_launch_count(self._ctx))
+
+    def sync(self):
+        _capi.check(self._lib.rbepwt_sync(self._ctx))
+
+    # -- the path --------------------------------------------------------------------------
+    def _prep(self, imgs, labels, mode):
+        dev = _is_torch_cuda(imgs)
+        u8 = False
+        if dev:
+            import torch
+            if imgs.dtype != torch.float64 or not imgs.is_contiguous():
+                raise ValueError("device images must be contiguous float64")
+            if labels is not None and (not _is_torch_cuda(labels) or labels.dtype != torch.int32
+                                       or not labels.is_contiguous()):
+                raise ValueError("device labels must be contiguous int32 CUDA tensors")
+            shape = tuple(imgs.shape)
+        else:
+            imgs = np.asarray(imgs)
+            u8 = imgs.dtype == np.uint8
+            imgs = np.ascontiguousarray(imgs, dtype=np.float64)
+            if labels is not None:
+                lab = np.asarray(labels)
+                lab32 = np.ascontiguousarray(lab, dtype=np.int32)
+                if lab.dtype != np.int32 and not np.array_equal(lab32, lab):
+                    raise ValueError("labels must be integers representable as int32")
+                labels = lab32
+            shape = imgs.shape
+        if len(shape) == 2:
+            shape = (1,) + tuple(shape)
+        if len(shape) != 3:
+            raise ValueError("images must be [H,W] or [B,H,W]")
+        if mode != _capi.PATH_EPWT:
+            if labels is None:
+                raise ValueError("a label map is required for path_type='easypath'")
+            lshape = tuple(labels.shape)
+            if (lshape if len(lshape) == 3 else (1,) + lshape) != tuple(shape):
+                raise ValueError("labels must have the shape of the images")
+        else:
+            labels = None
+        return imgs, labels, shape, dev, u8
+
+    def encode(self, imgs, labels, levels, wavelet, path_type="easypath", euclidean_distance=True):
+        mode = path_mode(path_type, euclidean_distance)
+        imgs, labels, shape, dev, u8 = self._prep(imgs, labels, mode)
+        self.set_wavelet(wavelet)
+        flags = (_capi.DEVICE_PTRS if dev else 0) | (_capi.U8_WRAP if (u8 and mode == _capi.PATH_EPWT) else 0)
+        B, H, W = shape
+        self._keep = [imgs, labels]
+        _capi.check(self._lib.rbepwt_encode(self._ctx, _ptr(imgs), _ptr(labels), B, H, W, int(levels), mode, flags))
+        self.shape, self.levels, self.mode = shape, int(levels), mode
+        return self
+
+    def threshold(self, k):
+        _capi.check(self._lib.rbepwt_threshold(self._ctx, int(k)))
+        return self
+
+    def decode(self, out=None):
+        """Decoded images, float64 [B,H,W], clipped to [0,255].  `out` may be a torch CUDA tensor
+        (device path) or a numpy array (host path); default: a new numpy array."""
+        if self.shape is None:
+            raise Exception("There is no saved encoding to decode")
+        if out is None:
+            out = np.empty(self.shape, dtype=np.float64)
+        dev = _is_torch_cuda(out)
+        if not dev and not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous):
+            raise ValueError("out must be a contiguous float64 numpy array or CUDA tensor")
+        _capi.check(self._lib.rbepwt_decode(self._ctx, _ptr(out), _capi.DEVICE_PTRS if dev else 0))
+        return out
+
+    def full_decode(self, coefs, labels, levels, wavelet, path_type="easypath", euclidean_distance=True):
+        """Decoder side (reference full_decode, rbepwt.py:106-130): paths regenerated from labels."""
+        mode = path_mode(path_type, euclidean_distance)
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        shape = labels.shape if labels.ndim == 3 else (1,) + labels.shape
+        coefs = np.ascontiguousarray(coefs, dtype=np.float64).reshape(shape[0], -1)
+        self.set_wavelet(wavelet)
+        out = np.empty(shape, dtype=np.float64)
+        B, H, W = shape
+        _capi.check(self._lib.rbepwt_full_decode(self._ctx, _ptr(coefs), _ptr(labels), B, H, W, int(levels), mode,
+                                                 _ptr(out), 0))
+        self.shape, self.levels, self.mode = shape, int(levels), mode
+        return out
+
+    def psnr(self, a, b):
+        dev = _is_torch_cuda(a)
+        if not dev:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            b = np.ascontiguousarray(b, dtype=np.float64)
+        shape = tuple(a.shape)
+        B = shape[0] if len(shape) == 3 else 1
+        n = int(np.prod(shape)) // B
+        out = np.empty(B, dtype=np.float64)
+        _capi.check(self._lib.rbepwt_psnr(self._ctx, _ptr(a), _ptr(b), B, n, _ptr(out), _capi.DEVICE_PTRS if dev else 0))
+        return out
+
+    def nonzero_coefs(self):
+        out = np.empty(self.shape[0], dtype=np.int64)
+        _capi.check(self._lib.rbepwt_nonzero_coefs(self._ctx, _ptr(out)))
+        return out
+
+    # -- views (host copies) ---------------------------------------------------------------
+    @property
+    def npix(self):
+        return self.shape[1] * self.shape[2]
+
+    def coefs(self, b=0):
+        out = np.empty(self.npix, dtype=np.float64)
+        _capi.check(self._lib.rbepwt_get_coefs(self._ctx, int(b), _ptr(out)))
+        return out
+
+    def set_coefs(self, flat, b=0):
+        flat = np.ascontiguousarray(flat, dtype=np.float64)
+        if flat.size != self.npix:
+            raise ValueError("flat coefficient vector must have H*W entries")
+        _capi.check(self._lib.rbepwt_set_coefs(self._ctx, int(b), _ptr(flat)))
+
+    def region_count(self, b=0):
+        r = ctypes.c_int32()
+        _capi.check(self._lib.rbepwt_region_count(self._ctx, int(b), ctypes.byref(r)))
+        return int(r.value)
+
+    def region_offsets(self, b=0, level=1):
+        """int32 [R+1] offsets of the regions in the level's concatenated signal."""
+        off = np.empty(self.region_count(b) + 1, dtype=np.int32)
+        _capi.check(self._lib.rbepwt_region_offsets(self._ctx, int(b), _ptr(off)))
+        if level > 1:
+            sh = level - 1
+            off = ((off.astype(np.int64) + (1 << sh) - 1) >> sh).astype(np.int32)
+        return off
+
+    def region_labels(self, b=0):
+        lab = np.empty(self.region_count(b), dtype=np.int32)
+        _capi.check(self._lib.rbepwt_region_labels(self._ctx, int(b), _ptr(lab)))
+        return lab
+
+    def paths(self, b=0, level=1):
+        """Pixel ids in path order at `level` (0: level-1 incoming order, L+1: approximation points)."""
+        n = self.npix >> max(level - 1, 0)
+        out = np.empty(n, dtype=np.int32)
+        _capi.check(self._lib.rbepwt_get_paths(self._ctx, int(b), int(level), _ptr(out)))
+        return out
+
+    def perm(self, b=0, level=1):
+        out = np.empty(self.npix >> (level - 1), dtype=np.int32)
+        _capi.check(self._lib.rbepwt_get_perm(self._ctx, int(b), int(level), _ptr(out)))
+        return out
+
+    def level_values(self, b=0, level=1):
+        out = np.empty(self.npix >> (level - 1), dtype=np.float64)
+        _capi.check(self._lib.rbepwt_get_level_values(self._ctx, int(b), int(level), _ptr(out)))
+        return out
+
+
+def encode_threshold_decode(imgs, labels, levels, wavelet, ncoefs, path_type="easypath",
+                            euclidean_distance=True, codec=None, out=None):
+    """The whole hot path for a batch in one call; returns the decoded images."""
+    codec = codec or BatchCodec()
+    codec.encode(imgs, labels, levels, wavelet, path_type, euclidean_distance)
+    codec.threshold(ncoefs)
+    return codec.decode(out)

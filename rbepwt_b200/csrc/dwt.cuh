@@ -1,0 +1,128 @@
+// K3 / K5: one level of the periodized 1-D DWT / IDWT along the concatenated paths.
+//
+// Replaces, per level, the concatenation of the regions' path-ordered values
+// (RegionCollection.add_region, /root/reference/rbepwt.py:1550, 2036), the ONE global
+// pywt.dwt(values, wavelet, 'periodization') of the level (rbepwt.py:2041) and the value part of
+// RegionCollection.reduce (1578); inverse: pywt.idwt (2067) + RegionCollection.expand (1586-1613)
+// + the final scatter and clip of Image.decode_rbepwt (307-317).
+//
+// Values are addressed BY PIXEL: V is an H*W array, the level signal is s[t] = V[Q_l[t]].
+// The low-pass output cA[o] belongs to the point at even path position 2o (reduce keeps the even
+// global positions), so it is scattered to Vout[Q_l[2o]]; the next level gathers it through its
+// own paths.  This is the reference's permutation algebra without ever materialising
+// `permutation` / `invperm`.
+//
+// Arithmetic (PyWavelets' periodization mode, restated -- see oracle/pywt_port.py):
+//   cA[o] = sum_{j=0}^{F-1} dec_lo[j] * s[(2o + F/2 - j) mod n]   ascending j, one multiply and one
+//   add per tap (explicit _rn intrinsics, never contracted into FMA), fp64;
+//   s[t]  = (sum_m rec_lo[m] cA[o]) + (sum_m rec_hi[m] cD[o]),  m ascending over the taps with
+//           t + F/2 - 1 - m even, o = (t + F/2 - 1 - m)/2 mod n/2.
+#pragma once
+#include "common.cuh"
+
+namespace rbepwt {
+
+constexpr int FMAX = 128;       // longest supported filter
+constexpr int DWT_THREADS = 256;
+constexpr int FWD_TILE = 512;   // low-pass outputs per CTA
+constexpr int INV_TILE = 1024;  // reconstructed samples per CTA
+
+struct DwtParams {
+  const double *vin;   // pixel-addressed input values, image stride vin_stride (level 1: the image)
+  size_t vin_stride;
+  double *vout;        // pixel-addressed output values (next level's input), stride N
+  const int32_t *Q;    // [chunk][2N] paths
+  double *coefs;       // [chunk][N] flat coefficients: details[1] | ... | details[L] | approx
+  const double *filt;  // dec_lo[FMAX] dec_hi[FMAX] rec_lo[FMAX] rec_hi[FMAX]
+  double *out_img;     // decode, level 1: clipped image
+  int flen, N, lev, levels;
+};
+
+__global__ void __launch_bounds__(DWT_THREADS) k3_dwt_level(DwtParams P) {
+  __shared__ double s_e[FWD_TILE + FMAX / 2 + 2], s_o[FWD_TILE + FMAX / 2 + 2];
+  __shared__ int s_q[FWD_TILE];
+  __shared__ double s_lo[FMAX], s_hi[FMAX];
+  const int tid = threadIdx.x, nt = blockDim.x, F = P.flen, N = P.N, lev = P.lev;
+  const int n = N >> (lev - 1), half = n >> 1, mask = n - 1;
+  const size_t img = blockIdx.y;
+  const int32_t *Ql = P.Q + img * 2 * (size_t)N + level_off((size_t)N, lev);
+  const double *vin = P.vin + img * P.vin_stride;
+  double *coefs = P.coefs + img * (size_t)N;
+  const int o0 = blockIdx.x * FWD_TILE, nout = min(FWD_TILE, half - o0);
+  const int tstart = 2 * o0 - F / 2 + 1, cnt = 2 * (nout - 1) + F;
+  for (int i = tid; i < F; i += nt) { s_lo[i] = P.filt[i]; s_hi[i] = P.filt[FMAX + i]; }
+  for (int i = tid; i < cnt; i += nt) {
+    const int tt = tstart + i;
+    const int pix = Ql[tt & mask];
+    const double v = vin[pix];
+    if (i & 1) s_o[i >> 1] = v; else s_e[i >> 1] = v;
+    if (!(tt & 1)) {
+      const int ol = (tt - 2 * o0) >> 1;
+      if (ol >= 0 && ol < nout) s_q[ol] = pix;
+    }
+  }
+  __syncthreads();
+  const bool last = lev == P.levels;
+  double *vout = P.vout + img * (size_t)N;
+  const size_t det_off = (size_t)N - (size_t)n;            // sum_{l<lev} N >> l
+  const size_t app_off = (size_t)N - (size_t)(N >> P.levels);
+  for (int ol = tid; ol < nout; ol += nt) {
+    double a = 0.0, d = 0.0;
+    // local sample index of tap j: 2*ol + F-1-j  (odd for even j)
+    for (int j = 0; j < F; j += 2) {
+      const int q = ol + ((F - 2 - j) >> 1);
+      const double x1 = s_o[q], x2 = s_e[q];
+      a = __dadd_rn(a, __dmul_rn(s_lo[j], x1));
+      d = __dadd_rn(d, __dmul_rn(s_hi[j], x1));
+      a = __dadd_rn(a, __dmul_rn(s_lo[j + 1], x2));
+      d = __dadd_rn(d, __dmul_rn(s_hi[j + 1], x2));
+    }
+    coefs[det_off + o0 + ol] = d;
+    if (last) coefs[app_off + o0 + ol] = a;
+    else vout[s_q[ol]] = a;
+  }
+}
+
+__global__ void __launch_bounds__(DWT_THREADS) k5_idwt_level(DwtParams P) {
+  __shared__ double s_a[INV_TILE / 2 + FMAX / 2 + 2], s_d[INV_TILE / 2 + FMAX / 2 + 2];
+  __shared__ double s_lo[FMAX], s_hi[FMAX];
+  const int tid = threadIdx.x, nt = blockDim.x, F = P.flen, N = P.N, lev = P.lev;
+  const int n = N >> (lev - 1), half = n >> 1, hmask = half - 1;
+  const size_t img = blockIdx.y;
+  const int32_t *Ql = P.Q + img * 2 * (size_t)N + level_off((size_t)N, lev);
+  const double *vin = P.vin + img * P.vin_stride;
+  const double *coefs = P.coefs + img * (size_t)N;
+  const int t0 = blockIdx.x * INV_TILE, nout = min(INV_TILE, n - t0);
+  const int omin = (t0 - F / 2) >> 1;  // floor
+  const int omax = (t0 + nout - 1 + F / 2 - 1) >> 1;
+  const int cnt = omax - omin + 1;
+  const bool deepest = lev == P.levels;
+  const size_t det_off = (size_t)N - (size_t)n;
+  const size_t app_off = (size_t)N - (size_t)(N >> P.levels);
+  for (int i = tid; i < F; i += nt) { s_lo[i] = P.filt[2 * FMAX + i]; s_hi[i] = P.filt[3 * FMAX + i]; }
+  for (int i = tid; i < cnt; i += nt) {
+    const int ow = (omin + i) & hmask;
+    s_a[i] = deepest ? coefs[app_off + ow] : vin[Ql[2 * ow]];
+    s_d[i] = coefs[det_off + ow];
+  }
+  __syncthreads();
+  for (int tl = tid; tl < nout; tl += nt) {
+    const int t = t0 + tl, base = t + F / 2 - 1;
+    double slo = 0.0, shi = 0.0;
+    for (int m = base & 1; m < F; m += 2) {
+      const int oi = ((base - m) >> 1) - omin;
+      slo = __dadd_rn(slo, __dmul_rn(s_lo[m], s_a[oi]));
+      shi = __dadd_rn(shi, __dmul_rn(s_hi[m], s_d[oi]));
+    }
+    double x = __dadd_rn(slo, shi);
+    const int pix = Ql[t];
+    if (lev == 1) {  // Image.decode_rbepwt: clip, no rounding (rbepwt.py:312-314)
+      x = x > 255.0 ? 255.0 : (x < 0.0 ? 0.0 : x);
+      P.out_img[img * (size_t)N + pix] = x;
+    } else {
+      P.vout[img * (size_t)N + pix] = x;
+    }
+  }
+}
+
+}  // namespace rbepwt

@@ -1,0 +1,334 @@
+// K1: easy-path construction.
+//
+// Replaces Region.easy_path (/root/reference/rbepwt.py:1273-1347, helpers neighborhood 84-104 and
+// rotate 78-82), the start-point rule of Region.__init_dict_and_extreme_values__ (1020-1036) and
+// the point bookkeeping of RegionCollection.reduce / Region.reduce_points (1563-1584, 1349-1375).
+//
+// One warp owns one region and walks its greedy path; the region's unvisited points are a bitmap
+// over the region's bounding box (shared memory; global scratch for boxes too large).
+//
+// Step rule (exactly the reference's, restated order-independently):
+//   candidates = unvisited points of the region inside the smallest square of half-width
+//                r = 1,2,4,8,... around the current point that contains any;
+//   choose the candidate maximising the lexicographic key (-dist, sp1, sp2) where
+//     dist = di^2+dj^2 (euclid; the reference compares sqrt of it), max(|di|,|dj|) (chebyshev) or
+//            |value[cur]-value[cand]| (EPWT),
+//     sp1  = fma(v1, p1, v0*p0)  with v = (di,dj)/sqrt(di^2+dj^2) in IEEE fp64 -- this is what
+//            np.dot(v, prefered_direc) evaluates to (OpenBLAS ddot tail),
+//     sp2  = v . rotate(pref, -pi/2), consulted only when sp1 ties exactly, in which case the two
+//            candidates are mirror images about pref and sp2 orders like the integer cross
+//            product di*p1 - dj*p0;
+//   pref = (0,1) at the start of a region, afterwards chosen - current (integer, not normalised).
+//   A complete tie (possible only in EPWT mode: collinear candidates with bit-identical |dv|)
+//   depends on CPython set order in the reference (unpinned); here the nearer point wins.
+//
+// For the geometric modes paths never read pixel values, and the region offsets of every level
+// follow from the level-1 sizes alone (a region occupying [a, a+n) keeps its even global
+// positions: [ceil(a/2), ceil((a+n)/2)) at the next level), so one warp builds the region's
+// whole path pyramid, levels 1..L, without any inter-region synchronisation.
+//
+// Output: Q[level][a + t] = pixel id (row*W+col) of the t-th path point.  The transform kernels
+// address values by pixel, so the reference's per-region `permutation` lists are not needed on the
+// hot path (they are derived on demand, perm.cuh).
+#pragma once
+#include "common.cuh"
+#include "regions.cuh"
+
+namespace rbepwt {
+
+constexpr int MODE_EUCLID = 0, MODE_CHEB = 1, MODE_EPWT = 2;
+constexpr int K1_SLOT_WORDS = 1024;  // shared-memory bitmap words per warp in the small-region kernel
+constexpr int K1_WARPS = 8;
+
+struct PathParams {
+  const int32_t *labels;  // [B][N]
+  int H, W, logW, N, levels;
+  RegionArrays reg;
+  const int32_t *queue;
+  int *qmeta;
+  int32_t *Q;  // [B][2N]
+  // big-region kernel
+  uint32_t *gscratch;          // global bitmap scratch, one slab per CTA (used when smem is too small)
+  size_t gscratch_words;       // words per slab
+  int big_smem_words;          // dynamic shared-memory words available per CTA in the big kernel
+};
+
+struct Best {
+  double dist;  // integer-valued in the geometric modes
+  double sp1;
+  int cross, d2, i, j;
+  bool have, has_sp1;
+};
+
+// sp1 of the reference's tie-break, bit for bit.
+__device__ __forceinline__ double tie_sp1(int di, int dj, int d2, int p0, int p1) {
+  const double nrm = sqrt((double)d2);  // IEEE-correct in fp64
+  const double v0 = (double)di / nrm, v1 = (double)dj / nrm;
+  double s = fma(v1, (double)p1, __dmul_rn(v0, (double)p0));
+  if (s == 0.0) s = 0.0;  // -0.0 -> +0.0 (compares equal in the reference)
+  return s;
+}
+
+template <int MODE>
+__device__ __forceinline__ void consider(Best &b, int i, int j, int ci, int cj, int p0, int p1, double curval,
+                                         const double *__restrict__ vals, int pix, bool u8wrap) {
+  const int di = i - ci, dj = j - cj;
+  const int d2 = di * di + dj * dj;
+  double dist;
+  if (MODE == MODE_EUCLID) {
+    dist = (double)d2;
+  } else if (MODE == MODE_CHEB) {
+    dist = (double)max(abs(di), abs(dj));
+  } else {
+    const double dv = curval - __ldcg(vals + pix);
+    dist = u8wrap ? (dv < 0.0 ? dv + 256.0 : dv) : fabs(dv);
+  }
+  if (b.have && dist > b.dist) return;
+  const int cross = di * p1 - dj * p0;
+  if (!b.have || dist < b.dist) {
+    b.have = true; b.has_sp1 = false;
+    b.dist = dist; b.cross = cross; b.d2 = d2; b.i = i; b.j = j;
+    return;
+  }
+  // equal dist: direction tie-break
+  if (!b.has_sp1) {
+    b.sp1 = tie_sp1(b.i - ci, b.j - cj, b.d2, p0, p1);
+    b.has_sp1 = true;
+  }
+  const double sp1 = tie_sp1(di, dj, d2, p0, p1);
+  bool better;
+  if (sp1 != b.sp1) better = sp1 > b.sp1;
+  else if (cross != b.cross) better = cross > b.cross;
+  else better = d2 < b.d2;
+  if (better) { b.sp1 = sp1; b.cross = cross; b.d2 = d2; b.i = i; b.j = j; }
+}
+
+// Warp-cooperative search for the next path point.  bm: h x ws words, bit (i,j) set <=> unvisited.
+// Returns false if no unvisited point exists in the whole bounding box (corrupt state).
+template <int MODE>
+__device__ __forceinline__ bool find_next(const uint32_t *bm, int h, int w, int ws, int ci, int cj, int p0, int p1,
+                                          const double *__restrict__ vals, int r0, int c0, int logW, bool u8wrap,
+                                          int &bi, int &bj) {
+  const int lane = (int)lane_id();
+  Best b;
+  b.have = false; b.has_sp1 = false; b.dist = 0.0; b.sp1 = 0.0; b.cross = 0; b.d2 = 0; b.i = 0; b.j = 0;
+  double curval = 0.0;
+  if (MODE == MODE_EPWT) curval = __ldcg(vals + (((r0 + ci) << logW) + c0 + cj));
+  for (int rad = 1;; rad <<= 1) {  // half-width 2^(k-1), k = 1,2,...   rbepwt.py:1296-1299, 90-92
+    const int i0 = max(ci - rad, 0), i1 = min(ci + rad, h - 1);
+    const int j0 = max(cj - rad, 0), j1 = min(cj + rad, w - 1);
+    const int w0 = j0 >> 5, w1 = j1 >> 5;
+    for (int i = i0 + lane; i <= i1; i += 32) {
+      for (int wd = w0; wd <= w1; wd++) {
+        uint32_t bits = bm[i * ws + wd];
+        const int lo = wd << 5;
+        if (lo < j0) bits &= 0xffffffffu << (j0 - lo);
+        if (lo + 31 > j1) bits &= 0xffffffffu >> (lo + 31 - j1);
+        while (bits) {
+          const int j = lo + __ffs(bits) - 1;
+          bits &= bits - 1;
+          consider<MODE>(b, i, j, ci, cj, p0, p1, curval, vals, ((r0 + i) << logW) + c0 + j, u8wrap);
+        }
+      }
+    }
+    if (__any_sync(FULL_MASK, b.have)) break;
+    if (i0 == 0 && j0 == 0 && i1 == h - 1 && j1 == w - 1) return false;
+  }
+  // cross-lane arg-best: (dist asc, sp1 desc, cross desc, d2 asc)
+  unsigned tied;
+  if (MODE == MODE_EPWT) {
+    const unsigned long long k = b.have ? (unsigned long long)__double_as_longlong(b.dist) : ~0ull;  // dist >= 0
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_min_sync(FULL_MASK, hi);
+    const unsigned ml = __reduce_min_sync(FULL_MASK, hi == mh ? lo : 0xffffffffu);
+    tied = __ballot_sync(FULL_MASK, b.have && hi == mh && lo == ml);
+  } else {
+    const int d = b.have ? (int)b.dist : INT32_MAX;
+    const int dm = __reduce_min_sync(FULL_MASK, d);
+    tied = __ballot_sync(FULL_MASK, b.have && d == dm);
+  }
+  if (__popc(tied) > 1) {
+    const bool in = (tied >> lane) & 1u;
+    if (in && !b.has_sp1) b.sp1 = tie_sp1(b.i - ci, b.j - cj, b.d2, p0, p1);
+    const unsigned long long k = in ? orderable(b.sp1) : 0ull;
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_max_sync(FULL_MASK, hi);
+    const unsigned ml = __reduce_max_sync(FULL_MASK, (in && hi == mh) ? lo : 0u);
+    tied = __ballot_sync(FULL_MASK, in && hi == mh && lo == ml);
+    if (__popc(tied) > 1) {
+      const bool in2 = (tied >> lane) & 1u;
+      const int mc = __reduce_max_sync(FULL_MASK, in2 ? b.cross : INT32_MIN);
+      tied = __ballot_sync(FULL_MASK, in2 && b.cross == mc);
+      if (__popc(tied) > 1) {
+        const bool in3 = (tied >> lane) & 1u;
+        const int md = __reduce_min_sync(FULL_MASK, in3 ? b.d2 : INT32_MAX);
+        tied = __ballot_sync(FULL_MASK, in3 && b.d2 == md);
+      }
+    }
+  }
+  const int src = __ffs(tied) - 1;
+  bi = __shfl_sync(FULL_MASK, b.i, src);
+  bj = __shfl_sync(FULL_MASK, b.j, src);
+  return true;
+}
+
+// Walk one region's path at one level.  (ci,cj) = start point (bitmap coordinates, bit still set).
+// Ql[t], t = 0..n-1, receives the pixel ids in path order.  The bitmap is all-zero afterwards.
+template <int MODE>
+__device__ __forceinline__ bool run_path(uint32_t *bm, int h, int w, int ws, int ci, int cj, int n, int r0, int c0,
+                                         int logW, const double *__restrict__ vals, bool u8wrap,
+                                         int32_t *__restrict__ Ql) {
+  const int lane = (int)lane_id();
+  int myq = 0;
+  if (lane == 0) {
+    myq = ((r0 + ci) << logW) + c0 + cj;
+    bm[ci * ws + (cj >> 5)] &= ~(1u << (cj & 31));
+  }
+  __syncwarp();
+  int p0 = 0, p1 = 1;  // prefered_direc = (0,1)   rbepwt.py:1290
+  for (int t = 1; t < n; t++) {
+    int bi, bj;
+    if (!find_next<MODE>(bm, h, w, ws, ci, cj, p0, p1, vals, r0, c0, logW, u8wrap, bi, bj)) return false;
+    if (lane == 0) bm[bi * ws + (bj >> 5)] &= ~(1u << (bj & 31));
+    __syncwarp();
+    if ((t & 31) == lane) myq = ((r0 + bi) << logW) + c0 + bj;
+    if ((t & 31) == 31) Ql[t - 31 + lane] = myq;  // coalesced flush of 32 path points
+    p0 = bi - ci; p1 = bj - cj;  // rbepwt.py:1331
+    ci = bi; cj = bj;
+  }
+  if (lane < (n & 31)) Ql[(n & ~31) + lane] = myq;
+  return true;
+}
+
+// After a level: the points at even GLOBAL position a+t survive (RegionCollection.reduce,
+// rbepwt.py:1563-1584).  Re-marks them in the (all-zero) bitmap, returns the smallest surviving
+// pixel id = next level's start point (lexicographic min (row,col), rbepwt.py:1035-1036).
+__device__ __forceinline__ int reduce_points(uint32_t *bm, int ws, int a, int n, int r0, int c0, int logW,
+                                             const int32_t *Ql) {
+  const int lane = (int)lane_id();
+  const int Wm = (1 << logW) - 1;
+  __syncwarp();
+  int minpix = INT32_MAX;
+  for (int t = lane; t < n; t += 32) {
+    if (((a + t) & 1) == 0) {
+      const int pix = __ldcg(Ql + t);
+      const int i = (pix >> logW) - r0, j = (pix & Wm) - c0;
+      atomicOr(&bm[i * ws + (j >> 5)], 1u << (j & 31));
+      minpix = min(minpix, pix);
+    }
+  }
+  minpix = __reduce_min_sync(FULL_MASK, minpix);
+  __syncwarp();
+  return minpix;
+}
+
+// Geometric modes: the whole pyramid of one region.
+template <int MODE>
+__device__ void region_pyramid(const PathParams &P, int g, uint32_t *bm) {
+  const int lane = (int)lane_id();
+  const int logW = P.logW, W = P.W, N = P.N;
+  const int img = P.reg.img[g], label = P.reg.label[g], first = P.reg.first[g];
+  int n = P.reg.size[g], a = P.reg.off[g];
+  const int r0 = first >> logW, c0 = P.reg.cmin[g];
+  const int h = P.reg.rmax[g] - r0 + 1, w = P.reg.cmax[g] - c0 + 1, ws = (w + 31) >> 5;
+  const int32_t *lab = P.labels + (size_t)img * N;
+  int32_t *Q = P.Q + (size_t)img * 2 * (size_t)N;
+
+  for (int i = 0; i < h; i++)
+    for (int wd = 0; wd < ws; wd++) {
+      const int col = c0 + (wd << 5) + lane;
+      const bool in = col < c0 + w && lab[((r0 + i) << logW) + col] == label;
+      const unsigned bits = __ballot_sync(FULL_MASK, in);
+      if (lane == 0) bm[i * ws + wd] = bits;
+    }
+  __syncwarp();
+  int si = 0, sj = (first & (W - 1)) - c0;
+  for (int lev = 1; lev <= P.levels && n > 0; lev++) {
+    int32_t *Ql = Q + level_off((size_t)N, lev) + a;
+    if (!run_path<MODE>(bm, h, w, ws, si, sj, n, r0, c0, logW, nullptr, false, Ql)) {
+      if (lane == 0) atomicExch(&P.qmeta[QM_ERR], 1);
+      return;
+    }
+    if (lev == P.levels) break;
+    const int minpix = reduce_points(bm, ws, a, n, r0, c0, logW, Ql);
+    const int na = (a + 1) >> 1, nb = (a + n + 1) >> 1;
+    a = na; n = nb - na;
+    if (n > 0) { si = (minpix >> logW) - r0; sj = (minpix & (W - 1)) - c0; }
+  }
+}
+
+// Small regions: bitmap in a per-warp shared-memory slot; warps pull regions from the queue.
+template <int MODE>
+__global__ void __launch_bounds__(K1_WARPS * 32) k1_paths_small(PathParams P) {
+  __shared__ uint32_t s_bm[K1_WARPS][K1_SLOT_WORDS];
+  const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
+  const int nbig = P.qmeta[QM_NBIG], nsmall = P.qmeta[QM_NREG] - nbig;
+  while (true) {
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(&P.qmeta[QM_CUR_SMALL], 1);
+    idx = __shfl_sync(FULL_MASK, idx, 0);
+    if (idx >= nsmall) break;
+    region_pyramid<MODE>(P, P.queue[nbig + idx], s_bm[warp]);
+    __syncwarp();
+  }
+}
+
+// Big regions: one warp per CTA, bitmap in dynamic shared memory if it fits, else global scratch.
+template <int MODE>
+__global__ void __launch_bounds__(32) k1_paths_big(PathParams P) {
+  extern __shared__ uint32_t s_big[];
+  const int lane = (int)lane_id();
+  const int nbig = P.qmeta[QM_NBIG];
+  uint32_t *gs = P.gscratch + (size_t)blockIdx.x * P.gscratch_words;
+  while (true) {
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(&P.qmeta[QM_CUR_BIG], 1);
+    idx = __shfl_sync(FULL_MASK, idx, 0);
+    if (idx >= nbig) break;
+    const int g = P.queue[idx];
+    const int words = region_bitmap_words(P.reg, g, P.logW);
+    region_pyramid<MODE>(P, g, words <= P.big_smem_words ? s_big : gs);
+    __syncwarp();
+  }
+}
+
+// EPWT: one region per image, paths depend on the level's values, so one launch per level
+// (rbepwt.py:2004-2006, 2031).  vals = pixel-addressed values of this level ([B][N]).
+struct EpwtParams {
+  int H, W, logW, N, lev, img0;
+  const double *vals;
+  int32_t *Q;        // [B][2N]
+  uint32_t *gscratch;
+  size_t gscratch_words;
+  int smem_words;
+  int u8wrap;
+  int *qmeta;
+};
+
+__global__ void __launch_bounds__(32) k1_epwt_level(EpwtParams P) {
+  extern __shared__ uint32_t s_big[];
+  const int lane = (int)lane_id();
+  const int img = P.img0 + blockIdx.x;
+  const int H = P.H, W = P.W, N = P.N, logW = P.logW, ws = (W + 31) >> 5, words = H * ws;
+  uint32_t *bm = words <= P.smem_words ? s_big : P.gscratch + (size_t)blockIdx.x * P.gscratch_words;
+  int32_t *Q = P.Q + (size_t)img * 2 * (size_t)N;
+  const double *vals = P.vals + (size_t)img * N;
+  const int n = N >> (P.lev - 1);
+  int32_t *Ql = Q + level_off((size_t)N, P.lev);
+  int start;
+  if (P.lev == 1) {
+    const uint32_t full = W >= 32 ? 0xffffffffu : ((1u << W) - 1u);
+    for (int i = lane; i < words; i += 32) bm[i] = full;
+    __syncwarp();
+    start = 0;
+  } else {
+    for (int i = lane; i < words; i += 32) bm[i] = 0u;
+    __syncwarp();
+    start = reduce_points(bm, ws, 0, N >> (P.lev - 2), 0, 0, logW, Q + level_off((size_t)N, P.lev - 1));
+  }
+  const bool ok = run_path<MODE_EPWT>(bm, H, W, ws, start >> logW, start & (W - 1), n, 0, 0, logW, vals,
+                                      P.u8wrap && P.lev == 1, Ql);
+  if (!ok && lane == 0) atomicExch(&P.qmeta[QM_ERR], 1);
+}
+
+}  // namespace rbepwt

@@ -1,0 +1,744 @@
+// rbepwt_b200: context, launch sequencing and the C ABI declared in include/rbepwt_b200.h.
+// There is no CPU implementation in this library: without a CUDA device rbepwt_create fails.
+#include "../../include/rbepwt_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "dwt.cuh"
+#include "paths.cuh"
+#include "perm.cuh"
+#include "regions.cuh"
+#include "select.cuh"
+
+using namespace rbepwt;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(RBEPWT_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {  // contents not preserved
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  cudaError_t ensure_keep(size_t bytes, size_t used, cudaStream_t s) {  // first `used` bytes preserved
+    if (bytes <= cap) return cudaSuccess;
+    size_t ncap = std::max(bytes, cap * 2);
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, ncap);
+    if (e != cudaSuccess) return e;
+    if (p && used) {
+      e = cudaMemcpyAsync(q, p, used, cudaMemcpyDeviceToDevice, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+    if (p) cudaFree(p);
+    p = q; cap = ncap;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct StageEv { int stage; cudaEvent_t a, b; };
+
+struct rbepwt_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  // wavelet
+  bool has_wavelet = false;
+  int flen = 0;
+  DevBuf filt;
+  // state of the encoded batch
+  bool has_encoding = false, has_paths = false;
+  int B = 0, H = 0, W = 0, N = 0, logW = 0, levels = 0, mode = 0;
+  unsigned enc_flags = 0;
+  const int32_t *labels_dev = nullptr;  // ours (labels_own) or the caller's device pointer
+  const double *img_dev = nullptr;
+  DevBuf labels_own, img_own, out_own, coef_up;
+  DevBuf Q, coefs;
+  DevBuf reg[8];
+  int totalR = 0;
+  DevBuf img_R, img_rbase, img_labmin, img_direct;
+  std::vector<int32_t> h_R, h_rbase;
+  // workspace
+  DevBuf tbl, slot_rid, VA, VB, queue, qhist, qmeta, gscratch, scratch_i32, scratch_i32b, psnr_out, nz_out;
+  // timing
+  bool timing = false;
+  std::vector<StageEv> evs;
+  std::vector<cudaEvent_t> ev_pool;
+  long long launches = 0;
+
+  RegionArrays regs() const {
+    RegionArrays r;
+    r.label = reg[0].as<int32_t>(); r.first = reg[1].as<int32_t>(); r.size = reg[2].as<int32_t>();
+    r.off = reg[3].as<int32_t>(); r.rmax = reg[4].as<int32_t>(); r.cmin = reg[5].as<int32_t>();
+    r.cmax = reg[6].as<int32_t>(); r.img = reg[7].as<int32_t>();
+    return r;
+  }
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+cudaEvent_t get_event(rbepwt_ctx *c) {
+  if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+
+struct StageTimer {  // records a pair of events around a stage when timing is enabled
+  rbepwt_ctx *c; StageEv ev; bool on;
+  StageTimer(rbepwt_ctx *c_, int stage) : c(c_), on(c_->timing) {
+    if (on) { ev.stage = stage; ev.a = get_event(c); ev.b = get_event(c); cudaEventRecord(ev.a, c->stream); }
+  }
+  ~StageTimer() { if (on) { cudaEventRecord(ev.b, c->stream); c->evs.push_back(ev); } }
+};
+
+void clear_events(rbepwt_ctx *c) {
+  for (auto &e : c->evs) { c->ev_pool.push_back(e.a); c->ev_pool.push_back(e.b); }
+  c->evs.clear();
+}
+
+int ilog2(int x) { int l = 0; while ((1 << l) < x) l++; return l; }
+
+// images per chunk: bounded by a workspace budget (hash table + slot ids + two value planes = 40 N bytes/image)
+int chunk_images(const rbepwt_ctx *c, int B, int N) {
+  const size_t per = (size_t)N * 40;
+  size_t budget = (size_t)6 << 30;
+  int m = (int)std::max<size_t>(1, budget / per);
+  return std::min(std::min(m, 512), B);
+}
+
+int check_path_error(rbepwt_ctx *c) {
+  int err = 0;
+  CK(cudaMemcpyAsync(&err, c->qmeta.as<int>() + QM_ERR, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (err) return fail(RBEPWT_E_CUDA, "path kernel found no unvisited point (corrupt region state)");
+  return RBEPWT_OK;
+}
+
+int validate_shape(int B, int H, int W, int levels, int path_mode) {
+  if (B < 1 || H < 1 || W < 1) return fail(RBEPWT_E_ARG, "B, H, W must be positive");
+  const long long n = (long long)H * W;
+  if (n & (n - 1)) return fail(RBEPWT_E_NOT_POW2, "Image size must be a power of 2");
+  if (n > (1ll << 30) || W > 32768 || H > 32768) return fail(RBEPWT_E_ARG, "image too large (H*W <= 2^30)");
+  if (levels < 1 || levels > 30 || (1ll << levels) > n)
+    return fail(RBEPWT_E_LEVELS, "2^levels must be smaller or equal to the number of pixels in the image");
+  if (path_mode < 0 || path_mode > 2) return fail(RBEPWT_E_ARG, "unknown path mode %d", path_mode);
+  return RBEPWT_OK;
+}
+
+// K0 + K1 for the geometric modes, K0' for EPWT: region records and (geometric) the whole path pyramid.
+// With EPWT the paths depend on the level's values, so they are built inside transform_chunk().
+int build_regions_and_paths(rbepwt_ctx *c, int c0, int nb) {
+  const int N = c->N, T = 2 * N;
+  cudaStream_t s = c->stream;
+  if (c->mode == RBEPWT_PATH_EPWT) {
+    StageTimer t(c, RBEPWT_T_REGIONS);
+    for (int i = 0; i < 8; i++) CK(c->reg[i].ensure_keep((size_t)c->B * 4, (size_t)c0 * 4, s));
+    k0_single_region<<<(nb + 127) / 128, 128, 0, s>>>(c0, nb, c->H, c->W, c->regs(), c->img_R.as<int32_t>(),
+                                                     c->img_rbase.as<int32_t>());
+    c->launches++;
+    for (int i = 0; i < nb; i++) { c->h_R[c0 + i] = 1; c->h_rbase[c0 + i] = c0 + i; }
+    c->totalR = c0 + nb;
+    CK(cudaGetLastError());
+    return RBEPWT_OK;
+  }
+  int g0, nreg;
+  {
+    StageTimer t(c, RBEPWT_T_REGIONS);
+    k0_count<<<nb, K0_THREADS, 0, s>>>(c->labels_dev, c0, N, c->tbl.as<unsigned long long>(), T,
+                                       c->img_R.as<int32_t>(), c->img_labmin.as<int32_t>(),
+                                       c->img_direct.as<int32_t>());
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_R.data() + c0, c->img_R.as<int32_t>() + c0, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    g0 = c->totalR;
+    for (int i = 0; i < nb; i++) { c->h_rbase[c0 + i] = c->totalR; c->totalR += c->h_R[c0 + i]; }
+    nreg = c->totalR - g0;
+    for (int i = 0; i < 8; i++) CK(c->reg[i].ensure_keep((size_t)c->totalR * 4, (size_t)g0 * 4, s));
+    CK(cudaMemcpyAsync(c->img_rbase.as<int32_t>() + c0, c->h_rbase.data() + c0, (size_t)nb * 4,
+                       cudaMemcpyHostToDevice, s));
+    k0_regions<<<nb, K0_THREADS, 0, s>>>(c->labels_dev, c0, N, c->logW, c->tbl.as<unsigned long long>(),
+                                         c->slot_rid.as<int32_t>(), T, c->img_R.as<int32_t>(),
+                                         c->img_labmin.as<int32_t>(), c->img_direct.as<int32_t>(),
+                                         c->img_rbase.as<int32_t>(), c->regs());
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(c->queue.ensure((size_t)nreg * 4));
+    const int qb = std::max(1, std::min((nreg + 255) / 256, c->sm_count * 8));
+    kq_hist<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, K1_SLOT_WORDS, c->qhist.as<int>());
+    kq_scan<<<1, 32, 0, s>>>(c->qhist.as<int>(), c->qmeta.as<int>(), nreg);
+    kq_scatter<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, K1_SLOT_WORDS, c->qmeta.as<int>(),
+                                  c->queue.as<int32_t>());
+    c->launches += 3;
+    CK(cudaGetLastError());
+  }
+  {
+    StageTimer t(c, RBEPWT_T_PATHS);
+    PathParams P;
+    P.labels = c->labels_dev;
+    P.H = c->H; P.W = c->W; P.logW = c->logW; P.N = N; P.levels = c->levels;
+    P.reg = c->regs();
+    P.queue = c->queue.as<int32_t>();
+    P.qmeta = c->qmeta.as<int>();
+    P.Q = c->Q.as<int32_t>();
+    // big-region kernel: whole-image bitmap in dynamic shared memory when it fits
+    const size_t img_words = (size_t)c->H * ((c->W + 31) / 32);
+    const size_t smem_cap = std::min<size_t>(c->smem_optin, (size_t)200 * 1024);
+    const size_t smem_bytes = std::min(img_words * 4, smem_cap);
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)220 * 1024) / (smem_bytes + 1024)));
+    const int big_ctas = c->sm_count * per_sm;
+    P.big_smem_words = (int)(smem_bytes / 4);
+    P.gscratch = nullptr; P.gscratch_words = 0;
+    if (img_words * 4 > smem_bytes) {
+      CK(c->gscratch.ensure(img_words * 4 * (size_t)big_ctas));
+      P.gscratch = c->gscratch.as<uint32_t>();
+      P.gscratch_words = img_words;
+    }
+    const int small_ctas = c->sm_count * 6;
+    if (c->mode == RBEPWT_PATH_EUCLID) {
+      CK(cudaFuncSetAttribute(k1_paths_big<MODE_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      k1_paths_big<MODE_EUCLID><<<big_ctas, 32, smem_bytes, s>>>(P);
+      k1_paths_small<MODE_EUCLID><<<small_ctas, K1_WARPS * 32, 0, s>>>(P);
+    } else {
+      CK(cudaFuncSetAttribute(k1_paths_big<MODE_CHEB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      k1_paths_big<MODE_CHEB><<<big_ctas, 32, smem_bytes, s>>>(P);
+      k1_paths_small<MODE_CHEB><<<small_ctas, K1_WARPS * 32, 0, s>>>(P);
+    }
+    c->launches += 2;
+    CK(cudaGetLastError());
+  }
+  return RBEPWT_OK;
+}
+
+// K3 for every level of the chunk (EPWT: K1 level kernel before each level's DWT).
+int transform_chunk(rbepwt_ctx *c, int c0, int nb) {
+  const int N = c->N;
+  cudaStream_t s = c->stream;
+  DwtParams D;
+  D.Q = c->Q.as<int32_t>() + (size_t)c0 * 2 * N;
+  D.coefs = c->coefs.as<double>() + (size_t)c0 * N;
+  D.filt = c->filt.as<double>();
+  D.out_img = nullptr;
+  D.flen = c->flen; D.N = N; D.levels = c->levels;
+  double *V[2] = {c->VA.as<double>(), c->VB.as<double>()};
+  EpwtParams E;
+  size_t epwt_smem = 0;
+  if (c->mode == RBEPWT_PATH_EPWT) {
+    const size_t img_words = (size_t)c->H * ((c->W + 31) / 32);
+    const size_t smem_cap = std::min<size_t>(c->smem_optin, (size_t)200 * 1024);
+    epwt_smem = std::min(img_words * 4, smem_cap);
+    E.H = c->H; E.W = c->W; E.logW = c->logW; E.N = N; E.img0 = 0;
+    E.Q = const_cast<int32_t *>(D.Q);
+    E.smem_words = (int)(epwt_smem / 4);
+    E.gscratch = nullptr; E.gscratch_words = 0;
+    if (img_words * 4 > epwt_smem) {
+      CK(c->gscratch.ensure(img_words * 4 * (size_t)nb));
+      E.gscratch = c->gscratch.as<uint32_t>();
+      E.gscratch_words = img_words;
+    }
+    E.u8wrap = (c->enc_flags & RBEPWT_U8_WRAP) ? 1 : 0;
+    E.qmeta = c->qmeta.as<int>();
+    CK(cudaFuncSetAttribute(k1_epwt_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)epwt_smem));
+  }
+  for (int lev = 1; lev <= c->levels; lev++) {
+    D.lev = lev;
+    if (lev == 1) { D.vin = c->img_dev + (size_t)c0 * N; D.vin_stride = N; }
+    else { D.vin = V[(lev - 1) & 1]; D.vin_stride = N; }
+    D.vout = V[lev & 1];
+    if (c->mode == RBEPWT_PATH_EPWT) {
+      StageTimer t(c, RBEPWT_T_PATHS);
+      E.lev = lev;
+      E.vals = D.vin;
+      k1_epwt_level<<<nb, 32, epwt_smem, s>>>(E);
+      c->launches++;
+    }
+    {
+      StageTimer t(c, RBEPWT_T_DWT);
+      const int half = (N >> (lev - 1)) >> 1;
+      dim3 grid((half + FWD_TILE - 1) / FWD_TILE, nb);
+      k3_dwt_level<<<grid, DWT_THREADS, 0, s>>>(D);
+      c->launches++;
+    }
+  }
+  CK(cudaGetLastError());
+  return RBEPWT_OK;
+}
+
+int alloc_state(rbepwt_ctx *c, int B, int H, int W, int levels, int path_mode, unsigned flags) {
+  c->has_encoding = false; c->has_paths = false;
+  c->B = B; c->H = H; c->W = W; c->N = H * W; c->logW = ilog2(W); c->levels = levels; c->mode = path_mode;
+  c->enc_flags = flags;
+  c->totalR = 0;
+  c->h_R.assign(B, 0); c->h_rbase.assign(B, 0);
+  const size_t N = c->N;
+  CK(c->Q.ensure((size_t)B * 2 * N * 4));
+  CK(c->coefs.ensure((size_t)B * N * 8));
+  CK(c->img_R.ensure((size_t)B * 4)); CK(c->img_rbase.ensure((size_t)B * 4));
+  CK(c->img_labmin.ensure((size_t)B * 4)); CK(c->img_direct.ensure((size_t)B * 4));
+  const int Bc = chunk_images(c, B, c->N);
+  if (path_mode != RBEPWT_PATH_EPWT) {
+    CK(c->tbl.ensure((size_t)Bc * 2 * N * 8));
+    CK(c->slot_rid.ensure((size_t)Bc * 2 * N * 4));
+  }
+  CK(c->VA.ensure((size_t)Bc * N * 8));
+  CK(c->VB.ensure((size_t)Bc * N * 8));
+  if (!c->qhist.p) {
+    CK(c->qhist.ensure(Q_BINS * 4));
+    CK(cudaMemsetAsync(c->qhist.p, 0, Q_BINS * 4, c->stream));
+  }
+  if (!c->qmeta.p) CK(c->qmeta.ensure(QM_SIZE * 4));
+  CK(cudaMemsetAsync(c->qmeta.p, 0, QM_SIZE * 4, c->stream));
+  return RBEPWT_OK;
+}
+
+int upload_labels(rbepwt_ctx *c, const int32_t *labels, unsigned flags) {
+  if (c->mode == RBEPWT_PATH_EPWT) { c->labels_dev = nullptr; return RBEPWT_OK; }
+  if (!labels) return fail(RBEPWT_E_ARG, "labels are required unless path_mode is EPWT");
+  if (flags & RBEPWT_DEVICE_PTRS) { c->labels_dev = labels; return RBEPWT_OK; }
+  StageTimer t(c, RBEPWT_T_H2D);
+  const size_t bytes = (size_t)c->B * c->N * 4;
+  CK(c->labels_own.ensure(bytes));
+  CK(cudaMemcpyAsync(c->labels_own.p, labels, bytes, cudaMemcpyHostToDevice, c->stream));
+  c->labels_dev = c->labels_own.as<int32_t>();
+  return RBEPWT_OK;
+}
+
+int decode_all(rbepwt_ctx *c, double *out_dev) {
+  const int N = c->N, B = c->B;
+  cudaStream_t s = c->stream;
+  const int Bc = chunk_images(c, B, N);
+  CK(c->VA.ensure((size_t)Bc * N * 8));
+  CK(c->VB.ensure((size_t)Bc * N * 8));
+  double *V[2] = {c->VA.as<double>(), c->VB.as<double>()};
+  StageTimer t(c, RBEPWT_T_IDWT);
+  for (int c0 = 0; c0 < B; c0 += Bc) {
+    const int nb = std::min(Bc, B - c0);
+    DwtParams D;
+    D.Q = c->Q.as<int32_t>() + (size_t)c0 * 2 * N;
+    D.coefs = c->coefs.as<double>() + (size_t)c0 * N;
+    D.filt = c->filt.as<double>();
+    D.out_img = out_dev + (size_t)c0 * N;
+    D.flen = c->flen; D.N = N; D.levels = c->levels;
+    for (int lev = c->levels; lev >= 1; lev--) {
+      D.lev = lev;
+      D.vin = V[(lev + 1) & 1]; D.vin_stride = N;
+      D.vout = V[lev & 1];
+      const int n = N >> (lev - 1);
+      dim3 grid((n + INV_TILE - 1) / INV_TILE, nb);
+      k5_idwt_level<<<grid, DWT_THREADS, 0, s>>>(D);
+      c->launches++;
+    }
+  }
+  CK(cudaGetLastError());
+  return RBEPWT_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------- C ABI --------
+
+extern "C" {
+
+const char *rbepwt_last_error(void) { return g_err.c_str(); }
+
+int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
+  if (!out) return fail(RBEPWT_E_ARG, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(RBEPWT_E_NO_GPU, "no CUDA device available (%s); rbepwt_b200 has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= ndev) return fail(RBEPWT_E_ARG, "device %d out of range (%d devices)", device, ndev);
+  CK(cudaSetDevice(device));
+  rbepwt_ctx *c = new rbepwt_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+  else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  CK(c->filt.ensure(4 * FMAX * sizeof(double)));
+  *out = c;
+  return RBEPWT_OK;
+}
+
+void rbepwt_destroy(rbepwt_ctx *c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  cudaStreamSynchronize(c->stream);
+  clear_events(c);
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  DevBuf *bufs[] = {&c->filt, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->coefs, &c->img_R,
+                    &c->img_rbase, &c->img_labmin, &c->img_direct, &c->tbl, &c->slot_rid, &c->VA, &c->VB, &c->queue,
+                    &c->qhist, &c->qmeta, &c->gscratch, &c->scratch_i32, &c->scratch_i32b, &c->psnr_out, &c->nz_out};
+  for (auto b : bufs) b->release();
+  for (auto &b : c->reg) b.release();
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int rbepwt_sync(rbepwt_ctx *c) {
+  if (!c) return fail(RBEPWT_E_ARG, "ctx is NULL");
+  DeviceGuard g(c->device);
+  CK(cudaStreamSynchronize(c->stream));
+  return RBEPWT_OK;
+}
+
+int rbepwt_set_wavelet(rbepwt_ctx *c, int flen, const double *dec_lo, const double *dec_hi, const double *rec_lo,
+                       const double *rec_hi) {
+  if (!c) return fail(RBEPWT_E_ARG, "ctx is NULL");
+  if (flen < 2 || flen > FMAX || (flen & 1)) return fail(RBEPWT_E_ARG, "filter length must be even, 2..%d", FMAX);
+  DeviceGuard g(c->device);
+  std::vector<double> h(4 * FMAX, 0.0);
+  memcpy(&h[0], dec_lo, flen * 8); memcpy(&h[FMAX], dec_hi, flen * 8);
+  memcpy(&h[2 * FMAX], rec_lo, flen * 8); memcpy(&h[3 * FMAX], rec_hi, flen * 8);
+  CK(cudaMemcpyAsync(c->filt.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->flen = flen;
+  c->has_wavelet = true;
+  return RBEPWT_OK;
+}
+
+int rbepwt_encode(rbepwt_ctx *c, const double *img, const int32_t *labels, int B, int H, int W, int levels,
+                  int path_mode, unsigned flags) {
+  if (!c || !img) return fail(RBEPWT_E_ARG, "ctx / img is NULL");
+  int rc = validate_shape(B, H, W, levels, path_mode);
+  if (rc) return rc;
+  if (!c->has_wavelet) return fail(RBEPWT_E_NO_WAVELET, "rbepwt_set_wavelet has not been called");
+  DeviceGuard g(c->device);
+  clear_events(c);
+  if ((rc = alloc_state(c, B, H, W, levels, path_mode, flags))) return rc;
+  if ((rc = upload_labels(c, labels, flags))) return rc;
+  if (flags & RBEPWT_DEVICE_PTRS) {
+    c->img_dev = img;
+  } else {
+    StageTimer t(c, RBEPWT_T_H2D);
+    const size_t bytes = (size_t)B * c->N * 8;
+    CK(c->img_own.ensure(bytes));
+    CK(cudaMemcpyAsync(c->img_own.p, img, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->img_dev = c->img_own.as<double>();
+  }
+  const int Bc = chunk_images(c, B, c->N);
+  for (int c0 = 0; c0 < B; c0 += Bc) {
+    const int nb = std::min(Bc, B - c0);
+    if ((rc = build_regions_and_paths(c, c0, nb))) return rc;
+    if ((rc = transform_chunk(c, c0, nb))) return rc;
+  }
+  c->has_paths = true;
+  c->has_encoding = true;
+  if (!(flags & RBEPWT_DEVICE_PTRS)) return check_path_error(c);  // host-pointer calls are synchronous
+  return RBEPWT_OK;
+}
+
+int rbepwt_threshold(rbepwt_ctx *c, int64_t k) {
+  if (!c) return fail(RBEPWT_E_ARG, "ctx is NULL");
+  if (!c->has_encoding) return fail(RBEPWT_E_NO_ENCODING, "There is no saved encoding to decode");
+  DeviceGuard g(c->device);
+  {
+    StageTimer t(c, RBEPWT_T_SELECT);
+    k4_threshold<<<c->B, SEL_THREADS, 0, c->stream>>>(c->coefs.as<double>(), c->N, (long long)k);
+    c->launches++;
+  }
+  CK(cudaGetLastError());
+  return RBEPWT_OK;
+}
+
+int rbepwt_decode(rbepwt_ctx *c, double *out_img, unsigned flags) {
+  if (!c || !out_img) return fail(RBEPWT_E_ARG, "ctx / out is NULL");
+  if (!c->has_encoding) return fail(RBEPWT_E_NO_ENCODING, "There is no saved encoding to decode");
+  DeviceGuard g(c->device);
+  const size_t bytes = (size_t)c->B * c->N * 8;
+  double *out_dev = out_img;
+  if (!(flags & RBEPWT_DEVICE_PTRS)) {
+    CK(c->out_own.ensure(bytes));
+    out_dev = c->out_own.as<double>();
+  }
+  int rc = decode_all(c, out_dev);
+  if (rc) return rc;
+  if (!(flags & RBEPWT_DEVICE_PTRS)) {
+    {
+      StageTimer t(c, RBEPWT_T_D2H);
+      CK(cudaMemcpyAsync(out_img, out_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return check_path_error(c);
+  }
+  return RBEPWT_OK;
+}
+
+int rbepwt_full_decode(rbepwt_ctx *c, const double *coefs, const int32_t *labels, int B, int H, int W, int levels,
+                       int path_mode, double *out_img, unsigned flags) {
+  if (!c || !coefs || !out_img) return fail(RBEPWT_E_ARG, "ctx / coefs / out is NULL");
+  int rc = validate_shape(B, H, W, levels, path_mode);
+  if (rc) return rc;
+  if (path_mode == RBEPWT_PATH_EPWT)
+    return fail(RBEPWT_E_ARG, "full_decode needs value-independent paths (EPWT paths depend on the image)");
+  if (!c->has_wavelet) return fail(RBEPWT_E_NO_WAVELET, "rbepwt_set_wavelet has not been called");
+  DeviceGuard g(c->device);
+  clear_events(c);
+  if ((rc = alloc_state(c, B, H, W, levels, path_mode, flags))) return rc;
+  if ((rc = upload_labels(c, labels, flags))) return rc;
+  c->img_dev = nullptr;
+  const int Bc = chunk_images(c, B, c->N);
+  for (int c0 = 0; c0 < B; c0 += Bc)
+    if ((rc = build_regions_and_paths(c, c0, std::min(Bc, B - c0)))) return rc;
+  c->has_paths = true;
+  const size_t bytes = (size_t)B * c->N * 8;
+  CK(cudaMemcpyAsync(c->coefs.p, coefs, bytes,
+                     (flags & RBEPWT_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+  c->has_encoding = true;
+  return rbepwt_decode(c, out_img, flags);
+}
+
+int rbepwt_psnr(rbepwt_ctx *c, const double *a, const double *b, int B, int64_t n, double *out, unsigned flags) {
+  if (!c || !a || !b || !out || B < 1 || n < 1) return fail(RBEPWT_E_ARG, "bad psnr arguments");
+  DeviceGuard g(c->device);
+  const size_t bytes = (size_t)B * n * 8;
+  const double *da = a, *db = b;
+  if (!(flags & RBEPWT_DEVICE_PTRS)) {
+    CK(c->scratch_i32.ensure(bytes)); CK(c->scratch_i32b.ensure(bytes));
+    CK(cudaMemcpyAsync(c->scratch_i32.p, a, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->scratch_i32b.p, b, bytes, cudaMemcpyHostToDevice, c->stream));
+    da = c->scratch_i32.as<double>(); db = c->scratch_i32b.as<double>();
+  }
+  CK(c->psnr_out.ensure((size_t)B * 8));
+  k6_psnr<<<B, 1024, 0, c->stream>>>(da, db, (long long)n, c->psnr_out.as<double>());
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, c->psnr_out.p, (size_t)B * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return RBEPWT_OK;
+}
+
+int rbepwt_nonzero_coefs(rbepwt_ctx *c, int64_t *out) {
+  if (!c || !out) return fail(RBEPWT_E_ARG, "ctx / out is NULL");
+  if (!c->has_encoding) return fail(RBEPWT_E_NO_ENCODING, "There is no saved encoding to decode");
+  DeviceGuard g(c->device);
+  CK(c->nz_out.ensure((size_t)c->B * 8));
+  k_nonzero<<<c->B, 256, 0, c->stream>>>(c->coefs.as<double>(), c->N, c->nz_out.as<long long>());
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, c->nz_out.p, (size_t)c->B * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return RBEPWT_OK;
+}
+
+static int check_img(rbepwt_ctx *c, int b, bool need_enc) {
+  if (!c) return fail(RBEPWT_E_ARG, "ctx is NULL");
+  if (need_enc ? !c->has_encoding : !c->has_paths) return fail(RBEPWT_E_NO_ENCODING, "There is no saved encoding to decode");
+  if (b < 0 || b >= c->B) return fail(RBEPWT_E_ARG, "image index %d out of range", b);
+  return RBEPWT_OK;
+}
+
+int rbepwt_get_coefs(rbepwt_ctx *c, int b, double *flat) {
+  int rc = check_img(c, b, true);
+  if (rc) return rc;
+  DeviceGuard g(c->device);
+  CK(cudaMemcpyAsync(flat, c->coefs.as<double>() + (size_t)b * c->N, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+  return check_path_error(c);
+}
+
+int rbepwt_set_coefs(rbepwt_ctx *c, int b, const double *flat) {
+  int rc = check_img(c, b, true);
+  if (rc) return rc;
+  DeviceGuard g(c->device);
+  CK(cudaMemcpyAsync(c->coefs.as<double>() + (size_t)b * c->N, flat, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return RBEPWT_OK;
+}
+
+int rbepwt_region_count(rbepwt_ctx *c, int b, int32_t *R) {
+  int rc = check_img(c, b, false);
+  if (rc) return rc;
+  *R = c->h_R[b];
+  return RBEPWT_OK;
+}
+
+static int copy_region_array(rbepwt_ctx *c, int b, int which, int32_t *out) {
+  DeviceGuard g(c->device);
+  CK(cudaMemcpyAsync(out, c->reg[which].as<int32_t>() + c->h_rbase[b], (size_t)c->h_R[b] * 4, cudaMemcpyDeviceToHost,
+                     c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return RBEPWT_OK;
+}
+
+int rbepwt_region_offsets(rbepwt_ctx *c, int b, int32_t *off) {
+  int rc = check_img(c, b, false);
+  if (rc) return rc;
+  if ((rc = copy_region_array(c, b, 3, off))) return rc;
+  off[c->h_R[b]] = c->N;
+  return RBEPWT_OK;
+}
+
+int rbepwt_region_labels(rbepwt_ctx *c, int b, int32_t *labels) {
+  int rc = check_img(c, b, false);
+  if (rc) return rc;
+  return copy_region_array(c, b, 0, labels);
+}
+
+// level-1 incoming order of image b into scratch_i32 (device)
+static int level1_incoming(rbepwt_ctx *c, int b) {
+  CK(c->scratch_i32.ensure((size_t)c->N * 8));
+  int32_t *inc = c->scratch_i32.as<int32_t>();
+  if (c->mode == RBEPWT_PATH_EPWT) {  // one region, row-major
+    std::vector<int32_t> id(c->N);
+    for (int i = 0; i < c->N; i++) id[i] = i;
+    CK(cudaMemcpyAsync(inc, id.data(), (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return RBEPWT_OK;
+  }
+  const int R = c->h_R[b];
+  k_level1_incoming<<<(R * 32 + 255) / 256, 256, 0, c->stream>>>(c->labels_dev + (size_t)b * c->N, c->logW, c->regs(),
+                                                                 c->h_rbase[b], R, inc);
+  c->launches++;
+  CK(cudaGetLastError());
+  return RBEPWT_OK;
+}
+
+int rbepwt_get_paths(rbepwt_ctx *c, int b, int level, int32_t *pix) {
+  int rc = check_img(c, b, c && c->mode == RBEPWT_PATH_EPWT);
+  if (rc) return rc;
+  if (level < 0 || level > c->levels + 1) return fail(RBEPWT_E_ARG, "level %d out of range", level);
+  DeviceGuard g(c->device);
+  const size_t N = c->N;
+  const int32_t *Q = c->Q.as<int32_t>() + (size_t)b * 2 * N;
+  if (level == 0) {
+    if ((rc = level1_incoming(c, b))) return rc;
+    CK(cudaMemcpyAsync(pix, c->scratch_i32.p, N * 4, cudaMemcpyDeviceToHost, c->stream));
+  } else if (level <= c->levels) {
+    CK(cudaMemcpyAsync(pix, Q + level_off(N, level), (N >> (level - 1)) * 4, cudaMemcpyDeviceToHost, c->stream));
+  } else {  // approximation's points: even positions of the last level's paths
+    const size_t n = N >> (level - 1);
+    CK(cudaMemcpy2DAsync(pix, 4, Q + level_off(N, c->levels), 8, 4, n, cudaMemcpyDeviceToHost, c->stream));
+  }
+  return check_path_error(c);
+}
+
+int rbepwt_get_perm(rbepwt_ctx *c, int b, int level, int32_t *perm) {
+  int rc = check_img(c, b, c && c->mode == RBEPWT_PATH_EPWT);
+  if (rc) return rc;
+  if (level < 1 || level > c->levels) return fail(RBEPWT_E_ARG, "level %d out of range", level);
+  DeviceGuard g(c->device);
+  const size_t N = c->N;
+  const int n = (int)(N >> (level - 1));
+  const int32_t *Q = c->Q.as<int32_t>() + (size_t)b * 2 * N;
+  CK(c->scratch_i32b.ensure(N * 8));
+  int32_t *inv = c->scratch_i32b.as<int32_t>(), *out = inv + N;
+  if (level == 1) {
+    if ((rc = level1_incoming(c, b))) return rc;
+    k_inv_scatter<<<(n + 255) / 256, 256, 0, c->stream>>>(c->scratch_i32.as<int32_t>(), 1, n, inv);
+  } else {
+    k_inv_scatter<<<(n + 255) / 256, 256, 0, c->stream>>>(Q + level_off(N, level - 1), 2, n, inv);
+  }
+  k_perm_gather<<<(n + 255) / 256, 256, 0, c->stream>>>(Q + level_off(N, level), n, inv,
+                                                        c->reg[3].as<int32_t>() + c->h_rbase[b], c->h_R[b], level, out);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(perm, out, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  return check_path_error(c);
+}
+
+int rbepwt_get_level_values(rbepwt_ctx *c, int b, int level, double *vals) {
+  int rc = check_img(c, b, true);
+  if (rc) return rc;
+  if (level < 1 || level > c->levels) return fail(RBEPWT_E_ARG, "level %d out of range", level);
+  if (!c->img_dev) return fail(RBEPWT_E_ARG, "no image is attached to this encoding");
+  DeviceGuard g(c->device);
+  const size_t N = c->N;
+  const int n = (int)(N >> (level - 1));
+  cudaStream_t s = c->stream;
+  CK(c->coef_up.ensure(N * 8 * 2));
+  double *scratch = c->coef_up.as<double>(), *out = scratch + N;
+  double *V[2] = {c->VA.as<double>(), c->VB.as<double>()};
+  DwtParams D;
+  D.Q = c->Q.as<int32_t>() + (size_t)b * 2 * N;
+  D.coefs = scratch;
+  D.filt = c->filt.as<double>();
+  D.out_img = nullptr;
+  D.flen = c->flen; D.N = c->N; D.levels = 31;  // never the "last" level: low-pass always goes to vout
+  for (int lev = 1; lev < level; lev++) {
+    D.lev = lev;
+    D.vin = lev == 1 ? c->img_dev + (size_t)b * N : V[(lev - 1) & 1];
+    D.vin_stride = N;
+    D.vout = V[lev & 1];
+    const int half = (int)((N >> (lev - 1)) >> 1);
+    k3_dwt_level<<<dim3((half + FWD_TILE - 1) / FWD_TILE, 1), DWT_THREADS, 0, s>>>(D);
+    c->launches++;
+  }
+  const int32_t *Q = c->Q.as<int32_t>() + (size_t)b * 2 * N;
+  if (level == 1) {
+    if ((rc = level1_incoming(c, b))) return rc;
+    k_gather_values<<<(n + 255) / 256, 256, 0, s>>>(c->img_dev + (size_t)b * N, c->scratch_i32.as<int32_t>(), 1, n, out);
+  } else {
+    k_gather_values<<<(n + 255) / 256, 256, 0, s>>>(V[(level - 1) & 1], Q + level_off(N, level - 1), 2, n, out);
+  }
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(vals, out, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  return check_path_error(c);
+}
+
+int rbepwt_enable_timing(rbepwt_ctx *c, int on) {
+  if (!c) return fail(RBEPWT_E_ARG, "ctx is NULL");
+  c->timing = on != 0;
+  if (!on) { DeviceGuard g(c->device); cudaStreamSynchronize(c->stream); clear_events(c); }
+  return RBEPWT_OK;
+}
+
+int rbepwt_get_timings(rbepwt_ctx *c, float *ms, int n) {
+  if (!c || !ms) return fail(RBEPWT_E_ARG, "ctx / ms is NULL");
+  DeviceGuard g(c->device);
+  CK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n; i++) ms[i] = 0.f;
+  for (auto &e : c->evs) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, e.a, e.b));
+    if (e.stage < n) ms[e.stage] += t;
+  }
+  clear_events(c);
+  return RBEPWT_T_COUNT;
+}
+
+int64_t rbepwt_launch_count(rbepwt_ctx *c) { return c ? c->launches : 0; }
+
+}  // extern "C"

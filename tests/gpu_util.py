@@ -1,0 +1,48 @@
+"""Helpers for the -m gpu parity tests: run the CUDA path through the public Python API (which calls
+the C ABI) and lay the results out like oracle.c_oracle.run / ref_harness.run_reference."""
+import numpy as np
+
+
+def cuda_run(img, labels, levels, wavelet, path_type="easypath", euclidean_distance=True, ncoefs=None,
+             with_perm=True):
+    import rbepwt_b200 as rb
+
+    img = np.asarray(img)
+    H, W = img.shape
+    c = rb.BatchCodec()
+    c.encode(img[None], None if labels is None else np.asarray(labels)[None], levels, wavelet, path_type,
+             euclidean_distance)
+    out = {"perm": {}, "roff": {}, "points": {}, "codec": c}
+    for lev in range(1, levels + 2):
+        out["roff"][lev] = c.region_offsets(0, lev)
+        pix = c.paths(0, lev)
+        out["points"][lev] = np.stack([pix // W, pix % W], axis=1).astype(np.int32)
+        if lev <= levels and with_perm:
+            out["perm"][lev] = c.perm(0, lev)
+    out["coefs"] = c.coefs(0)
+    if ncoefs is not None:
+        c.threshold(ncoefs)
+        th = c.coefs(0)
+        out["thresholded"] = th
+        out["kept"] = np.flatnonzero(th != 0).astype(np.int64)
+        dec = c.decode()[0]
+        out["decoded"] = dec
+        out["psnr"] = float(c.psnr(np.asarray(img, dtype=np.float64)[None], dec[None])[0])
+        out["nonzero_coefs"] = int(c.nonzero_coefs()[0])
+    return out
+
+
+def assert_same_as_oracle(out, orc, levels, coef_rtol=1e-12):
+    """CUDA vs C oracle on identical inputs and identical filter banks: integer work bit-exact; the
+    fp64 arithmetic follows the same operation order, so coefficients agree to rounding."""
+    for lev in range(1, levels + 2):
+        np.testing.assert_array_equal(out["roff"][lev], orc["roff"][lev], err_msg="roff level %d" % lev)
+        np.testing.assert_array_equal(out["points"][lev], orc["points"][lev], err_msg="points level %d" % lev)
+    for lev in out["perm"]:
+        np.testing.assert_array_equal(out["perm"][lev], orc["perm"][lev], err_msg="perm level %d" % lev)
+    scale = np.max(np.abs(orc["coefs"]))
+    assert np.max(np.abs(out["coefs"] - orc["coefs"])) <= coef_rtol * scale
+    if "kept" in orc:
+        np.testing.assert_array_equal(out["kept"], orc["kept"])
+        assert np.max(np.abs(out["decoded"] - orc["decoded"])) <= 1e-9 * 255
+        assert abs(out["psnr"] - orc["psnr"]) < 5e-7

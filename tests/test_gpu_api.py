@@ -1,0 +1,133 @@
+"""-m gpu: the reference-shaped facade (rbepwt_b200.Image) used the way the reference's scripts use it."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _image(g):
+    import rbepwt_b200 as rbepwt
+
+    im = rbepwt.Image()
+    im.read_array(g["img"])
+    if g["labels"] is not None:
+        im.set_labels(g["labels"])
+    return im
+
+
+def test_image_facade_matches_golden():
+    g = load_golden("vor64_euclid_bior44")
+    im = _image(g)
+    with contextlib.redirect_stdout(io.StringIO()):
+        im.encode_rbepwt(g["levels"], g["wavelet"], path_type=g["path_type"], euclidean_distance=True)
+        assert im.method == "rbepwt" and im.rbepwt.levels == g["levels"]
+        flat = im.rbepwt.flat_wavelet()
+        assert np.max(np.abs(flat - g["coefs"])) <= 1e-9 * np.abs(g["coefs"]).max()
+        # region views: permutation, path-ordered base points
+        rc1 = im.rbepwt.region_collection_at_level[1]
+        off = g["roff_by_level"][1]
+        for r in (0, 1, len(off) - 2):
+            reg = rc1[r]
+            a, b = off[r], off[r + 1]
+            assert reg.permutation == list(g["perm_by_level"][1][a:b])
+            assert reg.base_points == tuple(map(tuple, g["points_by_level"][1][a:b]))
+        im.threshold_coefs(g["ncoefs"])
+        assert im.nonzero_coefs() == g["nonzero_coefs"]
+        im.decode_rbepwt()
+    assert im.has_decoded_img
+    assert np.max(np.abs(im.decoded_img - g["decoded"])) <= 1e-9 * 255
+    assert abs(im.psnr() - g["psnr"]) < 5e-7
+
+
+def test_epwt_facade_and_method_quirk():
+    g = load_golden("epwt32_smooth_haar")
+    im = _image(g)
+    with contextlib.redirect_stdout(io.StringIO()):
+        im.encode_epwt(g["levels"], g["wavelet"])
+        assert im.method == "rbepwt"  # encode_rbepwt overwrites 'epwt' (rbepwt.py:335-337)
+        im.threshold_coefs(g["ncoefs"])
+        im.decode_epwt()
+    assert np.max(np.abs(im.decoded_img - g["decoded"])) <= 1e-9 * 255
+    rc = im.rbepwt.region_collection_at_level
+    assert len(rc[1]) == 1 and len(rc[1][0]) == g["img"].size
+    assert rc[2][0].base_points == tuple(map(tuple, g["points_by_level"][2]))
+
+
+def test_edit_coefficients_then_decode_like_compute_basis_elements():
+    """scripts/compute_basis_elements.py:58-81: zero every array, set one coefficient, decode."""
+    g = load_golden("vor32_euclid_bior44")
+    im = _image(g)
+    with contextlib.redirect_stdout(io.StringIO()):
+        im.encode_rbepwt(g["levels"], g["wavelet"])
+        L = im.rbepwt.levels
+        approx = im.rbepwt.region_collection_at_level[L + 1].values
+        for lev in range(1, L + 1):
+            im.rbepwt.wavelet_details[lev] = np.zeros_like(im.rbepwt.wavelet_details[lev])
+        im.rbepwt.region_collection_at_level[L + 1].values = np.zeros_like(approx)
+        im.rbepwt.region_collection_at_level[L + 1].values[0] = 1
+        im.decode_rbepwt()
+    from oracle import c_oracle
+    import rbepwt_b200 as rbepwt
+
+    enc = c_oracle.encode(g["img"], g["labels"], L, rbepwt.filter_bank(g["wavelet"]), c_oracle.MODE_EUCLID)
+    flat = np.zeros(g["img"].size)
+    flat[-1] = 1.0
+    want = c_oracle.decode(enc, flat, rbepwt.filter_bank(g["wavelet"]))
+    assert np.max(np.abs(im.decoded_img - want)) < 1e-12
+    assert im.nonzero_coefs() == 1
+
+
+def test_full_decode_equals_fast_decode():
+    """scripts/check_decode.py:47-74: decode with stored paths == decode with paths recomputed from labels."""
+    import rbepwt_b200 as rbepwt
+
+    g = load_golden("vor64_euclid_bior44")
+    im = _image(g)
+    with contextlib.redirect_stdout(io.StringIO()):
+        im.encode_rbepwt(g["levels"], g["wavelet"])
+        im.rbepwt.threshold_coefs(51)
+        im.decode_rbepwt()
+        L = g["levels"]
+        fdi = rbepwt.full_decode(im.rbepwt.wavelet_details, im.rbepwt.region_collection_at_level[L + 1].values,
+                                 im.label_img, g["wavelet"], "easypath")
+    np.testing.assert_array_equal(fdi, im.decoded_img)
+
+
+def test_guards_raise_the_reference_messages():
+    import rbepwt_b200 as rbepwt
+
+    im = rbepwt.Image()
+    im.read_array(np.zeros((6, 8)))
+    im.set_labels(np.zeros((6, 8), np.int32))
+    with pytest.raises(Exception, match="Image size must be a power of 2"):
+        im.encode_rbepwt(2, "haar")
+    im = rbepwt.Image()
+    im.read_array(np.zeros((4, 4)))
+    im.set_labels(np.zeros((4, 4), np.int32))
+    with pytest.raises(Exception, match="2\\^levels must be smaller or equal"):
+        im.encode_rbepwt(5, "haar")
+    c = rbepwt.BatchCodec()
+    with pytest.raises(Exception, match="There is no saved encoding to decode"):
+        c.threshold(3)
+
+
+def test_level_values_views():
+    g = load_golden("vor32_euclid_bior44")
+    im = _image(g)
+    with contextlib.redirect_stdout(io.StringIO()):
+        im.encode_rbepwt(g["levels"], g["wavelet"])
+    from oracle import c_oracle
+    import rbepwt_b200 as rbepwt
+
+    rc = im.rbepwt.region_collection_at_level
+    # level-1 collection values = pixel values in region order / row-major
+    pix0 = np.array([r * 32 + c for r, c in rc[1].base_points])
+    np.testing.assert_array_equal(rc[1].values, g["img"].ravel()[pix0])
+    # level-2 values = level-1 low-pass
+    enc = c_oracle.encode(g["img"], g["labels"], 1, rbepwt.filter_bank(g["wavelet"]), c_oracle.MODE_EUCLID)
+    np.testing.assert_allclose(rc[2].values, enc["coefs"][g["img"].size // 2:], rtol=0, atol=1e-10)

@@ -1,0 +1,189 @@
+"""-m gpu: the CUDA path (through the public API -> C ABI) against
+  (1) the golden fixtures produced by the unmodified reference,
+  (2) the C oracle on seeded inputs at sizes it finishes in seconds,
+  (3) size-independent properties at BASELINE.json's full sizes.
+Bar: paths / permutations / kept indices bit-exact; coefficients and pixels within 1e-9 relative (fp64);
+PSNR equal to 6 decimals."""
+import numpy as np
+import pytest
+
+from conftest import assert_matches_golden, golden_names, load_golden
+from gpu_util import assert_same_as_oracle, cuda_run
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_reproduces_reference_golden(name):
+    g = load_golden(name)
+    out = cuda_run(g["img"], g["labels"], g["levels"], g["wavelet"], g["path_type"], g["euclidean_distance"],
+                   ncoefs=g["ncoefs"])
+    assert_matches_golden(out, g)
+
+
+def _oracle(img, lab, levels, wavelet, ptype, euclid, k):
+    from oracle import c_oracle
+    import rbepwt_b200 as rb
+
+    return c_oracle.run(img, lab, levels, rb.filter_bank(wavelet), ptype, euclid, ncoefs=k)
+
+
+@pytest.mark.parametrize("wavelet,k", [("haar", 512), ("bior4.4", 2048), ("bior4.4", 8192), ("db6", 512)])
+def test_config2_512_vs_oracle(wavelet, k):
+    from rbepwt_b200 import synth
+
+    img, lab = synth.config_inputs("synthetic512")
+    out = cuda_run(img, lab, 16, wavelet, ncoefs=k)
+    assert_same_as_oracle(out, _oracle(img, lab, 16, wavelet, "easypath", True, k), 16)
+
+
+def test_config2_512_chebyshev_vs_oracle():
+    from rbepwt_b200 import synth
+
+    img, lab = synth.config_inputs("synthetic512", seed=11)
+    out = cuda_run(img, lab, 16, "bior4.4", euclidean_distance=False, ncoefs=2048)
+    assert_same_as_oracle(out, _oracle(img, lab, 16, "bior4.4", "easypath", False, 2048), 16)
+
+
+@pytest.mark.parametrize("wavelet", ["haar", "bior4.4"])
+def test_config3_epwt_512_vs_oracle(wavelet):
+    from rbepwt_b200 import synth
+
+    img, _ = synth.config_inputs("epwt512")
+    out = cuda_run(img, None, 16, wavelet, "epwt-easypath", ncoefs=2048, with_perm=False)
+    assert_same_as_oracle(out, _oracle(img, None, 16, wavelet, "epwt-easypath", True, 2048), 16)
+
+
+def test_config1_256_vs_oracle_other_seeds():
+    from rbepwt_b200 import synth
+
+    for seed in (21, 22):
+        img, lab = synth.config_inputs("cameraman256", seed=seed)
+        out = cuda_run(img, lab, 16, "bior4.4", ncoefs=512)
+        assert_same_as_oracle(out, _oracle(img, lab, 16, "bior4.4", "easypath", True, 512), 16)
+
+
+def test_config4_2048_many_small_regions():
+    """2048^2, ~65k regions: paths vs oracle bit-exact, perfect reconstruction, top-k count."""
+    from rbepwt_b200 import synth
+    import rbepwt_b200 as rb
+
+    img, lab = synth.config_inputs("small2048")
+    out = cuda_run(img, lab, 16, "bior4.4", ncoefs=None, with_perm=False)
+    orc = _oracle(img, lab, 16, "bior4.4", "easypath", True, None)
+    assert_same_as_oracle(out, orc, 16)
+    c = out["codec"]
+    dec = c.decode()[0]
+    assert np.max(np.abs(dec - img)) < 1e-9 * 255
+    c.threshold(8192)
+    assert int(c.nonzero_coefs()[0]) == 8192
+
+
+def test_hash_labels_and_disconnected_regions():
+    """Arbitrary int32 label values (negative, huge -> open-addressing table) and label classes
+    made of scattered pixels (every step is a jump)."""
+    rng = np.random.default_rng(5)
+    vals = np.array([-2147483648, -7, -1, 0, 3, 65536, 2147483647, 123456789], dtype=np.int64)
+    lab = vals[rng.integers(0, len(vals), size=(64, 64))].astype(np.int32)
+    img = rng.uniform(0, 255, size=(64, 64))
+    for euclid in (True, False):
+        out = cuda_run(img, lab, 12, "bior4.4", euclidean_distance=euclid, ncoefs=300)
+        assert_same_as_oracle(out, _oracle(img, lab, 12, "bior4.4", "easypath", euclid, 300), 12)
+
+
+def test_every_pixel_its_own_region_and_tiny_images():
+    rng = np.random.default_rng(6)
+    img = rng.uniform(0, 255, size=(16, 16))
+    lab = rng.permutation(256).reshape(16, 16).astype(np.int32)  # R == N
+    out = cuda_run(img, lab, 8, "db2", ncoefs=10)
+    assert_same_as_oracle(out, _oracle(img, lab, 8, "db2", "easypath", True, 10), 8)
+    for shape, levels in (((2, 2), 2), ((1, 4), 2), ((4, 1), 1), ((2, 8), 4)):
+        img = rng.uniform(0, 255, size=shape)
+        lab = rng.integers(0, 2, size=shape).astype(np.int32)
+        for wav in ("haar", "bior4.4"):
+            out = cuda_run(img, lab, levels, wav, ncoefs=2)
+            assert_same_as_oracle(out, _oracle(img, lab, levels, wav, "easypath", True, 2), levels)
+
+
+def test_large_regions_use_the_big_bitmap_path():
+    """Two interleaved label classes spanning the whole 256x256 image (bitmap > shared-memory slot)."""
+    rng = np.random.default_rng(7)
+    ii, jj = np.meshgrid(np.arange(256), np.arange(256), indexing="ij")
+    lab = (((ii // 5) + (jj // 3)) % 2).astype(np.int32)
+    img = rng.uniform(0, 255, size=(256, 256))
+    out = cuda_run(img, lab, 16, "haar", ncoefs=1000)
+    assert_same_as_oracle(out, _oracle(img, lab, 16, "haar", "easypath", True, 1000), 16)
+
+
+def test_batch_equals_singles_and_threshold_properties():
+    from rbepwt_b200 import synth
+    import rbepwt_b200 as rb
+
+    imgs, labs = [], []
+    for s in range(5):
+        lab = synth.voronoi_labels(128, 128, 60 + 10 * s, seed=40 + s)
+        labs.append(lab)
+        imgs.append(synth.piecewise_smooth_image(lab, seed=40 + s))
+    imgs, labs = np.stack(imgs), np.stack(labs)
+    c = rb.BatchCodec()
+    c.encode(imgs, labs, 14, "bior4.4")
+    full = np.stack([c.coefs(b) for b in range(5)])
+    dec_all = c.decode()
+    assert np.max(np.abs(dec_all - imgs)) < 1e-9 * 255  # perfect reconstruction without thresholding
+    c.threshold(777)
+    th = np.stack([c.coefs(b) for b in range(5)])
+    np.testing.assert_array_equal(c.nonzero_coefs(), [777] * 5)
+    for b in range(5):
+        kept = th[b] != 0
+        np.testing.assert_array_equal(th[b][kept], full[b][kept])          # survivors untouched
+        assert np.abs(full[b][kept]).min() >= np.abs(full[b][~kept]).max()  # and they are the largest
+    c.threshold(777)                                                       # idempotent
+    np.testing.assert_array_equal(np.stack([c.coefs(b) for b in range(5)]), th)
+    dec = c.decode()
+    for b in (0, 3):
+        one = cuda_run(imgs[b], labs[b], 14, "bior4.4", ncoefs=777, with_perm=False)
+        np.testing.assert_array_equal(one["coefs"], full[b])
+        np.testing.assert_array_equal(one["decoded"], dec[b])
+    # k quirks of the reference: 0 and >= N keep everything
+    c2 = rb.BatchCodec()
+    c2.encode(imgs[:1], labs[:1], 14, "bior4.4")
+    before = c2.coefs(0)
+    for k in (0, -3, 128 * 128, 10 ** 9):
+        c2.threshold(k)
+        np.testing.assert_array_equal(c2.coefs(0), before)
+
+
+def test_threshold_ties_keep_highest_index():
+    import rbepwt_b200 as rb
+
+    img = np.full((8, 8), 7.0)
+    lab = np.zeros((8, 8), np.int32)
+    c = rb.BatchCodec()
+    c.encode(img[None], lab[None], 2, "haar")
+    flat = np.zeros(64)
+    flat[[3, 10, 20, 33, 50]] = [5.0, -5.0, 5.0, 9.0, -5.0]
+    c.set_coefs(flat, 0)
+    c.threshold(3)
+    got = c.coefs(0)
+    np.testing.assert_array_equal(np.flatnonzero(got), [20, 33, 50])
+    from oracle import c_oracle
+    np.testing.assert_array_equal(got, c_oracle.threshold(flat, 3))
+
+
+def test_device_pointer_path_matches_host_path():
+    torch = pytest.importorskip("torch")
+    from rbepwt_b200 import synth
+    import rbepwt_b200 as rb
+
+    lab = synth.voronoi_labels(64, 64, 30, seed=3)
+    img = synth.piecewise_smooth_image(lab, seed=3)
+    host = cuda_run(img, lab, 12, "bior4.4", ncoefs=200, with_perm=False)
+    timg = torch.from_numpy(img[None].copy()).cuda()
+    tlab = torch.from_numpy(lab[None].copy()).cuda()
+    c = rb.BatchCodec(stream=torch.cuda.current_stream().cuda_stream)
+    c.encode(timg, tlab, 12, "bior4.4")
+    c.threshold(200)
+    out = torch.empty_like(timg)
+    c.decode(out)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy()[0], host["decoded"])
