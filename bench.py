@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- encode + threshold + decode throughput of the RBEPWT path (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+One "step" = one pass of the hot path (rbepwt_encode -> rbepwt_threshold -> rbepwt_decode through the
+C ABI) over one batch of B distinct synthetic 512x512 images per GPU (warped-Voronoi label maps of
+1024 regions, per-region ramps + noise, float64), 16 levels, bior4.4, k = 2048 kept coefficients,
+path_type='easypath', euclidean_distance=True.  Weak scaling: every rank holds its own B images
+(image batch sharded by image, no collective on the data path -- SURVEY.md section 8e); at N = 8 and
+the default B = 512 that is BASELINE.json's "4096 x 512^2" configuration.
+
+`value`      images/s with the batch already resident in HBM (CUDA events on the context's stream,
+             barrier + synchronize both sides, max over ranks).
+`e2e`        the same through the public host-buffer API (BatchCodec with numpy views of pinned host
+             memory): H2D of images + labels and D2H of the decoded images inside the timed region.
+`roofline`   the dominant kernel (largest share of the step's device time), algorithmic bytes per launch
+             / its CUDA-event duration measured over the timed steps, against MEASURED_PEAKS.json.
+`cpu_baseline` the C oracle (oracle/rbepwt_oracle.c, a port of the reference's algorithm) on host cores,
+             bounded sample of the same workload; rank 0, N = 1 only.
+`--impl reference` times that CPU port with all host threads (the reference itself is pure Python +
+             PyWavelets, cannot travel to the GPU box and needs ~1 h per 512^2 image).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H = W = 512
+LEVELS = 16
+WAVELET = "bior4.4"
+NCOEFS = 2048
+NSEEDS = 1024
+SEED0 = 1000
+METRIC = "encode+threshold+decode images/sec (512x512, 16 levels bior4.4)"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(batch):
+    return {"workload": "512x512 float64 synthetic (warped Voronoi labels, 1024 regions/image, distinct per image), "
+                        "easypath euclidean, 16 levels bior4.4, keep 2048 coefs",
+            "images_per_gpu_per_step": batch, "height": H, "width": W, "levels": LEVELS, "wavelet": WAVELET,
+            "ncoefs": NCOEFS, "path_type": "easypath", "euclidean_distance": True,
+            "parallelism": "image batch sharded by image, no collective",
+            "l2": "inputs larger than L2 (%.0f MB of images+labels per step vs 126 MB L2)" % (batch * H * W * 12 / 1e6)}
+
+
+# ------------------------------------------------------------------------------ clocks -----
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self._stop_ev = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop_ev.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop_ev.wait(self.period)
+
+    def finish(self):
+        self._stop_ev.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:  # noqa: BLE001
+            return local
+    return local
+
+
+# ------------------------------------------------------------------------------ CPU arm ----
+def cpu_port_throughput(imgs, labs, threads):
+    """images/s of the C oracle (encode + threshold + decode) over the given host arrays with `threads`
+    host threads (ctypes releases the GIL).  TEST-INFRASTRUCTURE code, used here only as the baseline."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import c_oracle, pywt_port
+
+    fb = pywt_port.filter_bank(WAVELET)
+    c_oracle.lib()
+
+    def one(i):
+        enc = c_oracle.encode(imgs[i], labs[i], LEVELS, fb, c_oracle.MODE_EUCLID)
+        th = c_oracle.threshold(enc["coefs"], NCOEFS)
+        return c_oracle.decode(enc, th, fb)
+
+    one(0)  # warm (page in the library, allocate)
+    t0 = time.perf_counter()
+    if threads == 1:
+        for i in range(len(imgs)):
+            one(i)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(one, range(len(imgs))))
+    return len(imgs) / (time.perf_counter() - t0)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+
+    from rbepwt_b200 import synth
+
+    cores = host_cores()
+    # ~0.2 s per image per core: size the sample so that every step is a few seconds of all-core work
+    nimg = args.cpu_sample or max(cores, min(4 * cores, 64))
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    imgs, labs = synth.torch_batch(nimg, H, W, NSEEDS, SEED0, device=dev)
+    imgs, labs = imgs.cpu().numpy(), labs.cpu().numpy()
+    for _ in range(args.warmup):
+        cpu_port_throughput(imgs[:cores], labs[:cores], cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_throughput(imgs, labs, cores)
+    dt = time.perf_counter() - t0
+    v = nimg * args.steps / dt
+    sample = "%d distinct images of the workload per step, %d host threads, C port of the reference algorithm" % (nimg, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload(nimg),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "the reference itself is pure Python (+PyWavelets) and cannot run on the GPU box; measured in the "
+                    "build container it needs ~1 h per 512x512 image (BASELINE.md section 2). This arm times the C "
+                    "port of its algorithm (oracle/), which is orders of magnitude faster than the reference."}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------ our arm ----
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import rbepwt_b200 as rb
+    from rbepwt_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; rbepwt_b200 has no CPU path")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, K, Wm = args.batch, args.steps, args.warmup
+    N = H * W
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    imgs, labs = synth.torch_batch(B, H, W, NSEEDS, SEED0 + rank * B, device="cuda")
+    out = torch.empty_like(imgs)
+    torch.cuda.synchronize()
+    # a dedicated (non-default) stream: the library launches on it and the timing events are recorded on it
+    stream = torch.cuda.Stream()
+    assert stream.cuda_stream != 0
+    codec = rb.BatchCodec(device=local, stream=stream.cuda_stream)
+
+    def step():
+        codec.encode(imgs, labs, LEVELS, WAVELET, "easypath", True)
+        codec.threshold(NCOEFS)
+        codec.decode(out)
+
+    for _ in range(max(Wm, 1)):
+        step()
+    torch.cuda.synchronize()
+    # correctness guard of the measured configuration: untouched survivors + PSNR is finite
+    nz = codec.nonzero_coefs()
+    assert int(nz.min()) == NCOEFS and int(nz.max()) == NCOEFS, nz
+    psnr0 = float(codec.psnr(imgs[:1], out[:1])[0])
+
+    sampler = ClockSampler(physical_gpu_index(local))
+    codec.enable_timing(True)
+    codec.timings()  # drop events of anything before
+    l0 = codec.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0.record(stream)
+    for _ in range(K):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.finish()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = codec.launch_count() - l0
+    stage_ms = codec.timings()
+    stage_n = codec.stage_launches()
+    codec.enable_timing(False)
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- e2e: the public host-buffer API, pinned host memory, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_img = torch.empty((B, H, W), dtype=torch.float64, pin_memory=True)
+        h_lab = torch.empty((B, H, W), dtype=torch.int32, pin_memory=True)
+        h_out = torch.empty((B, H, W), dtype=torch.float64, pin_memory=True)
+        h_img.copy_(imgs)
+        h_lab.copy_(labs)
+        torch.cuda.synchronize()
+        n_img, n_lab, n_out = h_img.numpy(), h_lab.numpy(), h_out.numpy()
+        hcodec = rb.BatchCodec(device=local)
+
+        def hstep():
+            hcodec.encode(n_img, n_lab, LEVELS, WAVELET, "easypath", True)
+            hcodec.threshold(NCOEFS)
+            hcodec.decode(n_out)  # returns after the D2H copy completed
+
+        for _ in range(max(Wm, 1)):
+            hstep()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            hstep()
+        hcodec.sync()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        assert np.array_equal(n_out[0], out[0].cpu().numpy()), "host-buffer path and device path disagree"
+        e2e = {"value": world * B * K / dt, "unit": UNIT, "h2d_bytes_per_step": B * N * 12, "d2h_bytes_per_step": B * N * 8,
+               "ms_per_step": 1e3 * dt / K, "api": "rbepwt_b200.BatchCodec.encode/threshold/decode with numpy views of "
+                                                   "pinned host memory (C ABI host-pointer path)"}
+        hcodec.close()
+
+    # ---- roofline of the dominant kernel (stage with the largest share of the device time)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    peak, peak_src = (float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    S = 2 * N - (N >> (LEVELS - 1))  # sum of the level lengths
+    # algorithmic bytes per image of each kernel family
+    alg = {
+        "regions": ("k0_count+k0_regions+queue", 3 * 4 * N),              # three passes over the labels
+        "paths": ("k1_paths_small", 4 * N + 4 * S),                        # labels in, path pixel ids out
+        "paths_big": ("k1_paths_big", 4 * N + 4 * S),
+        "dwt": ("k3_dwt_level", 4 * S + 8 * S + 8 * S),                    # paths + gathered values in, cA/cD out
+        "select": ("k4_threshold", 8 * N + 8 * N),
+        "idwt": ("k5_idwt_level", 4 * S + 8 * S + 8 * S),
+    }
+    kern_stages = [s for s in alg if stage_ms.get(s, 0.0) > 0.0]
+    total_kernel_ms = sum(stage_ms[s] for s in kern_stages)
+    dom = max(kern_stages, key=lambda s: stage_ms[s])
+    dom_launches = max(stage_n.get(dom, 0), 1)
+    dom_ms_per_launch = stage_ms[dom] / dom_launches
+    bytes_per_launch = alg[dom][1] * B * K / dom_launches
+    achieved = bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": alg[dom][0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": dom_ms_per_launch, "launches": dom_launches,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "share_of_step": stage_ms[dom] / total_kernel_ms,
+                "note": "k1 path construction is a dependent chain (latency/issue bound), not an HBM-bound kernel; "
+                        "see `kernels` for the HBM-bound ones"}
+    kernels = {}
+    for s in kern_stages:
+        n = max(stage_n.get(s, 0), 1)
+        gbs = alg[s][1] * B * K / (stage_ms[s] * 1e-3) / 1e9
+        kernels[alg[s][0]] = {"ms_per_step": stage_ms[s] / K, "launches_per_step": n / K, "share": stage_ms[s] / total_kernel_ms,
+                              "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+    path_gbs = 68 * N * B * K / (ms * 1e-3) / 1e9  # per GPU
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload(B), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "kernels": kernels,
+            "whole_path": {"algorithmic_bytes_per_image": 68 * N, "achieved_GBps_per_gpu": path_gbs,
+                           "frac_of_hbm_peak": path_gbs / peak},
+            "psnr_image0": psnr0}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ns = args.cpu_sample or 64  # ~0.2 s per image on one core -> ~13 s
+        si, sl = imgs[:ns].cpu().numpy(), labs[:ns].cpu().numpy()
+        v = cpu_port_throughput(si, sl, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "first %d images of the step's batch, single-threaded C port of the reference "
+                                          "algorithm (oracle/rbepwt_oracle.c); the Python reference itself needs ~1 h per "
+                                          "512x512 image (BASELINE.md)" % ns}
+    if rank == 0:
+        print(json.dumps(line))
+    codec.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    world_env = os.environ.get("WORLD_SIZE")
+    if args.gpus > 1 and world_env is None:
+        # convenience: relaunch under torchrun, one rank per GPU
+        import subprocess
+        port = os.environ.get("MASTER_PORT", "29517")
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", port, os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

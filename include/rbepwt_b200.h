@@ -128,14 +128,19 @@ int rbepwt_get_level_values(rbepwt_ctx *ctx, int b, int level, double *vals);
  * encode / threshold / decode when enabled.  ms[RBEPWT_T_*]; returns the number of stages. */
 #define RBEPWT_T_H2D 0
 #define RBEPWT_T_REGIONS 1 /* K0: label map -> region records + work queue */
-#define RBEPWT_T_PATHS 2   /* K1: easy-path pyramid */
+#define RBEPWT_T_PATHS 2   /* K1: easy-path pyramid, regions whose bitmap fits a per-warp shared-memory slot */
 #define RBEPWT_T_DWT 3     /* K3: gather + analysis filter bank, all levels */
 #define RBEPWT_T_SELECT 4  /* K4: top-k radix select + zeroing */
 #define RBEPWT_T_IDWT 5    /* K5: synthesis filter bank + scatter, all levels */
 #define RBEPWT_T_D2H 6
-#define RBEPWT_T_COUNT 7
+#define RBEPWT_T_PATHS_BIG 7 /* K1: regions with a large bounding box (one warp per CTA, whole-image bitmap) */
+#define RBEPWT_T_COUNT 8
 int rbepwt_enable_timing(rbepwt_ctx *ctx, int on);
+/* Sums the stage events recorded since the previous call (they accumulate across encode /
+ * threshold / decode calls), synchronises the stream, returns RBEPWT_T_COUNT. */
 int rbepwt_get_timings(rbepwt_ctx *ctx, float *ms, int n);
+/* Kernel launches per stage covered by the last rbepwt_get_timings call. */
+int rbepwt_get_stage_launches(rbepwt_ctx *ctx, int64_t *launches, int n);
 /* Number of kernel launches issued by this context since creation. */
 int64_t rbepwt_launch_count(rbepwt_ctx *ctx);
 

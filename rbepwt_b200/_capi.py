@@ -10,14 +10,15 @@ _lib = None
 E_NOT_POW2, E_LEVELS, E_NO_ENCODING, E_NO_GPU = -2, -3, -4, -7
 PATH_EUCLID, PATH_CHEB, PATH_EPWT = 0, 1, 2
 DEVICE_PTRS, U8_WRAP = 1, 2
-T_NAMES = ["h2d", "regions", "paths", "dwt", "select", "idwt", "d2h"]
+T_NAMES = ["h2d", "regions", "paths", "dwt", "select", "idwt", "d2h", "paths_big"]
 
 EXPORTS = [
     "rbepwt_create", "rbepwt_destroy", "rbepwt_last_error", "rbepwt_sync", "rbepwt_set_wavelet",
     "rbepwt_encode", "rbepwt_threshold", "rbepwt_decode", "rbepwt_full_decode", "rbepwt_psnr",
     "rbepwt_nonzero_coefs", "rbepwt_get_coefs", "rbepwt_set_coefs", "rbepwt_region_count",
     "rbepwt_region_offsets", "rbepwt_region_labels", "rbepwt_get_paths", "rbepwt_get_perm",
-    "rbepwt_get_level_values", "rbepwt_enable_timing", "rbepwt_get_timings", "rbepwt_launch_count",
+    "rbepwt_get_level_values", "rbepwt_enable_timing", "rbepwt_get_timings", "rbepwt_get_stage_launches",
+    "rbepwt_launch_count",
 ]
 
 
@@ -62,6 +63,7 @@ def lib():
     L.rbepwt_get_level_values.argtypes = [vp, i32, i32, vp]
     L.rbepwt_enable_timing.argtypes = [vp, i32]
     L.rbepwt_get_timings.argtypes = [vp, vp, i32]
+    L.rbepwt_get_stage_launches.argtypes = [vp, vp, i32]
     L.rbepwt_launch_count.argtypes = [vp]
     L.rbepwt_launch_count.restype = i64
     _lib = L

@@ -53,6 +53,7 @@ class BatchCodec:
         self.levels = None
         self.wavelet = None
         self._keep = []         # keeps device inputs alive while the library references them
+        self._bank_key = None
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -68,17 +69,28 @@ class BatchCodec:
     # -- configuration -----------------------------------------------------------------
     def set_wavelet(self, wavelet):
         dl, dh, rl, rh = filter_bank(wavelet)
-        _capi.check(self._lib.rbepwt_set_wavelet(self._ctx, dl.size, _ptr(dl), _ptr(dh), _ptr(rl), _ptr(rh)))
+        key = b"".join(f.tobytes() for f in (dl, dh, rl, rh))
+        if key != self._bank_key:  # the upload synchronises the stream: skip it when nothing changed
+            _capi.check(self._lib.rbepwt_set_wavelet(self._ctx, dl.size, _ptr(dl), _ptr(dh), _ptr(rl), _ptr(rh)))
+            self._bank_key = key
         self.wavelet = wavelet
 
     def enable_timing(self, on=True):
         _capi.check(self._lib.rbepwt_enable_timing(self._ctx, int(bool(on))))
 
     def timings(self):
-        """{stage: ms} of the calls since the last encode (CUDA events on the context's stream)."""
-        ms = (ctypes.c_float * 7)()
-        self._lib.rbepwt_get_timings(self._ctx, ms, 7)
+        """{stage: ms} summed over the calls since the previous timings() (CUDA events on the context's stream)."""
+        n = len(_capi.T_NAMES)
+        ms = (ctypes.c_float * n)()
+        _capi.check(min(0, self._lib.rbepwt_get_timings(self._ctx, ms, n)))
         return dict(zip(_capi.T_NAMES, [float(v) for v in ms]))
+
+    def stage_launches(self):
+        """{stage: kernel launches} covered by the last timings() call."""
+        n = len(_capi.T_NAMES)
+        cnt = (ctypes.c_int64 * n)()
+        self._lib.rbepwt_get_stage_launches(self._ctx, cnt, n)
+        return dict(zip(_capi.T_NAMES, [int(v) for v in cnt]))
 
     def launch_count(self):
         return int(self._lib.rbepwt_launch_count(self._ctx))

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "dwt.cuh"
 #include "paths.cuh"
+#include "paths_tpr.cuh"
 #include "perm.cuh"
 #include "regions.cuh"
 #include "select.cuh"
@@ -68,7 +69,7 @@ struct DevBuf {
   template <typename T> T *as() const { return static_cast<T *>(p); }
 };
 
-struct StageEv { int stage; cudaEvent_t a, b; };
+struct StageEv { int stage; int launches; cudaEvent_t a, b; };
 
 struct rbepwt_ctx {
   int device = 0;
@@ -99,6 +100,7 @@ struct rbepwt_ctx {
   std::vector<StageEv> evs;
   std::vector<cudaEvent_t> ev_pool;
   long long launches = 0;
+  long long stage_launches[RBEPWT_T_COUNT] = {};
 
   RegionArrays regs() const {
     RegionArrays r;
@@ -123,11 +125,13 @@ cudaEvent_t get_event(rbepwt_ctx *c) {
 }
 
 struct StageTimer {  // records a pair of events around a stage when timing is enabled
-  rbepwt_ctx *c; StageEv ev; bool on;
-  StageTimer(rbepwt_ctx *c_, int stage) : c(c_), on(c_->timing) {
+  rbepwt_ctx *c; StageEv ev; bool on; long long l0;
+  StageTimer(rbepwt_ctx *c_, int stage) : c(c_), on(c_->timing), l0(c_->launches) {
     if (on) { ev.stage = stage; ev.a = get_event(c); ev.b = get_event(c); cudaEventRecord(ev.a, c->stream); }
   }
-  ~StageTimer() { if (on) { cudaEventRecord(ev.b, c->stream); c->evs.push_back(ev); } }
+  ~StageTimer() {
+    if (on) { cudaEventRecord(ev.b, c->stream); ev.launches = (int)(c->launches - l0); c->evs.push_back(ev); }
+  }
 };
 
 void clear_events(rbepwt_ctx *c) {
@@ -212,7 +216,6 @@ int build_regions_and_paths(rbepwt_ctx *c, int c0, int nb) {
     CK(cudaGetLastError());
   }
   {
-    StageTimer t(c, RBEPWT_T_PATHS);
     PathParams P;
     P.labels = c->labels_dev;
     P.H = c->H; P.W = c->W; P.logW = c->logW; P.N = N; P.levels = c->levels;
@@ -233,17 +236,24 @@ int build_regions_and_paths(rbepwt_ctx *c, int c0, int nb) {
       P.gscratch = c->gscratch.as<uint32_t>();
       P.gscratch_words = img_words;
     }
-    const int small_ctas = c->sm_count * 6;
-    if (c->mode == RBEPWT_PATH_EUCLID) {
-      CK(cudaFuncSetAttribute(k1_paths_big<MODE_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-      k1_paths_big<MODE_EUCLID><<<big_ctas, 32, smem_bytes, s>>>(P);
-      k1_paths_small<MODE_EUCLID><<<small_ctas, K1_WARPS * 32, 0, s>>>(P);
-    } else {
-      CK(cudaFuncSetAttribute(k1_paths_big<MODE_CHEB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-      k1_paths_big<MODE_CHEB><<<big_ctas, 32, smem_bytes, s>>>(P);
-      k1_paths_small<MODE_CHEB><<<small_ctas, K1_WARPS * 32, 0, s>>>(P);
+    const int small_ctas = c->sm_count * 8;  // k1_paths_tpr: 4 KB of arena per warp, 4 warps per CTA
+    {
+      StageTimer tb(c, RBEPWT_T_PATHS_BIG);
+      if (c->mode == RBEPWT_PATH_EUCLID) {
+        CK(cudaFuncSetAttribute(k1_paths_big<MODE_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        k1_paths_big<MODE_EUCLID><<<big_ctas, 32, smem_bytes, s>>>(P);
+      } else {
+        CK(cudaFuncSetAttribute(k1_paths_big<MODE_CHEB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        k1_paths_big<MODE_CHEB><<<big_ctas, 32, smem_bytes, s>>>(P);
+      }
+      c->launches++;
     }
-    c->launches += 2;
+    {
+      StageTimer t(c, RBEPWT_T_PATHS);
+      if (c->mode == RBEPWT_PATH_EUCLID) k1_paths_tpr<MODE_EUCLID><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
+      else k1_paths_tpr<MODE_CHEB><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
+      c->launches++;
+    }
     CK(cudaGetLastError());
   }
   return RBEPWT_OK;
@@ -447,7 +457,7 @@ int rbepwt_encode(rbepwt_ctx *c, const double *img, const int32_t *labels, int B
   if (rc) return rc;
   if (!c->has_wavelet) return fail(RBEPWT_E_NO_WAVELET, "rbepwt_set_wavelet has not been called");
   DeviceGuard g(c->device);
-  clear_events(c);
+  if (c->evs.size() > 65536) clear_events(c);  // stage events accumulate until rbepwt_get_timings reads them
   if ((rc = alloc_state(c, B, H, W, levels, path_mode, flags))) return rc;
   if ((rc = upload_labels(c, labels, flags))) return rc;
   if (flags & RBEPWT_DEVICE_PTRS) {
@@ -515,7 +525,7 @@ int rbepwt_full_decode(rbepwt_ctx *c, const double *coefs, const int32_t *labels
     return fail(RBEPWT_E_ARG, "full_decode needs value-independent paths (EPWT paths depend on the image)");
   if (!c->has_wavelet) return fail(RBEPWT_E_NO_WAVELET, "rbepwt_set_wavelet has not been called");
   DeviceGuard g(c->device);
-  clear_events(c);
+  if (c->evs.size() > 65536) clear_events(c);  // stage events accumulate until rbepwt_get_timings reads them
   if ((rc = alloc_state(c, B, H, W, levels, path_mode, flags))) return rc;
   if ((rc = upload_labels(c, labels, flags))) return rc;
   c->img_dev = nullptr;
@@ -730,12 +740,20 @@ int rbepwt_get_timings(rbepwt_ctx *c, float *ms, int n) {
   DeviceGuard g(c->device);
   CK(cudaStreamSynchronize(c->stream));
   for (int i = 0; i < n; i++) ms[i] = 0.f;
+  for (int i = 0; i < RBEPWT_T_COUNT; i++) c->stage_launches[i] = 0;
   for (auto &e : c->evs) {
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, e.a, e.b));
     if (e.stage < n) ms[e.stage] += t;
+    c->stage_launches[e.stage] += e.launches;
   }
   clear_events(c);
+  return RBEPWT_T_COUNT;
+}
+
+int rbepwt_get_stage_launches(rbepwt_ctx *c, int64_t *launches, int n) {
+  if (!c || !launches) return fail(RBEPWT_E_ARG, "ctx / launches is NULL");
+  for (int i = 0; i < n; i++) launches[i] = i < RBEPWT_T_COUNT ? c->stage_launches[i] : 0;
   return RBEPWT_T_COUNT;
 }
 

@@ -88,3 +88,42 @@ def config_inputs(name, seed=None):
         lab = voronoi_labels(2048, 2048, 65536, seed=s, warp=1.0)
         return piecewise_smooth_image(lab, seed=s), lab
     raise KeyError(name)
+
+
+def torch_batch(nimg, h, w, n_seeds, seed0, device="cpu", noise=2.0, warp=3.0):
+    """`nimg` distinct (image float64 [h,w], labels int32 [h,w]) pairs as torch tensors on `device`:
+    the config-2/5 generator (warped Voronoi labels + per-region affine ramps + noise), image i seeded
+    with seed0 + i.  All randomness is drawn on the host with numpy, so CPU and CUDA runs see the same
+    inputs; only the nearest-seed search runs on `device` (benchmark plumbing, not the hot path)."""
+    import torch
+
+    dev = torch.device(device)
+    imgs = torch.empty((nimg, h, w), dtype=torch.float64, device=dev)
+    labs = torch.empty((nimg, h, w), dtype=torch.int32, device=dev)
+    ii, jj = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=dev),
+                            torch.arange(w, dtype=torch.float32, device=dev), indexing="ij")
+    k = 2 * np.pi / max(16.0, min(h, w) / 6.0)
+    rows = max(1, (1 << 26) // max(n_seeds, 1))
+    for i in range(nimg):
+        rng = np.random.default_rng(seed0 + i)
+        pts = torch.from_numpy(rng.uniform(0, [h, w], size=(n_seeds, 2)).astype(np.float32)).to(dev)
+        ph = rng.uniform(0, 2 * np.pi, size=6)
+        ids = torch.from_numpy(rng.permutation(n_seeds).astype(np.int32)).to(dev)
+        base = torch.from_numpy(rng.uniform(20, 235, size=n_seeds)).to(dev)
+        sl = torch.from_numpy(rng.uniform(-0.5, 0.5, size=(n_seeds, 2))).to(dev)
+        nz = torch.from_numpy(rng.normal(0, noise, size=(h, w))).to(dev)
+        di = warp * (torch.sin(k * jj + ph[0]) + 0.6 * torch.sin(2.3 * k * ii + ph[1])
+                     + 0.4 * torch.sin(3.1 * k * (ii + jj) + ph[2]))
+        dj = warp * (torch.sin(k * ii + ph[3]) + 0.6 * torch.sin(2.7 * k * jj + ph[4])
+                     + 0.4 * torch.sin(3.7 * k * (ii - jj) + ph[5]))
+        q = torch.stack([(ii + di).reshape(-1), (jj + dj).reshape(-1)], dim=1)
+        cell = torch.empty(h * w, dtype=torch.int64, device=dev)
+        p2 = (pts * pts).sum(1)
+        for a in range(0, h * w, rows):
+            qa = q[a:a + rows]
+            cell[a:a + rows] = (p2[None, :] - 2.0 * (qa @ pts.T)).argmin(dim=1)
+        cell = cell.reshape(h, w)
+        labs[i] = ids[cell]
+        x = base[cell] + sl[cell, 0] * (ii.double() - h / 2) + sl[cell, 1] * (jj.double() - w / 2) + nz
+        imgs[i] = x.clamp_(0.0, 255.0)
+    return imgs, labs
