@@ -4,8 +4,11 @@
 // rotate 78-82), the start-point rule of Region.__init_dict_and_extreme_values__ (1020-1036) and
 // the point bookkeeping of RegionCollection.reduce / Region.reduce_points (1563-1584, 1349-1375).
 //
-// One warp owns one region and walks its greedy path; the region's unvisited points are a bitmap
-// over the region's bounding box (shared memory; global scratch for boxes too large).
+// This file: the warp-per-region form -- one warp owns one region and walks its greedy path, the
+// lanes share the rows of the search window.  It serves the regions whose bounding-box bitmap is too
+// large for the thread-per-region kernel (paths_tpr.cuh, the common case) and the EPWT mode (one
+// region per image, values read per candidate).  The unvisited points are a bitmap over the region's
+// bounding box (shared memory; global scratch for boxes too large).
 //
 // Step rule (exactly the reference's, restated order-independently):
 //   candidates = unvisited points of the region inside the smallest square of half-width
@@ -37,14 +40,13 @@
 namespace rbepwt {
 
 constexpr int MODE_EUCLID = 0, MODE_CHEB = 1, MODE_EPWT = 2;
-constexpr int K1_SLOT_WORDS = 1024;  // shared-memory bitmap words per warp in the small-region kernel
-constexpr int K1_WARPS = 8;
 
 struct PathParams {
   const int32_t *labels;  // [B][N]
   int H, W, logW, N, levels;
   RegionArrays reg;
   const int32_t *queue;
+  const int32_t *chunk_start, *chunk_cnt;  // chunk table of the thread-per-region kernel (regions.cuh)
   int *qmeta;
   int32_t *Q;  // [B][2N]
   // big-region kernel
@@ -254,22 +256,6 @@ __device__ void region_pyramid(const PathParams &P, int g, uint32_t *bm) {
     const int na = (a + 1) >> 1, nb = (a + n + 1) >> 1;
     a = na; n = nb - na;
     if (n > 0) { si = (minpix >> logW) - r0; sj = (minpix & (W - 1)) - c0; }
-  }
-}
-
-// Small regions: bitmap in a per-warp shared-memory slot; warps pull regions from the queue.
-template <int MODE>
-__global__ void __launch_bounds__(K1_WARPS * 32) k1_paths_small(PathParams P) {
-  __shared__ uint32_t s_bm[K1_WARPS][K1_SLOT_WORDS];
-  const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
-  const int nbig = P.qmeta[QM_NBIG], nsmall = P.qmeta[QM_NREG] - nbig;
-  while (true) {
-    int idx = 0;
-    if (lane == 0) idx = atomicAdd(&P.qmeta[QM_CUR_SMALL], 1);
-    idx = __shfl_sync(FULL_MASK, idx, 0);
-    if (idx >= nsmall) break;
-    region_pyramid<MODE>(P, P.queue[nbig + idx], s_bm[warp]);
-    __syncwarp();
   }
 }
 

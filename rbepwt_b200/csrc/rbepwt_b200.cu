@@ -94,7 +94,7 @@ struct rbepwt_ctx {
   DevBuf img_R, img_rbase, img_labmin, img_direct;
   std::vector<int32_t> h_R, h_rbase;
   // workspace
-  DevBuf tbl, slot_rid, VA, VB, queue, qhist, qmeta, gscratch, scratch_i32, scratch_i32b, psnr_out, nz_out;
+  DevBuf tbl, slot_rid, VA, VB, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch, scratch_i32, scratch_i32b, psnr_out, nz_out;
   // timing
   bool timing = false;
   std::vector<StageEv> evs;
@@ -208,11 +208,14 @@ int build_regions_and_paths(rbepwt_ctx *c, int c0, int nb) {
     CK(cudaGetLastError());
     CK(c->queue.ensure((size_t)nreg * 4));
     const int qb = std::max(1, std::min((nreg + 255) / 256, c->sm_count * 8));
-    kq_hist<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, K1_SLOT_WORDS, c->qhist.as<int>());
-    kq_scan<<<1, 32, 0, s>>>(c->qhist.as<int>(), c->qmeta.as<int>(), nreg);
-    kq_scatter<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, K1_SLOT_WORDS, c->qmeta.as<int>(),
-                                  c->queue.as<int32_t>());
-    c->launches += 3;
+    CK(c->chunk_start.ensure(((size_t)nreg + Q_BINS) * 4));
+    CK(c->chunk_cnt.ensure(((size_t)nreg + Q_BINS) * 4));
+    kq_hist<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, c->qhist.as<int>());
+    kq_scan<<<1, 32, 0, s>>>(c->qhist.as<int>(), c->qmeta.as<int>(), c->qbins.as<int>(), nreg);
+    kq_scatter<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, c->qmeta.as<int>(), c->queue.as<int32_t>());
+    kq_chunks<<<((Q_BINS - Q_SIZE_BINS) * 32 + 255) / 256, 256, 0, s>>>(c->qbins.as<int>(), c->chunk_start.as<int32_t>(),
+                                                                        c->chunk_cnt.as<int32_t>());
+    c->launches += 4;
     CK(cudaGetLastError());
   }
   {
@@ -221,6 +224,8 @@ int build_regions_and_paths(rbepwt_ctx *c, int c0, int nb) {
     P.H = c->H; P.W = c->W; P.logW = c->logW; P.N = N; P.levels = c->levels;
     P.reg = c->regs();
     P.queue = c->queue.as<int32_t>();
+    P.chunk_start = c->chunk_start.as<int32_t>();
+    P.chunk_cnt = c->chunk_cnt.as<int32_t>();
     P.qmeta = c->qmeta.as<int>();
     P.Q = c->Q.as<int32_t>();
     // big-region kernel: whole-image bitmap in dynamic shared memory when it fits
@@ -236,7 +241,7 @@ int build_regions_and_paths(rbepwt_ctx *c, int c0, int nb) {
       P.gscratch = c->gscratch.as<uint32_t>();
       P.gscratch_words = img_words;
     }
-    const int small_ctas = c->sm_count * 8;  // k1_paths_tpr: 4 KB of arena per warp, 4 warps per CTA
+    const int small_ctas = c->sm_count * 7;  // k1_paths_tpr: 8 KB of arena per warp, 4 warps per CTA -> 7 CTAs per SM
     {
       StageTimer tb(c, RBEPWT_T_PATHS_BIG);
       if (c->mode == RBEPWT_PATH_EUCLID) {
@@ -336,6 +341,7 @@ int alloc_state(rbepwt_ctx *c, int B, int H, int W, int levels, int path_mode, u
     CK(cudaMemsetAsync(c->qhist.p, 0, Q_BINS * 4, c->stream));
   }
   if (!c->qmeta.p) CK(c->qmeta.ensure(QM_SIZE * 4));
+  if (!c->qbins.p) CK(c->qbins.ensure(3 * Q_BINS * 4));
   CK(cudaMemsetAsync(c->qmeta.p, 0, QM_SIZE * 4, c->stream));
   return RBEPWT_OK;
 }
@@ -421,7 +427,7 @@ void rbepwt_destroy(rbepwt_ctx *c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   DevBuf *bufs[] = {&c->filt, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->coefs, &c->img_R,
                     &c->img_rbase, &c->img_labmin, &c->img_direct, &c->tbl, &c->slot_rid, &c->VA, &c->VB, &c->queue,
-                    &c->qhist, &c->qmeta, &c->gscratch, &c->scratch_i32, &c->scratch_i32b, &c->psnr_out, &c->nz_out};
+                    &c->qhist, &c->qmeta, &c->qbins, &c->chunk_start, &c->chunk_cnt, &c->gscratch, &c->scratch_i32, &c->scratch_i32b, &c->psnr_out, &c->nz_out};
   for (auto b : bufs) b->release();
   for (auto &b : c->reg) b.release();
   if (c->own_stream) cudaStreamDestroy(c->stream);

@@ -209,10 +209,18 @@ __global__ void k0_single_region(int img0, int nimg, int H, int W, RegionArrays 
 }
 
 // ---------------------------------------------------------------- work queue -------------
-// Regions are processed largest first (longest sequential chain first).  128 bins:
-// class (0 = bitmap too large for a shared-memory slot, 1 = fits) x 64 size bins (descending).
+// The path kernels pull regions from a queue ordered so that (a) regions whose bounding-box bitmap
+// does not fit a warp's shared-memory arena come first (class 0, one warp per region, paths.cuh),
+// (b) the others are grouped by bitmap size class, largest first: class c >= 1 holds bitmaps of at most
+// TPR_ARENA_WORDS >> (Q_NCLS-1-c) words, so 32 >> (Q_NCLS-1-c) of them always fit one arena together,
+// (c) inside a class regions are sorted by pixel count, descending, in quarter-octave bins: the lanes
+// of a warp walk chains of similar length, and the longest chains start first.
+// A chunk = the regions one warp walks together (thread per region, paths_tpr.cuh).
 
-constexpr int Q_BINS = 128;
+constexpr int TPR_ARENA_WORDS = 2048;  // shared-memory words per warp of k1_paths_tpr
+constexpr int Q_NCLS = 7;              // class 0 = big; classes 1..6 = 1, 2, 4, 8, 16, 32 regions per chunk
+constexpr int Q_SIZE_BINS = 128;
+constexpr int Q_BINS = Q_NCLS * Q_SIZE_BINS;
 
 __device__ __forceinline__ int region_bitmap_words(const RegionArrays &reg, int g, int logW) {
   const int h = reg.rmax[g] - (reg.first[g] >> logW) + 1;
@@ -220,50 +228,90 @@ __device__ __forceinline__ int region_bitmap_words(const RegionArrays &reg, int 
   return h * ((w + 31) >> 5);
 }
 
-__device__ __forceinline__ int queue_bin(int size, int words, int slot_words) {
-  const int lg = 31 - __clz(size);                                   // size >= 1
-  const int key = size >= 2 ? 2 * lg + ((size >> (lg - 1)) & 1) : 0;  // <= 61
-  return (words > slot_words ? 0 : 64) + 63 - key;
+__host__ __device__ __forceinline__ int class_chunk_size(int cls) { return cls == 0 ? 1 : 32 >> (Q_NCLS - 1 - cls); }
+
+__device__ __forceinline__ int queue_bin(int size, int words) {
+  const int lg = 31 - __clz(size);                                        // size >= 1
+  const int key = size >= 4 ? 4 * lg + ((size >> (lg - 2)) & 3) : size;    // <= 4*30+3, monotone in size
+  int cls = 0;
+  if (words <= TPR_ARENA_WORDS) {
+    cls = Q_NCLS - 1;
+    int cap = TPR_ARENA_WORDS >> 5;  // words per region when 32 share the arena
+    while (words > cap) { cap <<= 1; cls--; }
+  }
+  return cls * Q_SIZE_BINS + (Q_SIZE_BINS - 1 - key);
 }
 
-__global__ void kq_hist(RegionArrays reg, int g0, int nreg, int logW, int slot_words, int *qhist) {
+__global__ void kq_hist(RegionArrays reg, int g0, int nreg, int logW, int *qhist) {
   __shared__ int s_h[Q_BINS];
   for (int i = threadIdx.x; i < Q_BINS; i += blockDim.x) s_h[i] = 0;
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreg; i += gridDim.x * blockDim.x) {
     const int g = g0 + i;
-    atomicAdd(&s_h[queue_bin(reg.size[g], region_bitmap_words(reg, g, logW), slot_words)], 1);
+    atomicAdd(&s_h[queue_bin(reg.size[g], region_bitmap_words(reg, g, logW))], 1);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < Q_BINS; i += blockDim.x)
     if (s_h[i]) atomicAdd(&qhist[i], s_h[i]);
 }
 
-// qmeta: [0..127] bin write cursors, [128] = number of class-0 (big) regions, [129] = nreg,
-//        [130] big-queue consumer cursor, [131] small-queue consumer cursor, [132] error flag
-constexpr int QM_NBIG = 128, QM_NREG = 129, QM_CUR_BIG = 130, QM_CUR_SMALL = 131, QM_ERR = 132, QM_SIZE = 136;
+// qmeta: [0, Q_BINS) bin write cursors (scatter), then the named slots below.
+// qbins: [0, Q_BINS) bin start, [Q_BINS, 2 Q_BINS) bin count, [2 Q_BINS, 3 Q_BINS) first chunk of the bin.
+constexpr int QM_NBIG = Q_BINS, QM_NREG = Q_BINS + 1, QM_CUR_BIG = Q_BINS + 2, QM_CUR_SMALL = Q_BINS + 3,
+              QM_ERR = Q_BINS + 4, QM_NCHUNKS = Q_BINS + 5, QM_SIZE = Q_BINS + 8;
 
-__global__ void kq_scan(int *qhist, int *qmeta, int nreg) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    int acc = 0;
-    for (int i = 0; i < Q_BINS; i++) {
-      if (i == 64) qmeta[QM_NBIG] = acc;
-      qmeta[i] = acc;
-      acc += qhist[i];
-      qhist[i] = 0;  // ready for the next chunk
+__global__ void kq_scan(int *qhist, int *qmeta, int *qbins, int nreg) {
+  // one warp: exclusive scans of the bin counts (queue offsets) and of the bins' chunk counts
+  const int lane = threadIdx.x;
+  int acc = 0, cacc = 0;
+  for (int base = 0; base < Q_BINS; base += 32) {
+    const int b = base + lane;
+    const int cnt = qhist[b];
+    const int cls = b / Q_SIZE_BINS;
+    const int cs = class_chunk_size(cls);
+    const int nch = cls == 0 ? 0 : (cnt + cs - 1) / cs;
+    int inc = cnt, cinc = nch;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_up_sync(FULL_MASK, inc, d), cy = __shfl_up_sync(FULL_MASK, cinc, d);
+      if (lane >= d) { inc += y; cinc += cy; }
     }
+    qmeta[b] = acc + inc - cnt;
+    qbins[b] = acc + inc - cnt;
+    qbins[Q_BINS + b] = cnt;
+    qbins[2 * Q_BINS + b] = cacc + cinc - nch;
+    qhist[b] = 0;  // ready for the next chunk of images
+    if (b == Q_SIZE_BINS) qmeta[QM_NBIG] = acc + inc - cnt;  // first bin of class 1
+    acc += __shfl_sync(FULL_MASK, inc, 31);
+    cacc += __shfl_sync(FULL_MASK, cinc, 31);
+  }
+  if (lane == 0) {
     qmeta[QM_NREG] = nreg;
     qmeta[QM_CUR_BIG] = 0;
     qmeta[QM_CUR_SMALL] = 0;
+    qmeta[QM_NCHUNKS] = cacc;
   }
 }
 
-__global__ void kq_scatter(RegionArrays reg, int g0, int nreg, int logW, int slot_words, int *qmeta,
-                           int32_t *queue) {
+__global__ void kq_scatter(RegionArrays reg, int g0, int nreg, int logW, int *qmeta, int32_t *queue) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreg; i += gridDim.x * blockDim.x) {
     const int g = g0 + i;
-    const int bin = queue_bin(reg.size[g], region_bitmap_words(reg, g, logW), slot_words);
+    const int bin = queue_bin(reg.size[g], region_bitmap_words(reg, g, logW));
     queue[atomicAdd(&qmeta[bin], 1)] = g;
+  }
+}
+
+// One warp per bin of the classes >= 1: chunk table (queue offset, regions in the chunk).
+__global__ void kq_chunks(const int *qbins, int32_t *chunk_start, int32_t *chunk_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int b = Q_SIZE_BINS + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (b >= Q_BINS) return;
+  const int start = qbins[b], cnt = qbins[Q_BINS + b], c0 = qbins[2 * Q_BINS + b];
+  const int cs = class_chunk_size(b / Q_SIZE_BINS);
+  const int nch = (cnt + cs - 1) / cs;
+  for (int k = lane; k < nch; k += 32) {
+    chunk_start[c0 + k] = start + k * cs;
+    chunk_cnt[c0 + k] = min(cs, cnt - k * cs);
   }
 }
 
