@@ -32,6 +32,17 @@
 // steps).  Only for the remaining prefs (after jumps) is the fp64 expression evaluated, bit for bit
 // as in paths.cuh.  Chebyshev mode compares candidates of different norms and always uses fp64 sp1.
 //
+// Branch-free candidate selection (euclid mode).  In one bitmap row only the nearest unvisited point
+// on each side of the current column can win (both k and d2 grow with |dj|), so a word contributes at
+// most two candidates, found with clz/ffs, and a candidate is one 64-bit key
+// (k << 44 | d2 << 22 | 2^21 - dot) -- valid because the kernel only takes regions whose bounding box
+// has sides <= TPR_MAX_SIDE = 1024 (d2, |dot| < 2^21).  All lanes execute the same instructions.
+//
+// Unit-step fast path.  When the window half-width is 1 and pref is one of the 8 unit steps (the
+// common case at level 1: 88 % of the steps), the 3x3 neighbourhood is gathered into a 9-bit mask and
+// the answer is read from a 9 x 512 table in shared memory.  The table is filled at kernel start by
+// the same candidate code the generic path runs, so it cannot disagree with it.
+//
 // Shared memory: one arena of TPR_ARENA_WORDS words per warp holds the bounding-box bitmaps of the
 // chunk's regions (chunk table: regions.cuh; a chunk always fits).
 #pragma once
@@ -47,65 +58,127 @@ __device__ __forceinline__ bool pref_ties_exactly(int p0, int p1) {
   return a == b && (a & (a - 1)) == 0;
 }
 
-struct LaneBest {
-  int key;             // euclid: d2; chebyshev: Chebyshev distance
-  int k;               // probe index ceil(log2(Chebyshev distance))
-  int dot, d2, di, dj;
-  int adi, adj;        // euclid: mirror partner with the same (k, d2, dot)
-  double sp1;          // chebyshev: lazily computed
-  bool have, alt, has_sp1;
-};
+__device__ __forceinline__ int probe_index(int c) { return c <= 1 ? 0 : 32 - __clz(c - 1); }  // ceil(log2(c))
 
 template <int MODE>
-__device__ __forceinline__ void lane_consider(LaneBest &b, int di, int dj, int p0, int p1) {
-  const int d2 = di * di + dj * dj;
-  const int c = max(abs(di), abs(dj));
-  if (MODE == MODE_EUCLID) {
-    const int k = c <= 1 ? 0 : 32 - __clz(c - 1);
-    if (b.have && (k > b.k || (k == b.k && d2 > b.key))) return;
-    const int dot = di * p0 + dj * p1;
-    if (!b.have || k < b.k || d2 < b.key || dot > b.dot) {
-      b.have = true; b.alt = false; b.k = k; b.key = d2; b.dot = dot; b.di = di; b.dj = dj;
-    } else if (dot == b.dot) {
-      b.alt = true; b.adi = di; b.adj = dj;
+struct Search;
+
+// ---- euclid: packed integer keys, fp64 only for mirror pairs under a non-exact pref ----------------
+template <>
+struct Search<MODE_EUCLID> {
+  unsigned long long best;
+  int di, dj, adi, adj;
+  bool alt;
+
+  __device__ __forceinline__ void reset() { best = ~0ull; alt = false; di = dj = adi = adj = 0; }
+  __device__ __forceinline__ bool have() const { return best != ~0ull; }
+
+  __device__ __forceinline__ void consider(bool valid, int cdi, int cdj, int p0, int p1) {
+    const int k = probe_index(max(abs(cdi), abs(cdj)));
+    const int d2 = cdi * cdi + cdj * cdj, dot = cdi * p0 + cdj * p1;
+    const unsigned long long key =
+        valid ? ((unsigned long long)k << 44) | ((unsigned long long)d2 << 22) | (unsigned)((1 << 21) - dot) : ~0ull;
+    if (key < best) {
+      best = key; di = cdi; dj = cdj; alt = false;
+    } else if (valid && key == best) {  // mirror image of the incumbent about pref
+      alt = true; adi = cdi; adj = cdj;
     }
-  } else {  // k is a function of c, so c alone orders the probes
-    if (b.have && c > b.key) return;
-    if (!b.have || c < b.key) {
-      b.have = true; b.has_sp1 = false; b.key = c; b.k = c <= 1 ? 0 : 32 - __clz(c - 1);
-      b.d2 = d2; b.di = di; b.dj = dj;
+  }
+
+  // one bitmap word of row ci+rdi: columns lo..lo+31, already masked to the window
+  __device__ __forceinline__ void scan_word(uint32_t bits, int lo, int rdi, int cj, int p0, int p1) {
+    const int rel = min(cj - lo, 31);
+    const uint32_t lmask = rel < 0 ? 0u : (2u << rel) - 1u;  // columns <= cj
+    const uint32_t left = bits & lmask, right = bits & ~lmask;
+    consider(left != 0u, rdi, lo + 31 - __clz(left) - cj, p0, p1);
+    consider(right != 0u, rdi, lo + __ffs(right) - 1 - cj, p0, p1);
+  }
+
+  __device__ __forceinline__ void finish(int p0, int p1, int &odi, int &odj, int &k) {
+    if (alt) {
+      const int cb = di * p1 - dj * p0, ca = adi * p1 - adj * p0;
+      bool alt_better;
+      if (pref_ties_exactly(p0, p1)) {
+        alt_better = ca > cb;
+      } else {
+        const int d2 = (int)((best >> 22) & 0x3fffffu);
+        const double sb = tie_sp1(di, dj, d2, p0, p1), sa = tie_sp1(adi, adj, d2, p0, p1);
+        alt_better = sa != sb ? sa > sb : ca > cb;
+      }
+      if (alt_better) { di = adi; dj = adj; }
+    }
+    odi = di; odj = dj; k = (int)(best >> 44);
+  }
+};
+
+// ---- chebyshev: every point of the nearest ring competes through the fp64 sp1 ----------------------
+template <>
+struct Search<MODE_CHEB> {
+  int c, d2, di, dj;
+  double sp1;
+  bool found, has_sp1;
+
+  __device__ __forceinline__ void reset() { found = false; has_sp1 = false; c = d2 = di = dj = 0; sp1 = 0.0; }
+  __device__ __forceinline__ bool have() const { return found; }
+
+  __device__ __forceinline__ void consider(bool valid, int cdi, int cdj, int p0, int p1) {
+    if (!valid) return;
+    const int cc = max(abs(cdi), abs(cdj)), cd2 = cdi * cdi + cdj * cdj;
+    if (found && cc > c) return;
+    if (!found || cc < c) {
+      found = true; has_sp1 = false; c = cc; d2 = cd2; di = cdi; dj = cdj;
       return;
     }
-    if (!b.has_sp1) { b.sp1 = tie_sp1(b.di, b.dj, b.d2, p0, p1); b.has_sp1 = true; }
-    const double sp1 = tie_sp1(di, dj, d2, p0, p1);
-    bool better;
-    if (sp1 != b.sp1) better = sp1 > b.sp1;
-    else better = (di * p1 - dj * p0) > (b.di * p1 - b.dj * p0);
-    if (better) { b.sp1 = sp1; b.d2 = d2; b.di = di; b.dj = dj; }
+    if (!has_sp1) { sp1 = tie_sp1(di, dj, d2, p0, p1); has_sp1 = true; }
+    const double s = tie_sp1(cdi, cdj, cd2, p0, p1);
+    const bool better = s != sp1 ? s > sp1 : (cdi * p1 - cdj * p0) > (di * p1 - dj * p0);
+    if (better) { sp1 = s; d2 = cd2; di = cdi; dj = cdj; }
   }
-}
 
-// euclid: settle a mirror pair (equal d2 and equal integer dot product)
-__device__ __forceinline__ void lane_resolve_mirror(LaneBest &b, int p0, int p1) {
-  const int cb = b.di * p1 - b.dj * p0, ca = b.adi * p1 - b.adj * p0;
-  bool alt_better;
-  if (pref_ties_exactly(p0, p1)) {
-    alt_better = ca > cb;
-  } else {
-    const double sb = tie_sp1(b.di, b.dj, b.key, p0, p1), sa = tie_sp1(b.adi, b.adj, b.key, p0, p1);
-    alt_better = sa != sb ? sa > sb : ca > cb;
+  __device__ __forceinline__ void scan_word(uint32_t bits, int lo, int rdi, int cj, int p0, int p1) {
+    while (bits) {
+      const int j = lo + __ffs(bits) - 1;
+      bits &= bits - 1;
+      consider(true, rdi, j - cj, p0, p1);
+    }
   }
-  if (alt_better) { b.di = b.adi; b.dj = b.adj; }
-}
+
+  __device__ __forceinline__ void finish(int, int, int &odi, int &odj, int &k) {
+    odi = di; odj = dj; k = probe_index(c);
+  }
+};
+
+constexpr int TPR_LUT_ROWS = 9, TPR_LUT_COLS = 512;
 
 template <int MODE>
 __global__ void __launch_bounds__(TPR_WARPS * 32) k1_paths_tpr(PathParams P) {
   __shared__ uint32_t s_arena[TPR_WARPS][TPR_ARENA_WORDS];
+  __shared__ uint8_t s_lut[TPR_LUT_ROWS * TPR_LUT_COLS];
   const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
   uint32_t *arena = s_arena[warp];
   const int nbig = P.qmeta[QM_NBIG], nchunks = P.qmeta[QM_NCHUNKS];
   const int logW = P.logW, W = P.W, N = P.N, L = P.levels;
   const int Wm = W - 1;
+  (void)nbig;
+
+  // unit-step table: s_lut[q * 512 + m] = index (di+1)*3 + (dj+1) of the winner among the neighbours
+  // present in the 9-bit mask m, for pref = (q/3 - 1, q%3 - 1)
+  for (int e = threadIdx.x; e < TPR_LUT_ROWS * TPR_LUT_COLS; e += blockDim.x) {
+    const int q = e / TPR_LUT_COLS, m = e % TPR_LUT_COLS;
+    const int p0 = q / 3 - 1, p1 = q % 3 - 1;
+    uint8_t v = 0xff;
+    if (q != 4 && !(m & 16) && m) {
+      Search<MODE> S;
+      S.reset();
+      for (int bpos = 0; bpos < 9; bpos++)
+        if (m & (1 << bpos)) S.consider(true, bpos / 3 - 1, bpos % 3 - 1, p0, p1);
+      int odi, odj, k;
+      S.finish(p0, p1, odi, odj, k);
+      v = (uint8_t)((odi + 1) * 3 + (odj + 1));
+    }
+    s_lut[e] = v;
+  }
+  __syncthreads();
 
   while (true) {
     int chunk = 0;
@@ -158,14 +231,14 @@ __global__ void __launch_bounds__(TPR_WARPS * 32) k1_paths_tpr(PathParams P) {
       int32_t *Ql = Qimg + level_off((size_t)N, lev) + a;
       int t = n, ci = si, cj = sj, p0 = 0, p1 = 1;  // prefered_direc = (0,1)   rbepwt.py:1290
       int rad = 1, i = 0, wd = 0, i1 = 0, j0 = 0, j1 = 0, w0 = 0, w1 = 0;
-      LaneBest b;
-      b.have = false; b.alt = false; b.has_sp1 = false;
-      b.key = 0; b.k = 0; b.dot = 0; b.d2 = 0; b.di = 0; b.dj = 0; b.adi = 0; b.adj = 0; b.sp1 = 0.0;
+      bool fresh = true;  // at the first word of a window
+      Search<MODE> S;
+      S.reset();
 #define TPR_SET_WINDOW()                                            \
   do {                                                              \
     i = max(ci - rad, 0); i1 = min(ci + rad, h - 1);                \
     j0 = max(cj - rad, 0); j1 = min(cj + rad, w - 1);               \
-    w0 = j0 >> 5; w1 = j1 >> 5; wd = w0;                            \
+    w0 = j0 >> 5; w1 = j1 >> 5; wd = w0; fresh = true;              \
   } while (0)
       if (live) {
         bm[si * ws + (sj >> 5)] &= ~(1u << (sj & 31));
@@ -175,36 +248,68 @@ __global__ void __launch_bounds__(TPR_WARPS * 32) k1_paths_tpr(PathParams P) {
       }
       while (__any_sync(FULL_MASK, t < n)) {
         if (t < n) {
-          uint32_t bits = bm[i * ws + wd];
-          const int lo = wd << 5;
-          if (lo < j0) bits &= 0xffffffffu << (j0 - lo);
-          if (lo + 31 > j1) bits &= 0xffffffffu >> (lo + 31 - j1);
-          while (bits) {
-            const int j = lo + __ffs(bits) - 1;
-            bits &= bits - 1;
-            lane_consider<MODE>(b, i - ci, j - cj, p0, p1);
+          bool commit = false, expand = false;
+          int fdi = 0, fdj = 0, fk = 0;
+          if (fresh && rad == 1 && (unsigned)(p0 + 1) <= 2u && (unsigned)(p1 + 1) <= 2u) {
+            // unit-step fast path: 3x3 neighbourhood -> 9-bit mask -> table
+            const int wq = cj >> 5, bq = cj & 31;
+            unsigned m = 0;
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) {
+              const int ri = ci + rr - 1;
+              unsigned three = 0;
+              if (ri >= 0 && ri < h) {
+                const uint32_t *row = bm + ri * ws;
+                const uint32_t x = row[wq];
+                if (bq == 0) three = ((x << 1) | (wq > 0 ? row[wq - 1] >> 31 : 0u)) & 7u;
+                else if (bq == 31) three = ((x >> 30) | ((wq + 1 < ws ? row[wq + 1] : 0u) << 2)) & 7u;
+                else three = (x >> (bq - 1)) & 7u;
+              }
+              m |= three << (3 * rr);
+            }
+            if (m) {
+              const int idx = s_lut[((p0 + 1) * 3 + (p1 + 1)) * TPR_LUT_COLS + m];
+              fdi = idx / 3 - 1; fdj = idx % 3 - 1; fk = 0;
+              commit = true;
+            } else {
+              expand = true;
+            }
+          } else {
+            fresh = false;
+            uint32_t bits = bm[i * ws + wd];
+            const int lo = wd << 5;
+            if (lo < j0) bits &= 0xffffffffu << (j0 - lo);
+            if (lo + 31 > j1) bits &= 0xffffffffu >> (lo + 31 - j1);
+            S.scan_word(bits, lo, i - ci, cj, p0, p1);
+            if (wd < w1) {
+              wd++;
+            } else if (i < i1) {
+              i++; wd = w0;
+            } else if (S.have()) {
+              S.finish(p0, p1, fdi, fdj, fk);
+              commit = true;
+            } else {
+              expand = true;
+            }
           }
-          if (wd < w1) {
-            wd++;
-          } else if (i < i1) {
-            i++; wd = w0;
-          } else if (b.have) {  // window exhausted: commit the step
-            if (MODE == MODE_EUCLID && b.alt) lane_resolve_mirror(b, p0, p1);
-            const int bi = ci + b.di, bj = cj + b.dj;
+          if (commit) {
+            const int bi = ci + fdi, bj = cj + fdj;
             bm[bi * ws + (bj >> 5)] &= ~(1u << (bj & 31));
             Ql[t] = ((r0 + bi) << logW) + c0 + bj;
-            p0 = b.di; p1 = b.dj;  // rbepwt.py:1331
+            p0 = fdi; p1 = fdj;  // rbepwt.py:1331
             ci = bi; cj = bj;
             t++;
-            rad = 1 << b.k;
-            b.have = false; b.alt = false; b.has_sp1 = false;
+            rad = 1 << fk;
+            S.reset();
             TPR_SET_WINDOW();
-          } else if (ci - rad <= 0 && cj - rad <= 0 && ci + rad >= h - 1 && cj + rad >= w - 1) {
-            atomicExch(&P.qmeta[QM_ERR], 1);  // nothing unvisited in the whole box: corrupt state
-            t = n; live = false;
-          } else {
-            rad <<= 1;
-            TPR_SET_WINDOW();
+          } else if (expand) {
+            if (ci - rad <= 0 && cj - rad <= 0 && ci + rad >= h - 1 && cj + rad >= w - 1) {
+              atomicExch(&P.qmeta[QM_ERR], 1);  // nothing unvisited in the whole box: corrupt state
+              t = n; live = false;
+            } else {
+              rad <<= 1;
+              TPR_SET_WINDOW();
+            }
           }
         }
       }

@@ -241,7 +241,12 @@ int build_regions_and_paths(rbepwt_ctx *c, int c0, int nb) {
       P.gscratch = c->gscratch.as<uint32_t>();
       P.gscratch_words = img_words;
     }
-    const int small_ctas = c->sm_count * 7;  // k1_paths_tpr: 8 KB of arena per warp, 4 warps per CTA -> 7 CTAs per SM
+    int tpr_per_sm = 1;  // persistent grid: as many CTAs as are resident at once
+    if (c->mode == RBEPWT_PATH_EUCLID)
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_paths_tpr<MODE_EUCLID>, TPR_WARPS * 32, 0));
+    else
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_paths_tpr<MODE_CHEB>, TPR_WARPS * 32, 0));
+    const int small_ctas = c->sm_count * std::max(tpr_per_sm, 1);
     {
       StageTimer tb(c, RBEPWT_T_PATHS_BIG);
       if (c->mode == RBEPWT_PATH_EUCLID) {

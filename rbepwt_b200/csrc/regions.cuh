@@ -222,10 +222,19 @@ constexpr int Q_NCLS = 7;              // class 0 = big; classes 1..6 = 1, 2, 4,
 constexpr int Q_SIZE_BINS = 128;
 constexpr int Q_BINS = Q_NCLS * Q_SIZE_BINS;
 
+constexpr int TPR_MAX_SIDE = 1024;     // bounding-box side limit of k1_paths_tpr (its packed candidate key)
+
 __device__ __forceinline__ int region_bitmap_words(const RegionArrays &reg, int g, int logW) {
   const int h = reg.rmax[g] - (reg.first[g] >> logW) + 1;
   const int w = reg.cmax[g] - reg.cmin[g] + 1;
   return h * ((w + 31) >> 5);
+}
+
+// Bitmap words used for the queue class: regions with a side above TPR_MAX_SIDE count as oversized.
+__device__ __forceinline__ int region_class_words(const RegionArrays &reg, int g, int logW) {
+  const int h = reg.rmax[g] - (reg.first[g] >> logW) + 1;
+  const int w = reg.cmax[g] - reg.cmin[g] + 1;
+  return (h > TPR_MAX_SIDE || w > TPR_MAX_SIDE) ? INT32_MAX : h * ((w + 31) >> 5);
 }
 
 __host__ __device__ __forceinline__ int class_chunk_size(int cls) { return cls == 0 ? 1 : 32 >> (Q_NCLS - 1 - cls); }
@@ -248,7 +257,7 @@ __global__ void kq_hist(RegionArrays reg, int g0, int nreg, int logW, int *qhist
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreg; i += gridDim.x * blockDim.x) {
     const int g = g0 + i;
-    atomicAdd(&s_h[queue_bin(reg.size[g], region_bitmap_words(reg, g, logW))], 1);
+    atomicAdd(&s_h[queue_bin(reg.size[g], region_class_words(reg, g, logW))], 1);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < Q_BINS; i += blockDim.x)
@@ -296,7 +305,7 @@ __global__ void kq_scan(int *qhist, int *qmeta, int *qbins, int nreg) {
 __global__ void kq_scatter(RegionArrays reg, int g0, int nreg, int logW, int *qmeta, int32_t *queue) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreg; i += gridDim.x * blockDim.x) {
     const int g = g0 + i;
-    const int bin = queue_bin(reg.size[g], region_bitmap_words(reg, g, logW));
+    const int bin = queue_bin(reg.size[g], region_class_words(reg, g, logW));
     queue[atomicAdd(&qmeta[bin], 1)] = g;
   }
 }
