@@ -58,7 +58,7 @@ __device__ __forceinline__ bool pref_ties_exactly(int p0, int p1) {
   return a == b && (a & (a - 1)) == 0;
 }
 
-__device__ __forceinline__ int probe_index(int c) { return c <= 1 ? 0 : 32 - __clz(c - 1); }  // ceil(log2(c))
+__device__ __forceinline__ int probe_index(int c) { return 32 - __clz(max(c - 1, 0)); }  // ceil(log2(c)), c >= 1
 
 template <int MODE>
 struct Search;
@@ -78,11 +78,15 @@ struct Search<MODE_EUCLID> {
     const int d2 = cdi * cdi + cdj * cdj, dot = cdi * p0 + cdj * p1;
     const unsigned long long key =
         valid ? ((unsigned long long)k << 44) | ((unsigned long long)d2 << 22) | (unsigned)((1 << 21) - dot) : ~0ull;
-    if (key < best) {
-      best = key; di = cdi; dj = cdj; alt = false;
-    } else if (valid && key == best) {  // mirror image of the incumbent about pref
-      alt = true; adi = cdi; adj = cdj;
-    }
+    // selects, not branches: every lane executes the same instructions
+    const bool lt = key < best;
+    const bool eq = valid && key == best;  // mirror image of the incumbent about pref
+    best = lt ? key : best;
+    di = lt ? cdi : di;
+    dj = lt ? cdj : dj;
+    alt = lt ? false : (alt || eq);
+    adi = eq ? cdi : adi;
+    adj = eq ? cdj : adj;
   }
 
   // one bitmap word of row ci+rdi: columns lo..lo+31, already masked to the window
@@ -281,35 +285,35 @@ __global__ void __launch_bounds__(TPR_WARPS * 32) k1_paths_tpr(PathParams P) {
             if (lo < j0) bits &= 0xffffffffu << (j0 - lo);
             if (lo + 31 > j1) bits &= 0xffffffffu >> (lo + 31 - j1);
             S.scan_word(bits, lo, i - ci, cj, p0, p1);
-            if (wd < w1) {
-              wd++;
-            } else if (i < i1) {
-              i++; wd = w0;
-            } else if (S.have()) {
-              S.finish(p0, p1, fdi, fdj, fk);
-              commit = true;
-            } else {
-              expand = true;
+            const bool more_w = wd < w1, more_i = i < i1;
+            wd = more_w ? wd + 1 : w0;
+            i += (!more_w && more_i) ? 1 : 0;
+            if (!more_w && !more_i) {  // window exhausted
+              if (S.have()) {
+                S.finish(p0, p1, fdi, fdj, fk);
+                commit = true;
+              } else {
+                expand = true;
+              }
             }
           }
-          if (commit) {
-            const int bi = ci + fdi, bj = cj + fdj;
-            bm[bi * ws + (bj >> 5)] &= ~(1u << (bj & 31));
-            Ql[t] = ((r0 + bi) << logW) + c0 + bj;
-            p0 = fdi; p1 = fdj;  // rbepwt.py:1331
-            ci = bi; cj = bj;
-            t++;
-            rad = 1 << fk;
-            S.reset();
-            TPR_SET_WINDOW();
-          } else if (expand) {
-            if (ci - rad <= 0 && cj - rad <= 0 && ci + rad >= h - 1 && cj + rad >= w - 1) {
+          if (commit || expand) {
+            if (commit) {
+              const int bi = ci + fdi, bj = cj + fdj;
+              bm[bi * ws + (bj >> 5)] &= ~(1u << (bj & 31));
+              Ql[t] = ((r0 + bi) << logW) + c0 + bj;
+              p0 = fdi; p1 = fdj;  // rbepwt.py:1331
+              ci = bi; cj = bj;
+              t++;
+              rad = 1 << fk;
+              S.reset();
+            } else if (ci - rad <= 0 && cj - rad <= 0 && ci + rad >= h - 1 && cj + rad >= w - 1) {
               atomicExch(&P.qmeta[QM_ERR], 1);  // nothing unvisited in the whole box: corrupt state
               t = n; live = false;
             } else {
               rad <<= 1;
-              TPR_SET_WINDOW();
             }
+            TPR_SET_WINDOW();
           }
         }
       }
