@@ -43,6 +43,15 @@
 // the answer is read from a 9 x 512 table in shared memory.  The table is filled at kernel start by
 // the same candidate code the generic path runs, so it cannot disagree with it.
 //
+// Three rows per trip.  For half-widths <= 15 a window row is one 32-bit word after a funnel shift
+// that puts column cj at bit 15, so a trip examines up to three rows with straight-line code; wider
+// windows (scattered regions) fall back to one bitmap word per trip.
+//
+// List mode.  From the first level at which a region keeps <= 32 points (spacing large, windows wide
+// and mostly empty) the lane drops the bitmap and holds the points as a list of packed (row, col) in
+// its arena slot; a step scans the remaining points (a 32-bit unvisited mask) with the same candidate
+// code, so the cost per step is the number of points left instead of the window area.
+//
 // Shared memory: one arena of TPR_ARENA_WORDS words per warp holds the bounding-box bitmaps of the
 // chunk's regions (chunk table: regions.cuh; a chunk always fits).
 #pragma once
@@ -68,12 +77,13 @@ template <>
 struct Search<MODE_EUCLID> {
   unsigned long long best;
   int di, dj, adi, adj;
+  int tag, atag;  // caller's payload of the incumbent / its mirror partner (list mode: list index)
   bool alt;
 
-  __device__ __forceinline__ void reset() { best = ~0ull; alt = false; di = dj = adi = adj = 0; }
+  __device__ __forceinline__ void reset() { best = ~0ull; alt = false; di = dj = adi = adj = 0; tag = atag = 0; }
   __device__ __forceinline__ bool have() const { return best != ~0ull; }
 
-  __device__ __forceinline__ void consider(bool valid, int cdi, int cdj, int p0, int p1) {
+  __device__ __forceinline__ void consider(bool valid, int cdi, int cdj, int p0, int p1, int ctag = 0) {
     const int k = probe_index(max(abs(cdi), abs(cdj)));
     const int d2 = cdi * cdi + cdj * cdj, dot = cdi * p0 + cdj * p1;
     const unsigned long long key =
@@ -87,6 +97,8 @@ struct Search<MODE_EUCLID> {
     alt = lt ? false : (alt || eq);
     adi = eq ? cdi : adi;
     adj = eq ? cdj : adj;
+    tag = lt ? ctag : tag;
+    atag = eq ? ctag : atag;
   }
 
   // one bitmap word of row ci+rdi: columns lo..lo+31, already masked to the window
@@ -96,6 +108,13 @@ struct Search<MODE_EUCLID> {
     const uint32_t left = bits & lmask, right = bits & ~lmask;
     consider(left != 0u, rdi, lo + 31 - __clz(left) - cj, p0, p1);
     consider(right != 0u, rdi, lo + __ffs(right) - 1 - cj, p0, p1);
+  }
+
+  // one window row as an aligned word: bit 15 + dj <-> column cj + dj
+  __device__ __forceinline__ void scan_row(uint32_t x, int rdi, int p0, int p1) {
+    const uint32_t left = x & 0x7fffu, right = x >> 15;
+    consider(left != 0u, rdi, 16 - __clz(left), p0, p1);  // highest set bit hb -> dj = hb - 15
+    consider(right != 0u, rdi, __ffs(right) - 1, p0, p1);
   }
 
   __device__ __forceinline__ void finish(int p0, int p1, int &odi, int &odj, int &k) {
@@ -109,7 +128,7 @@ struct Search<MODE_EUCLID> {
         const double sb = tie_sp1(di, dj, d2, p0, p1), sa = tie_sp1(adi, adj, d2, p0, p1);
         alt_better = sa != sb ? sa > sb : ca > cb;
       }
-      if (alt_better) { di = adi; dj = adj; }
+      if (alt_better) { di = adi; dj = adj; tag = atag; }
     }
     odi = di; odj = dj; k = (int)(best >> 44);
   }
@@ -118,25 +137,25 @@ struct Search<MODE_EUCLID> {
 // ---- chebyshev: every point of the nearest ring competes through the fp64 sp1 ----------------------
 template <>
 struct Search<MODE_CHEB> {
-  int c, d2, di, dj;
+  int c, d2, di, dj, tag;
   double sp1;
   bool found, has_sp1;
 
-  __device__ __forceinline__ void reset() { found = false; has_sp1 = false; c = d2 = di = dj = 0; sp1 = 0.0; }
+  __device__ __forceinline__ void reset() { found = false; has_sp1 = false; c = d2 = di = dj = tag = 0; sp1 = 0.0; }
   __device__ __forceinline__ bool have() const { return found; }
 
-  __device__ __forceinline__ void consider(bool valid, int cdi, int cdj, int p0, int p1) {
+  __device__ __forceinline__ void consider(bool valid, int cdi, int cdj, int p0, int p1, int ctag = 0) {
     if (!valid) return;
     const int cc = max(abs(cdi), abs(cdj)), cd2 = cdi * cdi + cdj * cdj;
     if (found && cc > c) return;
     if (!found || cc < c) {
-      found = true; has_sp1 = false; c = cc; d2 = cd2; di = cdi; dj = cdj;
+      found = true; has_sp1 = false; c = cc; d2 = cd2; di = cdi; dj = cdj; tag = ctag;
       return;
     }
     if (!has_sp1) { sp1 = tie_sp1(di, dj, d2, p0, p1); has_sp1 = true; }
     const double s = tie_sp1(cdi, cdj, cd2, p0, p1);
     const bool better = s != sp1 ? s > sp1 : (cdi * p1 - cdj * p0) > (di * p1 - dj * p0);
-    if (better) { sp1 = s; d2 = cd2; di = cdi; dj = cdj; }
+    if (better) { sp1 = s; d2 = cd2; di = cdi; dj = cdj; tag = ctag; }
   }
 
   __device__ __forceinline__ void scan_word(uint32_t bits, int lo, int rdi, int cj, int p0, int p1) {
@@ -147,12 +166,38 @@ struct Search<MODE_CHEB> {
     }
   }
 
+  __device__ __forceinline__ void scan_row(uint32_t x, int rdi, int p0, int p1) {
+    while (x) {
+      const int b = __ffs(x) - 1;
+      x &= x - 1;
+      consider(true, rdi, b - 15, p0, p1);
+    }
+  }
+
   __device__ __forceinline__ void finish(int, int, int &odi, int &odj, int &k) {
     odi = di; odj = dj; k = probe_index(c);
   }
 };
 
+
 constexpr int TPR_LUT_ROWS = 9, TPR_LUT_COLS = 512;
+#ifdef TPR_STATS  // debug build only: trips and lanes served per level and trip kind
+__device__ unsigned long long g_tpr_stats[16 * 4 * 2 + 32];
+#endif
+constexpr int TPR_LIST_MAX = 32;   // list mode from the first level with at most this many points
+constexpr int TPR_SLOT_MIN = 48;   // arena words per lane: list buffers A = [0,32), B = [32,48) ping-pong
+constexpr int TPR_ROWS_PER_TRIP = 3;
+constexpr int TPR_MAX_RAD = 8;     // widest aligned-row window; beyond it the whole bitmap is scanned
+
+// Window row as one word: bit 15 + dj  <->  column cj + dj, dj in [-15, 16]; columns outside the
+// bitmap read as 0.
+__device__ __forceinline__ uint32_t row_window(const uint32_t *row, int ws, int cj) {
+  const int s = cj - 15;
+  const int wlo = s >> 5;  // -1 when s < 0
+  const uint32_t lo = (wlo >= 0 && wlo < ws) ? row[wlo] : 0u;
+  const uint32_t hi = (wlo + 1 < ws) ? row[wlo + 1] : 0u;
+  return __funnelshift_r(lo, hi, s & 31);
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(TPR_WARPS * 32) k1_paths_tpr(PathParams P) {
@@ -160,10 +205,9 @@ __global__ void __launch_bounds__(TPR_WARPS * 32) k1_paths_tpr(PathParams P) {
   __shared__ uint8_t s_lut[TPR_LUT_ROWS * TPR_LUT_COLS];
   const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
   uint32_t *arena = s_arena[warp];
-  const int nbig = P.qmeta[QM_NBIG], nchunks = P.qmeta[QM_NCHUNKS];
+  const int nchunks = P.qmeta[QM_NCHUNKS];
   const int logW = P.logW, W = P.W, N = P.N, L = P.levels;
   const int Wm = W - 1;
-  (void)nbig;
 
   // unit-step table: s_lut[q * 512 + m] = index (di+1)*3 + (dj+1) of the winner among the neighbours
   // present in the 9-bit mask m, for pref = (q/3 - 1, q%3 - 1)
@@ -199,14 +243,14 @@ __global__ void __launch_bounds__(TPR_WARPS * 32) k1_paths_tpr(PathParams P) {
       r0 = first >> logW; c0 = P.reg.cmin[g];
       h = P.reg.rmax[g] - r0 + 1; w = P.reg.cmax[g] - c0 + 1; ws = (w + 31) >> 5;
     }
-    const int words = h * ws;  // 0 for idle lanes
-    int inc = words;
+    const int slot = mine ? max(h * ws, TPR_SLOT_MIN) : 0;  // the chunk table guarantees the sum fits
+    int inc = slot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int y = __shfl_up_sync(FULL_MASK, inc, d);
       if (lane >= d) inc += y;
     }
-    const int base = inc - words;
+    const int base = inc - slot;
     uint32_t *bm = arena + base;
 
     // cooperative bitmap build: one ballot per bitmap word, lanes = columns
@@ -227,117 +271,187 @@ __global__ void __launch_bounds__(TPR_WARPS * 32) k1_paths_tpr(PathParams P) {
     __syncwarp();
 
     // every lane walks its own region; the warp advances level by level
-    bool live = mine;
+    bool live = mine, list = false;
     int n = mine ? size : 0, a = off;
-    int si = 0, sj = (first & Wm) - c0;
+    int si = 0, sj = (first & Wm) - c0;  // bitmap mode: start point
+    int lb = 0, sidx = 0;                // list mode: buffer offset of the level's list, index of its start point
     int32_t *Qimg = P.Q + (size_t)img * 2 * (size_t)N;
     for (int lev = 1; lev <= L; lev++) {
       int32_t *Ql = Qimg + level_off((size_t)N, lev) + a;
+      const bool keep = lev < L;  // the next level exists: collect the survivors
       int t = n, ci = si, cj = sj, p0 = 0, p1 = 1;  // prefered_direc = (0,1)   rbepwt.py:1290
-      int rad = 1, i = 0, wd = 0, i1 = 0, j0 = 0, j1 = 0, w0 = 0, w1 = 0;
-      bool fresh = true;  // at the first word of a window
+      int rad = 1, i = 0, wd = 0, i1 = 0;
+      bool fresh = true;     // at the first row of a window
+      unsigned U = 0;        // list mode: unvisited mask
+      int ncnt = 0;          // list mode: survivors appended to the other buffer
+      uint32_t nmin = 0xffffffffu;
+      int nminidx = 0;
       Search<MODE> S;
       S.reset();
 #define TPR_SET_WINDOW()                                            \
   do {                                                              \
+    rad = min(rad, 2 * TPR_MAX_RAD);                                \
     i = max(ci - rad, 0); i1 = min(ci + rad, h - 1);                \
-    j0 = max(cj - rad, 0); j1 = min(cj + rad, w - 1);               \
-    w0 = j0 >> 5; w1 = j1 >> 5; wd = w0; fresh = true;              \
+    wd = 0; fresh = true;                                           \
+  } while (0)
+#define TPR_LIST_KEEP(entry)                                        \
+  do {                                                              \
+    bm[(lb ^ 32) + ncnt] = (entry);                                 \
+    if ((entry) < nmin) { nmin = (entry); nminidx = ncnt; }         \
+    ncnt++;                                                         \
   } while (0)
       if (live) {
-        bm[si * ws + (sj >> 5)] &= ~(1u << (sj & 31));
-        Ql[0] = ((r0 + si) << logW) + c0 + sj;
+        if (list) {
+          const uint32_t e = bm[lb + sidx];
+          ci = (int)(e >> 16); cj = (int)(e & 0xffffu);
+          U = (n >= 32 ? 0xffffffffu : (1u << n) - 1u) & ~(1u << sidx);
+          if (keep && (a & 1) == 0) TPR_LIST_KEEP(e);
+        } else {
+          bm[si * ws + (sj >> 5)] &= ~(1u << (sj & 31));
+          TPR_SET_WINDOW();
+        }
+        Ql[0] = ((r0 + ci) << logW) + c0 + cj;
         t = 1;
-        TPR_SET_WINDOW();
       }
       while (__any_sync(FULL_MASK, t < n)) {
         if (t < n) {
           bool commit = false, expand = false;
           int fdi = 0, fdj = 0, fk = 0;
-          if (fresh && rad == 1 && (unsigned)(p0 + 1) <= 2u && (unsigned)(p1 + 1) <= 2u) {
-            // unit-step fast path: 3x3 neighbourhood -> 9-bit mask -> table
-            const int wq = cj >> 5, bq = cj & 31;
-            unsigned m = 0;
-#pragma unroll
-            for (int rr = 0; rr < 3; rr++) {
-              const int ri = ci + rr - 1;
-              unsigned three = 0;
-              if (ri >= 0 && ri < h) {
-                const uint32_t *row = bm + ri * ws;
-                const uint32_t x = row[wq];
-                if (bq == 0) three = ((x << 1) | (wq > 0 ? row[wq - 1] >> 31 : 0u)) & 7u;
-                else if (bq == 31) three = ((x >> 30) | ((wq + 1 < ws ? row[wq + 1] : 0u) << 2)) & 7u;
-                else three = (x >> (bq - 1)) & 7u;
-              }
-              m |= three << (3 * rr);
+#ifdef TPR_STATS
+          {
+            const int kind = list ? 3 : (fresh && rad == 1 && (unsigned)(p0 + 1) <= 2u && (unsigned)(p1 + 1) <= 2u) ? 0
+                                    : (rad <= TPR_MAX_RAD ? 1 : 2);
+            atomicAdd(&g_tpr_stats[((min(lev, 16) - 1) * 4 + kind) * 2 + 1], 1ull);
+            if (lane == __ffs(__activemask()) - 1) atomicAdd(&g_tpr_stats[128 + min(lev, 16) - 1], 1ull);
+          }
+#endif
+          if (list) {
+            // ---- list mode: one whole step, candidates = the points still unvisited
+            for (unsigned u = U; u; u &= u - 1) {
+              const int idx = __ffs(u) - 1;
+              const uint32_t e = bm[lb + idx];
+              S.consider(true, (int)(e >> 16) - ci, (int)(e & 0xffffu) - cj, p0, p1, idx);
             }
-            if (m) {
-              const int idx = s_lut[((p0 + 1) * 3 + (p1 + 1)) * TPR_LUT_COLS + m];
-              fdi = idx / 3 - 1; fdj = idx % 3 - 1; fk = 0;
-              commit = true;
-            } else {
-              expand = true;
-            }
+            S.finish(p0, p1, fdi, fdj, fk);
+            const int idx = S.tag;
+            U &= ~(1u << idx);
+            if (keep && ((a + t) & 1) == 0) TPR_LIST_KEEP(bm[lb + idx]);
+            ci += fdi; cj += fdj;
+            Ql[t] = ((r0 + ci) << logW) + c0 + cj;
+            p0 = fdi; p1 = fdj;
+            t++;
+            S.reset();
           } else {
-            fresh = false;
-            uint32_t bits = bm[i * ws + wd];
-            const int lo = wd << 5;
-            if (lo < j0) bits &= 0xffffffffu << (j0 - lo);
-            if (lo + 31 > j1) bits &= 0xffffffffu >> (lo + 31 - j1);
-            S.scan_word(bits, lo, i - ci, cj, p0, p1);
-            const bool more_w = wd < w1, more_i = i < i1;
-            wd = more_w ? wd + 1 : w0;
-            i += (!more_w && more_i) ? 1 : 0;
-            if (!more_w && !more_i) {  // window exhausted
-              if (S.have()) {
-                S.finish(p0, p1, fdi, fdj, fk);
+            if (fresh && rad == 1 && (unsigned)(p0 + 1) <= 2u && (unsigned)(p1 + 1) <= 2u) {
+              // ---- unit-step fast path: 3x3 neighbourhood -> 9-bit mask -> table
+              unsigned m = 0;
+#pragma unroll
+              for (int rr = 0; rr < 3; rr++) {
+                const int ri = ci + rr - 1;
+                const uint32_t x = (ri >= 0 && ri < h) ? row_window(bm + ri * ws, ws, cj) : 0u;
+                m |= ((x >> 14) & 7u) << (3 * rr);
+              }
+              if (m) {
+                const int idx = s_lut[((p0 + 1) * 3 + (p1 + 1)) * TPR_LUT_COLS + m];
+                fdi = idx / 3 - 1; fdj = idx % 3 - 1; fk = 0;
                 commit = true;
               } else {
                 expand = true;
               }
-            }
-          }
-          if (commit || expand) {
-            if (commit) {
-              const int bi = ci + fdi, bj = cj + fdj;
-              bm[bi * ws + (bj >> 5)] &= ~(1u << (bj & 31));
-              Ql[t] = ((r0 + bi) << logW) + c0 + bj;
-              p0 = fdi; p1 = fdj;  // rbepwt.py:1331
-              ci = bi; cj = bj;
-              t++;
-              rad = 1 << fk;
-              S.reset();
-            } else if (ci - rad <= 0 && cj - rad <= 0 && ci + rad >= h - 1 && cj + rad >= w - 1) {
-              atomicExch(&P.qmeta[QM_ERR], 1);  // nothing unvisited in the whole box: corrupt state
-              t = n; live = false;
+            } else if (rad <= TPR_MAX_RAD) {
+              // ---- up to three window rows, each one aligned word
+              fresh = false;
+              const uint32_t wmask = ((2u << (2 * rad)) - 1u) << (15 - rad);
+#pragma unroll
+              for (int u = 0; u < TPR_ROWS_PER_TRIP; u++) {
+                const bool act = i <= i1;
+                const int ri = min(i, h - 1);
+                const uint32_t x = act ? (row_window(bm + ri * ws, ws, cj) & wmask) : 0u;
+                S.scan_row(x, ri - ci, p0, p1);
+                i += act ? 1 : 0;
+              }
+              if (i > i1) {
+                if (S.have()) { S.finish(p0, p1, fdi, fdj, fk); commit = true; }
+                else expand = true;
+              }
             } else {
-              rad <<= 1;
+              // ---- nothing within TPR_MAX_RAD: scan the region's whole bitmap, four words per trip.
+              // Ranking by (k, d2, dot) makes this equal to the remaining probes 2*TPR_MAX_RAD, ... in turn.
+              fresh = false;
+              const int nwords = h * ws;
+              uint32_t b4[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) b4[u] = wd + u < nwords ? bm[wd + u] : 0u;
+              if (b4[0] | b4[1] | b4[2] | b4[3]) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                  const int wi = wd + u, ri = wi / ws;
+                  S.scan_word(b4[u], (wi - ri * ws) << 5, ri - ci, cj, p0, p1);
+                }
+              }
+              wd += 4;
+              if (wd >= nwords) {
+                if (S.have()) { S.finish(p0, p1, fdi, fdj, fk); commit = true; }
+                else expand = true;  // the box is covered: reported as corrupt state below
+              }
             }
-            TPR_SET_WINDOW();
+            if (commit || expand) {
+              if (commit) {
+                const int bi = ci + fdi, bj = cj + fdj;
+                bm[bi * ws + (bj >> 5)] &= ~(1u << (bj & 31));
+                Ql[t] = ((r0 + bi) << logW) + c0 + bj;
+                p0 = fdi; p1 = fdj;  // rbepwt.py:1331
+                ci = bi; cj = bj;
+                t++;
+                rad = 1 << fk;
+                S.reset();
+              } else if (rad > TPR_MAX_RAD) {
+                atomicExch(&P.qmeta[QM_ERR], 1);  // nothing unvisited in the whole box: corrupt state
+                t = n; live = false;
+              } else {
+                rad <<= 1;
+              }
+              TPR_SET_WINDOW();
+            }
           }
         }
       }
-#undef TPR_SET_WINDOW
       if (lev == L) break;
       // RegionCollection.reduce: the points at even GLOBAL position a+t survive (rbepwt.py:1563-1584);
-      // the bitmap is all-zero here, re-mark them; the smallest surviving pixel id is the next start
-      // point (lexicographic min, rbepwt.py:1035-1036)
-      int minpix = INT32_MAX;
-      if (live) {
-        for (int tt = a & 1; tt < n; tt += 2) {
-          const int pix = __ldcg(Ql + tt);
-          const int pi = (pix >> logW) - r0, pj = (pix & Wm) - c0;
-          bm[pi * ws + (pj >> 5)] |= 1u << (pj & 31);
-          minpix = min(minpix, pix);
+      // the next start point is the lexicographically smallest survivor (rbepwt.py:1035-1036)
+      const int na = (a + 1) >> 1, nb = (a + n + 1) >> 1;
+      const int nnext = nb - na;
+      if (live && nnext > 0) {
+        if (list) {  // survivors were appended to the other buffer during the walk
+          lb ^= 32; sidx = nminidx;
+        } else if (nnext <= TPR_LIST_MAX) {  // bitmap (all-zero now, dead) -> list in buffer A
+          list = true; lb = 0;
+          uint32_t mn = 0xffffffffu;
+          int k = 0;
+          for (int tt = a & 1; tt < n; tt += 2, k++) {
+            const int pix = __ldcg(Ql + tt);
+            const uint32_t e = (uint32_t)(((pix >> logW) - r0) << 16) | (uint32_t)((pix & Wm) - c0);
+            bm[k] = e;
+            if (e < mn) { mn = e; sidx = k; }
+          }
+        } else {  // re-mark the survivors in the (all-zero) bitmap
+          int minpix = INT32_MAX;
+          for (int tt = a & 1; tt < n; tt += 2) {
+            const int pix = __ldcg(Ql + tt);
+            const int pi = (pix >> logW) - r0, pj = (pix & Wm) - c0;
+            bm[pi * ws + (pj >> 5)] |= 1u << (pj & 31);
+            minpix = min(minpix, pix);
+          }
+          si = (minpix >> logW) - r0; sj = (minpix & Wm) - c0;
         }
       }
-      const int na = (a + 1) >> 1, nb = (a + n + 1) >> 1;
-      a = na; n = nb - na;
+      a = na; n = nnext;
       live = live && n > 0;
       if (!live) n = 0;
-      if (live) { si = (minpix >> logW) - r0; sj = (minpix & Wm) - c0; }
       if (!__any_sync(FULL_MASK, live)) break;
     }
+#undef TPR_SET_WINDOW
+#undef TPR_LIST_KEEP
     __syncwarp();
   }
 }

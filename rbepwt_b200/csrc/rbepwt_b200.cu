@@ -770,4 +770,14 @@ int rbepwt_get_stage_launches(rbepwt_ctx *c, int64_t *launches, int n) {
 
 int64_t rbepwt_launch_count(rbepwt_ctx *c) { return c ? c->launches : 0; }
 
+#ifdef TPR_STATS
+int rbepwt_debug_tpr_stats(rbepwt_ctx *c, unsigned long long *out, int reset) {
+  DeviceGuard g(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaMemcpyFromSymbol(out, g_tpr_stats, sizeof(unsigned long long) * 160);
+  if (reset) { unsigned long long z[160] = {}; cudaMemcpyToSymbol(g_tpr_stats, z, sizeof z); }
+  return 0;
+}
+#endif
+
 }  // extern "C"
