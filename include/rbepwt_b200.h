@@ -70,6 +70,19 @@ int rbepwt_set_wavelet(rbepwt_ctx *ctx, int filter_len, const double *dec_lo, co
 int rbepwt_encode(rbepwt_ctx *ctx, const double *img, const int32_t *labels, int B, int H, int W,
                   int levels, int path_mode, unsigned flags);
 
+/* Execution options (set between calls).
+ *   RBEPWT_OPT_STREAMS : 1 or 2 (default 2) units of each kind in flight: the batch is cut into path groups and
+ *                        transform sub-batches whose copies, path kernels and transform kernels overlap on
+ *                        internal streams; every call is still ordered on the context's stream.
+ *                        1 = all kernels on one stream (per-kernel timing).
+ *   RBEPWT_OPT_SUBBATCH: images per transform sub-batch (0 = auto: about 2^24 pixels).
+ *   RBEPWT_OPT_PATHGROUP: images per path group -- label scan + path pyramid (0 = auto: about 2^26 pixels;
+ *                        rounded to a multiple of the sub-batch). */
+#define RBEPWT_OPT_STREAMS 1
+#define RBEPWT_OPT_SUBBATCH 2
+#define RBEPWT_OPT_PATHGROUP 3
+int rbepwt_set_option(rbepwt_ctx *ctx, int option, int64_t value);
+
 /* Rbepwt.threshold_coefs(ncoefs), per image                                 rbepwt.py:2081-2112
  * k <= 0 or k >= H*W keeps everything (reference quirk).  Ties at the k-th magnitude are
  * unpinned in the reference; here the highest flat index survives. */
@@ -79,6 +92,13 @@ int rbepwt_threshold(rbepwt_ctx *ctx, int64_t k);
  *                                                           rbepwt.py:2055-2079, 1586-1613, 307-317
  * out: float64 [B][H][W]. */
 int rbepwt_decode(rbepwt_ctx *ctx, double *out_img, unsigned flags);
+
+/* encode -> threshold(k) -> decode in ONE call: the three reference calls above back to back
+ * (rbepwt.py:298, 441, 307), with the sub-batches pipelined so that, for host pointers, the input copy of
+ * one sub-batch, the kernels of the next and the output copy of the previous overlap.  Leaves the same
+ * state as the three calls (thresholded coefficients, paths).  out_img: float64 [B][H][W]. */
+int rbepwt_transcode(rbepwt_ctx *ctx, const double *img, const int32_t *labels, int B, int H, int W,
+                     int levels, int path_mode, int64_t k, double *out_img, unsigned flags);
 
 /* Decoder-side path regeneration (full_decode): build all paths from label maps alone, then
  * decode caller-supplied coefficients (flat layout below, [B][H*W]).          rbepwt.py:106-130

@@ -10,11 +10,13 @@ _lib = None
 E_NOT_POW2, E_LEVELS, E_NO_ENCODING, E_NO_GPU = -2, -3, -4, -7
 PATH_EUCLID, PATH_CHEB, PATH_EPWT = 0, 1, 2
 DEVICE_PTRS, U8_WRAP = 1, 2
+OPT_STREAMS, OPT_SUBBATCH, OPT_PATHGROUP = 1, 2, 3
 T_NAMES = ["h2d", "regions", "paths", "dwt", "select", "idwt", "d2h", "paths_big"]
 
 EXPORTS = [
     "rbepwt_create", "rbepwt_destroy", "rbepwt_last_error", "rbepwt_sync", "rbepwt_set_wavelet",
-    "rbepwt_encode", "rbepwt_threshold", "rbepwt_decode", "rbepwt_full_decode", "rbepwt_psnr",
+    "rbepwt_encode", "rbepwt_threshold", "rbepwt_decode", "rbepwt_transcode", "rbepwt_set_option",
+    "rbepwt_full_decode", "rbepwt_psnr",
     "rbepwt_nonzero_coefs", "rbepwt_get_coefs", "rbepwt_set_coefs", "rbepwt_region_count",
     "rbepwt_region_offsets", "rbepwt_region_labels", "rbepwt_get_paths", "rbepwt_get_perm",
     "rbepwt_get_level_values", "rbepwt_enable_timing", "rbepwt_get_timings", "rbepwt_get_stage_launches",
@@ -50,6 +52,8 @@ def lib():
     L.rbepwt_encode.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, u32]
     L.rbepwt_threshold.argtypes = [vp, i64]
     L.rbepwt_decode.argtypes = [vp, vp, u32]
+    L.rbepwt_transcode.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i64, vp, u32]
+    L.rbepwt_set_option.argtypes = [vp, i32, i64]
     L.rbepwt_full_decode.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, u32]
     L.rbepwt_psnr.argtypes = [vp, vp, vp, i32, i64, vp, u32]
     L.rbepwt_nonzero_coefs.argtypes = [vp, vp]

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
-LIB_PATH = os.path.join(LIB_DIR, "librbepwt_b200.so")
+LIB_PATH = os.environ.get("RBEPWT_B200_LIB") or os.path.join(LIB_DIR, "librbepwt_b200.so")  # env: experiments only
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -27,6 +27,8 @@ def sources():
 
 
 def needs_build():
+    if os.environ.get("RBEPWT_B200_LIB"):
+        return False
     if not os.path.isfile(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)

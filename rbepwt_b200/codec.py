@@ -146,6 +146,40 @@ class BatchCodec:
         self.shape, self.levels, self.mode = shape, int(levels), mode
         return self
 
+    def set_option(self, streams=None, sub_batch=None, path_group=None):
+        """streams: 1 (all kernels on one stream) or 2 units in flight; sub_batch / path_group: images per
+        transform sub-batch / per path group (0 = auto)."""
+        if path_group is not None:
+            _capi.check(self._lib.rbepwt_set_option(self._ctx, _capi.OPT_PATHGROUP, int(path_group)))
+        if streams is not None:
+            _capi.check(self._lib.rbepwt_set_option(self._ctx, _capi.OPT_STREAMS, int(streams)))
+        if sub_batch is not None:
+            _capi.check(self._lib.rbepwt_set_option(self._ctx, _capi.OPT_SUBBATCH, int(sub_batch)))
+
+    def transcode(self, imgs, labels, levels, wavelet, ncoefs, path_type="easypath", euclidean_distance=True, out=None):
+        """encode -> threshold(ncoefs) -> decode in one pipelined call (rbepwt_transcode); returns the decoded
+        images.  Inputs and `out` must be all numpy (host path) or all torch CUDA tensors (device path)."""
+        mode = path_mode(path_type, euclidean_distance)
+        imgs, labels, shape, dev, u8 = self._prep(imgs, labels, mode)
+        self.set_wavelet(wavelet)
+        if out is None:
+            if dev:
+                import torch
+                out = torch.empty_like(imgs)
+            else:
+                out = np.empty(shape, dtype=np.float64)
+        if _is_torch_cuda(out) != dev:
+            raise ValueError("`out` must live where the inputs live")
+        if not dev and not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous):
+            raise ValueError("out must be a contiguous float64 numpy array or CUDA tensor")
+        flags = (_capi.DEVICE_PTRS if dev else 0) | (_capi.U8_WRAP if (u8 and mode == _capi.PATH_EPWT) else 0)
+        B, H, W = shape
+        self._keep = [imgs, labels, out]
+        _capi.check(self._lib.rbepwt_transcode(self._ctx, _ptr(imgs), _ptr(labels), B, H, W, int(levels), mode, int(ncoefs),
+                                               _ptr(out), flags))
+        self.shape, self.levels, self.mode = shape, int(levels), mode
+        return out
+
     def threshold(self, k):
         _capi.check(self._lib.rbepwt_threshold(self._ctx, int(k)))
         return self
@@ -249,8 +283,6 @@ class BatchCodec:
 
 def encode_threshold_decode(imgs, labels, levels, wavelet, ncoefs, path_type="easypath",
                             euclidean_distance=True, codec=None, out=None):
-    """The whole hot path for a batch in one call; returns the decoded images."""
+    """The whole hot path for a batch in one call (pipelined, rbepwt_transcode); returns the decoded images."""
     codec = codec or BatchCodec()
-    codec.encode(imgs, labels, levels, wavelet, path_type, euclidean_distance)
-    codec.threshold(ncoefs)
-    return codec.decode(out)
+    return codec.transcode(imgs, labels, levels, wavelet, ncoefs, path_type, euclidean_distance, out)

@@ -43,7 +43,7 @@ static int fail(int code, const char *fmt, ...) {
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
-  cudaError_t ensure(size_t bytes) {  // contents not preserved
+  cudaError_t ensure(size_t bytes) {  // contents not preserved; cudaFree waits for work in flight on the old buffer
     if (bytes <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
@@ -51,6 +51,7 @@ struct DevBuf {
     if (e == cudaSuccess) cap = bytes;
     return e;
   }
+  cudaError_t ensure_slack(size_t bytes) { return bytes <= cap ? cudaSuccess : ensure(bytes + bytes / 4); }
   cudaError_t ensure_keep(size_t bytes, size_t used, cudaStream_t s) {  // first `used` bytes preserved
     if (bytes <= cap) return cudaSuccess;
     size_t ncap = std::max(bytes, cap * 2);
@@ -71,12 +72,36 @@ struct DevBuf {
 
 struct StageEv { int stage; int launches; cudaEvent_t a, b; };
 
+constexpr int NSLOT = 2;
+
+// Workspace + stream of one unit of work in flight.  The batch is cut twice: into PATH GROUPS (label scan,
+// region records, path pyramid -- large, the path kernel has a long tail and wants many regions per launch)
+// and into TRANSFORM SUB-BATCHES (DWT, top-k, IDWT, copies -- small, so that copies and kernels overlap).
+// Units alternate between NSLOT slots per kind, so the issue-bound path kernel of one group overlaps the
+// memory-bound transform kernels and the PCIe copies of other units.
+struct Slot {
+  cudaStream_t s = nullptr;
+  DevBuf VA, VB, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch;
+  cudaEvent_t done = nullptr;
+};
+
 struct rbepwt_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;  // the caller-visible stream: every call is ordered on it
   bool own_stream = false;
   int sm_count = 0;
   size_t smem_optin = 0;
+  // internal streams: input copies + label scan, output copies, one per slot
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  Slot slot[2 * NSLOT];   // [0, NSLOT): path groups, [NSLOT, 2 NSLOT): transform sub-batches
+  int nslot = NSLOT;      // RBEPWT_OPT_STREAMS
+  int sub_images = 0;     // RBEPWT_OPT_SUBBATCH (0 = auto)
+  int group_images = 0;   // RBEPWT_OPT_PATHGROUP (0 = auto)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<cudaEvent_t> ev_lab, ev_path, ev_img, ev_done;
+  int32_t *pin_R = nullptr, *pin_rbase = nullptr;  // pinned staging, capacity pin_cap images
+  int *pin_err = nullptr;
+  int pin_cap = 0;
   // wavelet
   bool has_wavelet = false;
   int flen = 0;
@@ -93,8 +118,8 @@ struct rbepwt_ctx {
   int totalR = 0;
   DevBuf img_R, img_rbase, img_labmin, img_direct;
   std::vector<int32_t> h_R, h_rbase;
-  // workspace
-  DevBuf tbl, slot_rid, VA, VB, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch, scratch_i32, scratch_i32b, psnr_out, nz_out;
+  // workspace shared by the sub-batches of a chunk / by the getters
+  DevBuf tbl, slot_rid, scratch_i32, scratch_i32b, psnr_out, nz_out;
   // timing
   bool timing = false;
   std::vector<StageEv> evs;
@@ -113,6 +138,8 @@ struct rbepwt_ctx {
 
 namespace {
 
+enum { DO_PATHS = 1, DO_DWT = 2, DO_THRESH = 4, DO_DECODE = 8 };
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
@@ -124,13 +151,13 @@ cudaEvent_t get_event(rbepwt_ctx *c) {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 
-struct StageTimer {  // records a pair of events around a stage when timing is enabled
-  rbepwt_ctx *c; StageEv ev; bool on; long long l0;
-  StageTimer(rbepwt_ctx *c_, int stage) : c(c_), on(c_->timing), l0(c_->launches) {
-    if (on) { ev.stage = stage; ev.a = get_event(c); ev.b = get_event(c); cudaEventRecord(ev.a, c->stream); }
+struct StageTimer {  // records a pair of events around a stage, on the stream the stage runs on
+  rbepwt_ctx *c; cudaStream_t s; StageEv ev; bool on; long long l0;
+  StageTimer(rbepwt_ctx *c_, int stage, cudaStream_t s_) : c(c_), s(s_), on(c_->timing), l0(c_->launches) {
+    if (on) { ev.stage = stage; ev.a = get_event(c); ev.b = get_event(c); cudaEventRecord(ev.a, s); }
   }
   ~StageTimer() {
-    if (on) { cudaEventRecord(ev.b, c->stream); ev.launches = (int)(c->launches - l0); c->evs.push_back(ev); }
+    if (on) { cudaEventRecord(ev.b, s); ev.launches = (int)(c->launches - l0); c->evs.push_back(ev); }
   }
 };
 
@@ -141,19 +168,64 @@ void clear_events(rbepwt_ctx *c) {
 
 int ilog2(int x) { int l = 0; while ((1 << l) < x) l++; return l; }
 
-// images per chunk: bounded by a workspace budget (hash table + slot ids + two value planes = 40 N bytes/image)
+// images per chunk: the label table + slot ids (24 N bytes/image) live for a whole chunk
 int chunk_images(const rbepwt_ctx *c, int B, int N) {
-  const size_t per = (size_t)N * 40;
+  const size_t per = (size_t)N * 24;
   size_t budget = (size_t)6 << 30;
   int m = (int)std::max<size_t>(1, budget / per);
-  return std::min(std::min(m, 512), B);
+  return std::min(std::min(m, 1024), B);
+}
+
+// images per sub-batch: enough regions to fill the path kernel's persistent grid (about 2^24 pixels),
+// few enough that copies and kernels of neighbouring sub-batches overlap
+int sub_images(const rbepwt_ctx *c, int nb, int N) {
+  if (c->sub_images > 0) return std::min(c->sub_images, nb);
+  const int m = (int)std::max<long long>(1, (1ll << 24) / N);
+  return std::min(m, nb);
+}
+
+// images per path group: about 2^26 pixels (256 images of 512^2), a multiple of the sub-batch
+int group_images(const rbepwt_ctx *c, int nb, int N, int Bs) {
+  long long m = c->group_images > 0 ? c->group_images : std::max<long long>(1, (1ll << 26) / N);
+  m = std::max<long long>(Bs, m / Bs * Bs);
+  return (int)std::min<long long>(m, (nb + Bs - 1) / Bs * Bs);
+}
+
+int sync_internal(rbepwt_ctx *c) {
+  CK(cudaStreamSynchronize(c->s_in));
+  CK(cudaStreamSynchronize(c->s_out));
+  for (int i = 0; i < 2 * NSLOT; i++) CK(cudaStreamSynchronize(c->slot[i].s));
+  return RBEPWT_OK;
+}
+
+// every internal stream starts after what the caller already queued on ctx->stream ...
+int fork_streams(rbepwt_ctx *c) {
+  CK(cudaEventRecord(c->ev_fork, c->stream));
+  CK(cudaStreamWaitEvent(c->s_in, c->ev_fork, 0));
+  CK(cudaStreamWaitEvent(c->s_out, c->ev_fork, 0));
+  for (int i = 0; i < 2 * NSLOT; i++) CK(cudaStreamWaitEvent(c->slot[i].s, c->ev_fork, 0));
+  return RBEPWT_OK;
+}
+
+// ... and ctx->stream continues after all of them
+int join_streams(rbepwt_ctx *c) {
+  cudaStream_t all[2 * NSLOT + 2] = {c->s_in, c->s_out};
+  for (int i = 0; i < 2 * NSLOT; i++) all[2 + i] = c->slot[i].s;
+  for (cudaStream_t s : all) {
+    CK(cudaEventRecord(c->ev_join, s));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  }
+  return RBEPWT_OK;
 }
 
 int check_path_error(rbepwt_ctx *c) {
-  int err = 0;
-  CK(cudaMemcpyAsync(&err, c->qmeta.as<int>() + QM_ERR, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  if (err) return fail(RBEPWT_E_CUDA, "path kernel found no unvisited point (corrupt region state)");
+  for (int i = 0; i < 2 * NSLOT; i++) {
+    if (!c->slot[i].qmeta.p) continue;
+    CK(cudaMemcpyAsync(c->pin_err, c->slot[i].qmeta.as<int>() + QM_ERR, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (*c->pin_err) return fail(RBEPWT_E_CUDA, "path kernel found no unvisited point (corrupt region state)");
+  }
   return RBEPWT_OK;
 }
 
@@ -168,118 +240,172 @@ int validate_shape(int B, int H, int W, int levels, int path_mode) {
   return RBEPWT_OK;
 }
 
-// K0 + K1 for the geometric modes, K0' for EPWT: region records and (geometric) the whole path pyramid.
-// With EPWT the paths depend on the level's values, so they are built inside transform_chunk().
-int build_regions_and_paths(rbepwt_ctx *c, int c0, int nb) {
-  const int N = c->N, T = 2 * N;
-  cudaStream_t s = c->stream;
-  if (c->mode == RBEPWT_PATH_EPWT) {
-    StageTimer t(c, RBEPWT_T_REGIONS);
-    for (int i = 0; i < 8; i++) CK(c->reg[i].ensure_keep((size_t)c->B * 4, (size_t)c0 * 4, s));
-    k0_single_region<<<(nb + 127) / 128, 128, 0, s>>>(c0, nb, c->H, c->W, c->regs(), c->img_R.as<int32_t>(),
-                                                     c->img_rbase.as<int32_t>());
-    c->launches++;
-    for (int i = 0; i < nb; i++) { c->h_R[c0 + i] = 1; c->h_rbase[c0 + i] = c0 + i; }
-    c->totalR = c0 + nb;
-    CK(cudaGetLastError());
-    return RBEPWT_OK;
-  }
-  int g0, nreg;
-  {
-    StageTimer t(c, RBEPWT_T_REGIONS);
-    k0_count<<<nb, K0_THREADS, 0, s>>>(c->labels_dev, c0, N, c->tbl.as<unsigned long long>(), T,
-                                       c->img_R.as<int32_t>(), c->img_labmin.as<int32_t>(),
-                                       c->img_direct.as<int32_t>());
-    c->launches++;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c->h_R.data() + c0, c->img_R.as<int32_t>() + c0, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    g0 = c->totalR;
-    for (int i = 0; i < nb; i++) { c->h_rbase[c0 + i] = c->totalR; c->totalR += c->h_R[c0 + i]; }
-    nreg = c->totalR - g0;
-    for (int i = 0; i < 8; i++) CK(c->reg[i].ensure_keep((size_t)c->totalR * 4, (size_t)g0 * 4, s));
-    CK(cudaMemcpyAsync(c->img_rbase.as<int32_t>() + c0, c->h_rbase.data() + c0, (size_t)nb * 4,
-                       cudaMemcpyHostToDevice, s));
-    k0_regions<<<nb, K0_THREADS, 0, s>>>(c->labels_dev, c0, N, c->logW, c->tbl.as<unsigned long long>(),
-                                         c->slot_rid.as<int32_t>(), T, c->img_R.as<int32_t>(),
-                                         c->img_labmin.as<int32_t>(), c->img_direct.as<int32_t>(),
-                                         c->img_rbase.as<int32_t>(), c->regs());
-    c->launches++;
-    CK(cudaGetLastError());
-    CK(c->queue.ensure((size_t)nreg * 4));
-    const int qb = std::max(1, std::min((nreg + 255) / 256, c->sm_count * 8));
-    CK(c->chunk_start.ensure(((size_t)nreg + Q_BINS) * 4));
-    CK(c->chunk_cnt.ensure(((size_t)nreg + Q_BINS) * 4));
-    kq_hist<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, c->qhist.as<int>());
-    kq_scan<<<1, 32, 0, s>>>(c->qhist.as<int>(), c->qmeta.as<int>(), c->qbins.as<int>(), nreg);
-    kq_scatter<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, c->qmeta.as<int>(), c->queue.as<int32_t>());
-    kq_chunks<<<((Q_BINS - Q_SIZE_BINS) * 32 + 255) / 256, 256, 0, s>>>(c->qbins.as<int>(), c->chunk_start.as<int32_t>(),
-                                                                        c->chunk_cnt.as<int32_t>());
-    c->launches += 4;
-    CK(cudaGetLastError());
-  }
-  {
-    PathParams P;
-    P.labels = c->labels_dev;
-    P.H = c->H; P.W = c->W; P.logW = c->logW; P.N = N; P.levels = c->levels;
-    P.reg = c->regs();
-    P.queue = c->queue.as<int32_t>();
-    P.chunk_start = c->chunk_start.as<int32_t>();
-    P.chunk_cnt = c->chunk_cnt.as<int32_t>();
-    P.qmeta = c->qmeta.as<int>();
-    P.Q = c->Q.as<int32_t>();
-    // big-region kernel: whole-image bitmap in dynamic shared memory when it fits
-    const size_t img_words = (size_t)c->H * ((c->W + 31) / 32);
-    const size_t smem_cap = std::min<size_t>(c->smem_optin, (size_t)200 * 1024);
-    const size_t smem_bytes = std::min(img_words * 4, smem_cap);
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)220 * 1024) / (smem_bytes + 1024)));
-    const int big_ctas = c->sm_count * per_sm;
-    P.big_smem_words = (int)(smem_bytes / 4);
-    P.gscratch = nullptr; P.gscratch_words = 0;
-    if (img_words * 4 > smem_bytes) {
-      CK(c->gscratch.ensure(img_words * 4 * (size_t)big_ctas));
-      P.gscratch = c->gscratch.as<uint32_t>();
-      P.gscratch_words = img_words;
-    }
-    int tpr_per_sm = 1;  // persistent grid: as many CTAs as are resident at once
-    if (c->mode == RBEPWT_PATH_EUCLID)
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_paths_tpr<MODE_EUCLID>, TPR_WARPS * 32, 0));
-    else
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_paths_tpr<MODE_CHEB>, TPR_WARPS * 32, 0));
-    const int small_ctas = c->sm_count * std::max(tpr_per_sm, 1);
-    {
-      StageTimer tb(c, RBEPWT_T_PATHS_BIG);
-      if (c->mode == RBEPWT_PATH_EUCLID) {
-        CK(cudaFuncSetAttribute(k1_paths_big<MODE_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        k1_paths_big<MODE_EUCLID><<<big_ctas, 32, smem_bytes, s>>>(P);
-      } else {
-        CK(cudaFuncSetAttribute(k1_paths_big<MODE_CHEB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        k1_paths_big<MODE_CHEB><<<big_ctas, 32, smem_bytes, s>>>(P);
-      }
-      c->launches++;
-    }
-    {
-      StageTimer t(c, RBEPWT_T_PATHS);
-      if (c->mode == RBEPWT_PATH_EUCLID) k1_paths_tpr<MODE_EUCLID><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
-      else k1_paths_tpr<MODE_CHEB><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
-      c->launches++;
-    }
-    CK(cudaGetLastError());
-  }
+// Region arrays are global over the batch and grow with the region count, which is only known sub-batch
+// by sub-batch; growing them means waiting for everything in flight (rare: the first guess is generous).
+int grow_regs(rbepwt_ctx *c, size_t need_entries, size_t used_entries) {
+  if (need_entries * 4 <= c->reg[0].cap) return RBEPWT_OK;
+  int rc = sync_internal(c);
+  if (rc) return rc;
+  for (int i = 0; i < 8; i++) CK(c->reg[i].ensure_keep(need_entries * 4, used_entries * 4, c->slot[0].s));
   return RBEPWT_OK;
 }
 
-// K3 for every level of the chunk (EPWT: K1 level kernel before each level's DWT).
-int transform_chunk(rbepwt_ctx *c, int c0, int nb) {
+int ensure_slot_workspace(rbepwt_ctx *c, Slot &sl, int nb) {  // nb = 0: no value planes (path slots)
+  const size_t N = c->N;
+  CK(sl.VA.ensure((size_t)nb * N * 8));
+  CK(sl.VB.ensure((size_t)nb * N * 8));
+  if (!sl.qhist.p) {
+    CK(sl.qhist.ensure(Q_BINS * 4));
+    CK(cudaMemsetAsync(sl.qhist.p, 0, Q_BINS * 4, c->stream));  // before the fork: ordered ahead of every stream
+  }
+  if (!sl.qmeta.p) {
+    CK(sl.qmeta.ensure(QM_SIZE * 4));
+    CK(cudaMemsetAsync(sl.qmeta.p, 0, QM_SIZE * 4, c->stream));
+  }
+  if (!sl.qbins.p) CK(sl.qbins.ensure(3 * Q_BINS * 4));
+  return RBEPWT_OK;
+}
+
+// Input stream, path group [a, a+nb): (host mode) copy its labels in, then scan them -- label table and
+// region count per image; the counts are read back for the host's bookkeeping.
+int stage_labels(rbepwt_ctx *c, int chunk0, int a, int nb, const int32_t *lab_host, cudaEvent_t ready) {
+  const size_t N = c->N;
+  cudaStream_t s = c->s_in;
+  if (c->mode != RBEPWT_PATH_EPWT) {
+    if (lab_host) {
+      StageTimer t(c, RBEPWT_T_H2D, s);
+      CK(cudaMemcpyAsync(c->labels_own.as<int32_t>() + (size_t)a * N, lab_host + (size_t)a * N, (size_t)nb * N * 4,
+                         cudaMemcpyHostToDevice, s));
+    }
+    StageTimer t(c, RBEPWT_T_REGIONS, s);
+    const int T = 2 * c->N;
+    k0_count<<<nb, K0_THREADS, 0, s>>>(c->labels_dev, a, c->N, c->tbl.as<unsigned long long>() + (size_t)(a - chunk0) * T, T,
+                                       c->img_R.as<int32_t>(), c->img_labmin.as<int32_t>(), c->img_direct.as<int32_t>());
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->pin_R + a, c->img_R.as<int32_t>() + a, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaEventRecord(ready, s));
+  return RBEPWT_OK;
+}
+
+// Input stream, transform sub-batch [a, a+nb): (host mode) copy its images in.
+int stage_images(rbepwt_ctx *c, int a, int nb, const double *img_host, cudaEvent_t ready) {
+  const size_t N = c->N;
+  StageTimer t(c, RBEPWT_T_H2D, c->s_in);
+  CK(cudaMemcpyAsync(c->img_own.as<double>() + (size_t)a * N, img_host + (size_t)a * N, (size_t)nb * N * 8,
+                     cudaMemcpyHostToDevice, c->s_in));
+  CK(cudaEventRecord(ready, c->s_in));
+  return RBEPWT_OK;
+}
+
+// K0 (region records, work queue) + K1 (path pyramid) of one path group on stream s (workspace: sl).
+// EPWT: one region per image; its paths depend on the level's values and are built in transform_sub().
+int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0, int a, int nb, cudaEvent_t ready) {
+  const int N = c->N, T = 2 * N;
+  if (c->mode == RBEPWT_PATH_EPWT) {
+    int rc = grow_regs(c, (size_t)c->B, (size_t)a);
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(s, ready, 0));
+    StageTimer t(c, RBEPWT_T_REGIONS, s);
+    k0_single_region<<<(nb + 127) / 128, 128, 0, s>>>(a, nb, c->H, c->W, c->regs(), c->img_R.as<int32_t>(),
+                                                     c->img_rbase.as<int32_t>());
+    c->launches++;
+    for (int i = 0; i < nb; i++) { c->h_R[a + i] = 1; c->h_rbase[a + i] = a + i; }
+    c->totalR = a + nb;
+    CK(cudaGetLastError());
+    return RBEPWT_OK;
+  }
+  CK(cudaEventSynchronize(ready));  // the host needs the sub-batch's region counts
+  const int g0 = c->totalR;
+  for (int i = 0; i < nb; i++) {
+    c->h_R[a + i] = c->pin_R[a + i];
+    c->h_rbase[a + i] = c->pin_rbase[a + i] = c->totalR;
+    c->totalR += c->h_R[a + i];
+  }
+  const int nreg = c->totalR - g0;
+  int rc = grow_regs(c, std::max<size_t>((size_t)c->totalR, (size_t)c->B * 2048 + 4096), (size_t)g0);
+  if (rc) return rc;
+  CK(sl.queue.ensure_slack((size_t)nreg * 4));
+  CK(sl.chunk_start.ensure_slack(((size_t)nreg + Q_BINS) * 4));
+  CK(sl.chunk_cnt.ensure_slack(((size_t)nreg + Q_BINS) * 4));
+  CK(cudaStreamWaitEvent(s, ready, 0));
+  {
+    StageTimer t(c, RBEPWT_T_REGIONS, s);
+    CK(cudaMemcpyAsync(c->img_rbase.as<int32_t>() + a, c->pin_rbase + a, (size_t)nb * 4, cudaMemcpyHostToDevice, s));
+    k0_regions<<<nb, K0_THREADS, 0, s>>>(c->labels_dev, a, N, c->logW,
+                                         c->tbl.as<unsigned long long>() + (size_t)(a - chunk0) * T,
+                                         c->slot_rid.as<int32_t>() + (size_t)(a - chunk0) * T, T, c->img_R.as<int32_t>(),
+                                         c->img_labmin.as<int32_t>(), c->img_direct.as<int32_t>(),
+                                         c->img_rbase.as<int32_t>(), c->regs());
+    const int qb = std::max(1, std::min((nreg + 255) / 256, c->sm_count * 8));
+    kq_hist<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, sl.qhist.as<int>());
+    kq_scan<<<1, 32, 0, s>>>(sl.qhist.as<int>(), sl.qmeta.as<int>(), sl.qbins.as<int>(), nreg);
+    kq_scatter<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, sl.qmeta.as<int>(), sl.queue.as<int32_t>());
+    kq_chunks<<<((Q_BINS - Q_SIZE_BINS) * 32 + 255) / 256, 256, 0, s>>>(sl.qbins.as<int>(), sl.chunk_start.as<int32_t>(),
+                                                                        sl.chunk_cnt.as<int32_t>());
+    c->launches += 5;
+    CK(cudaGetLastError());
+  }
+  PathParams P;
+  P.labels = c->labels_dev;
+  P.H = c->H; P.W = c->W; P.logW = c->logW; P.N = N; P.levels = c->levels;
+  P.reg = c->regs();
+  P.queue = sl.queue.as<int32_t>();
+  P.chunk_start = sl.chunk_start.as<int32_t>();
+  P.chunk_cnt = sl.chunk_cnt.as<int32_t>();
+  P.qmeta = sl.qmeta.as<int>();
+  P.Q = c->Q.as<int32_t>();
+  // big-region kernel: whole-image bitmap in dynamic shared memory when it fits
+  const size_t img_words = (size_t)c->H * ((c->W + 31) / 32);
+  const size_t smem_cap = std::min<size_t>(c->smem_optin, (size_t)200 * 1024);
+  const size_t smem_bytes = std::min(img_words * 4, smem_cap);
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)220 * 1024) / (smem_bytes + 1024)));
+  const int big_ctas = c->sm_count * per_sm;
+  P.big_smem_words = (int)(smem_bytes / 4);
+  P.gscratch = nullptr; P.gscratch_words = 0;
+  if (img_words * 4 > smem_bytes) {
+    CK(sl.gscratch.ensure(img_words * 4 * (size_t)big_ctas));
+    P.gscratch = sl.gscratch.as<uint32_t>();
+    P.gscratch_words = img_words;
+  }
+  int tpr_per_sm = 1;  // persistent grid: as many CTAs as are resident at once
+  if (c->mode == RBEPWT_PATH_EUCLID)
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_paths_tpr<MODE_EUCLID>, TPR_WARPS * 32, 0));
+  else
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_paths_tpr<MODE_CHEB>, TPR_WARPS * 32, 0));
+  const int small_ctas = c->sm_count * std::max(tpr_per_sm, 1);
+  {
+    StageTimer tb(c, RBEPWT_T_PATHS_BIG, s);
+    if (c->mode == RBEPWT_PATH_EUCLID) {
+      CK(cudaFuncSetAttribute(k1_paths_big<MODE_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      k1_paths_big<MODE_EUCLID><<<big_ctas, 32, smem_bytes, s>>>(P);
+    } else {
+      CK(cudaFuncSetAttribute(k1_paths_big<MODE_CHEB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      k1_paths_big<MODE_CHEB><<<big_ctas, 32, smem_bytes, s>>>(P);
+    }
+    c->launches++;
+  }
+  {
+    StageTimer t(c, RBEPWT_T_PATHS, s);
+    if (c->mode == RBEPWT_PATH_EUCLID) k1_paths_tpr<MODE_EUCLID><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
+    else k1_paths_tpr<MODE_CHEB><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
+    c->launches++;
+  }
+  CK(cudaGetLastError());
+  return RBEPWT_OK;
+}
+
+// K3 for every level of the sub-batch (EPWT: K1 level kernel before each level's DWT).
+int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
   const int N = c->N;
-  cudaStream_t s = c->stream;
   DwtParams D;
-  D.Q = c->Q.as<int32_t>() + (size_t)c0 * 2 * N;
-  D.coefs = c->coefs.as<double>() + (size_t)c0 * N;
+  D.Q = c->Q.as<int32_t>() + (size_t)a * 2 * N;
+  D.coefs = c->coefs.as<double>() + (size_t)a * N;
   D.filt = c->filt.as<double>();
   D.out_img = nullptr;
   D.flen = c->flen; D.N = N; D.levels = c->levels;
-  double *V[2] = {c->VA.as<double>(), c->VB.as<double>()};
+  double *V[2] = {sl.VA.as<double>(), sl.VB.as<double>()};
   EpwtParams E;
   size_t epwt_smem = 0;
   if (c->mode == RBEPWT_PATH_EPWT) {
@@ -291,33 +417,64 @@ int transform_chunk(rbepwt_ctx *c, int c0, int nb) {
     E.smem_words = (int)(epwt_smem / 4);
     E.gscratch = nullptr; E.gscratch_words = 0;
     if (img_words * 4 > epwt_smem) {
-      CK(c->gscratch.ensure(img_words * 4 * (size_t)nb));
-      E.gscratch = c->gscratch.as<uint32_t>();
+      CK(sl.gscratch.ensure(img_words * 4 * (size_t)nb));
+      E.gscratch = sl.gscratch.as<uint32_t>();
       E.gscratch_words = img_words;
     }
     E.u8wrap = (c->enc_flags & RBEPWT_U8_WRAP) ? 1 : 0;
-    E.qmeta = c->qmeta.as<int>();
+    E.qmeta = sl.qmeta.as<int>();
     CK(cudaFuncSetAttribute(k1_epwt_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)epwt_smem));
   }
   for (int lev = 1; lev <= c->levels; lev++) {
     D.lev = lev;
-    if (lev == 1) { D.vin = c->img_dev + (size_t)c0 * N; D.vin_stride = N; }
+    if (lev == 1) { D.vin = c->img_dev + (size_t)a * N; D.vin_stride = N; }
     else { D.vin = V[(lev - 1) & 1]; D.vin_stride = N; }
     D.vout = V[lev & 1];
     if (c->mode == RBEPWT_PATH_EPWT) {
-      StageTimer t(c, RBEPWT_T_PATHS);
+      StageTimer t(c, RBEPWT_T_PATHS, s);
       E.lev = lev;
       E.vals = D.vin;
       k1_epwt_level<<<nb, 32, epwt_smem, s>>>(E);
       c->launches++;
     }
     {
-      StageTimer t(c, RBEPWT_T_DWT);
+      StageTimer t(c, RBEPWT_T_DWT, s);
       const int half = (N >> (lev - 1)) >> 1;
       dim3 grid((half + FWD_TILE - 1) / FWD_TILE, nb);
       k3_dwt_level<<<grid, DWT_THREADS, 0, s>>>(D);
       c->launches++;
     }
+  }
+  CK(cudaGetLastError());
+  return RBEPWT_OK;
+}
+
+int threshold_sub(rbepwt_ctx *c, cudaStream_t s, int a, int nb, long long k) {
+  StageTimer t(c, RBEPWT_T_SELECT, s);
+  k4_threshold<<<nb, SEL_THREADS, 0, s>>>(c->coefs.as<double>() + (size_t)a * c->N, c->N, k);
+  c->launches++;
+  CK(cudaGetLastError());
+  return RBEPWT_OK;
+}
+
+int decode_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb, double *out_dev) {
+  const int N = c->N;
+  double *V[2] = {sl.VA.as<double>(), sl.VB.as<double>()};
+  StageTimer t(c, RBEPWT_T_IDWT, s);
+  DwtParams D;
+  D.Q = c->Q.as<int32_t>() + (size_t)a * 2 * N;
+  D.coefs = c->coefs.as<double>() + (size_t)a * N;
+  D.filt = c->filt.as<double>();
+  D.out_img = out_dev + (size_t)a * N;
+  D.flen = c->flen; D.N = N; D.levels = c->levels;
+  for (int lev = c->levels; lev >= 1; lev--) {
+    D.lev = lev;
+    D.vin = V[(lev + 1) & 1]; D.vin_stride = N;
+    D.vout = V[lev & 1];
+    const int n = N >> (lev - 1);
+    dim3 grid((n + INV_TILE - 1) / INV_TILE, nb);
+    k5_idwt_level<<<grid, DWT_THREADS, 0, s>>>(D);
+    c->launches++;
   }
   CK(cudaGetLastError());
   return RBEPWT_OK;
@@ -334,62 +491,118 @@ int alloc_state(rbepwt_ctx *c, int B, int H, int W, int levels, int path_mode, u
   CK(c->coefs.ensure((size_t)B * N * 8));
   CK(c->img_R.ensure((size_t)B * 4)); CK(c->img_rbase.ensure((size_t)B * 4));
   CK(c->img_labmin.ensure((size_t)B * 4)); CK(c->img_direct.ensure((size_t)B * 4));
+  if (B > c->pin_cap) {
+    if (c->pin_R) cudaFreeHost(c->pin_R);
+    if (c->pin_rbase) cudaFreeHost(c->pin_rbase);
+    c->pin_R = c->pin_rbase = nullptr; c->pin_cap = 0;
+    CK(cudaMallocHost((void **)&c->pin_R, (size_t)B * 4));
+    CK(cudaMallocHost((void **)&c->pin_rbase, (size_t)B * 4));
+    c->pin_cap = B;
+  }
   const int Bc = chunk_images(c, B, c->N);
   if (path_mode != RBEPWT_PATH_EPWT) {
     CK(c->tbl.ensure((size_t)Bc * 2 * N * 8));
     CK(c->slot_rid.ensure((size_t)Bc * 2 * N * 4));
   }
-  CK(c->VA.ensure((size_t)Bc * N * 8));
-  CK(c->VB.ensure((size_t)Bc * N * 8));
-  if (!c->qhist.p) {
-    CK(c->qhist.ensure(Q_BINS * 4));
-    CK(cudaMemsetAsync(c->qhist.p, 0, Q_BINS * 4, c->stream));
-  }
-  if (!c->qmeta.p) CK(c->qmeta.ensure(QM_SIZE * 4));
-  if (!c->qbins.p) CK(c->qbins.ensure(3 * Q_BINS * 4));
-  CK(cudaMemsetAsync(c->qmeta.p, 0, QM_SIZE * 4, c->stream));
+  for (int i = 0; i < 2 * NSLOT; i++)
+    if (c->slot[i].qmeta.p) CK(cudaMemsetAsync(c->slot[i].qmeta.p, 0, QM_SIZE * 4, c->stream));
   return RBEPWT_OK;
 }
 
-int upload_labels(rbepwt_ctx *c, const int32_t *labels, unsigned flags) {
-  if (c->mode == RBEPWT_PATH_EPWT) { c->labels_dev = nullptr; return RBEPWT_OK; }
-  if (!labels) return fail(RBEPWT_E_ARG, "labels are required unless path_mode is EPWT");
-  if (flags & RBEPWT_DEVICE_PTRS) { c->labels_dev = labels; return RBEPWT_OK; }
-  StageTimer t(c, RBEPWT_T_H2D);
-  const size_t bytes = (size_t)c->B * c->N * 4;
-  CK(c->labels_own.ensure(bytes));
-  CK(cudaMemcpyAsync(c->labels_own.p, labels, bytes, cudaMemcpyHostToDevice, c->stream));
-  c->labels_dev = c->labels_own.as<int32_t>();
-  return RBEPWT_OK;
-}
-
-int decode_all(rbepwt_ctx *c, double *out_dev) {
-  const int N = c->N, B = c->B;
-  cudaStream_t s = c->stream;
+// The pipeline behind encode / decode / transcode.
+//   img_host, lab_host : host inputs to copy in (NULL: inputs are already on the device)
+//   out_dev            : device destination of the decoded images (DO_DECODE)
+//   out_host           : host destination to copy them to (NULL: none)
+// Order on the input stream: all label groups first (the path stage needs nothing else and is the long
+// pole), then the images sub-batch by sub-batch.  With RBEPWT_OPT_STREAMS = 1 every kernel runs on one
+// stream (no overlap between kernels; copies still use their own streams).
+int run_pipeline(rbepwt_ctx *c, int what, long long k, const double *img_host, const int32_t *lab_host, double *out_dev,
+                 double *out_host) {
+  const int B = c->B, N = c->N;
   const int Bc = chunk_images(c, B, N);
-  CK(c->VA.ensure((size_t)Bc * N * 8));
-  CK(c->VB.ensure((size_t)Bc * N * 8));
-  double *V[2] = {c->VA.as<double>(), c->VB.as<double>()};
-  StageTimer t(c, RBEPWT_T_IDWT);
+  const bool serial = c->nslot == 1;
+  int rc;
+  auto need_events = [&](std::vector<cudaEvent_t> &v, int n) -> int {
+    while ((int)v.size() < n) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); v.push_back(e); }
+    return RBEPWT_OK;
+  };
   for (int c0 = 0; c0 < B; c0 += Bc) {
-    const int nb = std::min(Bc, B - c0);
-    DwtParams D;
-    D.Q = c->Q.as<int32_t>() + (size_t)c0 * 2 * N;
-    D.coefs = c->coefs.as<double>() + (size_t)c0 * N;
-    D.filt = c->filt.as<double>();
-    D.out_img = out_dev + (size_t)c0 * N;
-    D.flen = c->flen; D.N = N; D.levels = c->levels;
-    for (int lev = c->levels; lev >= 1; lev--) {
-      D.lev = lev;
-      D.vin = V[(lev + 1) & 1]; D.vin_stride = N;
-      D.vout = V[lev & 1];
-      const int n = N >> (lev - 1);
-      dim3 grid((n + INV_TILE - 1) / INV_TILE, nb);
-      k5_idwt_level<<<grid, DWT_THREADS, 0, s>>>(D);
-      c->launches++;
+    const int nbc = std::min(Bc, B - c0);
+    const int Bs = sub_images(c, nbc, N);
+    const int Bp = group_images(c, nbc, N, Bs);
+    const int nsub = (nbc + Bs - 1) / Bs, ngrp = (nbc + Bp - 1) / Bp;
+    if ((rc = need_events(c->ev_lab, ngrp)) || (rc = need_events(c->ev_path, ngrp)) || (rc = need_events(c->ev_img, nsub)) ||
+        (rc = need_events(c->ev_done, nsub)))
+      return rc;
+    for (int i = 0; i < c->nslot; i++) {
+      if ((what & DO_PATHS) && (rc = ensure_slot_workspace(c, c->slot[i], 0))) return rc;
+      if ((what & (DO_DWT | DO_DECODE)) && (rc = ensure_slot_workspace(c, c->slot[NSLOT + i], Bs))) return rc;
     }
+    if ((rc = fork_streams(c))) return rc;
+    if (what & DO_PATHS)
+      for (int g = 0; g < ngrp; g++) {
+        const int a = c0 + g * Bp, nb = std::min(Bp, c0 + nbc - a);
+        if ((rc = stage_labels(c, c0, a, nb, lab_host, c->ev_lab[g]))) return rc;
+      }
+    if ((what & DO_DWT) && img_host)
+      for (int s = 0; s < nsub; s++) {
+        const int a = c0 + s * Bs, nb = std::min(Bs, c0 + nbc - a);
+        if ((rc = stage_images(c, a, nb, img_host, c->ev_img[s]))) return rc;
+      }
+    if (what & DO_PATHS)
+      for (int g = 0; g < ngrp; g++) {
+        const int a = c0 + g * Bp, nb = std::min(Bp, c0 + nbc - a);
+        Slot &sl = c->slot[g % c->nslot];
+        cudaStream_t st = serial ? c->slot[0].s : sl.s;
+        if ((rc = build_regions_and_paths(c, sl, st, c0, a, nb, c->ev_lab[g]))) return rc;
+        CK(cudaEventRecord(c->ev_path[g], st));
+      }
+    if (what & (DO_DWT | DO_THRESH | DO_DECODE))
+      for (int s = 0; s < nsub; s++) {
+        const int a = c0 + s * Bs, nb = std::min(Bs, c0 + nbc - a);
+        Slot &sl = c->slot[NSLOT + s % c->nslot];
+        cudaStream_t st = serial ? c->slot[0].s : sl.s;
+        if (what & DO_PATHS) CK(cudaStreamWaitEvent(st, c->ev_path[(a - c0) / Bp], 0));
+        if ((what & DO_DWT) && img_host) CK(cudaStreamWaitEvent(st, c->ev_img[s], 0));
+        if (what & DO_DWT)
+          if ((rc = transform_sub(c, sl, st, a, nb))) return rc;
+        if (what & DO_THRESH)
+          if ((rc = threshold_sub(c, st, a, nb, k))) return rc;
+        if (what & DO_DECODE) {
+          if ((rc = decode_sub(c, sl, st, a, nb, out_dev))) return rc;
+          if (out_host) {
+            CK(cudaEventRecord(c->ev_done[s], st));
+            CK(cudaStreamWaitEvent(c->s_out, c->ev_done[s], 0));
+            StageTimer t(c, RBEPWT_T_D2H, c->s_out);
+            CK(cudaMemcpyAsync(out_host + (size_t)a * N, out_dev + (size_t)a * N, (size_t)nb * N * 8, cudaMemcpyDeviceToHost,
+                               c->s_out));
+          }
+        }
+      }
+    if ((rc = join_streams(c))) return rc;
   }
-  CK(cudaGetLastError());
+  return RBEPWT_OK;
+}
+
+// shared front end of encode / full_decode / transcode: validate, size the state, attach the inputs
+int begin_batch(rbepwt_ctx *c, const double *img, const int32_t *labels, int B, int H, int W, int levels, int path_mode,
+                unsigned flags, bool need_img) {
+  int rc = validate_shape(B, H, W, levels, path_mode);
+  if (rc) return rc;
+  if (!c->has_wavelet) return fail(RBEPWT_E_NO_WAVELET, "rbepwt_set_wavelet has not been called");
+  if (path_mode != RBEPWT_PATH_EPWT && !labels) return fail(RBEPWT_E_ARG, "labels are required unless path_mode is EPWT");
+  if (c->evs.size() > 65536) clear_events(c);  // stage events accumulate until rbepwt_get_timings reads them
+  if ((rc = alloc_state(c, B, H, W, levels, path_mode, flags))) return rc;
+  const size_t n = (size_t)B * c->N;
+  if (flags & RBEPWT_DEVICE_PTRS) {
+    c->labels_dev = path_mode == RBEPWT_PATH_EPWT ? nullptr : labels;
+    c->img_dev = img;
+  } else {
+    if (path_mode != RBEPWT_PATH_EPWT) { CK(c->labels_own.ensure(n * 4)); c->labels_dev = c->labels_own.as<int32_t>(); }
+    else c->labels_dev = nullptr;
+    if (need_img) { CK(c->img_own.ensure(n * 8)); c->img_dev = c->img_own.as<double>(); }
+    else c->img_dev = nullptr;
+  }
   return RBEPWT_OK;
 }
 
@@ -419,6 +632,15 @@ int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
   c->smem_optin = prop.sharedMemPerBlockOptin;
   if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
   else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2 * NSLOT; i++) {
+    CK(cudaStreamCreateWithFlags(&c->slot[i].s, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->slot[i].done, cudaEventDisableTiming));
+  }
+  CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  CK(cudaMallocHost((void **)&c->pin_err, sizeof(int)));
   CK(c->filt.ensure(4 * FMAX * sizeof(double)));
   *out = c;
   return RBEPWT_OK;
@@ -428,13 +650,28 @@ void rbepwt_destroy(rbepwt_ctx *c) {
   if (!c) return;
   DeviceGuard g(c->device);
   cudaStreamSynchronize(c->stream);
+  sync_internal(c);
   clear_events(c);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
+  for (auto *v : {&c->ev_lab, &c->ev_path, &c->ev_img, &c->ev_done})
+    for (auto e : *v) cudaEventDestroy(e);
   DevBuf *bufs[] = {&c->filt, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->coefs, &c->img_R,
-                    &c->img_rbase, &c->img_labmin, &c->img_direct, &c->tbl, &c->slot_rid, &c->VA, &c->VB, &c->queue,
-                    &c->qhist, &c->qmeta, &c->qbins, &c->chunk_start, &c->chunk_cnt, &c->gscratch, &c->scratch_i32, &c->scratch_i32b, &c->psnr_out, &c->nz_out};
+                    &c->img_rbase, &c->img_labmin, &c->img_direct, &c->tbl, &c->slot_rid, &c->scratch_i32,
+                    &c->scratch_i32b, &c->psnr_out, &c->nz_out};
   for (auto b : bufs) b->release();
   for (auto &b : c->reg) b.release();
+  for (int i = 0; i < 2 * NSLOT; i++) {
+    Slot &sl = c->slot[i];
+    DevBuf *sb[] = {&sl.VA, &sl.VB, &sl.queue, &sl.qhist, &sl.qmeta, &sl.qbins, &sl.chunk_start, &sl.chunk_cnt, &sl.gscratch};
+    for (auto b : sb) b->release();
+    cudaEventDestroy(sl.done);
+    cudaStreamDestroy(sl.s);
+  }
+  cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
+  cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);
+  if (c->pin_R) cudaFreeHost(c->pin_R);
+  if (c->pin_rbase) cudaFreeHost(c->pin_rbase);
+  if (c->pin_err) cudaFreeHost(c->pin_err);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -444,6 +681,25 @@ int rbepwt_sync(rbepwt_ctx *c) {
   DeviceGuard g(c->device);
   CK(cudaStreamSynchronize(c->stream));
   return RBEPWT_OK;
+}
+
+int rbepwt_set_option(rbepwt_ctx *c, int option, int64_t value) {
+  if (!c) return fail(RBEPWT_E_ARG, "ctx is NULL");
+  switch (option) {
+    case RBEPWT_OPT_STREAMS:
+      if (value < 1 || value > NSLOT) return fail(RBEPWT_E_ARG, "RBEPWT_OPT_STREAMS must be 1..%d", NSLOT);
+      c->nslot = (int)value;
+      return RBEPWT_OK;
+    case RBEPWT_OPT_SUBBATCH:
+      if (value < 0 || value > (1 << 20)) return fail(RBEPWT_E_ARG, "RBEPWT_OPT_SUBBATCH out of range");
+      c->sub_images = (int)value;
+      return RBEPWT_OK;
+    case RBEPWT_OPT_PATHGROUP:
+      if (value < 0 || value > (1 << 20)) return fail(RBEPWT_E_ARG, "RBEPWT_OPT_PATHGROUP out of range");
+      c->group_images = (int)value;
+      return RBEPWT_OK;
+  }
+  return fail(RBEPWT_E_ARG, "unknown option %d", option);
 }
 
 int rbepwt_set_wavelet(rbepwt_ctx *c, int flen, const double *dec_lo, const double *dec_hi, const double *rec_lo,
@@ -464,31 +720,14 @@ int rbepwt_set_wavelet(rbepwt_ctx *c, int flen, const double *dec_lo, const doub
 int rbepwt_encode(rbepwt_ctx *c, const double *img, const int32_t *labels, int B, int H, int W, int levels,
                   int path_mode, unsigned flags) {
   if (!c || !img) return fail(RBEPWT_E_ARG, "ctx / img is NULL");
-  int rc = validate_shape(B, H, W, levels, path_mode);
-  if (rc) return rc;
-  if (!c->has_wavelet) return fail(RBEPWT_E_NO_WAVELET, "rbepwt_set_wavelet has not been called");
   DeviceGuard g(c->device);
-  if (c->evs.size() > 65536) clear_events(c);  // stage events accumulate until rbepwt_get_timings reads them
-  if ((rc = alloc_state(c, B, H, W, levels, path_mode, flags))) return rc;
-  if ((rc = upload_labels(c, labels, flags))) return rc;
-  if (flags & RBEPWT_DEVICE_PTRS) {
-    c->img_dev = img;
-  } else {
-    StageTimer t(c, RBEPWT_T_H2D);
-    const size_t bytes = (size_t)B * c->N * 8;
-    CK(c->img_own.ensure(bytes));
-    CK(cudaMemcpyAsync(c->img_own.p, img, bytes, cudaMemcpyHostToDevice, c->stream));
-    c->img_dev = c->img_own.as<double>();
-  }
-  const int Bc = chunk_images(c, B, c->N);
-  for (int c0 = 0; c0 < B; c0 += Bc) {
-    const int nb = std::min(Bc, B - c0);
-    if ((rc = build_regions_and_paths(c, c0, nb))) return rc;
-    if ((rc = transform_chunk(c, c0, nb))) return rc;
-  }
+  int rc = begin_batch(c, img, labels, B, H, W, levels, path_mode, flags, true);
+  if (rc) return rc;
+  const bool host = !(flags & RBEPWT_DEVICE_PTRS);
+  if ((rc = run_pipeline(c, DO_PATHS | DO_DWT, 0, host ? img : nullptr, host ? labels : nullptr, nullptr, nullptr))) return rc;
   c->has_paths = true;
   c->has_encoding = true;
-  if (!(flags & RBEPWT_DEVICE_PTRS)) return check_path_error(c);  // host-pointer calls are synchronous
+  if (host) return check_path_error(c);  // host-pointer calls are synchronous
   return RBEPWT_OK;
 }
 
@@ -496,57 +735,62 @@ int rbepwt_threshold(rbepwt_ctx *c, int64_t k) {
   if (!c) return fail(RBEPWT_E_ARG, "ctx is NULL");
   if (!c->has_encoding) return fail(RBEPWT_E_NO_ENCODING, "There is no saved encoding to decode");
   DeviceGuard g(c->device);
-  {
-    StageTimer t(c, RBEPWT_T_SELECT);
-    k4_threshold<<<c->B, SEL_THREADS, 0, c->stream>>>(c->coefs.as<double>(), c->N, (long long)k);
-    c->launches++;
-  }
-  CK(cudaGetLastError());
-  return RBEPWT_OK;
+  return threshold_sub(c, c->stream, 0, c->B, (long long)k);
 }
 
 int rbepwt_decode(rbepwt_ctx *c, double *out_img, unsigned flags) {
   if (!c || !out_img) return fail(RBEPWT_E_ARG, "ctx / out is NULL");
   if (!c->has_encoding) return fail(RBEPWT_E_NO_ENCODING, "There is no saved encoding to decode");
   DeviceGuard g(c->device);
-  const size_t bytes = (size_t)c->B * c->N * 8;
+  const bool host = !(flags & RBEPWT_DEVICE_PTRS);
   double *out_dev = out_img;
-  if (!(flags & RBEPWT_DEVICE_PTRS)) {
-    CK(c->out_own.ensure(bytes));
+  if (host) {
+    CK(c->out_own.ensure((size_t)c->B * c->N * 8));
     out_dev = c->out_own.as<double>();
   }
-  int rc = decode_all(c, out_dev);
+  int rc = run_pipeline(c, DO_DECODE, 0, nullptr, nullptr, out_dev, host ? out_img : nullptr);
   if (rc) return rc;
-  if (!(flags & RBEPWT_DEVICE_PTRS)) {
-    {
-      StageTimer t(c, RBEPWT_T_D2H);
-      CK(cudaMemcpyAsync(out_img, out_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
-    }
-    return check_path_error(c);
+  if (host) return check_path_error(c);
+  return RBEPWT_OK;
+}
+
+int rbepwt_transcode(rbepwt_ctx *c, const double *img, const int32_t *labels, int B, int H, int W, int levels,
+                     int path_mode, int64_t k, double *out_img, unsigned flags) {
+  if (!c || !img || !out_img) return fail(RBEPWT_E_ARG, "ctx / img / out is NULL");
+  DeviceGuard g(c->device);
+  int rc = begin_batch(c, img, labels, B, H, W, levels, path_mode, flags, true);
+  if (rc) return rc;
+  const bool host = !(flags & RBEPWT_DEVICE_PTRS);
+  double *out_dev = out_img;
+  if (host) {
+    CK(c->out_own.ensure((size_t)B * c->N * 8));
+    out_dev = c->out_own.as<double>();
   }
+  if ((rc = run_pipeline(c, DO_PATHS | DO_DWT | DO_THRESH | DO_DECODE, (long long)k, host ? img : nullptr,
+                         host ? labels : nullptr, out_dev, host ? out_img : nullptr)))
+    return rc;
+  c->has_paths = true;
+  c->has_encoding = true;
+  if (host) return check_path_error(c);
   return RBEPWT_OK;
 }
 
 int rbepwt_full_decode(rbepwt_ctx *c, const double *coefs, const int32_t *labels, int B, int H, int W, int levels,
                        int path_mode, double *out_img, unsigned flags) {
   if (!c || !coefs || !out_img) return fail(RBEPWT_E_ARG, "ctx / coefs / out is NULL");
-  int rc = validate_shape(B, H, W, levels, path_mode);
-  if (rc) return rc;
-  if (path_mode == RBEPWT_PATH_EPWT)
+  if (path_mode == RBEPWT_PATH_EPWT) {
+    int rc = validate_shape(B, H, W, levels, path_mode);
+    if (rc) return rc;
     return fail(RBEPWT_E_ARG, "full_decode needs value-independent paths (EPWT paths depend on the image)");
-  if (!c->has_wavelet) return fail(RBEPWT_E_NO_WAVELET, "rbepwt_set_wavelet has not been called");
+  }
   DeviceGuard g(c->device);
-  if (c->evs.size() > 65536) clear_events(c);  // stage events accumulate until rbepwt_get_timings reads them
-  if ((rc = alloc_state(c, B, H, W, levels, path_mode, flags))) return rc;
-  if ((rc = upload_labels(c, labels, flags))) return rc;
-  c->img_dev = nullptr;
-  const int Bc = chunk_images(c, B, c->N);
-  for (int c0 = 0; c0 < B; c0 += Bc)
-    if ((rc = build_regions_and_paths(c, c0, std::min(Bc, B - c0)))) return rc;
+  int rc = begin_batch(c, nullptr, labels, B, H, W, levels, path_mode, flags, false);
+  if (rc) return rc;
+  const bool host = !(flags & RBEPWT_DEVICE_PTRS);
+  if ((rc = run_pipeline(c, DO_PATHS, 0, nullptr, host ? labels : nullptr, nullptr, nullptr))) return rc;
   c->has_paths = true;
-  const size_t bytes = (size_t)B * c->N * 8;
-  CK(cudaMemcpyAsync(c->coefs.p, coefs, bytes,
-                     (flags & RBEPWT_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->coefs.p, coefs, (size_t)B * c->N * 8, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                     c->stream));
   c->has_encoding = true;
   return rbepwt_decode(c, out_img, flags);
 }
@@ -710,7 +954,8 @@ int rbepwt_get_level_values(rbepwt_ctx *c, int b, int level, double *vals) {
   cudaStream_t s = c->stream;
   CK(c->coef_up.ensure(N * 8 * 2));
   double *scratch = c->coef_up.as<double>(), *out = scratch + N;
-  double *V[2] = {c->VA.as<double>(), c->VB.as<double>()};
+  if ((rc = ensure_slot_workspace(c, c->slot[NSLOT], 1))) return rc;
+  double *V[2] = {c->slot[NSLOT].VA.as<double>(), c->slot[NSLOT].VB.as<double>()};
   DwtParams D;
   D.Q = c->Q.as<int32_t>() + (size_t)b * 2 * N;
   D.coefs = scratch;

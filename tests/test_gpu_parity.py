@@ -187,3 +187,85 @@ def test_device_pointer_path_matches_host_path():
     c.decode(out)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(out.cpu().numpy()[0], host["decoded"])
+
+
+def _small_batch(n=5, size=64, seed0=70):
+    from rbepwt_b200 import synth
+
+    imgs, labs = [], []
+    for s in range(n):
+        lab = synth.voronoi_labels(size, size, 20 + 3 * s, seed=seed0 + s)
+        labs.append(lab)
+        imgs.append(synth.piecewise_smooth_image(lab, seed=seed0 + s))
+    return np.stack(imgs), np.stack(labs)
+
+
+@pytest.mark.parametrize("streams,sub,grp", [(2, 0, 0), (1, 0, 0), (2, 2, 2), (2, 1, 3), (1, 3, 3), (2, 1, 1)])
+def test_transcode_equals_three_calls_for_any_pipelining(streams, sub, grp):
+    """rbepwt_transcode (one pipelined call) == encode, threshold, decode; the sub-batch size and the
+    number of sub-batches in flight never change a bit of the result."""
+    import rbepwt_b200 as rb
+
+    imgs, labs = _small_batch()
+    ref = rb.BatchCodec()
+    ref.set_option(streams=1, sub_batch=0)
+    ref.encode(imgs, labs, 12, "bior4.4")
+    full = np.stack([ref.coefs(b) for b in range(len(imgs))])
+    ref.threshold(300)
+    want = ref.decode()
+    want_coefs = np.stack([ref.coefs(b) for b in range(len(imgs))])
+    want_paths = [ref.paths(b, 3) for b in range(len(imgs))]
+
+    c = rb.BatchCodec()
+    c.set_option(streams=streams, sub_batch=sub, path_group=grp)
+    got = c.transcode(imgs, labs, 12, "bior4.4", 300)
+    np.testing.assert_array_equal(got, want)
+    for b in range(len(imgs)):
+        np.testing.assert_array_equal(c.coefs(b), want_coefs[b])
+        np.testing.assert_array_equal(c.paths(b, 3), want_paths[b])
+        np.testing.assert_array_equal(c.region_offsets(b), ref.region_offsets(b))
+    # and the three separate calls under the same options
+    c.encode(imgs, labs, 12, "bior4.4")
+    np.testing.assert_array_equal(np.stack([c.coefs(b) for b in range(len(imgs))]), full)
+    c.threshold(300)
+    np.testing.assert_array_equal(c.decode(), want)
+
+
+def test_transcode_device_pointers_and_epwt():
+    torch = pytest.importorskip("torch")
+    import rbepwt_b200 as rb
+
+    imgs, labs = _small_batch(4, 32, 90)
+    want = rb.BatchCodec().transcode(imgs, labs, 10, "db2", 100)
+    s = torch.cuda.Stream()
+    c = rb.BatchCodec(stream=s.cuda_stream)
+    c.set_option(sub_batch=1)
+    timg, tlab = torch.from_numpy(imgs).cuda(), torch.from_numpy(labs).cuda()
+    torch.cuda.synchronize()
+    out = c.transcode(timg, tlab, 10, "db2", 100)
+    c.sync()
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+    # EPWT through the pipeline: batch == singles
+    e = rb.BatchCodec()
+    e.set_option(sub_batch=3)
+    got = e.transcode(imgs, None, 10, "haar", 50, path_type="epwt-easypath")
+    for b in (0, 3):
+        one = cuda_run(imgs[b], None, 10, "haar", "epwt-easypath", ncoefs=50, with_perm=False)
+        np.testing.assert_array_equal(got[b], one["decoded"])
+
+
+def test_region_arrays_grow_across_sub_batches():
+    """More regions than the first capacity guess (B * 2048 + 4096): the arrays are regrown mid-pipeline."""
+    import rbepwt_b200 as rb
+
+    rng = np.random.default_rng(12)
+    labs = np.stack([rng.permutation(128 * 128).reshape(128, 128).astype(np.int32) for _ in range(3)])  # R == N each
+    imgs = rng.uniform(0, 255, size=labs.shape)
+    c = rb.BatchCodec()
+    c.set_option(sub_batch=1)
+    c.encode(imgs, labs, 6, "haar")
+    assert [c.region_count(b) for b in range(3)] == [128 * 128] * 3
+    dec = c.decode()
+    assert np.max(np.abs(dec - imgs)) < 1e-9 * 255
+    for b in range(3):  # every region is one pixel: level-1 path order == order of first appearance == row-major
+        np.testing.assert_array_equal(c.paths(b, 1), np.arange(128 * 128))

@@ -1,0 +1,15 @@
+#!/bin/bash
+# usage (GPU box): tools/variants.sh "<name>:<-D flags>" ...   builds each variant into gpurun_out/ and runs the
+# serial kernel-timing part of the bench with it (experiments only)
+for v in "$@"; do
+  name=${v%%:*}; flags=${v#*:}
+  so=gpurun_out/lib_$name.so
+  nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -shared --cudart static $flags -o $so rbepwt_b200/csrc/rbepwt_b200.cu || exit 1
+  RBEPWT_B200_LIB=$PWD/$so python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/var_$name.json 2>gpurun_out/var_$name.err
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/var_$name.json"))
+k=d["kernels"]
+print("%-14s value %6.0f  k1 %.3f ms  k0 %.3f dwt %.3f sel %.3f idwt %.3f" % ("$name", d["value"], k["k1_paths_small"]["ms_per_step"], k["k0_count+k0_regions+queue"]["ms_per_step"], k["k3_dwt_level"]["ms_per_step"], k["k4_threshold"]["ms_per_step"], k["k5_idwt_level"]["ms_per_step"]))
+PY
+done
