@@ -34,9 +34,9 @@
 //
 // Branch-free candidate selection (euclid mode).  In one bitmap row only the nearest unvisited point
 // on each side of the current column can win (both k and d2 grow with |dj|), so a word contributes at
-// most two candidates, found with clz/ffs, and a candidate is one 64-bit key
-// (k << 44 | d2 << 22 | 2^21 - dot) -- valid because the kernel only takes regions whose bounding box
-// has sides <= TPR_MAX_SIDE = 1024 (d2, |dot| < 2^21).  All lanes execute the same instructions.
+// most two candidates (usually one: the nearer side), found with clz/ffs, and a candidate is a 32-bit key
+// (k << 21 | d2) plus its dot product -- valid because the kernel only takes regions whose bounding box
+// has sides <= TPR_MAX_SIDE = 1024 (d2 < 2^21).  Updates are selects: all lanes execute the same instructions.
 //
 // Unit-step fast path.  When the window half-width is 1 and pref is one of the 8 unit steps (the
 // common case at level 1: 88 % of the steps), the 3x3 neighbourhood is gathered into a 9-bit mask and
@@ -75,30 +75,41 @@ struct Search;
 // ---- euclid: packed integer keys, fp64 only for mirror pairs under a non-exact pref ----------------
 template <>
 struct Search<MODE_EUCLID> {
-  unsigned long long best;
-  int di, dj, adi, adj;
-  int tag, atag;  // caller's payload of the incumbent / its mirror partner (list mode: list index)
+  // incumbent: key = k << 21 | d2 (sides <= TPR_MAX_SIDE: d2 < 2^21, k <= 11), then the larger dot product;
+  // offsets packed (di << 16) | (dj & 0xffff)
+  unsigned key;
+  int dot, off, aoff;  // aoff: mirror partner with the same (key, dot)
+  int tag, atag;       // caller's payload of the incumbent / its mirror partner (list mode: list index)
   bool alt;
 
-  __device__ __forceinline__ void reset() { best = ~0ull; alt = false; di = dj = adi = adj = 0; tag = atag = 0; }
-  __device__ __forceinline__ bool have() const { return best != ~0ull; }
+  __device__ __forceinline__ void reset() { key = 0xffffffffu; dot = 0; off = aoff = 0; tag = atag = 0; alt = false; }
+  __device__ __forceinline__ bool have() const { return key != 0xffffffffu; }
 
   __device__ __forceinline__ void consider(bool valid, int cdi, int cdj, int p0, int p1, int ctag = 0) {
     const int k = probe_index(max(abs(cdi), abs(cdj)));
-    const int d2 = cdi * cdi + cdj * cdj, dot = cdi * p0 + cdj * p1;
-    const unsigned long long key =
-        valid ? ((unsigned long long)k << 44) | ((unsigned long long)d2 << 22) | (unsigned)((1 << 21) - dot) : ~0ull;
+    const unsigned ckey = valid ? ((unsigned)k << 21) | (unsigned)(cdi * cdi + cdj * cdj) : 0xffffffffu;
+    const int cdot = cdi * p0 + cdj * p1;
+    const int coff = (cdi << 16) | (cdj & 0xffff);
     // selects, not branches: every lane executes the same instructions
-    const bool lt = key < best;
-    const bool eq = valid && key == best;  // mirror image of the incumbent about pref
-    best = lt ? key : best;
-    di = lt ? cdi : di;
-    dj = lt ? cdj : dj;
-    alt = lt ? false : (alt || eq);
-    adi = eq ? cdi : adi;
-    adj = eq ? cdj : adj;
+    const bool same = ckey == key;
+    const bool lt = ckey < key || (same && cdot > dot);
+    const bool eq = valid && same && cdot == dot;  // mirror image of the incumbent about pref
+    key = lt ? ckey : key;
+    dot = lt ? cdot : dot;
+    off = lt ? coff : off;
     tag = lt ? ctag : tag;
+    alt = lt ? false : (alt || eq);
+    aoff = eq ? coff : aoff;
     atag = eq ? ctag : atag;
+  }
+
+  // Candidates of one row: the nearest unvisited column on the left (distance dl >= 1) and on the right
+  // (dr >= 0); the nearer one dominates the other in (k, d2), both compete only when dl == dr.
+  __device__ __forceinline__ void row_candidates(bool hl, int dl, bool hr, int dr, int rdi, int p0, int p1) {
+    if (!(hl || hr)) return;
+    const bool left_first = hl && (!hr || dl <= dr);
+    consider(true, rdi, left_first ? -dl : dr, p0, p1);
+    if (hl && hr && dl == dr) consider(true, rdi, dr, p0, p1);
   }
 
   // one bitmap word of row ci+rdi: columns lo..lo+31, already masked to the window
@@ -106,31 +117,31 @@ struct Search<MODE_EUCLID> {
     const int rel = min(cj - lo, 31);
     const uint32_t lmask = rel < 0 ? 0u : (2u << rel) - 1u;  // columns <= cj
     const uint32_t left = bits & lmask, right = bits & ~lmask;
-    consider(left != 0u, rdi, lo + 31 - __clz(left) - cj, p0, p1);
-    consider(right != 0u, rdi, lo + __ffs(right) - 1 - cj, p0, p1);
+    row_candidates(left != 0u, cj - (lo + 31 - __clz(left)), right != 0u, lo + __ffs(right) - 1 - cj, rdi, p0, p1);
   }
 
   // one window row as an aligned word: bit 15 + dj <-> column cj + dj
   __device__ __forceinline__ void scan_row(uint32_t x, int rdi, int p0, int p1) {
     const uint32_t left = x & 0x7fffu, right = x >> 15;
-    consider(left != 0u, rdi, 16 - __clz(left), p0, p1);  // highest set bit hb -> dj = hb - 15
-    consider(right != 0u, rdi, __ffs(right) - 1, p0, p1);
+    row_candidates(left != 0u, __clz(left) - 16, right != 0u, __ffs(right) - 1, rdi, p0, p1);  // hb = 31 - clz -> dl = 15 - hb
   }
 
   __device__ __forceinline__ void finish(int p0, int p1, int &odi, int &odj, int &k) {
+    int di = off >> 16, dj = (int)(short)(off & 0xffff);
     if (alt) {
+      const int adi = aoff >> 16, adj = (int)(short)(aoff & 0xffff);
       const int cb = di * p1 - dj * p0, ca = adi * p1 - adj * p0;
       bool alt_better;
       if (pref_ties_exactly(p0, p1)) {
         alt_better = ca > cb;
       } else {
-        const int d2 = (int)((best >> 22) & 0x3fffffu);
+        const int d2 = (int)(key & 0x1fffffu);
         const double sb = tie_sp1(di, dj, d2, p0, p1), sa = tie_sp1(adi, adj, d2, p0, p1);
         alt_better = sa != sb ? sa > sb : ca > cb;
       }
       if (alt_better) { di = adi; dj = adj; tag = atag; }
     }
-    odi = di; odj = dj; k = (int)(best >> 44);
+    odi = di; odj = dj; k = (int)(key >> 21);
   }
 };
 
@@ -252,6 +263,7 @@ __global__ void __launch_bounds__(TPR_WARPS * 32) k1_paths_tpr(PathParams P) {
     }
     const int base = inc - slot;
     uint32_t *bm = arena + base;
+    const float inv_ws = 1.0f / (float)max(ws, 1);
 
     // cooperative bitmap build: one ballot per bitmap word, lanes = columns
     for (int r = 0; r < cnt; r++) {
@@ -382,13 +394,13 @@ __global__ void __launch_bounds__(TPR_WARPS * 32) k1_paths_tpr(PathParams P) {
               uint32_t b4[4];
 #pragma unroll
               for (int u = 0; u < 4; u++) b4[u] = wd + u < nwords ? bm[wd + u] : 0u;
-              if (b4[0] | b4[1] | b4[2] | b4[3]) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                  const int wi = wd + u, ri = wi / ws;
+              for (int u = 0; u < 4; u++)
+                if (b4[u]) {
+                  const int wi = wd + u;
+                  const int ri = ws == 1 ? wi : (int)(((float)wi + 0.5f) * inv_ws);  // wi / ws (wi < 2^11: exact)
                   S.scan_word(b4[u], (wi - ri * ws) << 5, ri - ci, cj, p0, p1);
                 }
-              }
               wd += 4;
               if (wd >= nwords) {
                 if (S.have()) { S.finish(p0, p1, fdi, fdj, fk); commit = true; }
