@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sub-batch", type=int, default=0, help="images per transform sub-batch (0 = library default)")
+    ap.add_argument("--path-group", type=int, default=0, help="images per path group (0 = library default)")
     return ap.parse_args()
 
 
@@ -235,6 +237,7 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     assert stream.cuda_stream != 0
     codec = rb.BatchCodec(device=local, stream=stream.cuda_stream)
+    codec.set_option(sub_batch=args.sub_batch, path_group=args.path_group)
 
     def step():  # encode -> threshold -> decode, one pipelined C-ABI call (rbepwt_transcode), device pointers
         codec.transcode(imgs, labs, LEVELS, WAVELET, NCOEFS, "easypath", True, out)
@@ -294,6 +297,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         n_img, n_lab, n_out = h_img.numpy(), h_lab.numpy(), h_out.numpy()
         hcodec = rb.BatchCodec(device=local)
+        hcodec.set_option(sub_batch=args.sub_batch, path_group=args.path_group)
 
         def hstep():  # returns after the last D2H copy completed
             hcodec.transcode(n_img, n_lab, LEVELS, WAVELET, NCOEFS, "easypath", True, n_out)

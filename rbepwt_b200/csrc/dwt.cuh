@@ -27,10 +27,12 @@ constexpr int DWT_THREADS = 256;
 constexpr int FWD_TILE = 512;   // low-pass outputs per CTA
 constexpr int INV_TILE = 1024;  // reconstructed samples per CTA
 
+constexpr int TAIL_MAX_POINTS = 2048;  // levels with at most this many points per image run in the tail kernels
+
 struct DwtParams {
-  const double *vin;   // pixel-addressed input values, image stride vin_stride (level 1: the image)
+  const double *vin;   // level 1 of the forward transform: the images, image stride vin_stride
   size_t vin_stride;
-  double *vout;        // pixel-addressed output values (next level's input), stride N
+  double *plane[2];    // pixel-addressed value planes, image stride N: level l writes plane[l & 1]
   const int32_t *Q;    // [chunk][2N] paths
   double *coefs;       // [chunk][N] flat coefficients: details[1] | ... | details[L] | approx
   const double *filt;  // dec_lo[FMAX] dec_hi[FMAX] rec_lo[FMAX] rec_hi[FMAX]
@@ -38,32 +40,37 @@ struct DwtParams {
   int flen, N, lev, levels;
 };
 
-__global__ void __launch_bounds__(DWT_THREADS) k3_dwt_level(DwtParams P) {
-  __shared__ double s_e[FWD_TILE + FMAX / 2 + 2], s_o[FWD_TILE + FMAX / 2 + 2];
-  __shared__ int s_q[FWD_TILE];
-  __shared__ double s_lo[FMAX], s_hi[FMAX];
-  const int tid = threadIdx.x, nt = blockDim.x, F = P.flen, N = P.N, lev = P.lev;
+struct FwdSmem {
+  double e[FWD_TILE + FMAX / 2 + 2], o[FWD_TILE + FMAX / 2 + 2];
+  int q[FWD_TILE];
+  double lo[FMAX], hi[FMAX];
+};
+
+// One tile (FWD_TILE low-pass outputs) of level `lev` of image `img`.  The caller loads sm.lo / sm.hi once.
+// SAME_CTA: the input plane was written by this CTA (tail kernel) -> read it past L1.
+template <bool SAME_CTA>
+__device__ __forceinline__ void dwt_tile(const DwtParams &P, FwdSmem &sm, int lev, int tile, size_t img) {
+  const int tid = threadIdx.x, nt = blockDim.x, F = P.flen, N = P.N;
   const int n = N >> (lev - 1), half = n >> 1, mask = n - 1;
-  const size_t img = blockIdx.y;
   const int32_t *Ql = P.Q + img * 2 * (size_t)N + level_off((size_t)N, lev);
-  const double *vin = P.vin + img * P.vin_stride;
+  // level 1 reads the image; level l >= 2 reads the plane level l-1 wrote (ping-pong on the level's parity)
+  const double *vin = lev == 1 ? P.vin + img * P.vin_stride : P.plane[(lev - 1) & 1] + img * (size_t)N;
+  double *vout = P.plane[lev & 1] + img * (size_t)N;
   double *coefs = P.coefs + img * (size_t)N;
-  const int o0 = blockIdx.x * FWD_TILE, nout = min(FWD_TILE, half - o0);
+  const int o0 = tile * FWD_TILE, nout = min(FWD_TILE, half - o0);
   const int tstart = 2 * o0 - F / 2 + 1, cnt = 2 * (nout - 1) + F;
-  for (int i = tid; i < F; i += nt) { s_lo[i] = P.filt[i]; s_hi[i] = P.filt[FMAX + i]; }
   for (int i = tid; i < cnt; i += nt) {
     const int tt = tstart + i;
     const int pix = Ql[tt & mask];
-    const double v = vin[pix];
-    if (i & 1) s_o[i >> 1] = v; else s_e[i >> 1] = v;
+    const double v = SAME_CTA ? __ldcg(vin + pix) : vin[pix];
+    if (i & 1) sm.o[i >> 1] = v; else sm.e[i >> 1] = v;
     if (!(tt & 1)) {
       const int ol = (tt - 2 * o0) >> 1;
-      if (ol >= 0 && ol < nout) s_q[ol] = pix;
+      if (ol >= 0 && ol < nout) sm.q[ol] = pix;
     }
   }
   __syncthreads();
   const bool last = lev == P.levels;
-  double *vout = P.vout + img * (size_t)N;
   const size_t det_off = (size_t)N - (size_t)n;            // sum_{l<lev} N >> l
   const size_t app_off = (size_t)N - (size_t)(N >> P.levels);
   for (int ol = tid; ol < nout; ol += nt) {
@@ -71,39 +78,64 @@ __global__ void __launch_bounds__(DWT_THREADS) k3_dwt_level(DwtParams P) {
     // local sample index of tap j: 2*ol + F-1-j  (odd for even j)
     for (int j = 0; j < F; j += 2) {
       const int q = ol + ((F - 2 - j) >> 1);
-      const double x1 = s_o[q], x2 = s_e[q];
-      a = __dadd_rn(a, __dmul_rn(s_lo[j], x1));
-      d = __dadd_rn(d, __dmul_rn(s_hi[j], x1));
-      a = __dadd_rn(a, __dmul_rn(s_lo[j + 1], x2));
-      d = __dadd_rn(d, __dmul_rn(s_hi[j + 1], x2));
+      const double x1 = sm.o[q], x2 = sm.e[q];
+      a = __dadd_rn(a, __dmul_rn(sm.lo[j], x1));
+      d = __dadd_rn(d, __dmul_rn(sm.hi[j], x1));
+      a = __dadd_rn(a, __dmul_rn(sm.lo[j + 1], x2));
+      d = __dadd_rn(d, __dmul_rn(sm.hi[j + 1], x2));
     }
     coefs[det_off + o0 + ol] = d;
     if (last) coefs[app_off + o0 + ol] = a;
-    else vout[s_q[ol]] = a;
+    else vout[sm.q[ol]] = a;
   }
 }
 
-__global__ void __launch_bounds__(DWT_THREADS) k5_idwt_level(DwtParams P) {
-  __shared__ double s_a[INV_TILE / 2 + FMAX / 2 + 2], s_d[INV_TILE / 2 + FMAX / 2 + 2];
-  __shared__ double s_lo[FMAX], s_hi[FMAX];
-  const int tid = threadIdx.x, nt = blockDim.x, F = P.flen, N = P.N, lev = P.lev;
+// One level, one tile per CTA: the levels with many tiles per image.
+__global__ void __launch_bounds__(DWT_THREADS) k3_dwt_level(DwtParams P) {
+  __shared__ FwdSmem sm;
+  for (int i = threadIdx.x; i < P.flen; i += blockDim.x) { sm.lo[i] = P.filt[i]; sm.hi[i] = P.filt[FMAX + i]; }
+  dwt_tile<false>(P, sm, P.lev, blockIdx.x, blockIdx.y);
+}
+
+// Levels P.lev .. P.levels of one image in ONE CTA: the deep levels are a chain of tiny dependent passes
+// (a 512^2 image has 2048 + 1024 + ... + 4 points from level 8 on) -- one launch instead of nine.
+__global__ void __launch_bounds__(DWT_THREADS) k3_dwt_tail(DwtParams P) {
+  __shared__ FwdSmem sm;
+  for (int i = threadIdx.x; i < P.flen; i += blockDim.x) { sm.lo[i] = P.filt[i]; sm.hi[i] = P.filt[FMAX + i]; }
+  for (int lev = P.lev; lev <= P.levels; lev++) {
+    const int half = (P.N >> (lev - 1)) >> 1;
+    for (int tile = 0; tile * FWD_TILE < half; tile++) {
+      __syncthreads();  // shared tile reuse; also publishes the previous level's plane writes to the CTA
+      dwt_tile<true>(P, sm, lev, tile, blockIdx.x);
+    }
+  }
+}
+
+struct InvSmem {
+  double a[INV_TILE / 2 + FMAX / 2 + 2], d[INV_TILE / 2 + FMAX / 2 + 2];
+  double lo[FMAX], hi[FMAX];
+};
+
+// One tile (INV_TILE reconstructed samples) of level `lev` of image `img`.
+template <bool SAME_CTA>
+__device__ __forceinline__ void idwt_tile(const DwtParams &P, InvSmem &sm, int lev, int tile, size_t img) {
+  const int tid = threadIdx.x, nt = blockDim.x, F = P.flen, N = P.N;
   const int n = N >> (lev - 1), half = n >> 1, hmask = half - 1;
-  const size_t img = blockIdx.y;
   const int32_t *Ql = P.Q + img * 2 * (size_t)N + level_off((size_t)N, lev);
-  const double *vin = P.vin + img * P.vin_stride;
+  const double *vin = P.plane[(lev + 1) & 1] + img * (size_t)N;   // what level lev+1 reconstructed
+  double *vout = P.plane[lev & 1] + img * (size_t)N;
   const double *coefs = P.coefs + img * (size_t)N;
-  const int t0 = blockIdx.x * INV_TILE, nout = min(INV_TILE, n - t0);
+  const int t0 = tile * INV_TILE, nout = min(INV_TILE, n - t0);
   const int omin = (t0 - F / 2) >> 1;  // floor
   const int omax = (t0 + nout - 1 + F / 2 - 1) >> 1;
   const int cnt = omax - omin + 1;
   const bool deepest = lev == P.levels;
   const size_t det_off = (size_t)N - (size_t)n;
   const size_t app_off = (size_t)N - (size_t)(N >> P.levels);
-  for (int i = tid; i < F; i += nt) { s_lo[i] = P.filt[2 * FMAX + i]; s_hi[i] = P.filt[3 * FMAX + i]; }
   for (int i = tid; i < cnt; i += nt) {
     const int ow = (omin + i) & hmask;
-    s_a[i] = deepest ? coefs[app_off + ow] : vin[Ql[2 * ow]];
-    s_d[i] = coefs[det_off + ow];
+    sm.a[i] = deepest ? coefs[app_off + ow] : (SAME_CTA ? __ldcg(vin + Ql[2 * ow]) : vin[Ql[2 * ow]]);
+    sm.d[i] = coefs[det_off + ow];
   }
   __syncthreads();
   for (int tl = tid; tl < nout; tl += nt) {
@@ -111,8 +143,8 @@ __global__ void __launch_bounds__(DWT_THREADS) k5_idwt_level(DwtParams P) {
     double slo = 0.0, shi = 0.0;
     for (int m = base & 1; m < F; m += 2) {
       const int oi = ((base - m) >> 1) - omin;
-      slo = __dadd_rn(slo, __dmul_rn(s_lo[m], s_a[oi]));
-      shi = __dadd_rn(shi, __dmul_rn(s_hi[m], s_d[oi]));
+      slo = __dadd_rn(slo, __dmul_rn(sm.lo[m], sm.a[oi]));
+      shi = __dadd_rn(shi, __dmul_rn(sm.hi[m], sm.d[oi]));
     }
     double x = __dadd_rn(slo, shi);
     const int pix = Ql[t];
@@ -120,7 +152,26 @@ __global__ void __launch_bounds__(DWT_THREADS) k5_idwt_level(DwtParams P) {
       x = x > 255.0 ? 255.0 : (x < 0.0 ? 0.0 : x);
       P.out_img[img * (size_t)N + pix] = x;
     } else {
-      P.vout[img * (size_t)N + pix] = x;
+      vout[pix] = x;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DWT_THREADS) k5_idwt_level(DwtParams P) {
+  __shared__ InvSmem sm;
+  for (int i = threadIdx.x; i < P.flen; i += blockDim.x) { sm.lo[i] = P.filt[2 * FMAX + i]; sm.hi[i] = P.filt[3 * FMAX + i]; }
+  idwt_tile<false>(P, sm, P.lev, blockIdx.x, blockIdx.y);
+}
+
+// Levels P.levels down to P.lev of one image in ONE CTA (the deep levels, see k3_dwt_tail).
+__global__ void __launch_bounds__(DWT_THREADS) k5_idwt_tail(DwtParams P) {
+  __shared__ InvSmem sm;
+  for (int i = threadIdx.x; i < P.flen; i += blockDim.x) { sm.lo[i] = P.filt[2 * FMAX + i]; sm.hi[i] = P.filt[3 * FMAX + i]; }
+  for (int lev = P.levels; lev >= P.lev; lev--) {
+    const int n = P.N >> (lev - 1);
+    for (int tile = 0; tile * INV_TILE < n; tile++) {
+      __syncthreads();
+      idwt_tile<true>(P, sm, lev, tile, blockIdx.x);
     }
   }
 }

@@ -60,6 +60,9 @@
 namespace rbepwt {
 
 constexpr int TPR_WARPS = 4;
+#ifndef TPR_MIN_CTAS
+#define TPR_MIN_CTAS 5  // measured: capping registers for a 6th CTA per SM spills and is slower
+#endif
 
 __device__ __forceinline__ bool pref_ties_exactly(int p0, int p1) {
   if (p0 == 0 || p1 == 0) return true;
@@ -211,7 +214,7 @@ __device__ __forceinline__ uint32_t row_window(const uint32_t *row, int ws, int 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(TPR_WARPS * 32) k1_paths_tpr(PathParams P) {
+__global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(PathParams P) {
   __shared__ uint32_t s_arena[TPR_WARPS][TPR_ARENA_WORDS];
   __shared__ uint8_t s_lut[TPR_LUT_ROWS * TPR_LUT_COLS];
   const int lane = (int)lane_id(), warp = threadIdx.x >> 5;

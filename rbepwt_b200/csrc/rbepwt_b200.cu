@@ -425,22 +425,26 @@ int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
     E.qmeta = sl.qmeta.as<int>();
     CK(cudaFuncSetAttribute(k1_epwt_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)epwt_smem));
   }
+  D.vin = c->img_dev + (size_t)a * N; D.vin_stride = N;
+  D.plane[0] = V[0]; D.plane[1] = V[1];
   for (int lev = 1; lev <= c->levels; lev++) {
     D.lev = lev;
-    if (lev == 1) { D.vin = c->img_dev + (size_t)a * N; D.vin_stride = N; }
-    else { D.vin = V[(lev - 1) & 1]; D.vin_stride = N; }
-    D.vout = V[lev & 1];
+    const int n = N >> (lev - 1);
     if (c->mode == RBEPWT_PATH_EPWT) {
       StageTimer t(c, RBEPWT_T_PATHS, s);
       E.lev = lev;
-      E.vals = D.vin;
+      E.vals = lev == 1 ? D.vin : V[(lev - 1) & 1];
       k1_epwt_level<<<nb, 32, epwt_smem, s>>>(E);
       c->launches++;
+    } else if (n <= TAIL_MAX_POINTS) {  // all remaining levels in one launch, one CTA per image
+      StageTimer t(c, RBEPWT_T_DWT, s);
+      k3_dwt_tail<<<nb, DWT_THREADS, 0, s>>>(D);
+      c->launches++;
+      break;
     }
     {
       StageTimer t(c, RBEPWT_T_DWT, s);
-      const int half = (N >> (lev - 1)) >> 1;
-      dim3 grid((half + FWD_TILE - 1) / FWD_TILE, nb);
+      dim3 grid(((n >> 1) + FWD_TILE - 1) / FWD_TILE, nb);
       k3_dwt_level<<<grid, DWT_THREADS, 0, s>>>(D);
       c->launches++;
     }
@@ -467,10 +471,19 @@ int decode_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb, double *o
   D.filt = c->filt.as<double>();
   D.out_img = out_dev + (size_t)a * N;
   D.flen = c->flen; D.N = N; D.levels = c->levels;
-  for (int lev = c->levels; lev >= 1; lev--) {
+  D.vin = nullptr; D.vin_stride = N;
+  D.plane[0] = V[0]; D.plane[1] = V[1];
+  int top = c->levels;  // deepest level still to be inverted by a per-level launch
+  int first_tail = 1;
+  while (first_tail <= c->levels && (N >> (first_tail - 1)) > TAIL_MAX_POINTS) first_tail++;
+  if (first_tail <= c->levels) {  // levels L .. first_tail in one launch, one CTA per image
+    D.lev = first_tail;
+    k5_idwt_tail<<<nb, DWT_THREADS, 0, s>>>(D);
+    c->launches++;
+    top = first_tail - 1;
+  }
+  for (int lev = top; lev >= 1; lev--) {
     D.lev = lev;
-    D.vin = V[(lev + 1) & 1]; D.vin_stride = N;
-    D.vout = V[lev & 1];
     const int n = N >> (lev - 1);
     dim3 grid((n + INV_TILE - 1) / INV_TILE, nb);
     k5_idwt_level<<<grid, DWT_THREADS, 0, s>>>(D);
@@ -964,9 +977,9 @@ int rbepwt_get_level_values(rbepwt_ctx *c, int b, int level, double *vals) {
   D.flen = c->flen; D.N = c->N; D.levels = 31;  // never the "last" level: low-pass always goes to vout
   for (int lev = 1; lev < level; lev++) {
     D.lev = lev;
-    D.vin = lev == 1 ? c->img_dev + (size_t)b * N : V[(lev - 1) & 1];
+    D.vin = c->img_dev + (size_t)b * N;
     D.vin_stride = N;
-    D.vout = V[lev & 1];
+    D.plane[0] = V[0]; D.plane[1] = V[1];
     const int half = (int)((N >> (lev - 1)) >> 1);
     k3_dwt_level<<<dim3((half + FWD_TILE - 1) / FWD_TILE, 1), DWT_THREADS, 0, s>>>(D);
     c->launches++;
