@@ -6,11 +6,14 @@
 // RegionCollection.reduce (1578); inverse: pywt.idwt (2067) + RegionCollection.expand (1586-1613)
 // + the final scatter and clip of Image.decode_rbepwt (307-317).
 //
-// Values are addressed BY PIXEL: V is an H*W array, the level signal is s[t] = V[Q_l[t]].
-// The low-pass output cA[o] belongs to the point at even path position 2o (reduce keeps the even
-// global positions), so it is scattered to Vout[Q_l[2o]]; the next level gathers it through its
-// own paths.  This is the reference's permutation algebra without ever materialising
-// `permutation` / `invperm`.
+// Layout.  x^l (length n_l = N >> (l-1)) is the level's input in its INCOMING order: x^1 = the pixels,
+// x^(l+1) = cA of level l (reduce keeps the even positions of the path-ordered signal, so cA[o] is the value
+// of the point at path position 2o and the next level's incoming order is exactly the order of cA).
+// The level signal is s[t] = x^l[P_l[t]] where P_l is what the path kernel wrote: pixel ids at level 1
+// (Q), positions in the incoming order at levels >= 2 (Pm = the reference's generating permutation, region
+// offset included).  Forward: gather through P_l, dense coalesced cA / cD out.  Inverse: dense coalesced in,
+// x^l[P_l[t]] = s[t] scattered back (RegionCollection.expand's argsort, rbepwt.py:1600-1608, is this scatter).
+// The planes holding x^l are dense: plane[l & 1] holds x^(l+1), n_l / 2 doubles per image.
 //
 // Arithmetic (PyWavelets' periodization mode, restated -- see oracle/pywt_port.py):
 //   cA[o] = sum_{j=0}^{F-1} dec_lo[j] * s[(2o + F/2 - j) mod n]   ascending j, one multiply and one
@@ -32,8 +35,9 @@ constexpr int TAIL_MAX_POINTS = 2048;  // levels with at most this many points p
 struct DwtParams {
   const double *vin;   // level 1 of the forward transform: the images, image stride vin_stride
   size_t vin_stride;
-  double *plane[2];    // pixel-addressed value planes, image stride N: level l writes plane[l & 1]
-  const int32_t *Q;    // [chunk][2N] paths
+  double *plane[2];    // dense planes, image stride N/2: plane[l & 1] holds x^(l+1) (= cA of level l)
+  const int32_t *Q;    // [chunk][2N] paths as pixel ids (level 1 is used here)
+  const int32_t *Pm;   // [chunk][2N] paths as positions in the incoming order (levels >= 2)
   double *coefs;       // [chunk][N] flat coefficients: details[1] | ... | details[L] | approx
   const double *filt;  // dec_lo[FMAX] dec_hi[FMAX] rec_lo[FMAX] rec_hi[FMAX]
   double *out_img;     // decode, level 1: clipped image
@@ -42,7 +46,6 @@ struct DwtParams {
 
 struct FwdSmem {
   double e[FWD_TILE + FMAX / 2 + 2], o[FWD_TILE + FMAX / 2 + 2];
-  int q[FWD_TILE];
   double lo[FMAX], hi[FMAX];
 };
 
@@ -52,22 +55,17 @@ template <bool SAME_CTA>
 __device__ __forceinline__ void dwt_tile(const DwtParams &P, FwdSmem &sm, int lev, int tile, size_t img) {
   const int tid = threadIdx.x, nt = blockDim.x, F = P.flen, N = P.N;
   const int n = N >> (lev - 1), half = n >> 1, mask = n - 1;
-  const int32_t *Ql = P.Q + img * 2 * (size_t)N + level_off((size_t)N, lev);
+  const int32_t *Pl = (lev == 1 ? P.Q : P.Pm) + img * 2 * (size_t)N + level_off((size_t)N, lev);
   // level 1 reads the image; level l >= 2 reads the plane level l-1 wrote (ping-pong on the level's parity)
-  const double *vin = lev == 1 ? P.vin + img * P.vin_stride : P.plane[(lev - 1) & 1] + img * (size_t)N;
-  double *vout = P.plane[lev & 1] + img * (size_t)N;
+  const double *vin = lev == 1 ? P.vin + img * P.vin_stride : P.plane[(lev - 1) & 1] + img * (size_t)(N >> 1);
+  double *vout = P.plane[lev & 1] + img * (size_t)(N >> 1);
   double *coefs = P.coefs + img * (size_t)N;
   const int o0 = tile * FWD_TILE, nout = min(FWD_TILE, half - o0);
   const int tstart = 2 * o0 - F / 2 + 1, cnt = 2 * (nout - 1) + F;
   for (int i = tid; i < cnt; i += nt) {
-    const int tt = tstart + i;
-    const int pix = Ql[tt & mask];
-    const double v = SAME_CTA ? __ldcg(vin + pix) : vin[pix];
+    const int src = Pl[(tstart + i) & mask];
+    const double v = SAME_CTA ? __ldcg(vin + src) : vin[src];
     if (i & 1) sm.o[i >> 1] = v; else sm.e[i >> 1] = v;
-    if (!(tt & 1)) {
-      const int ol = (tt - 2 * o0) >> 1;
-      if (ol >= 0 && ol < nout) sm.q[ol] = pix;
-    }
   }
   __syncthreads();
   const bool last = lev == P.levels;
@@ -86,7 +84,7 @@ __device__ __forceinline__ void dwt_tile(const DwtParams &P, FwdSmem &sm, int le
     }
     coefs[det_off + o0 + ol] = d;
     if (last) coefs[app_off + o0 + ol] = a;
-    else vout[sm.q[ol]] = a;
+    else vout[o0 + ol] = a;
   }
 }
 
@@ -121,9 +119,9 @@ template <bool SAME_CTA>
 __device__ __forceinline__ void idwt_tile(const DwtParams &P, InvSmem &sm, int lev, int tile, size_t img) {
   const int tid = threadIdx.x, nt = blockDim.x, F = P.flen, N = P.N;
   const int n = N >> (lev - 1), half = n >> 1, hmask = half - 1;
-  const int32_t *Ql = P.Q + img * 2 * (size_t)N + level_off((size_t)N, lev);
-  const double *vin = P.plane[(lev + 1) & 1] + img * (size_t)N;   // what level lev+1 reconstructed
-  double *vout = P.plane[lev & 1] + img * (size_t)N;
+  const int32_t *Pl = (lev == 1 ? P.Q : P.Pm) + img * 2 * (size_t)N + level_off((size_t)N, lev);
+  const double *vin = P.plane[lev & 1] + img * (size_t)(N >> 1);    // x^(lev+1), reconstructed by level lev+1
+  double *vout = P.plane[(lev - 1) & 1] + img * (size_t)(N >> 1);  // x^lev
   const double *coefs = P.coefs + img * (size_t)N;
   const int t0 = tile * INV_TILE, nout = min(INV_TILE, n - t0);
   const int omin = (t0 - F / 2) >> 1;  // floor
@@ -134,7 +132,7 @@ __device__ __forceinline__ void idwt_tile(const DwtParams &P, InvSmem &sm, int l
   const size_t app_off = (size_t)N - (size_t)(N >> P.levels);
   for (int i = tid; i < cnt; i += nt) {
     const int ow = (omin + i) & hmask;
-    sm.a[i] = deepest ? coefs[app_off + ow] : (SAME_CTA ? __ldcg(vin + Ql[2 * ow]) : vin[Ql[2 * ow]]);
+    sm.a[i] = deepest ? coefs[app_off + ow] : (SAME_CTA ? __ldcg(vin + ow) : vin[ow]);
     sm.d[i] = coefs[det_off + ow];
   }
   __syncthreads();
@@ -147,12 +145,12 @@ __device__ __forceinline__ void idwt_tile(const DwtParams &P, InvSmem &sm, int l
       shi = __dadd_rn(shi, __dmul_rn(sm.hi[m], sm.d[oi]));
     }
     double x = __dadd_rn(slo, shi);
-    const int pix = Ql[t];
+    const int dst = Pl[t];
     if (lev == 1) {  // Image.decode_rbepwt: clip, no rounding (rbepwt.py:312-314)
       x = x > 255.0 ? 255.0 : (x < 0.0 ? 0.0 : x);
-      P.out_img[img * (size_t)N + pix] = x;
+      P.out_img[img * (size_t)N + dst] = x;
     } else {
-      vout[pix] = x;
+      vout[dst] = x;
     }
   }
 }
@@ -174,6 +172,18 @@ __global__ void __launch_bounds__(DWT_THREADS) k5_idwt_tail(DwtParams P) {
       idwt_tile<true>(P, sm, lev, tile, blockIdx.x);
     }
   }
+}
+
+// EPWT only: the path kernel of level l+1 compares VALUES by pixel, so the dense cA of level l is also laid
+// out by pixel: vpix[Q_l[2o]] = cA[o].
+__global__ void k_plane_to_pixels(const double *__restrict__ plane, const int32_t *__restrict__ Q, int N, int lev,
+                                  double *vpix) {
+  const size_t img = blockIdx.y;
+  const int half = (N >> (lev - 1)) >> 1;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= half) return;
+  const int32_t *Ql = Q + img * 2 * (size_t)N + level_off((size_t)N, lev);
+  vpix[img * (size_t)N + Ql[2 * o]] = plane[img * (size_t)(N >> 1) + o];
 }
 
 }  // namespace rbepwt

@@ -49,6 +49,8 @@ struct PathParams {
   const int32_t *chunk_start, *chunk_cnt;  // chunk table of the thread-per-region kernel (regions.cuh)
   int *qmeta;
   int32_t *Q;  // [B][2N]
+  int32_t *Pm;      // [B][2N] level l >= 2: position of the path point in the level's incoming order (= index into cA of level l-1)
+  int32_t *posmap;  // [B][N] scratch: pixel -> position in the next level's incoming order
   // big-region kernel
   uint32_t *gscratch;          // global bitmap scratch, one slab per CTA (used when smem is too small)
   size_t gscratch_words;       // words per slab
@@ -179,7 +181,7 @@ __device__ __forceinline__ bool find_next(const uint32_t *bm, int h, int w, int 
 template <int MODE>
 __device__ __forceinline__ bool run_path(uint32_t *bm, int h, int w, int ws, int ci, int cj, int n, int r0, int c0,
                                          int logW, const double *__restrict__ vals, bool u8wrap,
-                                         int32_t *__restrict__ Ql) {
+                                         int32_t *__restrict__ Ql, int32_t *__restrict__ Pl, const int32_t *posmap) {
   const int lane = (int)lane_id();
   int myq = 0;
   if (lane == 0) {
@@ -194,11 +196,17 @@ __device__ __forceinline__ bool run_path(uint32_t *bm, int h, int w, int ws, int
     if (lane == 0) bm[bi * ws + (bj >> 5)] &= ~(1u << (bj & 31));
     __syncwarp();
     if ((t & 31) == lane) myq = ((r0 + bi) << logW) + c0 + bj;
-    if ((t & 31) == 31) Ql[t - 31 + lane] = myq;  // coalesced flush of 32 path points
+    if ((t & 31) == 31) {  // coalesced flush of 32 path points (+ their positions in the incoming order)
+      Ql[t - 31 + lane] = myq;
+      if (Pl) Pl[t - 31 + lane] = __ldcg(posmap + myq);
+    }
     p0 = bi - ci; p1 = bj - cj;  // rbepwt.py:1331
     ci = bi; cj = bj;
   }
-  if (lane < (n & 31)) Ql[(n & ~31) + lane] = myq;
+  if (lane < (n & 31)) {
+    Ql[(n & ~31) + lane] = myq;
+    if (Pl) Pl[(n & ~31) + lane] = __ldcg(posmap + myq);
+  }
   return true;
 }
 
@@ -206,7 +214,7 @@ __device__ __forceinline__ bool run_path(uint32_t *bm, int h, int w, int ws, int
 // rbepwt.py:1563-1584).  Re-marks them in the (all-zero) bitmap, returns the smallest surviving
 // pixel id = next level's start point (lexicographic min (row,col), rbepwt.py:1035-1036).
 __device__ __forceinline__ int reduce_points(uint32_t *bm, int ws, int a, int n, int r0, int c0, int logW,
-                                             const int32_t *Ql) {
+                                             const int32_t *Ql, int32_t *posmap) {
   const int lane = (int)lane_id();
   const int Wm = (1 << logW) - 1;
   __syncwarp();
@@ -216,6 +224,7 @@ __device__ __forceinline__ int reduce_points(uint32_t *bm, int ws, int a, int n,
       const int pix = __ldcg(Ql + t);
       const int i = (pix >> logW) - r0, j = (pix & Wm) - c0;
       atomicOr(&bm[i * ws + (j >> 5)], 1u << (j & 31));
+      posmap[pix] = (a + t) >> 1;  // the survivor's place in the next level's incoming order
       minpix = min(minpix, pix);
     }
   }
@@ -235,6 +244,8 @@ __device__ void region_pyramid(const PathParams &P, int g, uint32_t *bm) {
   const int h = P.reg.rmax[g] - r0 + 1, w = P.reg.cmax[g] - c0 + 1, ws = (w + 31) >> 5;
   const int32_t *lab = P.labels + (size_t)img * N;
   int32_t *Q = P.Q + (size_t)img * 2 * (size_t)N;
+  int32_t *Pm = P.Pm + (size_t)img * 2 * (size_t)N;
+  int32_t *posmap = P.posmap + (size_t)img * N;
 
   for (int i = 0; i < h; i++)
     for (int wd = 0; wd < ws; wd++) {
@@ -247,12 +258,13 @@ __device__ void region_pyramid(const PathParams &P, int g, uint32_t *bm) {
   int si = 0, sj = (first & (W - 1)) - c0;
   for (int lev = 1; lev <= P.levels && n > 0; lev++) {
     int32_t *Ql = Q + level_off((size_t)N, lev) + a;
-    if (!run_path<MODE>(bm, h, w, ws, si, sj, n, r0, c0, logW, nullptr, false, Ql)) {
+    int32_t *Pl = lev >= 2 ? Pm + level_off((size_t)N, lev) + a : nullptr;
+    if (!run_path<MODE>(bm, h, w, ws, si, sj, n, r0, c0, logW, nullptr, false, Ql, Pl, posmap)) {
       if (lane == 0) atomicExch(&P.qmeta[QM_ERR], 1);
       return;
     }
     if (lev == P.levels) break;
-    const int minpix = reduce_points(bm, ws, a, n, r0, c0, logW, Ql);
+    const int minpix = reduce_points(bm, ws, a, n, r0, c0, logW, Ql, posmap);
     const int na = (a + 1) >> 1, nb = (a + n + 1) >> 1;
     a = na; n = nb - na;
     if (n > 0) { si = (minpix >> logW) - r0; sj = (minpix & (W - 1)) - c0; }
@@ -284,6 +296,8 @@ struct EpwtParams {
   int H, W, logW, N, lev, img0;
   const double *vals;
   int32_t *Q;        // [B][2N]
+  int32_t *Pm;       // [B][2N], see PathParams
+  int32_t *posmap;   // [B][N]
   uint32_t *gscratch;
   size_t gscratch_words;
   int smem_words;
@@ -298,6 +312,8 @@ __global__ void __launch_bounds__(32) k1_epwt_level(EpwtParams P) {
   const int H = P.H, W = P.W, N = P.N, logW = P.logW, ws = (W + 31) >> 5, words = H * ws;
   uint32_t *bm = words <= P.smem_words ? s_big : P.gscratch + (size_t)blockIdx.x * P.gscratch_words;
   int32_t *Q = P.Q + (size_t)img * 2 * (size_t)N;
+  int32_t *posmap = P.posmap + (size_t)img * N;
+  int32_t *Pl = P.lev >= 2 ? P.Pm + (size_t)img * 2 * (size_t)N + level_off((size_t)N, P.lev) : nullptr;
   const double *vals = P.vals + (size_t)img * N;
   const int n = N >> (P.lev - 1);
   int32_t *Ql = Q + level_off((size_t)N, P.lev);
@@ -310,10 +326,10 @@ __global__ void __launch_bounds__(32) k1_epwt_level(EpwtParams P) {
   } else {
     for (int i = lane; i < words; i += 32) bm[i] = 0u;
     __syncwarp();
-    start = reduce_points(bm, ws, 0, N >> (P.lev - 2), 0, 0, logW, Q + level_off((size_t)N, P.lev - 1));
+    start = reduce_points(bm, ws, 0, N >> (P.lev - 2), 0, 0, logW, Q + level_off((size_t)N, P.lev - 1), posmap);
   }
   const bool ok = run_path<MODE_EPWT>(bm, H, W, ws, start >> logW, start & (W - 1), n, 0, 0, logW, vals,
-                                      P.u8wrap && P.lev == 1, Ql);
+                                      P.u8wrap && P.lev == 1, Ql, Pl, posmap);
   if (!ok && lane == 0) atomicExch(&P.qmeta[QM_ERR], 1);
 }
 

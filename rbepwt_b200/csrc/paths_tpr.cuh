@@ -242,7 +242,10 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
   }
   __syncthreads();
 
-  while (true) {
+  // Each warp takes its share of the chunks and retires: the grid is several waves of CTAs, so SM slots keep
+  // freeing up for the (higher-priority) transform kernels of other units instead of being held to the end.
+  const int share = max(1, (nchunks + (int)gridDim.x * TPR_WARPS - 1) / ((int)gridDim.x * TPR_WARPS));
+  for (int taken = 0; taken < share; taken++) {
     int chunk = 0;
     if (lane == 0) chunk = atomicAdd(&P.qmeta[QM_CUR_SMALL], 1);
     chunk = __shfl_sync(FULL_MASK, chunk, 0);
@@ -291,8 +294,12 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
     int si = 0, sj = (first & Wm) - c0;  // bitmap mode: start point
     int lb = 0, sidx = 0;                // list mode: buffer offset of the level's list, index of its start point
     int32_t *Qimg = P.Q + (size_t)img * 2 * (size_t)N;
+    int32_t *Pimg = P.Pm + (size_t)img * 2 * (size_t)N;
+    int32_t *posmap = P.posmap + (size_t)img * N;  // pixel -> place in the next level's incoming order
     for (int lev = 1; lev <= L; lev++) {
       int32_t *Ql = Qimg + level_off((size_t)N, lev) + a;
+      int32_t *Pl = Pimg + level_off((size_t)N, lev) + a;
+
       const bool keep = lev < L;  // the next level exists: collect the survivors
       int t = n, ci = si, cj = sj, p0 = 0, p1 = 1;  // prefered_direc = (0,1)   rbepwt.py:1290
       int rad = 1, i = 0, wd = 0, i1 = 0;
@@ -325,7 +332,8 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
           bm[si * ws + (sj >> 5)] &= ~(1u << (sj & 31));
           TPR_SET_WINDOW();
         }
-        Ql[0] = ((r0 + ci) << logW) + c0 + cj;
+        const int pix0 = ((r0 + ci) << logW) + c0 + cj;
+        Ql[0] = pix0;
         t = 1;
       }
       while (__any_sync(FULL_MASK, t < n)) {
@@ -352,7 +360,8 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
             U &= ~(1u << idx);
             if (keep && ((a + t) & 1) == 0) TPR_LIST_KEEP(bm[lb + idx]);
             ci += fdi; cj += fdj;
-            Ql[t] = ((r0 + ci) << logW) + c0 + cj;
+            const int pix = ((r0 + ci) << logW) + c0 + cj;
+            Ql[t] = pix;
             p0 = fdi; p1 = fdj;
             t++;
             S.reset();
@@ -414,7 +423,8 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
               if (commit) {
                 const int bi = ci + fdi, bj = cj + fdj;
                 bm[bi * ws + (bj >> 5)] &= ~(1u << (bj & 31));
-                Ql[t] = ((r0 + bi) << logW) + c0 + bj;
+                const int pix = ((r0 + bi) << logW) + c0 + bj;
+                Ql[t] = pix;
                 p0 = fdi; p1 = fdj;  // rbepwt.py:1331
                 ci = bi; cj = bj;
                 t++;
@@ -431,14 +441,29 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
           }
         }
       }
+      // Pl[t] = place of the t-th path point in this level's incoming order (posmap was filled by the previous
+      // level's transition).  Done here, off the walk: independent loads, four in flight per lane.
+      if (lev >= 2) {
+        int tt = 0;
+        for (; tt + 4 <= n; tt += 4) {
+          const int q0 = __ldcg(Ql + tt), q1 = __ldcg(Ql + tt + 1), q2 = __ldcg(Ql + tt + 2), q3 = __ldcg(Ql + tt + 3);
+          const int v0 = __ldcg(posmap + q0), v1 = __ldcg(posmap + q1), v2 = __ldcg(posmap + q2), v3 = __ldcg(posmap + q3);
+          Pl[tt] = v0; Pl[tt + 1] = v1; Pl[tt + 2] = v2; Pl[tt + 3] = v3;
+        }
+        for (; tt < n; tt++) Pl[tt] = __ldcg(posmap + __ldcg(Ql + tt));
+      }
       if (lev == L) break;
       // RegionCollection.reduce: the points at even GLOBAL position a+t survive (rbepwt.py:1563-1584);
       // the next start point is the lexicographically smallest survivor (rbepwt.py:1035-1036)
       const int na = (a + 1) >> 1, nb = (a + n + 1) >> 1;
       const int nnext = nb - na;
       if (live && nnext > 0) {
-        if (list) {  // survivors were appended to the other buffer during the walk
+        if (list) {  // survivors were appended to the other buffer during the walk, in order: places na, na+1, ...
           lb ^= 32; sidx = nminidx;
+          for (int k = 0; k < ncnt; k++) {
+            const uint32_t e = bm[lb + k];
+            posmap[((r0 + (int)(e >> 16)) << logW) + c0 + (int)(e & 0xffffu)] = na + k;
+          }
         } else if (nnext <= TPR_LIST_MAX) {  // bitmap (all-zero now, dead) -> list in buffer A
           list = true; lb = 0;
           uint32_t mn = 0xffffffffu;
@@ -446,6 +471,7 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
           for (int tt = a & 1; tt < n; tt += 2, k++) {
             const int pix = __ldcg(Ql + tt);
             const uint32_t e = (uint32_t)(((pix >> logW) - r0) << 16) | (uint32_t)((pix & Wm) - c0);
+            posmap[pix] = (a + tt) >> 1;
             bm[k] = e;
             if (e < mn) { mn = e; sidx = k; }
           }
@@ -455,6 +481,7 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
             const int pix = __ldcg(Ql + tt);
             const int pi = (pix >> logW) - r0, pj = (pix & Wm) - c0;
             bm[pi * ws + (pj >> 5)] |= 1u << (pj & 31);
+            posmap[pix] = (a + tt) >> 1;
             minpix = min(minpix, pix);
           }
           si = (minpix >> logW) - r0; sj = (minpix & Wm) - c0;

@@ -73,6 +73,7 @@ struct DevBuf {
 struct StageEv { int stage; int launches; cudaEvent_t a, b; };
 
 constexpr int NSLOT = 2;
+constexpr int TPR_WAVES = 8;  // k1_paths_tpr grid = this many waves of resident CTAs (see paths_tpr.cuh)
 
 // Workspace + stream of one unit of work in flight.  The batch is cut twice: into PATH GROUPS (label scan,
 // region records, path pyramid -- large, the path kernel has a long tail and wants many regions per launch)
@@ -81,7 +82,7 @@ constexpr int NSLOT = 2;
 // memory-bound transform kernels and the PCIe copies of other units.
 struct Slot {
   cudaStream_t s = nullptr;
-  DevBuf VA, VB, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch;
+  DevBuf VA, VB, Vpix, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch;
   cudaEvent_t done = nullptr;
 };
 
@@ -113,7 +114,7 @@ struct rbepwt_ctx {
   const int32_t *labels_dev = nullptr;  // ours (labels_own) or the caller's device pointer
   const double *img_dev = nullptr;
   DevBuf labels_own, img_own, out_own, coef_up;
-  DevBuf Q, coefs;
+  DevBuf Q, Pm, posmap, coefs;
   DevBuf reg[8];
   int totalR = 0;
   DevBuf img_R, img_rbase, img_labmin, img_direct;
@@ -252,8 +253,9 @@ int grow_regs(rbepwt_ctx *c, size_t need_entries, size_t used_entries) {
 
 int ensure_slot_workspace(rbepwt_ctx *c, Slot &sl, int nb) {  // nb = 0: no value planes (path slots)
   const size_t N = c->N;
-  CK(sl.VA.ensure((size_t)nb * N * 8));
-  CK(sl.VB.ensure((size_t)nb * N * 8));
+  CK(sl.VA.ensure((size_t)nb * (N / 2) * 8));  // dense planes: x^(l+1) has at most N/2 entries
+  CK(sl.VB.ensure((size_t)nb * (N / 2) * 8));
+  if (c->mode == RBEPWT_PATH_EPWT) CK(sl.Vpix.ensure((size_t)nb * N * 8));
   if (!sl.qhist.p) {
     CK(sl.qhist.ensure(Q_BINS * 4));
     CK(cudaMemsetAsync(sl.qhist.p, 0, Q_BINS * 4, c->stream));  // before the fork: ordered ahead of every stream
@@ -356,6 +358,8 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   P.chunk_cnt = sl.chunk_cnt.as<int32_t>();
   P.qmeta = sl.qmeta.as<int>();
   P.Q = c->Q.as<int32_t>();
+  P.Pm = c->Pm.as<int32_t>();
+  P.posmap = c->posmap.as<int32_t>();
   // big-region kernel: whole-image bitmap in dynamic shared memory when it fits
   const size_t img_words = (size_t)c->H * ((c->W + 31) / 32);
   const size_t smem_cap = std::min<size_t>(c->smem_optin, (size_t)200 * 1024);
@@ -374,7 +378,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_paths_tpr<MODE_EUCLID>, TPR_WARPS * 32, 0));
   else
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_paths_tpr<MODE_CHEB>, TPR_WARPS * 32, 0));
-  const int small_ctas = c->sm_count * std::max(tpr_per_sm, 1);
+  const int small_ctas = c->sm_count * std::max(tpr_per_sm, 1) * TPR_WAVES;
   {
     StageTimer tb(c, RBEPWT_T_PATHS_BIG, s);
     if (c->mode == RBEPWT_PATH_EUCLID) {
@@ -401,6 +405,7 @@ int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
   const int N = c->N;
   DwtParams D;
   D.Q = c->Q.as<int32_t>() + (size_t)a * 2 * N;
+  D.Pm = c->Pm.as<int32_t>() + (size_t)a * 2 * N;
   D.coefs = c->coefs.as<double>() + (size_t)a * N;
   D.filt = c->filt.as<double>();
   D.out_img = nullptr;
@@ -414,6 +419,8 @@ int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
     epwt_smem = std::min(img_words * 4, smem_cap);
     E.H = c->H; E.W = c->W; E.logW = c->logW; E.N = N; E.img0 = 0;
     E.Q = const_cast<int32_t *>(D.Q);
+    E.Pm = c->Pm.as<int32_t>() + (size_t)a * 2 * N;
+    E.posmap = c->posmap.as<int32_t>() + (size_t)a * N;
     E.smem_words = (int)(epwt_smem / 4);
     E.gscratch = nullptr; E.gscratch_words = 0;
     if (img_words * 4 > epwt_smem) {
@@ -433,7 +440,7 @@ int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
     if (c->mode == RBEPWT_PATH_EPWT) {
       StageTimer t(c, RBEPWT_T_PATHS, s);
       E.lev = lev;
-      E.vals = lev == 1 ? D.vin : V[(lev - 1) & 1];
+      E.vals = lev == 1 ? D.vin : sl.Vpix.as<double>();  // values BY PIXEL: the image, then cA laid out by pixel
       k1_epwt_level<<<nb, 32, epwt_smem, s>>>(E);
       c->launches++;
     } else if (n <= TAIL_MAX_POINTS) {  // all remaining levels in one launch, one CTA per image
@@ -447,6 +454,10 @@ int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
       dim3 grid(((n >> 1) + FWD_TILE - 1) / FWD_TILE, nb);
       k3_dwt_level<<<grid, DWT_THREADS, 0, s>>>(D);
       c->launches++;
+      if (c->mode == RBEPWT_PATH_EPWT && lev < c->levels) {
+        k_plane_to_pixels<<<dim3(((n >> 1) + 255) / 256, nb), 256, 0, s>>>(V[lev & 1], D.Q, N, lev, sl.Vpix.as<double>());
+        c->launches++;
+      }
     }
   }
   CK(cudaGetLastError());
@@ -467,6 +478,7 @@ int decode_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb, double *o
   StageTimer t(c, RBEPWT_T_IDWT, s);
   DwtParams D;
   D.Q = c->Q.as<int32_t>() + (size_t)a * 2 * N;
+  D.Pm = c->Pm.as<int32_t>() + (size_t)a * 2 * N;
   D.coefs = c->coefs.as<double>() + (size_t)a * N;
   D.filt = c->filt.as<double>();
   D.out_img = out_dev + (size_t)a * N;
@@ -501,6 +513,8 @@ int alloc_state(rbepwt_ctx *c, int B, int H, int W, int levels, int path_mode, u
   c->h_R.assign(B, 0); c->h_rbase.assign(B, 0);
   const size_t N = c->N;
   CK(c->Q.ensure((size_t)B * 2 * N * 4));
+  CK(c->Pm.ensure((size_t)B * 2 * N * 4));
+  CK(c->posmap.ensure((size_t)B * N * 4));
   CK(c->coefs.ensure((size_t)B * N * 8));
   CK(c->img_R.ensure((size_t)B * 4)); CK(c->img_rbase.ensure((size_t)B * 4));
   CK(c->img_labmin.ensure((size_t)B * 4)); CK(c->img_direct.ensure((size_t)B * 4));
@@ -645,10 +659,13 @@ int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
   c->smem_optin = prop.sharedMemPerBlockOptin;
   if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
   else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-  CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  // copies and transform kernels outrank the long path kernels: when an SM slot frees up, their CTAs go first
+  int prio_lo = 0, prio_hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CK(cudaStreamCreateWithPriority(&c->s_in, cudaStreamNonBlocking, prio_hi));
+  CK(cudaStreamCreateWithPriority(&c->s_out, cudaStreamNonBlocking, prio_hi));
   for (int i = 0; i < 2 * NSLOT; i++) {
-    CK(cudaStreamCreateWithFlags(&c->slot[i].s, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&c->slot[i].s, cudaStreamNonBlocking, i < NSLOT ? prio_lo : prio_hi));
     CK(cudaEventCreateWithFlags(&c->slot[i].done, cudaEventDisableTiming));
   }
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -668,14 +685,14 @@ void rbepwt_destroy(rbepwt_ctx *c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   for (auto *v : {&c->ev_lab, &c->ev_path, &c->ev_img, &c->ev_done})
     for (auto e : *v) cudaEventDestroy(e);
-  DevBuf *bufs[] = {&c->filt, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->coefs, &c->img_R,
+  DevBuf *bufs[] = {&c->filt, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->img_R,
                     &c->img_rbase, &c->img_labmin, &c->img_direct, &c->tbl, &c->slot_rid, &c->scratch_i32,
                     &c->scratch_i32b, &c->psnr_out, &c->nz_out};
   for (auto b : bufs) b->release();
   for (auto &b : c->reg) b.release();
   for (int i = 0; i < 2 * NSLOT; i++) {
     Slot &sl = c->slot[i];
-    DevBuf *sb[] = {&sl.VA, &sl.VB, &sl.queue, &sl.qhist, &sl.qmeta, &sl.qbins, &sl.chunk_start, &sl.chunk_cnt, &sl.gscratch};
+    DevBuf *sb[] = {&sl.VA, &sl.VB, &sl.Vpix, &sl.queue, &sl.qhist, &sl.qmeta, &sl.qbins, &sl.chunk_start, &sl.chunk_cnt, &sl.gscratch};
     for (auto b : sb) b->release();
     cudaEventDestroy(sl.done);
     cudaStreamDestroy(sl.s);
@@ -971,6 +988,7 @@ int rbepwt_get_level_values(rbepwt_ctx *c, int b, int level, double *vals) {
   double *V[2] = {c->slot[NSLOT].VA.as<double>(), c->slot[NSLOT].VB.as<double>()};
   DwtParams D;
   D.Q = c->Q.as<int32_t>() + (size_t)b * 2 * N;
+  D.Pm = c->Pm.as<int32_t>() + (size_t)b * 2 * N;
   D.coefs = scratch;
   D.filt = c->filt.as<double>();
   D.out_img = nullptr;
@@ -984,12 +1002,11 @@ int rbepwt_get_level_values(rbepwt_ctx *c, int b, int level, double *vals) {
     k3_dwt_level<<<dim3((half + FWD_TILE - 1) / FWD_TILE, 1), DWT_THREADS, 0, s>>>(D);
     c->launches++;
   }
-  const int32_t *Q = c->Q.as<int32_t>() + (size_t)b * 2 * N;
   if (level == 1) {
     if ((rc = level1_incoming(c, b))) return rc;
     k_gather_values<<<(n + 255) / 256, 256, 0, s>>>(c->img_dev + (size_t)b * N, c->scratch_i32.as<int32_t>(), 1, n, out);
-  } else {
-    k_gather_values<<<(n + 255) / 256, 256, 0, s>>>(V[(level - 1) & 1], Q + level_off(N, level - 1), 2, n, out);
+  } else {  // x^level = cA of level-1, already in the incoming order
+    CK(cudaMemcpyAsync(out, V[(level - 1) & 1], (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
   }
   c->launches++;
   CK(cudaGetLastError());
