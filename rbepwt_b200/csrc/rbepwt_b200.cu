@@ -335,6 +335,11 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   {
     StageTimer t(c, RBEPWT_T_REGIONS, s);
     CK(cudaMemcpyAsync(c->img_rbase.as<int32_t>() + a, c->pin_rbase + a, (size_t)nb * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaFuncSetAttribute(k0_regions_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K0F_SMEM));
+    k0_regions_fast<<<nb, K0_THREADS, K0F_SMEM, s>>>(c->labels_dev, a, N, c->logW,
+                                                    c->tbl.as<unsigned long long>() + (size_t)(a - chunk0) * T, T,
+                                                    c->img_R.as<int32_t>(), c->img_labmin.as<int32_t>(),
+                                                    c->img_direct.as<int32_t>(), c->img_rbase.as<int32_t>(), c->regs());
     k0_regions<<<nb, K0_THREADS, 0, s>>>(c->labels_dev, a, N, c->logW,
                                          c->tbl.as<unsigned long long>() + (size_t)(a - chunk0) * T,
                                          c->slot_rid.as<int32_t>() + (size_t)(a - chunk0) * T, T, c->img_R.as<int32_t>(),
@@ -346,7 +351,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     kq_scatter<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, sl.qmeta.as<int>(), sl.queue.as<int32_t>());
     kq_chunks<<<((Q_BINS - Q_SIZE_BINS) * 32 + 255) / 256, 256, 0, s>>>(sl.qbins.as<int>(), sl.chunk_start.as<int32_t>(),
                                                                         sl.chunk_cnt.as<int32_t>());
-    c->launches += 5;
+    c->launches += 6;
     CK(cudaGetLastError());
   }
   PathParams P;

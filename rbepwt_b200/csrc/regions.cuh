@@ -104,11 +104,118 @@ __global__ void __launch_bounds__(K0_THREADS) k0_count(const int32_t *__restrict
   if (tid == 0) {
     img_R[img] = cnt;
     img_labmin[img] = lmin;
-    img_direct[img] = direct;
+    img_direct[img] = direct ? used : 0;  // slots of the direct table (>= 1), 0 = open addressing
   }
 }
 
-// Pass 2: region records.  rbase[img] = index of the image's region 0 in the global region arrays.
+// Pass 2, common case (dense label values, at most K0F_MAXR regions, rows a multiple of 8 pixels): the label
+// table and the per-region statistics live in shared memory, a thread handles 8 consecutive pixels, ranks and
+// statistics are produced in ONE sweep over the labels (a label's first pixel precedes all its other pixels in
+// row-major order, so its region id is known by the time they are counted).
+constexpr int K0F_MAXT = 8192, K0F_MAXR = 4096, K0F_PPT = 8;
+constexpr size_t K0F_SMEM = (size_t)(K0F_MAXT + 4 * K0F_MAXR) * sizeof(int);
+
+__host__ __device__ __forceinline__ bool k0_fast_eligible(int direct_slots, int R, int logW) {
+  return direct_slots > 0 && direct_slots <= K0F_MAXT && R <= K0F_MAXR && logW >= 3;
+}
+
+__global__ void __launch_bounds__(K0_THREADS) k0_regions_fast(const int32_t *__restrict__ labels, int img0, int N,
+                                                              int logW, const unsigned long long *tbl_all, int T,
+                                                              const int32_t *img_R, const int32_t *img_labmin,
+                                                              const int32_t *img_direct, const int32_t *img_rbase,
+                                                              RegionArrays reg) {
+  extern __shared__ int s_dyn[];
+  int *s_rid = s_dyn;                // slot -> first pixel | TAG, then -> region id
+  int *s_size = s_rid + K0F_MAXT, *s_rmax = s_size + K0F_MAXR, *s_cmin = s_rmax + K0F_MAXR, *s_cmax = s_cmin + K0F_MAXR;
+  __shared__ int s_scan[33];
+  __shared__ int s_running;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int img = img0 + blockIdx.x;
+  const int slots = img_direct[img], R = img_R[img];
+  if (!k0_fast_eligible(slots, R, logW)) return;  // k0_regions handles this image
+  const int32_t *lab = labels + (size_t)img * N;
+  const unsigned long long *tbl = tbl_all + (size_t)blockIdx.x * T;
+  const int W = 1 << logW, labmin = img_labmin[img], rb = img_rbase[img];
+  const int TAG = (int)0x80000000u;
+
+  for (int s = tid; s < slots; s += nt) {
+    const unsigned long long e = tbl[s];
+    s_rid[s] = e == TBL_EMPTY ? -1 : ((int)(uint32_t)e | TAG);
+  }
+  for (int r = tid; r < R; r += nt) { s_size[r] = 0; s_rmax[r] = 0; s_cmin[r] = W; s_cmax[r] = 0; }
+  if (tid == 0) s_running = 0;
+  __syncthreads();
+
+  for (int base = 0; base < N; base += nt * K0F_PPT) {
+    const int p0 = base + tid * K0F_PPT;
+    const bool valid = p0 < N;  // N is a multiple of 8 here: all of a thread's pixels are valid or none
+    int v[K0F_PPT];
+    int prevlab = 0;
+    if (valid) {
+      const int4 x = *reinterpret_cast<const int4 *>(lab + p0), y = *reinterpret_cast<const int4 *>(lab + p0 + 4);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+      prevlab = p0 > 0 ? lab[p0 - 1] : ~v[0];
+    }
+    // first appearances among the run heads
+    unsigned fmask = 0;
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < K0F_PPT; i++) {
+        const bool head = v[i] != (i == 0 ? prevlab : v[i - 1]);
+        if (head && s_rid[v[i] - labmin] == ((p0 + i) | TAG)) fmask |= 1u << i;
+      }
+    }
+    int total;
+    int rank = s_running + block_exclusive_scan(__popc(fmask), s_scan, &total);
+    while (fmask) {
+      const int i = __ffs(fmask) - 1;
+      fmask &= fmask - 1;
+      const int g = rb + rank;
+      s_rid[v[i] - labmin] = rank++;
+      reg.label[g] = v[i];
+      reg.first[g] = p0 + i;
+      reg.img[g] = img;
+    }
+    __syncthreads();
+    if (tid == 0) s_running += total;
+    // statistics, one update per run of equal labels inside the thread's 8 pixels (same row: 8 | W)
+    if (valid) {
+      const int row = p0 >> logW, col0 = p0 & (W - 1);
+      int i = 0;
+      while (i < K0F_PPT) {
+        int j = i;
+        while (j + 1 < K0F_PPT && v[j + 1] == v[i]) j++;
+        const int rid = s_rid[v[i] - labmin];
+        atomicAdd(&s_size[rid], j - i + 1);
+        atomicMax(&s_rmax[rid], row);
+        atomicMin(&s_cmin[rid], col0 + i);
+        atomicMax(&s_cmax[rid], col0 + j);
+        i = j + 1;
+      }
+    }
+  }
+  __syncthreads();
+  // level-1 offsets = exclusive scan of the sizes in region order
+  if (tid == 0) s_running = 0;
+  __syncthreads();
+  for (int base = 0; base < R; base += nt) {
+    const int r = base + tid;
+    const int sz = r < R ? s_size[r] : 0;
+    int total;
+    const int ex = s_running + block_exclusive_scan(sz, s_scan, &total);
+    if (r < R) {
+      const int g = rb + r;
+      reg.size[g] = sz; reg.off[g] = ex;
+      reg.rmax[g] = s_rmax[r]; reg.cmin[g] = s_cmin[r]; reg.cmax[g] = s_cmax[r];
+    }
+    __syncthreads();
+    if (tid == 0) s_running += total;
+    __syncthreads();
+  }
+}
+
+// Pass 2, general case (any int32 labels, any region count).  rbase[img] = index of the image's region 0 in the
+// global region arrays.
 __global__ void __launch_bounds__(K0_THREADS) k0_regions(const int32_t *__restrict__ labels, int img0, int N,
                                                          int logW, const unsigned long long *tbl_all,
                                                          int32_t *slot_rid_all, int T, const int32_t *img_R,
@@ -124,6 +231,7 @@ __global__ void __launch_bounds__(K0_THREADS) k0_regions(const int32_t *__restri
   const uint32_t tmask = (uint32_t)T - 1u;
   const int W = 1 << logW;
   const int labmin = img_labmin[img], direct = img_direct[img], R = img_R[img], rb = img_rbase[img];
+  if (k0_fast_eligible(direct, R, logW)) return;  // k0_regions_fast handles this image
 
   // A: rank the first-appearance pixels in row-major order -> region ids
   if (tid == 0) s_running = 0;
