@@ -278,13 +278,24 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
       const int h_r = __shfl_sync(FULL_MASK, h, r), w_r = __shfl_sync(FULL_MASK, w, r);
       const int ws_r = __shfl_sync(FULL_MASK, ws, r), base_r = __shfl_sync(FULL_MASK, base, r);
       const int32_t *lab = P.labels + (size_t)img_r * N;
-      for (int i = 0; i < h_r; i++)
-        for (int wd = 0; wd < ws_r; wd++) {
-          const int col = (wd << 5) + lane;
-          const bool in = col < w_r && lab[((r0_r + i) << logW) + c0_r + col] == label_r;
-          const unsigned bits = __ballot_sync(FULL_MASK, in);
-          if (lane == 0) arena[base_r + i * ws_r + wd] = bits;
+      const int words_r = h_r * ws_r;
+      for (int wi = 0; wi < words_r; wi += 4) {  // four independent label loads in flight per lane
+        int lv[4];
+        bool inb[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int w_ = wi + u;
+          const int i = ws_r == 1 ? w_ : w_ / ws_r;
+          const int col = ((w_ - i * ws_r) << 5) + lane;
+          inb[u] = w_ < words_r && col < w_r;
+          lv[u] = inb[u] ? lab[((r0_r + i) << logW) + c0_r + col] : 0;
         }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const unsigned bits = __ballot_sync(FULL_MASK, inb[u] && lv[u] == label_r);
+          if (lane == 0 && wi + u < words_r) arena[base_r + wi + u] = bits;
+        }
+      }
     }
     __syncwarp();
 
@@ -477,7 +488,20 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
           }
         } else {  // re-mark the survivors in the (all-zero) bitmap
           int minpix = INT32_MAX;
-          for (int tt = a & 1; tt < n; tt += 2) {
+          int tt = a & 1;
+          for (; tt + 6 < n; tt += 8) {  // four independent loads in flight
+            int px[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) px[u] = __ldcg(Ql + tt + 2 * u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int pi = (px[u] >> logW) - r0, pj = (px[u] & Wm) - c0;
+              bm[pi * ws + (pj >> 5)] |= 1u << (pj & 31);
+              posmap[px[u]] = (a + tt + 2 * u) >> 1;
+              minpix = min(minpix, px[u]);
+            }
+          }
+          for (; tt < n; tt += 2) {
             const int pix = __ldcg(Ql + tt);
             const int pi = (pix >> logW) - r0, pj = (pix & Wm) - c0;
             bm[pi * ws + (pj >> 5)] |= 1u << (pj & 31);
