@@ -201,6 +201,10 @@ __device__ unsigned long long g_tpr_stats[16 * 4 * 2 + 32];
 constexpr int TPR_LIST_MAX = 32;   // list mode from the first level with at most this many points
 constexpr int TPR_SLOT_MIN = 48;   // arena words per lane: list buffers A = [0,32), B = [32,48) ping-pong
 constexpr int TPR_ROWS_PER_TRIP = 3;
+#ifndef TPR_UNIT_STEPS_N
+#define TPR_UNIT_STEPS_N 2
+#endif
+constexpr int TPR_UNIT_STEPS = TPR_UNIT_STEPS_N;  // unit steps a lane may take per trip
 constexpr int TPR_MAX_RAD = 8;     // widest aligned-row window; beyond it the whole bitmap is scanned
 
 // Window row as one word: bit 15 + dj  <->  column cj + dj, dj in [-15, 16]; columns outside the
@@ -348,13 +352,44 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
         t = 1;
       }
       while (__any_sync(FULL_MASK, t < n)) {
-        if (t < n) {
+        // ---- phase 1, unit steps: 3x3 neighbourhood -> 9-bit mask -> table, up to TPR_UNIT_STEPS per trip
+        // (half-width 1, unit pref: the state every dense stretch of a path is in)
+#pragma unroll 1
+        for (int rep = 0; rep < TPR_UNIT_STEPS; rep++) {
+          const bool unit = t < n && !list && fresh && rad == 1 && (unsigned)(p0 + 1) <= 2u && (unsigned)(p1 + 1) <= 2u;
+          if (!__any_sync(FULL_MASK, unit)) break;
+          if (unit) {
+#ifdef TPR_STATS
+            atomicAdd(&g_tpr_stats[((min(lev, 16) - 1) * 4 + 0) * 2 + 1], 1ull);
+#endif
+            unsigned m = 0;
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) {
+              const int ri = ci + rr - 1;
+              const uint32_t x = (ri >= 0 && ri < h) ? row_window(bm + ri * ws, ws, cj) : 0u;
+              m |= ((x >> 14) & 7u) << (3 * rr);
+            }
+            if (m) {
+              const int idx = s_lut[((p0 + 1) * 3 + (p1 + 1)) * TPR_LUT_COLS + m];
+              p0 = idx / 3 - 1; p1 = idx % 3 - 1;  // rbepwt.py:1331
+              ci += p0; cj += p1;
+              bm[ci * ws + (cj >> 5)] &= ~(1u << (cj & 31));
+              Ql[t] = ((r0 + ci) << logW) + c0 + cj;
+              t++;  // still half-width 1, still at the start of a window
+            } else {
+              rad = 2;
+              TPR_SET_WINDOW();
+            }
+          }
+        }
+        // ---- phase 2: one unit of the other kinds
+        const bool unit_now = !list && fresh && rad == 1 && (unsigned)(p0 + 1) <= 2u && (unsigned)(p1 + 1) <= 2u;
+        if (t < n && !unit_now) {
           bool commit = false, expand = false;
           int fdi = 0, fdj = 0, fk = 0;
 #ifdef TPR_STATS
           {
-            const int kind = list ? 3 : (fresh && rad == 1 && (unsigned)(p0 + 1) <= 2u && (unsigned)(p1 + 1) <= 2u) ? 0
-                                    : (rad <= TPR_MAX_RAD ? 1 : 2);
+            const int kind = list ? 3 : (rad <= TPR_MAX_RAD ? 1 : 2);
             atomicAdd(&g_tpr_stats[((min(lev, 16) - 1) * 4 + kind) * 2 + 1], 1ull);
             if (lane == __ffs(__activemask()) - 1) atomicAdd(&g_tpr_stats[128 + min(lev, 16) - 1], 1ull);
           }
@@ -377,23 +412,7 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
             t++;
             S.reset();
           } else {
-            if (fresh && rad == 1 && (unsigned)(p0 + 1) <= 2u && (unsigned)(p1 + 1) <= 2u) {
-              // ---- unit-step fast path: 3x3 neighbourhood -> 9-bit mask -> table
-              unsigned m = 0;
-#pragma unroll
-              for (int rr = 0; rr < 3; rr++) {
-                const int ri = ci + rr - 1;
-                const uint32_t x = (ri >= 0 && ri < h) ? row_window(bm + ri * ws, ws, cj) : 0u;
-                m |= ((x >> 14) & 7u) << (3 * rr);
-              }
-              if (m) {
-                const int idx = s_lut[((p0 + 1) * 3 + (p1 + 1)) * TPR_LUT_COLS + m];
-                fdi = idx / 3 - 1; fdj = idx % 3 - 1; fk = 0;
-                commit = true;
-              } else {
-                expand = true;
-              }
-            } else if (rad <= TPR_MAX_RAD) {
+            if (rad <= TPR_MAX_RAD) {
               // ---- up to three window rows, each one aligned word
               fresh = false;
               const uint32_t wmask = ((2u << (2 * rad)) - 1u) << (15 - rad);
