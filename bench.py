@@ -70,7 +70,7 @@ def workload(batch):
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.sm_max = [], set(), None
@@ -195,7 +195,7 @@ def run_reference(args):
             "note": "the reference itself is pure Python (+PyWavelets) and cannot run on the GPU box; measured in the "
                     "build container it needs ~1 h per 512x512 image (BASELINE.md section 2). This arm times the C "
                     "port of its algorithm (oracle/), which is orders of magnitude faster than the reference."}
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -386,14 +386,23 @@ def run_ours(args):
                                           "algorithm (oracle/rbepwt_oracle.c); the Python reference itself needs ~1 h per "
                                           "512x512 image (BASELINE.md)" % ns}
     if rank == 0:
-        print(json.dumps(line))
+        _emit(line)
     codec.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def _emit(line):
+    """The ONE JSON line goes to the real stdout; everything else this process (or NCCL) prints goes to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
     world_env = os.environ.get("WORLD_SIZE")
     if args.gpus > 1 and world_env is None:
@@ -403,6 +412,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", port, os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # library banners (e.g. "NCCL version ...") must not precede the JSON line on stdout
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
