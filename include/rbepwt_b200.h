@@ -49,6 +49,8 @@ typedef struct rbepwt_ctx rbepwt_ctx;
 /* flags */
 #define RBEPWT_DEVICE_PTRS 1u /* pointer arguments are device pointers */
 #define RBEPWT_U8_WRAP 2u     /* EPWT level 1: |a-b| wraps modulo 256 like numpy uint8 scalars (rbepwt.py:1302) */
+#define RBEPWT_PATHS_FIRST_LEVEL 4u /* paths_first_level=True: Region.same_path (identity permutation) at every
+                                       level >= 2, paths are searched at level 1 only (rbepwt.py:1183-1188, 2024-2025) */
 
 /* Create a context on CUDA device `device`.  `stream` is a cudaStream_t to run on (e.g.
  * torch's current stream) or NULL to create a private one.  Fails with RBEPWT_E_NO_GPU when

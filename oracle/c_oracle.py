@@ -39,7 +39,7 @@ def lib():
         L.rbo_level_offset.argtypes = [ctypes.c_long, ctypes.c_int]
         L.rbo_encode.restype = ctypes.c_int
         L.rbo_encode.argtypes = [_f64p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                 ctypes.c_int, _f64p, _f64p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                 ctypes.c_int, _f64p, _f64p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                  _i32p, _i32p, _i32p, _i32p, _f64p]
         L.rbo_threshold.restype = ctypes.c_int
         L.rbo_threshold.argtypes = [_f64p, ctypes.c_int64, ctypes.c_int64]
@@ -64,7 +64,7 @@ def level_offset(n, lev):
     return sum(n >> (l - 1) for l in range(1, lev))
 
 
-def encode(img, labels, levels, wavelet, mode, u8wrap=None):
+def encode(img, labels, levels, wavelet, mode, u8wrap=None, paths_first_level=False):
     """Flat-array encode.  Returns dict(R, roff[(L+1),(R+1)], inc_pix, path_pix, perm, coefs)."""
     L = lib()
     if u8wrap is None:
@@ -85,7 +85,7 @@ def encode(img, labels, levels, wavelet, mode, u8wrap=None):
     perm = np.zeros(level_offset(N, levels + 1), dtype=np.int32)
     coefs = np.zeros(N, dtype=np.float64)
     rc = L.rbo_encode(img64, labp, H, W, levels, len(dec_lo), np.ascontiguousarray(dec_lo),
-                      np.ascontiguousarray(dec_hi), mode, int(bool(u8wrap)), R, roff, inc_pix,
+                      np.ascontiguousarray(dec_hi), mode, int(bool(u8wrap)), int(bool(paths_first_level)), R, roff, inc_pix,
                       path_pix, perm, coefs)
     if rc == -1:
         raise Exception("Image size must be a power of 2")
@@ -119,11 +119,12 @@ def psnr(a, b):
     return float(lib().rbo_psnr(a.ravel(), b.ravel(), a.size))
 
 
-def run(img, labels, levels, wavelet, path_type="easypath", euclidean_distance=True, ncoefs=None):
+def run(img, labels, levels, wavelet, path_type="easypath", euclidean_distance=True, ncoefs=None,
+        paths_first_level=False):
     """Same output dict as ref_harness.run_reference (perm/roff/points per level, coefs, kept,
     decoded, psnr) so the two can be compared key by key."""
     mode = path_mode(path_type, euclidean_distance)
-    enc = encode(img, labels, levels, wavelet, mode)
+    enc = encode(img, labels, levels, wavelet, mode, paths_first_level=paths_first_level)
     H, W = enc["H"], enc["W"]
     N = H * W
     out = {"perm": {}, "roff": {}, "points": {}, "enc": enc}

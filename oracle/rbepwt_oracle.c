@@ -217,7 +217,7 @@ long rbo_level_offset(long n, int lev) {
  * labels == NULL  <=>  one region holding every pixel (EPWT).
  */
 int rbo_encode(const double *img, const int32_t *labels, int H, int W, int levels, int flen,
-               const double *dec_lo, const double *dec_hi, int mode, int u8wrap, int R,
+               const double *dec_lo, const double *dec_hi, int mode, int u8wrap, int paths_first_level, int R,
                int32_t *roff, int32_t *inc_pix, int32_t *path_pix, int32_t *perm,
                double *coefs) {
   const int N = H * W;
@@ -265,7 +265,11 @@ int rbo_encode(const double *img, const int32_t *labels, int H, int W, int level
       for (long i = 0; i < nl; i++) valmap[ipix[i]] = val[i];
     for (int r = 0; r < R; r++) {
       int a = cur_off[r], n = cur_off[r + 1] - a;
-      easy_path(&c, r, ipix + a, n, mode, u8wrap && lev == 1, pm + a, ppix + a);
+      if (lev > 1 && paths_first_level) { /* Region.same_path: identity permutation (rbepwt.py:1183-1188, 2024-2025) */
+        for (int t = 0; t < n; t++) { pm[a + t] = t; ppix[a + t] = ipix[a + t]; }
+      } else {
+        easy_path(&c, r, ipix + a, n, mode, u8wrap && lev == 1, pm + a, ppix + a);
+      }
       for (int t = 0; t < n; t++) sig[a + t] = val[a + pm[a + t]];
     }
     dwt_per(sig, (int)nl, flen, dec_lo, dec_hi, ca, coefs + coef_off);

@@ -106,7 +106,7 @@ def make_image(img, labels=None):
 
 
 def run_reference(img, labels, levels, wavelet, path_type="easypath",
-                  euclidean_distance=True, ncoefs=None):
+                  euclidean_distance=True, ncoefs=None, paths_first_level=False):
     """Encode (+ threshold + decode) with the reference; returns a dict of plain
     numpy arrays in the flat layout of SURVEY.md section 8a:
 
@@ -122,7 +122,7 @@ def run_reference(img, labels, levels, wavelet, path_type="easypath",
     with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
         warnings.simplefilter("ignore")
         im.encode_rbepwt(levels, wavelet, path_type=path_type,
-                         euclidean_distance=euclidean_distance)
+                         euclidean_distance=euclidean_distance, paths_first_level=paths_first_level)
         rb = im.rbepwt
         perm, roff, points = {}, {}, {}
         for lev in range(1, levels + 2):

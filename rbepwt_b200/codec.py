@@ -135,11 +135,13 @@ class BatchCodec:
             labels = None
         return imgs, labels, shape, dev, u8
 
-    def encode(self, imgs, labels, levels, wavelet, path_type="easypath", euclidean_distance=True):
+    def encode(self, imgs, labels, levels, wavelet, path_type="easypath", euclidean_distance=True,
+               paths_first_level=False):
         mode = path_mode(path_type, euclidean_distance)
         imgs, labels, shape, dev, u8 = self._prep(imgs, labels, mode)
         self.set_wavelet(wavelet)
         flags = (_capi.DEVICE_PTRS if dev else 0) | (_capi.U8_WRAP if (u8 and mode == _capi.PATH_EPWT) else 0)
+        flags |= _capi.PATHS_FIRST_LEVEL if paths_first_level else 0
         B, H, W = shape
         self._keep = [imgs, labels]
         _capi.check(self._lib.rbepwt_encode(self._ctx, _ptr(imgs), _ptr(labels), B, H, W, int(levels), mode, flags))
@@ -156,7 +158,8 @@ class BatchCodec:
         if sub_batch is not None:
             _capi.check(self._lib.rbepwt_set_option(self._ctx, _capi.OPT_SUBBATCH, int(sub_batch)))
 
-    def transcode(self, imgs, labels, levels, wavelet, ncoefs, path_type="easypath", euclidean_distance=True, out=None):
+    def transcode(self, imgs, labels, levels, wavelet, ncoefs, path_type="easypath", euclidean_distance=True, out=None,
+                  paths_first_level=False):
         """encode -> threshold(ncoefs) -> decode in one pipelined call (rbepwt_transcode); returns the decoded
         images.  Inputs and `out` must be all numpy (host path) or all torch CUDA tensors (device path)."""
         mode = path_mode(path_type, euclidean_distance)
@@ -173,6 +176,7 @@ class BatchCodec:
         if not dev and not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous):
             raise ValueError("out must be a contiguous float64 numpy array or CUDA tensor")
         flags = (_capi.DEVICE_PTRS if dev else 0) | (_capi.U8_WRAP if (u8 and mode == _capi.PATH_EPWT) else 0)
+        flags |= _capi.PATHS_FIRST_LEVEL if paths_first_level else 0
         B, H, W = shape
         self._keep = [imgs, labels, out]
         _capi.check(self._lib.rbepwt_transcode(self._ctx, _ptr(imgs), _ptr(labels), B, H, W, int(levels), mode, int(ncoefs),
@@ -197,7 +201,8 @@ class BatchCodec:
         _capi.check(self._lib.rbepwt_decode(self._ctx, _ptr(out), _capi.DEVICE_PTRS if dev else 0))
         return out
 
-    def full_decode(self, coefs, labels, levels, wavelet, path_type="easypath", euclidean_distance=True):
+    def full_decode(self, coefs, labels, levels, wavelet, path_type="easypath", euclidean_distance=True,
+                    paths_first_level=False):
         """Decoder side (reference full_decode, rbepwt.py:106-130): paths regenerated from labels."""
         mode = path_mode(path_type, euclidean_distance)
         labels = np.ascontiguousarray(labels, dtype=np.int32)
@@ -207,7 +212,7 @@ class BatchCodec:
         out = np.empty(shape, dtype=np.float64)
         B, H, W = shape
         _capi.check(self._lib.rbepwt_full_decode(self._ctx, _ptr(coefs), _ptr(labels), B, H, W, int(levels), mode,
-                                                 _ptr(out), 0))
+                                                 _ptr(out), _capi.PATHS_FIRST_LEVEL if paths_first_level else 0))
         self.shape, self.levels, self.mode = shape, int(levels), mode
         return out
 

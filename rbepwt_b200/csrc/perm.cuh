@@ -51,6 +51,23 @@ __global__ void k_perm_gather(const int32_t *__restrict__ Ql, int n, const int32
   perm[t] = inv[Ql[t]] - ((off1[lo] + add) >> sh);
 }
 
+// paths_first_level (Region.same_path, rbepwt.py:1183-1188): at every level >= 2 the path is the incoming
+// order itself -- the points at the even positions of the level above, identity permutation.
+// One CTA per image, level after level.
+__global__ void __launch_bounds__(1024) k_same_paths(int32_t *Q_all, int32_t *Pm_all, int N, int levels) {
+  int32_t *Q = Q_all + (size_t)blockIdx.x * 2 * (size_t)N, *Pm = Pm_all + (size_t)blockIdx.x * 2 * (size_t)N;
+  for (int lev = 2; lev <= levels; lev++) {
+    const int n = N >> (lev - 1);
+    const int32_t *prev = Q + level_off((size_t)N, lev - 1);
+    int32_t *cur = Q + level_off((size_t)N, lev), *pos = Pm + level_off((size_t)N, lev);
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+      cur[t] = prev[2 * t];
+      pos[t] = t;
+    }
+    __syncthreads();  // the next level reads what this one wrote (same CTA)
+  }
+}
+
 // out[i] = V[src[i * stride]]
 __global__ void k_gather_values(const double *__restrict__ V, const int32_t *__restrict__ src, int stride, int n,
                                 double *out) {

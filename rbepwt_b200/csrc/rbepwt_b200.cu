@@ -356,7 +356,8 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   }
   PathParams P;
   P.labels = c->labels_dev;
-  P.H = c->H; P.W = c->W; P.logW = c->logW; P.N = N; P.levels = c->levels;
+  P.H = c->H; P.W = c->W; P.logW = c->logW; P.N = N;
+  P.levels = (c->enc_flags & RBEPWT_PATHS_FIRST_LEVEL) ? 1 : c->levels;
   P.reg = c->regs();
   P.queue = sl.queue.as<int32_t>();
   P.chunk_start = sl.chunk_start.as<int32_t>();
@@ -400,6 +401,11 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     if (c->mode == RBEPWT_PATH_EUCLID) k1_paths_tpr<MODE_EUCLID><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
     else k1_paths_tpr<MODE_CHEB><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
     c->launches++;
+    if ((c->enc_flags & RBEPWT_PATHS_FIRST_LEVEL) && c->levels > 1) {
+      k_same_paths<<<nb, 1024, 0, s>>>(c->Q.as<int32_t>() + (size_t)a * 2 * N, c->Pm.as<int32_t>() + (size_t)a * 2 * N, N,
+                                       c->levels);
+      c->launches++;
+    }
   }
   CK(cudaGetLastError());
   return RBEPWT_OK;
@@ -442,13 +448,19 @@ int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
   for (int lev = 1; lev <= c->levels; lev++) {
     D.lev = lev;
     const int n = N >> (lev - 1);
-    if (c->mode == RBEPWT_PATH_EPWT) {
+    const bool same_paths = (c->enc_flags & RBEPWT_PATHS_FIRST_LEVEL) != 0;
+    if (c->mode == RBEPWT_PATH_EPWT && !(same_paths && lev > 1)) {
       StageTimer t(c, RBEPWT_T_PATHS, s);
       E.lev = lev;
       E.vals = lev == 1 ? D.vin : sl.Vpix.as<double>();  // values BY PIXEL: the image, then cA laid out by pixel
       k1_epwt_level<<<nb, 32, epwt_smem, s>>>(E);
       c->launches++;
-    } else if (n <= TAIL_MAX_POINTS) {  // all remaining levels in one launch, one CTA per image
+      if (same_paths && c->levels > 1) {
+        k_same_paths<<<nb, 1024, 0, s>>>(c->Q.as<int32_t>() + (size_t)a * 2 * N, c->Pm.as<int32_t>() + (size_t)a * 2 * N, N,
+                                         c->levels);
+        c->launches++;
+      }
+    } else if (n <= TAIL_MAX_POINTS && (c->mode != RBEPWT_PATH_EPWT || same_paths)) {  // all remaining levels in one launch, one CTA per image
       StageTimer t(c, RBEPWT_T_DWT, s);
       k3_dwt_tail<<<nb, DWT_THREADS, 0, s>>>(D);
       c->launches++;
@@ -459,7 +471,7 @@ int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
       dim3 grid(((n >> 1) + FWD_TILE - 1) / FWD_TILE, nb);
       k3_dwt_level<<<grid, DWT_THREADS, 0, s>>>(D);
       c->launches++;
-      if (c->mode == RBEPWT_PATH_EPWT && lev < c->levels) {
+      if (c->mode == RBEPWT_PATH_EPWT && lev < c->levels && !same_paths) {
         k_plane_to_pixels<<<dim3(((n >> 1) + 255) / 256, nb), 256, 0, s>>>(V[lev & 1], D.Q, N, lev, sl.Vpix.as<double>());
         c->launches++;
       }

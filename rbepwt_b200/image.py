@@ -223,8 +223,6 @@ class Rbepwt:
             raise Exception("2^levels must be smaller or equal to the number of pixels in the image")
         if type(img).__name__ != "Image":  # rbepwt.py:1979-1980
             raise Exception("First argument must be an Image instance")
-        if paths_first_level:
-            raise NotImplementedError("paths_first_level=True (same_path at levels >= 2) is not on the B200 hot path yet")
         self.img = img
         self.levels = levels
         self.has_encoding = False
@@ -248,7 +246,8 @@ class Rbepwt:
             img.segment()
         labels = None if self.path_type == "epwt-easypath" else img.label_img
         self._codec = BatchCodec()
-        self._codec.encode(img.img, labels, self.levels, self.wavelet, self.path_type, euclidean_distance)
+        self._codec.encode(img.img, labels, self.levels, self.wavelet, self.path_type, euclidean_distance,
+                           paths_first_level=self.paths_first_level)
         self._details = self._flat = self._approx = None
         self.region_collection_at_level = _LevelDict(self)
         self.has_encoding = True

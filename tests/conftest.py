@@ -29,6 +29,7 @@ def load_golden(name):
     for k in ("wavelet", "path_type"):
         g[k] = str(g[k])
     g["euclidean_distance"] = bool(g["euclidean_distance"])
+    g["paths_first_level"] = bool(g["paths_first_level"]) if "paths_first_level" in g else False
     g["psnr"] = float(g["psnr"])
     if g["labels"].size == 0:
         g["labels"] = None

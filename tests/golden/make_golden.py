@@ -62,6 +62,12 @@ def cases(big):
     lab = synth.voronoi_labels(128, 128, 96, seed=9)
     c.append(("vor128_euclid_bior44", synth.piecewise_smooth_image(lab, seed=9), lab, 14, "bior4.4", "easypath", True, 512))
     c.append(("epwt128_smooth_bior44", synth.smooth_field_image(128, 128, seed=10, sigma=4.0), None, 14, "bior4.4", "epwt-easypath", True, 512))
+    # paths_first_level=True: Region.same_path (identity permutation) at every level >= 2 (rbepwt.py:1183-1188, 2024-2025)
+    lab = synth.voronoi_labels(32, 32, 17, seed=11)
+    img = synth.piecewise_smooth_image(lab, seed=11)
+    c.append(("pfl32_euclid_bior44", img, lab, 10, "bior4.4", "easypath", True, 40, True))
+    c.append(("pfl32_cheb_haar", img, noise_labels(32, 32, 6, 12), 10, "haar", "easypath", False, 40, True))
+    c.append(("pfl32_epwt_db2", synth.smooth_field_image(32, 32, seed=13, sigma=2.0), None, 10, "db2", "epwt-easypath", True, 40, True))
     if big:
         img, lab = synth.config_inputs("cameraman256")  # BASELINE.json configs[0]
         c.append(("config1_cameraman256", img, lab, 16, "bior4.4", "easypath", True, 512))
@@ -74,20 +80,22 @@ def main():
     ap.add_argument("--big", action="store_true")
     ap.add_argument("--force", action="store_true")
     args = ap.parse_args()
-    for name, img, lab, levels, wav, ptype, euclid, k in cases(args.big):
+    for case in cases(args.big):
+        name, img, lab, levels, wav, ptype, euclid, k = case[:8]
+        pfl = bool(case[8]) if len(case) > 8 else False
         if args.only and name not in args.only:
             continue
         path = os.path.join(HERE, name + ".npz")
         if os.path.exists(path) and not args.force:
             continue
         t0 = time.perf_counter()
-        out = ref_harness.run_reference(img, lab, levels, wav, ptype, euclid, ncoefs=k)
+        out = ref_harness.run_reference(img, lab, levels, wav, ptype, euclid, ncoefs=k, paths_first_level=pfl)
         dt = time.perf_counter() - t0
         np.savez_compressed(
             path,
             img=img,
             labels=(lab if lab is not None else np.zeros((0, 0), np.int32)),
-            levels=levels, wavelet=wav, path_type=ptype, euclidean_distance=euclid, ncoefs=k,
+            levels=levels, wavelet=wav, path_type=ptype, euclidean_distance=euclid, ncoefs=k, paths_first_level=pfl,
             perm=np.concatenate([out["perm"][l] for l in range(1, levels + 1)]).astype(np.int32),
             roff=np.stack([out["roff"][l] for l in range(1, levels + 2)]).astype(np.int32),
             points=np.concatenate([out["points"][l] for l in range(1, levels + 2)]).astype(np.int16),

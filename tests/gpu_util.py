@@ -4,14 +4,14 @@ import numpy as np
 
 
 def cuda_run(img, labels, levels, wavelet, path_type="easypath", euclidean_distance=True, ncoefs=None,
-             with_perm=True):
+             with_perm=True, paths_first_level=False):
     import rbepwt_b200 as rb
 
     img = np.asarray(img)
     H, W = img.shape
     c = rb.BatchCodec()
     c.encode(img[None], None if labels is None else np.asarray(labels)[None], levels, wavelet, path_type,
-             euclidean_distance)
+             euclidean_distance, paths_first_level=paths_first_level)
     out = {"perm": {}, "roff": {}, "points": {}, "codec": c}
     for lev in range(1, levels + 2):
         out["roff"][lev] = c.region_offsets(0, lev)

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 def test_cuda_reproduces_reference_golden(name):
     g = load_golden(name)
     out = cuda_run(g["img"], g["labels"], g["levels"], g["wavelet"], g["path_type"], g["euclidean_distance"],
-                   ncoefs=g["ncoefs"])
+                   ncoefs=g["ncoefs"], paths_first_level=g["paths_first_level"])
     assert_matches_golden(out, g)
 
 
@@ -269,3 +269,30 @@ def test_region_arrays_grow_across_sub_batches():
     assert np.max(np.abs(dec - imgs)) < 1e-9 * 255
     for b in range(3):  # every region is one pixel: level-1 path order == order of first appearance == row-major
         np.testing.assert_array_equal(c.paths(b, 1), np.arange(128 * 128))
+
+
+def test_paths_first_level_512_vs_oracle_and_facade():
+    """paths_first_level=True (Region.same_path at levels >= 2) at full size, batch and facade."""
+    from rbepwt_b200 import synth
+    from oracle import c_oracle
+    import rbepwt_b200 as rb
+
+    img, lab = synth.config_inputs("synthetic512", seed=31)
+    out = cuda_run(img, lab, 16, "bior4.4", ncoefs=2048, paths_first_level=True)
+    orc = c_oracle.run(img, lab, 16, rb.filter_bank("bior4.4"), "easypath", True, ncoefs=2048, paths_first_level=True)
+    assert_same_as_oracle(out, orc, 16)
+    for lev in (2, 5, 16):  # identity permutation inside every region
+        off = out["roff"][lev]
+        want = np.concatenate([np.arange(off[r + 1] - off[r]) for r in range(len(off) - 1)]) if len(off) > 1 else []
+        np.testing.assert_array_equal(out["perm"][lev], want)
+    im = rb.Image()
+    im.read_array(img)
+    im.set_labels(lab)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        im.encode_rbepwt(16, "bior4.4", paths_first_level=True)
+        im.threshold_coefs(2048)
+        im.decode_rbepwt()
+    np.testing.assert_array_equal(im.decoded_img, out["decoded"])
+    got = rb.BatchCodec().transcode(img[None], lab[None], 16, "bior4.4", 2048, paths_first_level=True)
+    np.testing.assert_array_equal(got[0], out["decoded"])

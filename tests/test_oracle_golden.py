@@ -11,7 +11,7 @@ from oracle import c_oracle
 def test_c_oracle_reproduces_reference(name):
     g = load_golden(name)
     out = c_oracle.run(g["img"], g["labels"], g["levels"], g["wavelet"], g["path_type"],
-                       g["euclidean_distance"], ncoefs=g["ncoefs"])
+                       g["euclidean_distance"], ncoefs=g["ncoefs"], paths_first_level=g["paths_first_level"])
     assert_matches_golden(out, g)
 
 
