@@ -296,3 +296,45 @@ def test_paths_first_level_512_vs_oracle_and_facade():
     np.testing.assert_array_equal(im.decoded_img, out["decoded"])
     got = rb.BatchCodec().transcode(img[None], lab[None], 16, "bior4.4", 2048, paths_first_level=True)
     np.testing.assert_array_equal(got[0], out["decoded"])
+
+
+def test_fuzz_random_small_cases_vs_oracle():
+    """80 random small cases over every switch of the path: shape (H != W too), label structure (blobs, noise,
+    stripes, few/many labels, arbitrary label values), path mode, paths_first_level, wavelet, levels, k."""
+    from rbepwt_b200 import synth
+    from oracle import c_oracle
+    import rbepwt_b200 as rb
+
+    rng = np.random.default_rng(2024)
+    wavelets = ["haar", "db2", "db3", "db4", "db7", "bior4.4", "bior2.2", "rbio3.1"]
+    for case in range(80):
+        lh, lw = int(rng.integers(0, 7)), int(rng.integers(0, 7))
+        if lh + lw < 2:
+            lw = 2 - lh
+        H, W = 1 << lh, 1 << lw
+        N = H * W
+        levels = int(rng.integers(1, lh + lw + 1))
+        kind = int(rng.integers(0, 4))
+        if kind == 0 and min(H, W) >= 8:
+            lab = synth.voronoi_labels(H, W, int(rng.integers(1, max(2, N // 24))), seed=case)
+        elif kind == 1:
+            lab = rng.integers(0, int(rng.integers(1, 9)), size=(H, W)).astype(np.int32)
+        elif kind == 2:
+            lab = ((np.arange(H)[:, None] // int(rng.integers(1, 4))) * 3 + (np.arange(W)[None, :] // int(rng.integers(1, 5)))).astype(np.int32)
+        else:
+            lab = rng.integers(-5, N, size=(H, W)).astype(np.int32)
+        lab = (lab.astype(np.int64) * int(rng.choice([1, 7, -3, 100003])) + int(rng.integers(-50, 50))).astype(np.int32)
+        img = rng.uniform(0, 255, size=(H, W))
+        mode = int(rng.integers(0, 3))
+        ptype, euclid = ("easypath", True) if mode == 0 else ("easypath", False) if mode == 1 else ("epwt-easypath", True)
+        pfl = bool(rng.integers(0, 2))
+        wav = wavelets[int(rng.integers(0, len(wavelets)))]
+        k = int(rng.integers(0, N + 2))
+        labs = None if mode == 2 else lab
+        try:
+            out = cuda_run(img, labs, levels, wav, ptype, euclid, ncoefs=k, paths_first_level=pfl)
+            orc = c_oracle.run(img, labs, levels, rb.filter_bank(wav), ptype, euclid, ncoefs=k, paths_first_level=pfl)
+            assert_same_as_oracle(out, orc, levels)
+        except AssertionError as e:
+            raise AssertionError("fuzz case %d: %dx%d L=%d kind=%d mode=%d pfl=%s wav=%s k=%d: %s"
+                                 % (case, H, W, levels, kind, mode, pfl, wav, k, e))
