@@ -281,7 +281,7 @@ int stage_labels(rbepwt_ctx *c, int chunk0, int a, int nb, const int32_t *lab_ho
     }
     StageTimer t(c, RBEPWT_T_REGIONS, s);
     const int T = 2 * c->N;
-    k0_count<<<nb, K0_THREADS, 0, s>>>(c->labels_dev, a, c->N, c->tbl.as<unsigned long long>() + (size_t)(a - chunk0) * T, T,
+    k0_count<<<nb * K0_CLUSTER, K0_THREADS, 0, s>>>(c->labels_dev, a, c->N, c->tbl.as<unsigned long long>() + (size_t)(a - chunk0) * T, T,
                                        c->img_R.as<int32_t>(), c->img_labmin.as<int32_t>(), c->img_direct.as<int32_t>());
     c->launches++;
     CK(cudaGetLastError());
@@ -340,7 +340,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
                                                     c->tbl.as<unsigned long long>() + (size_t)(a - chunk0) * T, T,
                                                     c->img_R.as<int32_t>(), c->img_labmin.as<int32_t>(),
                                                     c->img_direct.as<int32_t>(), c->img_rbase.as<int32_t>(), c->regs());
-    k0_regions<<<nb, K0_THREADS, 0, s>>>(c->labels_dev, a, N, c->logW,
+    k0_regions<<<nb * K0_CLUSTER, K0_THREADS, 0, s>>>(c->labels_dev, a, N, c->logW,
                                          c->tbl.as<unsigned long long>() + (size_t)(a - chunk0) * T,
                                          c->slot_rid.as<int32_t>() + (size_t)(a - chunk0) * T, T, c->img_R.as<int32_t>(),
                                          c->img_labmin.as<int32_t>(), c->img_direct.as<int32_t>(),

@@ -10,9 +10,13 @@
 // pixel, addressed directly (label - min) when the label range fits the table, else by open
 // addressing.  Only the used part of the table is cleared.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace rbepwt {
+
+namespace cg = cooperative_groups;
 
 constexpr unsigned long long TBL_EMPTY = ~0ull;
 constexpr int K0_THREADS = 1024;
@@ -46,33 +50,58 @@ __device__ __forceinline__ uint32_t tbl_lookup(const unsigned long long *tbl, ui
 }
 
 // Pass 1: per image, label -> first pixel table and the region count R.
-__global__ void __launch_bounds__(K0_THREADS) k0_count(const int32_t *__restrict__ labels, int img0, int N,
-                                                       unsigned long long *tbl_all, int T, int32_t *img_R,
-                                                       int32_t *img_labmin, int32_t *img_direct) {
+// One thread-block CLUSTER of K0_CLUSTER CTAs per image: every CTA owns a contiguous slice of the pixels, the
+// phases (min/max -> clear the table -> insert run heads -> count) are separated by cluster barriers, and the
+// per-CTA partial results are combined through distributed shared memory.
+constexpr int K0_CLUSTER = 8;
+
+__device__ __forceinline__ void k0_slice(int N, int rank, int &lo, int &hi) {
+  const int per = (((N + K0_CLUSTER - 1) / K0_CLUSTER) + 31) & ~31;  // warp-aligned slices
+  lo = min(N, rank * per);
+  hi = min(N, lo + per);
+}
+
+__global__ void __cluster_dims__(K0_CLUSTER, 1, 1) __launch_bounds__(K0_THREADS)
+    k0_count(const int32_t *__restrict__ labels, int img0, int N, unsigned long long *tbl_all, int T, int32_t *img_R,
+             int32_t *img_labmin, int32_t *img_direct) {
   __shared__ int s_red[33];
+  __shared__ int s_mm[2];
+  __shared__ int s_cnt;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int img = img0 + blockIdx.x;
+  const int li = blockIdx.x / K0_CLUSTER, img = img0 + li;
   const int32_t *lab = labels + (size_t)img * N;
-  unsigned long long *tbl = tbl_all + (size_t)blockIdx.x * T;
+  unsigned long long *tbl = tbl_all + (size_t)li * T;
   const uint32_t tmask = (uint32_t)T - 1u;
+  int lo, hi;
+  k0_slice(N, rank, lo, hi);
 
   int lmin = INT32_MAX, lmax = INT32_MIN;
-  for (int p = tid; p < N; p += nt) {
-    int v = lab[p];
+  for (int p = lo + tid; p < hi; p += nt) {
+    const int v = lab[p];
     lmin = min(lmin, v);
     lmax = max(lmax, v);
   }
   lmin = block_reduce(lmin, s_red, OpMin(), INT32_MAX);
   lmax = block_reduce(lmax, s_red, OpMax(), INT32_MIN);
+  if (tid == 0) { s_mm[0] = lmin; s_mm[1] = lmax; }
+  cluster.sync();
+  for (int r = 0; r < K0_CLUSTER; r++) {
+    const int *mm = cluster.map_shared_rank(s_mm, r);
+    lmin = min(lmin, mm[0]);
+    lmax = max(lmax, mm[1]);
+  }
   const long long range = (long long)lmax - (long long)lmin + 1;
   const int direct = range <= (long long)T;
   const int used = direct ? (int)range : T;
-  for (int s = tid; s < used; s += nt) tbl[s] = TBL_EMPTY;
-  __syncthreads();
+  for (int s = rank * nt + tid; s < used; s += K0_CLUSTER * nt) tbl[s] = TBL_EMPTY;
+  __threadfence();
+  cluster.sync();
 
-  for (int base = 0; base < N; base += nt) {
+  for (int base = lo; base < hi; base += nt) {
     const int p = base + tid;
-    const bool valid = p < N;
+    const bool valid = p < hi;
     const int v = valid ? lab[p] : 0;
     const int prev = __shfl_up_sync(FULL_MASK, v, 1);
     // run heads only: a lane whose left neighbour has the same label can never be the first pixel
@@ -97,15 +126,22 @@ __global__ void __launch_bounds__(K0_THREADS) k0_count(const int32_t *__restrict
       }
     }
   }
-  __syncthreads();
+  __threadfence();
+  cluster.sync();
+
   int cnt = 0;
-  for (int s = tid; s < used; s += nt) cnt += tbl[s] != TBL_EMPTY;
+  for (int s = rank * nt + tid; s < used; s += K0_CLUSTER * nt) cnt += __ldcg(&tbl[s]) != TBL_EMPTY;
   cnt = block_reduce(cnt, s_red, OpSum(), 0);
-  if (tid == 0) {
-    img_R[img] = cnt;
+  if (tid == 0) s_cnt = cnt;
+  cluster.sync();
+  if (rank == 0 && tid == 0) {
+    int total = 0;
+    for (int r = 0; r < K0_CLUSTER; r++) total += *cluster.map_shared_rank(&s_cnt, r);
+    img_R[img] = total;
     img_labmin[img] = lmin;
     img_direct[img] = direct ? used : 0;  // slots of the direct table (>= 1), 0 = open addressing
   }
+  cluster.sync();  // s_cnt stays readable until rank 0 has summed it
 }
 
 // Pass 2, common case (dense label values, at most K0F_MAXR regions, rows a multiple of 8 pixels): the label
@@ -214,42 +250,70 @@ __global__ void __launch_bounds__(K0_THREADS) k0_regions_fast(const int32_t *__r
   }
 }
 
-// Pass 2, general case (any int32 labels, any region count).  rbase[img] = index of the image's region 0 in the
-// global region arrays.
-__global__ void __launch_bounds__(K0_THREADS) k0_regions(const int32_t *__restrict__ labels, int img0, int N,
-                                                         int logW, const unsigned long long *tbl_all,
-                                                         int32_t *slot_rid_all, int T, const int32_t *img_R,
-                                                         const int32_t *img_labmin, const int32_t *img_direct,
-                                                         const int32_t *img_rbase, RegionArrays reg) {
+// Pass 2, general case (any int32 labels, any region count), one cluster of K0_CLUSTER CTAs per image like
+// k0_count.  rbase[img] = index of the image's region 0 in the global region arrays.
+//   A1 every CTA counts the first-appearance pixels of its slice; A2 ranks them after the cluster prefix;
+//   B  sizes and bounding boxes (warp-aggregated atomics);  C  level-1 offsets (rank 0).
+__device__ __forceinline__ bool k0_is_first(const unsigned long long *tbl, uint32_t tmask, int direct, int labmin,
+                                            const int32_t *lab, int p, int v, int prev_in_warp, uint32_t &slot) {
+  const int prev = lane_id() == 0 ? (p > 0 ? lab[p - 1] : ~v) : prev_in_warp;
+  if (prev == v) return false;  // not a run head: cannot be the label's first pixel
+  slot = tbl_lookup(tbl, tmask, direct, labmin, v);
+  return (uint32_t)__ldcg(&tbl[slot]) == (uint32_t)p;
+}
+
+__global__ void __cluster_dims__(K0_CLUSTER, 1, 1) __launch_bounds__(K0_THREADS)
+    k0_regions(const int32_t *__restrict__ labels, int img0, int N, int logW, const unsigned long long *tbl_all,
+               int32_t *slot_rid_all, int T, const int32_t *img_R, const int32_t *img_labmin, const int32_t *img_direct,
+               const int32_t *img_rbase, RegionArrays reg) {
   __shared__ int s_scan[33];
-  __shared__ int s_running;
+  __shared__ int s_running, s_cnt;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int img = img0 + blockIdx.x;
+  const int li = blockIdx.x / K0_CLUSTER, img = img0 + li;
   const int32_t *lab = labels + (size_t)img * N;
-  const unsigned long long *tbl = tbl_all + (size_t)blockIdx.x * T;
-  int32_t *slot_rid = slot_rid_all + (size_t)blockIdx.x * T;
+  const unsigned long long *tbl = tbl_all + (size_t)li * T;
+  int32_t *slot_rid = slot_rid_all + (size_t)li * T;
   const uint32_t tmask = (uint32_t)T - 1u;
   const int W = 1 << logW;
   const int labmin = img_labmin[img], direct = img_direct[img], R = img_R[img], rb = img_rbase[img];
-  if (k0_fast_eligible(direct, R, logW)) return;  // k0_regions_fast handles this image
+  if (k0_fast_eligible(direct, R, logW)) return;  // k0_regions_fast handles this image (uniform over the cluster)
+  int lo, hi;
+  k0_slice(N, rank, lo, hi);
 
-  // A: rank the first-appearance pixels in row-major order -> region ids
-  if (tid == 0) s_running = 0;
-  __syncthreads();
-  for (int base = 0; base < N; base += nt) {
+  // A1: first-appearance pixels in this slice
+  int cnt = 0;
+  for (int base = lo; base < hi; base += nt) {
     const int p = base + tid;
-    const bool valid = p < N;
+    const bool valid = p < hi;
     const int v = valid ? lab[p] : 0;
+    const int prev = __shfl_up_sync(FULL_MASK, v, 1);
+    uint32_t slot;
+    cnt += valid && k0_is_first(tbl, tmask, direct, labmin, lab, p, v, prev, slot);
+  }
+  cnt = block_reduce(cnt, s_scan, OpSum(), 0);
+  if (tid == 0) s_cnt = cnt;
+  cluster.sync();
+  if (tid == 0) {
+    int before = 0;
+    for (int r = 0; r < rank; r++) before += *cluster.map_shared_rank(&s_cnt, r);
+    s_running = before;
+  }
+  __syncthreads();
+
+  // A2: rank them in row-major order -> region ids
+  for (int base = lo; base < hi; base += nt) {
+    const int p = base + tid;
+    const bool valid = p < hi;
+    const int v = valid ? lab[p] : 0;
+    const int prev = __shfl_up_sync(FULL_MASK, v, 1);
     uint32_t slot = 0;
-    bool flag = false;
-    if (valid) {
-      slot = tbl_lookup(tbl, tmask, direct, labmin, v);
-      flag = (uint32_t)tbl[slot] == (uint32_t)p;
-    }
+    const bool flag = valid && k0_is_first(tbl, tmask, direct, labmin, lab, p, v, prev, slot);
     int total;
-    const int rank = s_running + block_exclusive_scan(flag ? 1 : 0, s_scan, &total);
+    const int rnk = s_running + block_exclusive_scan(flag ? 1 : 0, s_scan, &total);
     if (flag) {
-      const int g = rb + rank;
+      const int g = rb + rnk;
       reg.label[g] = v;
       reg.first[g] = p;
       reg.img[g] = img;
@@ -257,21 +321,21 @@ __global__ void __launch_bounds__(K0_THREADS) k0_regions(const int32_t *__restri
       reg.rmax[g] = 0;
       reg.cmin[g] = W;
       reg.cmax[g] = 0;
-      slot_rid[slot] = rank;
+      slot_rid[slot] = rnk;
     }
     __syncthreads();
     if (tid == 0) s_running += total;
     __syncthreads();
   }
-  __threadfence_block();
-  __syncthreads();
+  __threadfence();
+  cluster.sync();
 
   // B: sizes and bounding boxes (warp-aggregated atomics)
-  for (int base = 0; base < N; base += nt) {
+  for (int base = lo; base < hi; base += nt) {
     const int p = base + tid;
-    const bool valid = p < N;
+    const bool valid = p < hi;
     int rid = -1;
-    if (valid) rid = slot_rid[tbl_lookup(tbl, tmask, direct, labmin, lab[p])];
+    if (valid) rid = __ldcg(&slot_rid[tbl_lookup(tbl, tmask, direct, labmin, lab[p])]);
     const unsigned grp = __match_any_sync(FULL_MASK, rid);
     if (valid) {
       const int row = p >> logW, col = p & (W - 1);
@@ -286,15 +350,16 @@ __global__ void __launch_bounds__(K0_THREADS) k0_regions(const int32_t *__restri
       }
     }
   }
-  __threadfence_block();
-  __syncthreads();
+  __threadfence();
+  cluster.sync();
+  if (rank != 0) return;
 
   // C: level-1 offsets = exclusive scan of the sizes in region order
   if (tid == 0) s_running = 0;
   __syncthreads();
   for (int base = 0; base < R; base += nt) {
     const int r = base + tid;
-    const int sz = r < R ? reg.size[rb + r] : 0;
+    const int sz = r < R ? __ldcg(&reg.size[rb + r]) : 0;
     int total;
     const int ex = s_running + block_exclusive_scan(sz, s_scan, &total);
     if (r < R) reg.off[rb + r] = ex;
