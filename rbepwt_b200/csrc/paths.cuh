@@ -59,6 +59,7 @@ struct PathParams {
 
 struct Best {
   double dist;  // integer-valued in the geometric modes
+  double val;   // EPWT: the candidate's value (becomes the current value of the next step)
   double sp1;
   int cross, d2, i, j;
   bool have, has_sp1;
@@ -78,20 +79,21 @@ __device__ __forceinline__ void consider(Best &b, int i, int j, int ci, int cj, 
                                          const double *__restrict__ vals, int pix, bool u8wrap) {
   const int di = i - ci, dj = j - cj;
   const int d2 = di * di + dj * dj;
-  double dist;
+  double dist, val = 0.0;
   if (MODE == MODE_EUCLID) {
     dist = (double)d2;
   } else if (MODE == MODE_CHEB) {
     dist = (double)max(abs(di), abs(dj));
   } else {
-    const double dv = curval - __ldcg(vals + pix);
+    val = __ldcg(vals + pix);
+    const double dv = curval - val;
     dist = u8wrap ? (dv < 0.0 ? dv + 256.0 : dv) : fabs(dv);
   }
   if (b.have && dist > b.dist) return;
   const int cross = di * p1 - dj * p0;
   if (!b.have || dist < b.dist) {
     b.have = true; b.has_sp1 = false;
-    b.dist = dist; b.cross = cross; b.d2 = d2; b.i = i; b.j = j;
+    b.dist = dist; b.val = val; b.cross = cross; b.d2 = d2; b.i = i; b.j = j;
     return;
   }
   // equal dist: direction tie-break
@@ -104,21 +106,33 @@ __device__ __forceinline__ void consider(Best &b, int i, int j, int ci, int cj, 
   if (sp1 != b.sp1) better = sp1 > b.sp1;
   else if (cross != b.cross) better = cross > b.cross;
   else better = d2 < b.d2;
-  if (better) { b.sp1 = sp1; b.cross = cross; b.d2 = d2; b.i = i; b.j = j; }
+  if (better) { b.sp1 = sp1; b.val = val; b.cross = cross; b.d2 = d2; b.i = i; b.j = j; }
 }
 
 // Warp-cooperative search for the next path point.  bm: h x ws words, bit (i,j) set <=> unvisited.
 // Returns false if no unvisited point exists in the whole bounding box (corrupt state).
+// curval (EPWT): in = value at the current point, out = value at the chosen point.
 template <int MODE>
 __device__ __forceinline__ bool find_next(const uint32_t *bm, int h, int w, int ws, int ci, int cj, int p0, int p1,
                                           const double *__restrict__ vals, int r0, int c0, int logW, bool u8wrap,
-                                          int &bi, int &bj) {
+                                          double &curval, int &bi, int &bj) {
   const int lane = (int)lane_id();
   Best b;
-  b.have = false; b.has_sp1 = false; b.dist = 0.0; b.sp1 = 0.0; b.cross = 0; b.d2 = 0; b.i = 0; b.j = 0;
-  double curval = 0.0;
-  if (MODE == MODE_EPWT) curval = __ldcg(vals + (((r0 + ci) << logW) + c0 + cj));
-  for (int rad = 1;; rad <<= 1) {  // half-width 2^(k-1), k = 1,2,...   rbepwt.py:1296-1299, 90-92
+  b.have = false; b.has_sp1 = false; b.dist = 0.0; b.val = 0.0; b.sp1 = 0.0; b.cross = 0; b.d2 = 0; b.i = 0; b.j = 0;
+  int rad0 = 1;
+  if (MODE == MODE_EPWT) {
+    // half-width 1, the common case of the one-region walk: one LANE per neighbour, so the eight value
+    // loads (L2 latency each) are in flight together instead of one after the other inside a lane
+    const int i = ci + lane / 3 - 1, j = cj + lane % 3 - 1;
+    const bool cand = lane < 9 && lane != 4 && i >= 0 && i < h && j >= 0 && j < w && ((bm[i * ws + (j >> 5)] >> (j & 31)) & 1u);
+    if (__any_sync(FULL_MASK, cand)) {
+      if (cand) consider<MODE>(b, i, j, ci, cj, p0, p1, curval, vals, ((r0 + i) << logW) + c0 + j, u8wrap);
+      rad0 = 0;  // found: skip the window loop
+    } else {
+      rad0 = 2;
+    }
+  }
+  for (int rad = rad0; rad > 0; rad <<= 1) {  // half-width 2^(k-1), k = 1,2,...   rbepwt.py:1296-1299, 90-92
     const int i0 = max(ci - rad, 0), i1 = min(ci + rad, h - 1);
     const int j0 = max(cj - rad, 0), j1 = min(cj + rad, w - 1);
     const int w0 = j0 >> 5, w1 = j1 >> 5;
@@ -173,6 +187,7 @@ __device__ __forceinline__ bool find_next(const uint32_t *bm, int h, int w, int 
   const int src = __ffs(tied) - 1;
   bi = __shfl_sync(FULL_MASK, b.i, src);
   bj = __shfl_sync(FULL_MASK, b.j, src);
+  if (MODE == MODE_EPWT) curval = __shfl_sync(FULL_MASK, b.val, src);
   return true;
 }
 
@@ -190,9 +205,11 @@ __device__ __forceinline__ bool run_path(uint32_t *bm, int h, int w, int ws, int
   }
   __syncwarp();
   int p0 = 0, p1 = 1;  // prefered_direc = (0,1)   rbepwt.py:1290
+  double curval = 0.0;
+  if (MODE == MODE_EPWT) curval = __ldcg(vals + (((r0 + ci) << logW) + c0 + cj));
   for (int t = 1; t < n; t++) {
     int bi, bj;
-    if (!find_next<MODE>(bm, h, w, ws, ci, cj, p0, p1, vals, r0, c0, logW, u8wrap, bi, bj)) return false;
+    if (!find_next<MODE>(bm, h, w, ws, ci, cj, p0, p1, vals, r0, c0, logW, u8wrap, curval, bi, bj)) return false;
     if (lane == 0) bm[bi * ws + (bj >> 5)] &= ~(1u << (bj & 31));
     __syncwarp();
     if ((t & 31) == lane) myq = ((r0 + bi) << logW) + c0 + bj;
