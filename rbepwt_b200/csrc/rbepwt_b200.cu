@@ -574,7 +574,27 @@ int run_pipeline(rbepwt_ctx *c, int what, long long k, const double *img_host, c
     const int nbc = std::min(Bc, B - c0);
     const int Bs = sub_images(c, nbc, N);
     const int Bp = group_images(c, nbc, N, Bs);
-    const int nsub = (nbc + Bs - 1) / Bs, ngrp = (nbc + Bp - 1) / Bp;
+    const int nsub = (nbc + Bs - 1) / Bs;
+    // Path groups as [start, end) in sub-batches.  With host inputs the groups ramp up (1, 1, 2, 4, ...
+    // sub-batches up to the full group): the first decoded images leave for the host while most labels are
+    // still arriving, which is what lets the output copy overlap the input copy.
+    std::vector<int> gstart;
+    {
+      const int full = Bp / Bs;
+      int len = (lab_host && c->group_images == 0 && !serial) ? 1 : full, first = 1;
+      for (int s = 0; s < nsub;) {
+        gstart.push_back(s);
+        s += std::min(len, full);
+        if (len < full) { if (!first) len *= 2; first = 0; }
+      }
+      gstart.push_back(nsub);
+    }
+    const int ngrp = (int)gstart.size() - 1;
+    std::vector<int> group_of(nsub);
+    for (int g = 0; g < ngrp; g++)
+      for (int s = gstart[g]; s < gstart[g + 1]; s++) group_of[s] = g;
+    auto grp_a = [&](int g) { return c0 + gstart[g] * Bs; };
+    auto grp_nb = [&](int g) { return std::min(c0 + nbc, c0 + gstart[g + 1] * Bs) - grp_a(g); };
     if ((rc = need_events(c->ev_lab, ngrp)) || (rc = need_events(c->ev_path, ngrp)) || (rc = need_events(c->ev_img, nsub)) ||
         (rc = need_events(c->ev_done, nsub)))
       return rc;
@@ -584,10 +604,8 @@ int run_pipeline(rbepwt_ctx *c, int what, long long k, const double *img_host, c
     }
     if ((rc = fork_streams(c))) return rc;
     if (what & DO_PATHS)
-      for (int g = 0; g < ngrp; g++) {
-        const int a = c0 + g * Bp, nb = std::min(Bp, c0 + nbc - a);
-        if ((rc = stage_labels(c, c0, a, nb, lab_host, c->ev_lab[g]))) return rc;
-      }
+      for (int g = 0; g < ngrp; g++)
+        if ((rc = stage_labels(c, c0, grp_a(g), grp_nb(g), lab_host, c->ev_lab[g]))) return rc;
     if ((what & DO_DWT) && img_host)
       for (int s = 0; s < nsub; s++) {
         const int a = c0 + s * Bs, nb = std::min(Bs, c0 + nbc - a);
@@ -595,10 +613,9 @@ int run_pipeline(rbepwt_ctx *c, int what, long long k, const double *img_host, c
       }
     if (what & DO_PATHS)
       for (int g = 0; g < ngrp; g++) {
-        const int a = c0 + g * Bp, nb = std::min(Bp, c0 + nbc - a);
         Slot &sl = c->slot[g % c->nslot];
         cudaStream_t st = serial ? c->slot[0].s : sl.s;
-        if ((rc = build_regions_and_paths(c, sl, st, c0, a, nb, c->ev_lab[g]))) return rc;
+        if ((rc = build_regions_and_paths(c, sl, st, c0, grp_a(g), grp_nb(g), c->ev_lab[g]))) return rc;
         CK(cudaEventRecord(c->ev_path[g], st));
       }
     if (what & (DO_DWT | DO_THRESH | DO_DECODE))
@@ -606,7 +623,7 @@ int run_pipeline(rbepwt_ctx *c, int what, long long k, const double *img_host, c
         const int a = c0 + s * Bs, nb = std::min(Bs, c0 + nbc - a);
         Slot &sl = c->slot[NSLOT + s % c->nslot];
         cudaStream_t st = serial ? c->slot[0].s : sl.s;
-        if (what & DO_PATHS) CK(cudaStreamWaitEvent(st, c->ev_path[(a - c0) / Bp], 0));
+        if (what & DO_PATHS) CK(cudaStreamWaitEvent(st, c->ev_path[group_of[s]], 0));
         if ((what & DO_DWT) && img_host) CK(cudaStreamWaitEvent(st, c->ev_img[s], 0));
         if (what & DO_DWT)
           if ((rc = transform_sub(c, sl, st, a, nb))) return rc;
