@@ -83,7 +83,6 @@ constexpr int TPR_WAVES = 8;  // k1_paths_tpr grid = this many waves of resident
 struct Slot {
   cudaStream_t s = nullptr;
   DevBuf VA, VB, Vpix, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch;
-  cudaEvent_t done = nullptr;
 };
 
 struct rbepwt_ctx {
@@ -96,8 +95,8 @@ struct rbepwt_ctx {
   cudaStream_t s_in = nullptr, s_out = nullptr;
   Slot slot[2 * NSLOT];   // [0, NSLOT): path groups, [NSLOT, 2 NSLOT): transform sub-batches
   int nslot = NSLOT;      // RBEPWT_OPT_STREAMS
-  int sub_images = 0;     // RBEPWT_OPT_SUBBATCH (0 = auto)
-  int group_images = 0;   // RBEPWT_OPT_PATHGROUP (0 = auto)
+  int opt_sub = 0;        // RBEPWT_OPT_SUBBATCH (0 = auto)
+  int opt_group = 0;      // RBEPWT_OPT_PATHGROUP (0 = auto)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<cudaEvent_t> ev_lab, ev_path, ev_img, ev_done;
   int32_t *pin_R = nullptr, *pin_rbase = nullptr;  // pinned staging, capacity pin_cap images
@@ -177,17 +176,17 @@ int chunk_images(const rbepwt_ctx *c, int B, int N) {
   return std::min(std::min(m, 1024), B);
 }
 
-// images per sub-batch: enough regions to fill the path kernel's persistent grid (about 2^24 pixels),
-// few enough that copies and kernels of neighbouring sub-batches overlap
+// images per transform sub-batch: about 2^24 pixels -- enough CTAs per launch to fill the GPU, few enough that
+// copies and kernels of neighbouring sub-batches overlap
 int sub_images(const rbepwt_ctx *c, int nb, int N) {
-  if (c->sub_images > 0) return std::min(c->sub_images, nb);
+  if (c->opt_sub > 0) return std::min(c->opt_sub, nb);
   const int m = (int)std::max<long long>(1, (1ll << 24) / N);
   return std::min(m, nb);
 }
 
 // images per path group: about 2^26 pixels (256 images of 512^2), a multiple of the sub-batch
 int group_images(const rbepwt_ctx *c, int nb, int N, int Bs) {
-  long long m = c->group_images > 0 ? c->group_images : std::max<long long>(1, (1ll << 26) / N);
+  long long m = c->opt_group > 0 ? c->opt_group : std::max<long long>(1, (1ll << 26) / N);
   m = std::max<long long>(Bs, m / Bs * Bs);
   return (int)std::min<long long>(m, (nb + Bs - 1) / Bs * Bs);
 }
@@ -581,7 +580,7 @@ int run_pipeline(rbepwt_ctx *c, int what, long long k, const double *img_host, c
     std::vector<int> gstart;
     {
       const int full = Bp / Bs;
-      int len = (lab_host && c->group_images == 0 && !serial) ? 1 : full, first = 1;
+      int len = (lab_host && c->opt_group == 0 && !serial) ? 1 : full, first = 1;
       for (int s = 0; s < nsub;) {
         gstart.push_back(s);
         s += std::min(len, full);
@@ -700,7 +699,6 @@ int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
   CK(cudaStreamCreateWithPriority(&c->s_out, cudaStreamNonBlocking, prio_hi));
   for (int i = 0; i < 2 * NSLOT; i++) {
     CK(cudaStreamCreateWithPriority(&c->slot[i].s, cudaStreamNonBlocking, i < NSLOT ? prio_lo : prio_hi));
-    CK(cudaEventCreateWithFlags(&c->slot[i].done, cudaEventDisableTiming));
   }
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -728,7 +726,6 @@ void rbepwt_destroy(rbepwt_ctx *c) {
     Slot &sl = c->slot[i];
     DevBuf *sb[] = {&sl.VA, &sl.VB, &sl.Vpix, &sl.queue, &sl.qhist, &sl.qmeta, &sl.qbins, &sl.chunk_start, &sl.chunk_cnt, &sl.gscratch};
     for (auto b : sb) b->release();
-    cudaEventDestroy(sl.done);
     cudaStreamDestroy(sl.s);
   }
   cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
@@ -756,11 +753,11 @@ int rbepwt_set_option(rbepwt_ctx *c, int option, int64_t value) {
       return RBEPWT_OK;
     case RBEPWT_OPT_SUBBATCH:
       if (value < 0 || value > (1 << 20)) return fail(RBEPWT_E_ARG, "RBEPWT_OPT_SUBBATCH out of range");
-      c->sub_images = (int)value;
+      c->opt_sub = (int)value;
       return RBEPWT_OK;
     case RBEPWT_OPT_PATHGROUP:
       if (value < 0 || value > (1 << 20)) return fail(RBEPWT_E_ARG, "RBEPWT_OPT_PATHGROUP out of range");
-      c->group_images = (int)value;
+      c->opt_group = (int)value;
       return RBEPWT_OK;
   }
   return fail(RBEPWT_E_ARG, "unknown option %d", option);
