@@ -62,10 +62,19 @@ __device__ __forceinline__ void dwt_tile(const DwtParams &P, FwdSmem &sm, int le
   double *coefs = P.coefs + img * (size_t)N;
   const int o0 = tile * FWD_TILE, nout = min(FWD_TILE, half - o0);
   const int tstart = 2 * o0 - F / 2 + 1, cnt = 2 * (nout - 1) + F;
-  for (int i = tid; i < cnt; i += nt) {
-    const int src = Pl[(tstart + i) & mask];
-    const double v = SAME_CTA ? __ldcg(vin + src) : vin[src];
-    if (i & 1) sm.o[i >> 1] = v; else sm.e[i >> 1] = v;
+  // gather, four independent index -> value chains in flight per thread
+  for (int i0 = tid; i0 < cnt; i0 += 4 * nt) {
+    int src[4];
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) src[u] = i0 + u * nt < cnt ? Pl[(tstart + i0 + u * nt) & mask] : 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = i0 + u * nt < cnt ? (SAME_CTA ? __ldcg(vin + src[u]) : vin[src[u]]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * nt;
+      if (i < cnt) { if (i & 1) sm.o[i >> 1] = v[u]; else sm.e[i >> 1] = v[u]; }
+    }
   }
   __syncthreads();
   const bool last = lev == P.levels;

@@ -200,7 +200,10 @@ __device__ unsigned long long g_tpr_stats[16 * 4 * 2 + 32];
 #endif
 constexpr int TPR_LIST_MAX = 32;   // list mode from the first level with at most this many points
 constexpr int TPR_SLOT_MIN = 48;   // arena words per lane: list buffers A = [0,32), B = [32,48) ping-pong
-constexpr int TPR_ROWS_PER_TRIP = 3;
+#ifndef TPR_ROWS_N
+#define TPR_ROWS_N 3
+#endif
+constexpr int TPR_ROWS_PER_TRIP = TPR_ROWS_N;
 #ifndef TPR_UNIT_STEPS_N
 #define TPR_UNIT_STEPS_N 2
 #endif
