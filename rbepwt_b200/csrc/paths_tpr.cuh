@@ -220,13 +220,19 @@ __device__ __forceinline__ uint32_t row_window(const uint32_t *row, int ws, int 
   return __funnelshift_r(lo, hi, s & 31);
 }
 
-template <int MODE>
+// WIDEWIN = true: the instantiation for the chunks of large bitmaps (queue classes below Q_FIRST_NARROW_CLS):
+// beyond half-width TPR_MAX_RAD it scans windows of half-width 16, 32, ... word by word instead of the whole
+// bitmap, which for a 10^4-pixel region is the difference between tens and thousands of words per far jump.
+// The common instantiation (small bitmaps) keeps the flat whole-bitmap scan and stays compact.
+template <int MODE, bool WIDEWIN>
 __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(PathParams P) {
   __shared__ uint32_t s_arena[TPR_WARPS][TPR_ARENA_WORDS];
   __shared__ uint8_t s_lut[TPR_LUT_ROWS * TPR_LUT_COLS];
   const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
   uint32_t *arena = s_arena[warp];
-  const int nchunks = P.qmeta[QM_NCHUNKS];
+  const int chunk_lo = WIDEWIN ? 0 : P.qmeta[QM_CHUNK_SPLIT];
+  const int nchunks = (WIDEWIN ? P.qmeta[QM_CHUNK_SPLIT] : P.qmeta[QM_NCHUNKS]) - chunk_lo;
+  if (nchunks <= 0) return;
   const int logW = P.logW, W = P.W, N = P.N, L = P.levels;
   const int Wm = W - 1;
 
@@ -254,9 +260,10 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
   const int share = max(1, (nchunks + (int)gridDim.x * TPR_WARPS - 1) / ((int)gridDim.x * TPR_WARPS));
   for (int taken = 0; taken < share; taken++) {
     int chunk = 0;
-    if (lane == 0) chunk = atomicAdd(&P.qmeta[QM_CUR_SMALL], 1);
+    if (lane == 0) chunk = atomicAdd(&P.qmeta[WIDEWIN ? QM_CUR_WIDE : QM_CUR_SMALL], 1);
     chunk = __shfl_sync(FULL_MASK, chunk, 0);
     if (chunk >= nchunks) break;
+    chunk += chunk_lo;
     const int qstart = P.chunk_start[chunk], cnt = P.chunk_cnt[chunk];
     const bool mine = lane < cnt;
     int img = 0, label = 0, first = 0, size = 0, off = 0, r0 = 0, c0 = 0, h = 0, w = 0, ws = 0;
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
       S.reset();
 #define TPR_SET_WINDOW()                                            \
   do {                                                              \
-    rad = min(rad, 2 * TPR_MAX_RAD);                                \
+    if (!WIDEWIN) rad = min(rad, 2 * TPR_MAX_RAD);                  \
     i = max(ci - rad, 0); i1 = min(ci + rad, h - 1);                \
     wd = 0; fresh = true;                                           \
   } while (0)
@@ -432,24 +439,49 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
                 else expand = true;
               }
             } else {
-              // ---- nothing within TPR_MAX_RAD: scan the region's whole bitmap, four words per trip.
-              // Ranking by (k, d2, dot) makes this equal to the remaining probes 2*TPR_MAX_RAD, ... in turn.
               fresh = false;
-              const int nwords = h * ws;
-              uint32_t b4[4];
+              if (WIDEWIN) {
+                // ---- nothing within TPR_MAX_RAD: windows of half-width 16, 32, ... clipped to the box, rows
+                // i..i1, words w0..w1 of each, four words per trip.  Ranking by (k, d2, dot) lets each window
+                // start from scratch.
+                const int j0 = max(cj - rad, 0), j1 = min(cj + rad, w - 1);
+                const int w0 = j0 >> 5, w1 = j1 >> 5;
+                if (wd < w0) wd = w0;  // first trip of the window
 #pragma unroll
-              for (int u = 0; u < 4; u++) b4[u] = wd + u < nwords ? bm[wd + u] : 0u;
-#pragma unroll
-              for (int u = 0; u < 4; u++)
-                if (b4[u]) {
-                  const int wi = wd + u;
-                  const int ri = ws == 1 ? wi : (int)(((float)wi + 0.5f) * inv_ws);  // wi / ws (wi < 2^11: exact)
-                  S.scan_word(b4[u], (wi - ri * ws) << 5, ri - ci, cj, p0, p1);
+                for (int u = 0; u < 4; u++) {
+                  if (i <= i1) {
+                    uint32_t bits = bm[i * ws + wd];
+                    const int lo = wd << 5;
+                    if (lo < j0) bits &= 0xffffffffu << (j0 - lo);
+                    if (lo + 31 > j1) bits &= 0xffffffffu >> (lo + 31 - j1);
+                    if (bits) S.scan_word(bits, lo, i - ci, cj, p0, p1);
+                    if (wd < w1) wd++;
+                    else { wd = w0; i++; }
+                  }
                 }
-              wd += 4;
-              if (wd >= nwords) {
-                if (S.have()) { S.finish(p0, p1, fdi, fdj, fk); commit = true; }
-                else expand = true;  // the box is covered: reported as corrupt state below
+                if (i > i1) {
+                  if (S.have()) { S.finish(p0, p1, fdi, fdj, fk); commit = true; }
+                  else expand = true;
+                }
+              } else {
+                // ---- nothing within TPR_MAX_RAD: scan the region's whole (small) bitmap, four words per trip.
+                // Ranking by (k, d2, dot) makes this equal to the remaining probes 2*TPR_MAX_RAD, ... in turn.
+                const int nwords = h * ws;
+                uint32_t b4[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) b4[u] = wd + u < nwords ? bm[wd + u] : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                  if (b4[u]) {
+                    const int wi = wd + u;
+                    const int ri = ws == 1 ? wi : (int)(((float)wi + 0.5f) * inv_ws);  // wi / ws (wi < 2^11: exact)
+                    S.scan_word(b4[u], (wi - ri * ws) << 5, ri - ci, cj, p0, p1);
+                  }
+                wd += 4;
+                if (wd >= nwords) {
+                  if (S.have()) { S.finish(p0, p1, fdi, fdj, fk); commit = true; }
+                  else expand = true;  // the box is covered: reported as corrupt state below
+                }
               }
             }
             if (commit || expand) {
@@ -463,7 +495,8 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
                 t++;
                 rad = 1 << fk;
                 S.reset();
-              } else if (rad > TPR_MAX_RAD) {
+              } else if (rad > TPR_MAX_RAD &&
+                         (!WIDEWIN || (ci - rad <= 0 && cj - rad <= 0 && ci + rad >= h - 1 && cj + rad >= w - 1))) {
                 atomicExch(&P.qmeta[QM_ERR], 1);  // nothing unvisited in the whole box: corrupt state
                 t = n; live = false;
               } else {

@@ -82,6 +82,8 @@ constexpr int TPR_WAVES = 8;  // k1_paths_tpr grid = this many waves of resident
 // memory-bound transform kernels and the PCIe copies of other units.
 struct Slot {
   cudaStream_t s = nullptr;
+  cudaStream_t aux = nullptr;     // path slots: the large-bitmap path kernel runs beside the bulk one
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   DevBuf VA, VB, Vpix, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch;
 };
 
@@ -378,11 +380,11 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     P.gscratch = sl.gscratch.as<uint32_t>();
     P.gscratch_words = img_words;
   }
-  int tpr_per_sm = 1;  // persistent grid: as many CTAs as are resident at once
+  int tpr_per_sm = 1;  // grid = TPR_WAVES waves of resident CTAs
   if (c->mode == RBEPWT_PATH_EUCLID)
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_paths_tpr<MODE_EUCLID>, TPR_WARPS * 32, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_paths_tpr<MODE_EUCLID, false>, TPR_WARPS * 32, 0));
   else
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_paths_tpr<MODE_CHEB>, TPR_WARPS * 32, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_paths_tpr<MODE_CHEB, false>, TPR_WARPS * 32, 0));
   const int small_ctas = c->sm_count * std::max(tpr_per_sm, 1) * TPR_WAVES;
   {
     StageTimer tb(c, RBEPWT_T_PATHS_BIG, s);
@@ -397,9 +399,19 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   }
   {
     StageTimer t(c, RBEPWT_T_PATHS, s);
-    if (c->mode == RBEPWT_PATH_EUCLID) k1_paths_tpr<MODE_EUCLID><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
-    else k1_paths_tpr<MODE_CHEB><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
-    c->launches++;
+    // the large-bitmap chunks (few, the longest chains) run on the slot's auxiliary stream, beside the bulk
+    CK(cudaEventRecord(sl.ev_a, s));
+    CK(cudaStreamWaitEvent(sl.aux, sl.ev_a, 0));
+    if (c->mode == RBEPWT_PATH_EUCLID) {
+      k1_paths_tpr<MODE_EUCLID, true><<<c->sm_count * 2, TPR_WARPS * 32, 0, sl.aux>>>(P);
+      k1_paths_tpr<MODE_EUCLID, false><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
+    } else {
+      k1_paths_tpr<MODE_CHEB, true><<<c->sm_count * 2, TPR_WARPS * 32, 0, sl.aux>>>(P);
+      k1_paths_tpr<MODE_CHEB, false><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
+    }
+    CK(cudaEventRecord(sl.ev_b, sl.aux));
+    CK(cudaStreamWaitEvent(s, sl.ev_b, 0));
+    c->launches += 2;
     if ((c->enc_flags & RBEPWT_PATHS_FIRST_LEVEL) && c->levels > 1) {
       k_same_paths<<<nb, 1024, 0, s>>>(c->Q.as<int32_t>() + (size_t)a * 2 * N, c->Pm.as<int32_t>() + (size_t)a * 2 * N, N,
                                        c->levels);
@@ -699,6 +711,9 @@ int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
   CK(cudaStreamCreateWithPriority(&c->s_out, cudaStreamNonBlocking, prio_hi));
   for (int i = 0; i < 2 * NSLOT; i++) {
     CK(cudaStreamCreateWithPriority(&c->slot[i].s, cudaStreamNonBlocking, i < NSLOT ? prio_lo : prio_hi));
+    CK(cudaStreamCreateWithPriority(&c->slot[i].aux, cudaStreamNonBlocking, i < NSLOT ? prio_lo : prio_hi));
+    CK(cudaEventCreateWithFlags(&c->slot[i].ev_a, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->slot[i].ev_b, cudaEventDisableTiming));
   }
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -727,6 +742,8 @@ void rbepwt_destroy(rbepwt_ctx *c) {
     DevBuf *sb[] = {&sl.VA, &sl.VB, &sl.Vpix, &sl.queue, &sl.qhist, &sl.qmeta, &sl.qbins, &sl.chunk_start, &sl.chunk_cnt, &sl.gscratch};
     for (auto b : sb) b->release();
     cudaStreamDestroy(sl.s);
+    cudaStreamDestroy(sl.aux);
+    cudaEventDestroy(sl.ev_a); cudaEventDestroy(sl.ev_b);
   }
   cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
   cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);

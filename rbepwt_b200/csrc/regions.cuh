@@ -440,7 +440,9 @@ __global__ void kq_hist(RegionArrays reg, int g0, int nreg, int logW, int *qhist
 // qmeta: [0, Q_BINS) bin write cursors (scatter), then the named slots below.
 // qbins: [0, Q_BINS) bin start, [Q_BINS, 2 Q_BINS) bin count, [2 Q_BINS, 3 Q_BINS) first chunk of the bin.
 constexpr int QM_NBIG = Q_BINS, QM_NREG = Q_BINS + 1, QM_CUR_BIG = Q_BINS + 2, QM_CUR_SMALL = Q_BINS + 3,
-              QM_ERR = Q_BINS + 4, QM_NCHUNKS = Q_BINS + 5, QM_SIZE = Q_BINS + 8;
+              QM_ERR = Q_BINS + 4, QM_NCHUNKS = Q_BINS + 5, QM_CHUNK_SPLIT = Q_BINS + 6, QM_CUR_WIDE = Q_BINS + 7,
+              QM_SIZE = Q_BINS + 8;
+constexpr int Q_FIRST_NARROW_CLS = 5;  // classes 1..4 (bitmaps of more than 128 words): the windowed variant of k1_paths_tpr
 
 __global__ void kq_scan(int *qhist, int *qmeta, int *qbins, int nreg) {
   // one warp: exclusive scans of the bin counts (queue offsets) and of the bins' chunk counts
@@ -464,6 +466,7 @@ __global__ void kq_scan(int *qhist, int *qmeta, int *qbins, int nreg) {
     qbins[2 * Q_BINS + b] = cacc + cinc - nch;
     qhist[b] = 0;  // ready for the next chunk of images
     if (b == Q_SIZE_BINS) qmeta[QM_NBIG] = acc + inc - cnt;  // first bin of class 1
+    if (b == Q_FIRST_NARROW_CLS * Q_SIZE_BINS) qmeta[QM_CHUNK_SPLIT] = cacc + cinc - nch;  // first chunk of class 5
     acc += __shfl_sync(FULL_MASK, inc, 31);
     cacc += __shfl_sync(FULL_MASK, cinc, 31);
   }
@@ -471,6 +474,7 @@ __global__ void kq_scan(int *qhist, int *qmeta, int *qbins, int nreg) {
     qmeta[QM_NREG] = nreg;
     qmeta[QM_CUR_BIG] = 0;
     qmeta[QM_CUR_SMALL] = 0;
+    qmeta[QM_CUR_WIDE] = 0;
     qmeta[QM_NCHUNKS] = cacc;
   }
 }
