@@ -208,6 +208,11 @@ constexpr int TPR_ROWS_PER_TRIP = TPR_ROWS_N;
 #define TPR_UNIT_STEPS_N 2
 #endif
 constexpr int TPR_UNIT_STEPS = TPR_UNIT_STEPS_N;  // unit steps a lane may take per trip
+// The large-bitmap instantiation walks 1..8 long chains per warp: trip overhead dominates, so a trip does more.
+#ifndef TPR_WIDE_UNIT_N
+#define TPR_WIDE_UNIT_N 8
+#endif
+constexpr int TPR_UNIT_STEPS_WIDE = TPR_WIDE_UNIT_N;
 constexpr int TPR_MAX_RAD = 8;     // widest aligned-row window; beyond it the whole bitmap is scanned
 
 // Window row as one word: bit 15 + dj  <->  column cj + dj, dj in [-15, 16]; columns outside the
@@ -365,7 +370,7 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
         // ---- phase 1, unit steps: 3x3 neighbourhood -> 9-bit mask -> table, up to TPR_UNIT_STEPS per trip
         // (half-width 1, unit pref: the state every dense stretch of a path is in)
 #pragma unroll 1
-        for (int rep = 0; rep < TPR_UNIT_STEPS; rep++) {
+        for (int rep = 0; rep < (WIDEWIN ? TPR_UNIT_STEPS_WIDE : TPR_UNIT_STEPS); rep++) {
           const bool unit = t < n && !list && fresh && rad == 1 && (unsigned)(p0 + 1) <= 2u && (unsigned)(p1 + 1) <= 2u;
           if (!__any_sync(FULL_MASK, unit)) break;
           if (unit) {
@@ -426,13 +431,21 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
               // ---- up to three window rows, each one aligned word
               fresh = false;
               const uint32_t wmask = ((2u << (2 * rad)) - 1u) << (15 - rad);
+              if (WIDEWIN) {  // few long chains per warp: the whole window in one trip
+#pragma unroll 1
+                for (; i <= i1; i++) {
+                  const uint32_t x = row_window(bm + i * ws, ws, cj) & wmask;
+                  if (x) S.scan_row(x, i - ci, p0, p1);
+                }
+              } else {
 #pragma unroll
-              for (int u = 0; u < TPR_ROWS_PER_TRIP; u++) {
-                const bool act = i <= i1;
-                const int ri = min(i, h - 1);
-                const uint32_t x = act ? (row_window(bm + ri * ws, ws, cj) & wmask) : 0u;
-                S.scan_row(x, ri - ci, p0, p1);
-                i += act ? 1 : 0;
+                for (int u = 0; u < TPR_ROWS_PER_TRIP; u++) {
+                  const bool act = i <= i1;
+                  const int ri = min(i, h - 1);
+                  const uint32_t x = act ? (row_window(bm + ri * ws, ws, cj) & wmask) : 0u;
+                  S.scan_row(x, ri - ci, p0, p1);
+                  i += act ? 1 : 0;
+                }
               }
               if (i > i1) {
                 if (S.have()) { S.finish(p0, p1, fdi, fdj, fk); commit = true; }
