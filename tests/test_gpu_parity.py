@@ -338,3 +338,21 @@ def test_fuzz_random_small_cases_vs_oracle():
         except AssertionError as e:
             raise AssertionError("fuzz case %d: %dx%d L=%d kind=%d mode=%d pfl=%s wav=%s k=%d: %s"
                                  % (case, H, W, levels, kind, mode, pfl, wav, k, e))
+
+
+def test_batch_larger_than_one_chunk():
+    """More images than one internal chunk (1024): chunks are processed one after the other with the label
+    table reused; every image must equal its single-image result."""
+    import rbepwt_b200 as rb
+
+    rng = np.random.default_rng(77)
+    B = 1100
+    labs = rng.integers(0, 5, size=(B, 8, 8)).astype(np.int32)
+    imgs = rng.uniform(0, 255, size=(B, 8, 8))
+    c = rb.BatchCodec()
+    got = c.transcode(imgs, labs, 6, "db2", 20)
+    for b in (0, 1, 1023, 1024, 1025, 1099):
+        one = cuda_run(imgs[b], labs[b], 6, "db2", ncoefs=20, with_perm=False)
+        np.testing.assert_array_equal(got[b], one["decoded"])
+        np.testing.assert_array_equal(c.paths(b, 1), one["points"][1][:, 0] * 8 + one["points"][1][:, 1])
+        assert c.region_count(b) == len(one["roff"][1]) - 1
