@@ -57,6 +57,27 @@ struct PathParams {
   int big_smem_words;          // dynamic shared-memory words available per CTA in the big kernel
 };
 
+constexpr int TPR_LUT_ROWS = 9, TPR_LUT_COLS = 512;  // unit-step table: 9 prefs x 512 neighbourhood masks (paths_tpr.cuh)
+constexpr int COOP_MAX_SIDE = 16384;                 // find_next_geo: integer dot products stay below 2^30
+
+__device__ __forceinline__ bool pref_ties_exactly(int p0, int p1) {
+  if (p0 == 0 || p1 == 0) return true;
+  const int a = abs(p0), b = abs(p1);
+  return a == b && (a & (a - 1)) == 0;
+}
+
+__device__ __forceinline__ int probe_index(int c) { return 32 - __clz(max(c - 1, 0)); }  // ceil(log2(c)), c >= 1
+
+// Window row as one word: bit 15 + dj  <->  column cj + dj, dj in [-15, 16]; columns outside the
+// bitmap read as 0.
+__device__ __forceinline__ uint32_t row_window(const uint32_t *row, int ws, int cj) {
+  const int s = cj - 15;
+  const int wlo = s >> 5;  // -1 when s < 0
+  const uint32_t lo = (wlo >= 0 && wlo < ws) ? row[wlo] : 0u;
+  const uint32_t hi = (wlo + 1 < ws) ? row[wlo + 1] : 0u;
+  return __funnelshift_r(lo, hi, s & 31);
+}
+
 struct Best {
   double dist;  // integer-valued in the geometric modes
   double val;   // EPWT: the candidate's value (becomes the current value of the next step)
@@ -191,13 +212,119 @@ __device__ __forceinline__ bool find_next(const uint32_t *bm, int h, int w, int 
   return true;
 }
 
+// Warp-cooperative search, euclid mode, integer keys (the derivation is in paths_tpr.cuh): the lanes take the
+// rows of the window, every lane keeps the best candidate of its rows as (k, d2, dot) with k = probe index
+// ceil(log2(Chebyshev distance)), three warp reductions pick the winner, and a mirror pair (equal d2 and equal dot
+// product) is settled by the cross product or -- only for a pref where the reference's fp64 expression need
+// not tie exactly -- by that expression itself.  `rad` carries the half-width that resolved the previous step
+// (the window guess); with it == 1 and a unit pref the 3x3 table `lut` answers directly.
+// Requires box sides <= COOP_MAX_SIDE.
+struct GeoCand {
+  int k, d2, dot, di, dj;
+  bool have;
+  __device__ __forceinline__ void take(int cdi, int cdj, int p0, int p1, int &adi, int &adj, bool &alt) {
+    const int ck = probe_index(max(abs(cdi), abs(cdj))), cd2 = cdi * cdi + cdj * cdj, cdot = cdi * p0 + cdj * p1;
+    const bool same = have && ck == k && cd2 == d2;
+    const bool lt = !have || ck < k || (ck == k && cd2 < d2) || (same && cdot > dot);
+    if (lt) { have = true; k = ck; d2 = cd2; dot = cdot; di = cdi; dj = cdj; alt = false; }
+    else if (same && cdot == dot) { alt = true; adi = cdi; adj = cdj; }
+  }
+};
+
+__device__ __forceinline__ bool find_next_geo(const uint32_t *bm, int h, int w, int ws, int ci, int cj, int p0, int p1,
+                                              int &rad, const uint8_t *lut, int &bi, int &bj) {
+  const int lane = (int)lane_id();
+  if (lut && rad == 1 && (unsigned)(p0 + 1) <= 2u && (unsigned)(p1 + 1) <= 2u) {  // uniform over the warp
+    unsigned m = 0;
+#pragma unroll
+    for (int rr = 0; rr < 3; rr++) {
+      const int ri = ci + rr - 1;
+      const uint32_t x = (ri >= 0 && ri < h) ? row_window(bm + ri * ws, ws, cj) : 0u;
+      m |= ((x >> 14) & 7u) << (3 * rr);
+    }
+    if (m) {
+      const int idx = lut[((p0 + 1) * 3 + (p1 + 1)) * TPR_LUT_COLS + m];
+      bi = ci + idx / 3 - 1; bj = cj + idx % 3 - 1;
+      return true;
+    }
+    rad = 2;
+  }
+  GeoCand b;
+  b.have = false; b.k = 0; b.d2 = 0; b.dot = 0; b.di = 0; b.dj = 0;
+  int adi = 0, adj = 0;
+  bool alt = false;
+  for (;; rad <<= 1) {
+    const int i0 = max(ci - rad, 0), i1 = min(ci + rad, h - 1);
+    if (rad <= 15) {  // one aligned word per row
+      const uint32_t wmask = ((2u << (2 * rad)) - 1u) << (15 - rad);
+      const int i = i0 + lane;
+      if (i <= i1) {
+        const uint32_t x = row_window(bm + i * ws, ws, cj) & wmask;
+        const uint32_t left = x & 0x7fffu, right = x >> 15;
+        const int dl = __clz(left) - 16, dr = __ffs(right) - 1;  // nearest unvisited column on each side
+        if (left && (!right || dl <= dr)) b.take(i - ci, -dl, p0, p1, adi, adj, alt);
+        if (right && (!left || dr <= dl)) b.take(i - ci, dr, p0, p1, adi, adj, alt);
+      }
+    } else {
+      const int j0 = max(cj - rad, 0), j1 = min(cj + rad, w - 1);
+      const int w0 = j0 >> 5, w1 = j1 >> 5;
+      for (int i = i0 + lane; i <= i1; i += 32)
+        for (int wd = w0; wd <= w1; wd++) {
+          uint32_t bits = bm[i * ws + wd];
+          const int lo = wd << 5;
+          if (lo < j0) bits &= 0xffffffffu << (j0 - lo);
+          if (lo + 31 > j1) bits &= 0xffffffffu >> (lo + 31 - j1);
+          if (!bits) continue;
+          const int rel = min(cj - lo, 31);
+          const uint32_t lmask = rel < 0 ? 0u : (2u << rel) - 1u;  // columns <= cj
+          const uint32_t left = bits & lmask, right = bits & ~lmask;
+          if (left) b.take(i - ci, lo + 31 - __clz(left) - cj, p0, p1, adi, adj, alt);
+          if (right) b.take(i - ci, lo + __ffs(right) - 1 - cj, p0, p1, adi, adj, alt);
+        }
+    }
+    if (__any_sync(FULL_MASK, b.have)) break;
+    if (ci - rad <= 0 && cj - rad <= 0 && ci + rad >= h - 1 && cj + rad >= w - 1) return false;
+  }
+  // winner: smallest (k, d2), then largest dot product
+  const int kmin = __reduce_min_sync(FULL_MASK, b.have ? b.k : INT32_MAX);
+  const bool s1 = b.have && b.k == kmin;
+  const int dmin = __reduce_min_sync(FULL_MASK, s1 ? b.d2 : INT32_MAX);
+  const bool s2 = s1 && b.d2 == dmin;
+  const int dotmax = __reduce_max_sync(FULL_MASK, s2 ? b.dot : INT32_MIN);
+  const unsigned tied = __ballot_sync(FULL_MASK, s2 && b.dot == dotmax);
+  const int la = __ffs(tied) - 1;
+  int di = __shfl_sync(FULL_MASK, b.di, la), dj = __shfl_sync(FULL_MASK, b.dj, la);
+  // the mirror partner, if any: a second lane's best, or the first lane's own second candidate
+  const unsigned rest = tied & (tied - 1);
+  const bool alt_a = __shfl_sync(FULL_MASK, (int)alt, la) != 0;
+  if (rest || alt_a) {
+    const int lb = rest ? __ffs(rest) - 1 : la;
+    const int odi = __shfl_sync(FULL_MASK, rest ? b.di : adi, lb), odj = __shfl_sync(FULL_MASK, rest ? b.dj : adj, lb);
+    const int cb = di * p1 - dj * p0, ca = odi * p1 - odj * p0;
+    bool other_better;
+    if (pref_ties_exactly(p0, p1)) {
+      other_better = ca > cb;
+    } else {
+      const double sb = tie_sp1(di, dj, dmin, p0, p1), sa = tie_sp1(odi, odj, dmin, p0, p1);
+      other_better = sa != sb ? sa > sb : ca > cb;
+    }
+    if (other_better) { di = odi; dj = odj; }
+  }
+  bi = ci + di; bj = cj + dj;
+  rad = 1 << kmin;
+  return true;
+}
+
 // Walk one region's path at one level.  (ci,cj) = start point (bitmap coordinates, bit still set).
 // Ql[t], t = 0..n-1, receives the pixel ids in path order.  The bitmap is all-zero afterwards.
 template <int MODE>
 __device__ __forceinline__ bool run_path(uint32_t *bm, int h, int w, int ws, int ci, int cj, int n, int r0, int c0,
                                          int logW, const double *__restrict__ vals, bool u8wrap,
-                                         int32_t *__restrict__ Ql, int32_t *__restrict__ Pl, const int32_t *posmap) {
+                                         int32_t *__restrict__ Ql, int32_t *__restrict__ Pl, const int32_t *posmap,
+                                         const uint8_t *lut = nullptr) {
   const int lane = (int)lane_id();
+  const bool geo = MODE == MODE_EUCLID && h <= COOP_MAX_SIDE && w <= COOP_MAX_SIDE;
+  int rad = 1;
   int myq = 0;
   if (lane == 0) {
     myq = ((r0 + ci) << logW) + c0 + cj;
@@ -209,7 +336,11 @@ __device__ __forceinline__ bool run_path(uint32_t *bm, int h, int w, int ws, int
   if (MODE == MODE_EPWT) curval = __ldcg(vals + (((r0 + ci) << logW) + c0 + cj));
   for (int t = 1; t < n; t++) {
     int bi, bj;
-    if (!find_next<MODE>(bm, h, w, ws, ci, cj, p0, p1, vals, r0, c0, logW, u8wrap, curval, bi, bj)) return false;
+    if (geo) {
+      if (!find_next_geo(bm, h, w, ws, ci, cj, p0, p1, rad, lut, bi, bj)) return false;
+    } else if (!find_next<MODE>(bm, h, w, ws, ci, cj, p0, p1, vals, r0, c0, logW, u8wrap, curval, bi, bj)) {
+      return false;
+    }
     if (lane == 0) bm[bi * ws + (bj >> 5)] &= ~(1u << (bj & 31));
     __syncwarp();
     if ((t & 31) == lane) myq = ((r0 + bi) << logW) + c0 + bj;
@@ -252,7 +383,7 @@ __device__ __forceinline__ int reduce_points(uint32_t *bm, int ws, int a, int n,
 
 // Geometric modes: the whole pyramid of one region.
 template <int MODE>
-__device__ void region_pyramid(const PathParams &P, int g, uint32_t *bm) {
+__device__ void region_pyramid(const PathParams &P, int g, uint32_t *bm, const uint8_t *lut = nullptr) {
   const int lane = (int)lane_id();
   const int logW = P.logW, W = P.W, N = P.N;
   const int img = P.reg.img[g], label = P.reg.label[g], first = P.reg.first[g];
@@ -276,7 +407,7 @@ __device__ void region_pyramid(const PathParams &P, int g, uint32_t *bm) {
   for (int lev = 1; lev <= P.levels && n > 0; lev++) {
     int32_t *Ql = Q + level_off((size_t)N, lev) + a;
     int32_t *Pl = lev >= 2 ? Pm + level_off((size_t)N, lev) + a : nullptr;
-    if (!run_path<MODE>(bm, h, w, ws, si, sj, n, r0, c0, logW, nullptr, false, Ql, Pl, posmap)) {
+    if (!run_path<MODE>(bm, h, w, ws, si, sj, n, r0, c0, logW, nullptr, false, Ql, Pl, posmap, lut)) {
       if (lane == 0) atomicExch(&P.qmeta[QM_ERR], 1);
       return;
     }
@@ -285,25 +416,6 @@ __device__ void region_pyramid(const PathParams &P, int g, uint32_t *bm) {
     const int na = (a + 1) >> 1, nb = (a + n + 1) >> 1;
     a = na; n = nb - na;
     if (n > 0) { si = (minpix >> logW) - r0; sj = (minpix & (W - 1)) - c0; }
-  }
-}
-
-// Big regions: one warp per CTA, bitmap in dynamic shared memory if it fits, else global scratch.
-template <int MODE>
-__global__ void __launch_bounds__(32) k1_paths_big(PathParams P) {
-  extern __shared__ uint32_t s_big[];
-  const int lane = (int)lane_id();
-  const int nbig = P.qmeta[QM_NBIG];
-  uint32_t *gs = P.gscratch + (size_t)blockIdx.x * P.gscratch_words;
-  while (true) {
-    int idx = 0;
-    if (lane == 0) idx = atomicAdd(&P.qmeta[QM_CUR_BIG], 1);
-    idx = __shfl_sync(FULL_MASK, idx, 0);
-    if (idx >= nbig) break;
-    const int g = P.queue[idx];
-    const int words = region_bitmap_words(P.reg, g, P.logW);
-    region_pyramid<MODE>(P, g, words <= P.big_smem_words ? s_big : gs);
-    __syncwarp();
   }
 }
 

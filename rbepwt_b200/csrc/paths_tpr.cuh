@@ -64,14 +64,6 @@ constexpr int TPR_WARPS = 4;
 #define TPR_MIN_CTAS 5  // measured: capping registers for a 6th CTA per SM spills and is slower
 #endif
 
-__device__ __forceinline__ bool pref_ties_exactly(int p0, int p1) {
-  if (p0 == 0 || p1 == 0) return true;
-  const int a = abs(p0), b = abs(p1);
-  return a == b && (a & (a - 1)) == 0;
-}
-
-__device__ __forceinline__ int probe_index(int c) { return 32 - __clz(max(c - 1, 0)); }  // ceil(log2(c)), c >= 1
-
 template <int MODE>
 struct Search;
 
@@ -194,7 +186,6 @@ struct Search<MODE_CHEB> {
 };
 
 
-constexpr int TPR_LUT_ROWS = 9, TPR_LUT_COLS = 512;
 #ifdef TPR_STATS  // debug build only: trips and lanes served per level and trip kind
 __device__ unsigned long long g_tpr_stats[16 * 4 * 2 + 32];
 #endif
@@ -215,14 +206,25 @@ constexpr int TPR_UNIT_STEPS = TPR_UNIT_STEPS_N;  // unit steps a lane may take 
 constexpr int TPR_UNIT_STEPS_WIDE = TPR_WIDE_UNIT_N;
 constexpr int TPR_MAX_RAD = 8;     // widest aligned-row window; beyond it the whole bitmap is scanned
 
-// Window row as one word: bit 15 + dj  <->  column cj + dj, dj in [-15, 16]; columns outside the
-// bitmap read as 0.
-__device__ __forceinline__ uint32_t row_window(const uint32_t *row, int ws, int cj) {
-  const int s = cj - 15;
-  const int wlo = s >> 5;  // -1 when s < 0
-  const uint32_t lo = (wlo >= 0 && wlo < ws) ? row[wlo] : 0u;
-  const uint32_t hi = (wlo + 1 < ws) ? row[wlo + 1] : 0u;
-  return __funnelshift_r(lo, hi, s & 31);
+// Unit-step table: lut[q * 512 + m] = index (di+1)*3 + (dj+1) of the winner among the neighbours present in the
+// 9-bit mask m, for pref = (q/3 - 1, q%3 - 1).  Filled by the candidate code every other path takes.
+template <int MODE>
+__device__ __forceinline__ void build_unit_lut(uint8_t *lut) {
+  for (int e = threadIdx.x; e < TPR_LUT_ROWS * TPR_LUT_COLS; e += blockDim.x) {
+    const int q = e / TPR_LUT_COLS, m = e % TPR_LUT_COLS;
+    const int p0 = q / 3 - 1, p1 = q % 3 - 1;
+    uint8_t v = 0xff;
+    if (q != 4 && !(m & 16) && m) {
+      Search<MODE> S;
+      S.reset();
+      for (int bpos = 0; bpos < 9; bpos++)
+        if (m & (1 << bpos)) S.consider(true, bpos / 3 - 1, bpos % 3 - 1, p0, p1);
+      int odi, odj, k;
+      S.finish(p0, p1, odi, odj, k);
+      v = (uint8_t)((odi + 1) * 3 + (odj + 1));
+    }
+    lut[e] = v;
+  }
 }
 
 // WIDEWIN = true: the instantiation for the chunks of large bitmaps (queue classes below Q_FIRST_NARROW_CLS):
@@ -241,23 +243,7 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
   const int logW = P.logW, W = P.W, N = P.N, L = P.levels;
   const int Wm = W - 1;
 
-  // unit-step table: s_lut[q * 512 + m] = index (di+1)*3 + (dj+1) of the winner among the neighbours
-  // present in the 9-bit mask m, for pref = (q/3 - 1, q%3 - 1)
-  for (int e = threadIdx.x; e < TPR_LUT_ROWS * TPR_LUT_COLS; e += blockDim.x) {
-    const int q = e / TPR_LUT_COLS, m = e % TPR_LUT_COLS;
-    const int p0 = q / 3 - 1, p1 = q % 3 - 1;
-    uint8_t v = 0xff;
-    if (q != 4 && !(m & 16) && m) {
-      Search<MODE> S;
-      S.reset();
-      for (int bpos = 0; bpos < 9; bpos++)
-        if (m & (1 << bpos)) S.consider(true, bpos / 3 - 1, bpos % 3 - 1, p0, p1);
-      int odi, odj, k;
-      S.finish(p0, p1, odi, odj, k);
-      v = (uint8_t)((odi + 1) * 3 + (odj + 1));
-    }
-    s_lut[e] = v;
-  }
+  build_unit_lut<MODE>(s_lut);
   __syncthreads();
 
   // Each warp takes its share of the chunks and retires: the grid is several waves of CTAs, so SM slots keep
@@ -270,6 +256,15 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
     if (chunk >= nchunks) break;
     chunk += chunk_lo;
     const int qstart = P.chunk_start[chunk], cnt = P.chunk_cnt[chunk];
+    if (WIDEWIN && MODE == MODE_EUCLID && cnt == 1) {
+      // one long chain: the whole warp walks it together (paths.cuh, find_next_geo)
+      const int g = P.queue[qstart];
+      if (P.reg.size[g] >= TPR_COOP_MIN) {
+        region_pyramid<MODE>(P, g, arena, s_lut);
+        __syncwarp();
+        continue;
+      }
+    }
     const bool mine = lane < cnt;
     int img = 0, label = 0, first = 0, size = 0, off = 0, r0 = 0, c0 = 0, h = 0, w = 0, ws = 0;
     if (mine) {
@@ -589,5 +584,29 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
     __syncwarp();
   }
 }
+
+// Big regions: one warp per CTA, bitmap in dynamic shared memory if it fits, else global scratch.
+template <int MODE>
+__global__ void __launch_bounds__(32) k1_paths_big(PathParams P) {
+  extern __shared__ uint32_t s_big[];
+  __shared__ uint8_t s_lut[TPR_LUT_ROWS * TPR_LUT_COLS];
+  const int lane = (int)lane_id();
+  if (P.qmeta[QM_NBIG] == 0) return;  // the common case: nothing oversized in this group
+  build_unit_lut<MODE>(s_lut);
+  __syncthreads();
+  const int nbig = P.qmeta[QM_NBIG];
+  uint32_t *gs = P.gscratch + (size_t)blockIdx.x * P.gscratch_words;
+  while (true) {
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(&P.qmeta[QM_CUR_BIG], 1);
+    idx = __shfl_sync(FULL_MASK, idx, 0);
+    if (idx >= nbig) break;
+    const int g = P.queue[idx];
+    const int words = region_bitmap_words(P.reg, g, P.logW);
+    region_pyramid<MODE>(P, g, words <= P.big_smem_words ? s_big : gs, s_lut);
+    __syncwarp();
+  }
+}
+
 
 }  // namespace rbepwt

@@ -73,6 +73,9 @@ struct DevBuf {
 struct StageEv { int stage; int launches; cudaEvent_t a, b; };
 
 constexpr int NSLOT = 2;
+#ifndef TPR_WIDE_CTAS_PER_SM
+#define TPR_WIDE_CTAS_PER_SM 5
+#endif
 constexpr int TPR_WAVES = 8;  // k1_paths_tpr grid = this many waves of resident CTAs (see paths_tpr.cuh)
 
 // Workspace + stream of one unit of work in flight.  The batch is cut twice: into PATH GROUPS (label scan,
@@ -403,10 +406,10 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     CK(cudaEventRecord(sl.ev_a, s));
     CK(cudaStreamWaitEvent(sl.aux, sl.ev_a, 0));
     if (c->mode == RBEPWT_PATH_EUCLID) {
-      k1_paths_tpr<MODE_EUCLID, true><<<c->sm_count * 2, TPR_WARPS * 32, 0, sl.aux>>>(P);
+      k1_paths_tpr<MODE_EUCLID, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, TPR_WARPS * 32, 0, sl.aux>>>(P);
       k1_paths_tpr<MODE_EUCLID, false><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
     } else {
-      k1_paths_tpr<MODE_CHEB, true><<<c->sm_count * 2, TPR_WARPS * 32, 0, sl.aux>>>(P);
+      k1_paths_tpr<MODE_CHEB, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, TPR_WARPS * 32, 0, sl.aux>>>(P);
       k1_paths_tpr<MODE_CHEB, false><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
     }
     CK(cudaEventRecord(sl.ev_b, sl.aux));

@@ -395,6 +395,10 @@ constexpr int Q_NCLS = 7;              // class 0 = big; classes 1..6 = 1, 2, 4,
 constexpr int Q_SIZE_BINS = 128;
 constexpr int Q_BINS = Q_NCLS * Q_SIZE_BINS;
 
+#ifndef TPR_COOP_MIN_N
+#define TPR_COOP_MIN_N 2048
+#endif
+constexpr int TPR_COOP_MIN = TPR_COOP_MIN_N;  // regions of at least this many pixels are walked by a whole warp
 constexpr int TPR_MAX_SIDE = 1024;     // bounding-box side limit of k1_paths_tpr (its packed candidate key)
 
 __device__ __forceinline__ int region_bitmap_words(const RegionArrays &reg, int g, int logW) {
@@ -420,6 +424,7 @@ __device__ __forceinline__ int queue_bin(int size, int words) {
     cls = Q_NCLS - 1;
     int cap = TPR_ARENA_WORDS >> 5;  // words per region when 32 share the arena
     while (words > cap) { cap <<= 1; cls--; }
+    if (size >= TPR_COOP_MIN) cls = 1;  // a long chain gets a warp of its own (one region per chunk)
   }
   return cls * Q_SIZE_BINS + (Q_SIZE_BINS - 1 - key);
 }
