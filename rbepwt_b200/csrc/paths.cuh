@@ -48,6 +48,7 @@ struct PathParams {
   const int32_t *queue;
   const int32_t *chunk_start, *chunk_cnt;  // chunk table of the thread-per-region kernel (regions.cuh)
   int *qmeta;
+  int coop_min;  // regions of at least this many pixels get a warp of their own
   int32_t *Q;  // [B][2N]
   int32_t *Pm;      // [B][2N] level l >= 2: position of the path point in the level's incoming order (= index into cA of level l-1)
   int32_t *posmap;  // [B][N] scratch: pixel -> position in the next level's incoming order

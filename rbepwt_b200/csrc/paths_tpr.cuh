@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
     if (WIDEWIN && MODE == MODE_EUCLID && cnt == 1) {
       // one long chain: the whole warp walks it together (paths.cuh, find_next_geo)
       const int g = P.queue[qstart];
-      if (P.reg.size[g] >= TPR_COOP_MIN) {
+      if (P.reg.size[g] >= P.coop_min) {
         region_pyramid<MODE>(P, g, arena, s_lut);
         __syncwarp();
         continue;

@@ -330,6 +330,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     c->totalR += c->h_R[a + i];
   }
   const int nreg = c->totalR - g0;
+  int coop_min = TPR_COOP_MIN;
   int rc = grow_regs(c, std::max<size_t>((size_t)c->totalR, (size_t)c->B * 2048 + 4096), (size_t)g0);
   if (rc) return rc;
   CK(sl.queue.ensure_slack((size_t)nreg * 4));
@@ -350,9 +351,11 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
                                          c->img_labmin.as<int32_t>(), c->img_direct.as<int32_t>(),
                                          c->img_rbase.as<int32_t>(), c->regs());
     const int qb = std::max(1, std::min((nreg + 255) / 256, c->sm_count * 8));
-    kq_hist<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, sl.qhist.as<int>());
+    // few regions in flight (single images, small batches): every region gets its own warp -- latency, not throughput
+    coop_min = (c->mode == RBEPWT_PATH_EUCLID && nreg <= TPR_COOP_ALL_BELOW) ? 1 : TPR_COOP_MIN;
+    kq_hist<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, coop_min, sl.qhist.as<int>());
     kq_scan<<<1, 32, 0, s>>>(sl.qhist.as<int>(), sl.qmeta.as<int>(), sl.qbins.as<int>(), nreg);
-    kq_scatter<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, sl.qmeta.as<int>(), sl.queue.as<int32_t>());
+    kq_scatter<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, coop_min, sl.qmeta.as<int>(), sl.queue.as<int32_t>());
     kq_chunks<<<((Q_BINS - Q_SIZE_BINS) * 32 + 255) / 256, 256, 0, s>>>(sl.qbins.as<int>(), sl.chunk_start.as<int32_t>(),
                                                                         sl.chunk_cnt.as<int32_t>());
     c->launches += 6;
@@ -367,6 +370,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   P.chunk_start = sl.chunk_start.as<int32_t>();
   P.chunk_cnt = sl.chunk_cnt.as<int32_t>();
   P.qmeta = sl.qmeta.as<int>();
+  P.coop_min = coop_min;
   P.Q = c->Q.as<int32_t>();
   P.Pm = c->Pm.as<int32_t>();
   P.posmap = c->posmap.as<int32_t>();

@@ -399,6 +399,7 @@ constexpr int Q_BINS = Q_NCLS * Q_SIZE_BINS;
 #define TPR_COOP_MIN_N 2048
 #endif
 constexpr int TPR_COOP_MIN = TPR_COOP_MIN_N;  // regions of at least this many pixels are walked by a whole warp
+constexpr int TPR_COOP_ALL_BELOW = 4096;      // ... and every region, when the whole group has at most this many
 constexpr int TPR_MAX_SIDE = 1024;     // bounding-box side limit of k1_paths_tpr (its packed candidate key)
 
 __device__ __forceinline__ int region_bitmap_words(const RegionArrays &reg, int g, int logW) {
@@ -416,7 +417,7 @@ __device__ __forceinline__ int region_class_words(const RegionArrays &reg, int g
 
 __host__ __device__ __forceinline__ int class_chunk_size(int cls) { return cls == 0 ? 1 : 32 >> (Q_NCLS - 1 - cls); }
 
-__device__ __forceinline__ int queue_bin(int size, int words) {
+__device__ __forceinline__ int queue_bin(int size, int words, int coop_min) {
   const int lg = 31 - __clz(size);                                        // size >= 1
   const int key = size >= 4 ? 4 * lg + ((size >> (lg - 2)) & 3) : size;    // <= 4*30+3, monotone in size
   int cls = 0;
@@ -424,18 +425,18 @@ __device__ __forceinline__ int queue_bin(int size, int words) {
     cls = Q_NCLS - 1;
     int cap = TPR_ARENA_WORDS >> 5;  // words per region when 32 share the arena
     while (words > cap) { cap <<= 1; cls--; }
-    if (size >= TPR_COOP_MIN) cls = 1;  // a long chain gets a warp of its own (one region per chunk)
+    if (size >= coop_min) cls = 1;  // a long chain gets a warp of its own (one region per chunk)
   }
   return cls * Q_SIZE_BINS + (Q_SIZE_BINS - 1 - key);
 }
 
-__global__ void kq_hist(RegionArrays reg, int g0, int nreg, int logW, int *qhist) {
+__global__ void kq_hist(RegionArrays reg, int g0, int nreg, int logW, int coop_min, int *qhist) {
   __shared__ int s_h[Q_BINS];
   for (int i = threadIdx.x; i < Q_BINS; i += blockDim.x) s_h[i] = 0;
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreg; i += gridDim.x * blockDim.x) {
     const int g = g0 + i;
-    atomicAdd(&s_h[queue_bin(reg.size[g], region_class_words(reg, g, logW))], 1);
+    atomicAdd(&s_h[queue_bin(reg.size[g], region_class_words(reg, g, logW), coop_min)], 1);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < Q_BINS; i += blockDim.x)
@@ -484,10 +485,10 @@ __global__ void kq_scan(int *qhist, int *qmeta, int *qbins, int nreg) {
   }
 }
 
-__global__ void kq_scatter(RegionArrays reg, int g0, int nreg, int logW, int *qmeta, int32_t *queue) {
+__global__ void kq_scatter(RegionArrays reg, int g0, int nreg, int logW, int coop_min, int *qmeta, int32_t *queue) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreg; i += gridDim.x * blockDim.x) {
     const int g = g0 + i;
-    const int bin = queue_bin(reg.size[g], region_class_words(reg, g, logW));
+    const int bin = queue_bin(reg.size[g], region_class_words(reg, g, logW), coop_min);
     queue[atomicAdd(&qmeta[bin], 1)] = g;
   }
 }
