@@ -396,13 +396,24 @@ __device__ void region_pyramid(const PathParams &P, int g, uint32_t *bm, const u
   int32_t *Pm = P.Pm + (size_t)img * 2 * (size_t)N;
   int32_t *posmap = P.posmap + (size_t)img * N;
 
-  for (int i = 0; i < h; i++)
-    for (int wd = 0; wd < ws; wd++) {
-      const int col = c0 + (wd << 5) + lane;
-      const bool in = col < c0 + w && lab[((r0 + i) << logW) + col] == label;
-      const unsigned bits = __ballot_sync(FULL_MASK, in);
-      if (lane == 0) bm[i * ws + wd] = bits;
+  const int words = h * ws;
+  for (int wi = 0; wi < words; wi += 4) {  // four independent label loads in flight per lane
+    int lv[4];
+    bool inb[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int w_ = wi + u;
+      const int i = ws == 1 ? w_ : w_ / ws;
+      const int col = ((w_ - i * ws) << 5) + lane;
+      inb[u] = w_ < words && col < w;
+      lv[u] = inb[u] ? lab[((r0 + i) << logW) + c0 + col] : 0;
     }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const unsigned bits = __ballot_sync(FULL_MASK, inb[u] && lv[u] == label);
+      if (lane == 0 && wi + u < words) bm[wi + u] = bits;
+    }
+  }
   __syncwarp();
   int si = 0, sj = (first & (W - 1)) - c0;
   for (int lev = 1; lev <= P.levels && n > 0; lev++) {

@@ -41,6 +41,30 @@ def _shared_codec():
     return _codec
 
 
+# GPU contexts of Rbepwt objects that were garbage-collected: a loop over many images re-uses their streams and
+# device buffers instead of paying context creation and cudaMalloc for every image.
+_idle_codecs = []
+_MAX_IDLE_CODECS = 4
+
+
+def _acquire_codec():
+    while _idle_codecs:
+        codec = _idle_codecs.pop()
+        if getattr(codec, "_ctx", None):
+            return codec
+    return BatchCodec()
+
+
+def _release_codec(codec):
+    # (the cyclic garbage collector may already have finalised -- closed -- the codec of an unreachable Image)
+    if codec is None or not getattr(codec, "_ctx", None):
+        return
+    if len(_idle_codecs) < _MAX_IDLE_CODECS:
+        _idle_codecs.append(codec)
+    else:
+        codec.close()
+
+
 class Segmentation:
     """Holder of an externally produced label map (rbepwt.py:770-848).  Region order = first
     appearance of the label in a row-major scan; computed on the GPU at encode time (K0)."""
@@ -245,12 +269,19 @@ class Rbepwt:
             print("Segmenting image with default parameters...")  # rbepwt.py:2001-2003
             img.segment()
         labels = None if self.path_type == "epwt-easypath" else img.label_img
-        self._codec = BatchCodec()
+        _release_codec(self._codec)
+        self._codec = _acquire_codec()
         self._codec.encode(img.img, labels, self.levels, self.wavelet, self.path_type, euclidean_distance,
                            paths_first_level=self.paths_first_level)
         self._details = self._flat = self._approx = None
         self.region_collection_at_level = _LevelDict(self)
         self.has_encoding = True
+
+    def __del__(self):
+        try:
+            _release_codec(self.__dict__.pop("_codec", None))
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
 
     def _level_slices(self):
         n, off, out = self.img.size, 0, {}
@@ -445,4 +476,8 @@ def full_decode(wavelet_details_dict, wavelet_approx, label_img, wavelet, path_t
     label_img = np.asarray(label_img)
     if flat.size != label_img.size:
         raise Exception("coefficient count does not match the label image")
-    return BatchCodec().full_decode(flat[None], label_img[None], levels, wavelet, path_type, euclidean_distance)[0]
+    codec = _acquire_codec()
+    try:
+        return codec.full_decode(flat[None], label_img[None], levels, wavelet, path_type, euclidean_distance)[0]
+    finally:
+        _release_codec(codec)
