@@ -30,6 +30,7 @@ constexpr int DWT_THREADS = 256;
 constexpr int FWD_TILE = 512;   // low-pass outputs per CTA
 constexpr int INV_TILE = 1024;  // reconstructed samples per CTA
 
+constexpr int FT_MAX = 10;  // filter lengths up to this have kernels with the taps unrolled (bior4.4 = 10)
 constexpr int TAIL_MAX_POINTS = 2048;  // levels with at most this many points per image run in the tail kernels
 
 struct DwtParams {
@@ -40,6 +41,7 @@ struct DwtParams {
   const int32_t *Pm;   // [chunk][2N] paths as positions in the incoming order (levels >= 2)
   double *coefs;       // [chunk][N] flat coefficients: details[1] | ... | details[L] | approx
   const double *filt;  // dec_lo[FMAX] dec_hi[FMAX] rec_lo[FMAX] rec_hi[FMAX]
+  double tap_lo[FT_MAX], tap_hi[FT_MAX];  // the direction's two filters by value (constant bank) when flen <= FT_MAX
   double *out_img;     // decode, level 1: clipped image
   int flen, N, lev, levels;
 };
@@ -51,9 +53,10 @@ struct FwdSmem {
 
 // One tile (FWD_TILE low-pass outputs) of level `lev` of image `img`.  The caller loads sm.lo / sm.hi once.
 // SAME_CTA: the input plane was written by this CTA (tail kernel) -> read it past L1.
-template <bool SAME_CTA>
+// FT > 0: compile-time filter length, taps read from the kernel parameters; FT = 0: any length, taps in shared memory.
+template <bool SAME_CTA, int FT>
 __device__ __forceinline__ void dwt_tile(const DwtParams &P, FwdSmem &sm, int lev, int tile, size_t img) {
-  const int tid = threadIdx.x, nt = blockDim.x, F = P.flen, N = P.N;
+  const int tid = threadIdx.x, nt = blockDim.x, F = FT ? FT : P.flen, N = P.N;
   const int n = N >> (lev - 1), half = n >> 1, mask = n - 1;
   const int32_t *Pl = (lev == 1 ? P.Q : P.Pm) + img * 2 * (size_t)N + level_off((size_t)N, lev);
   // level 1 reads the image; level l >= 2 reads the plane level l-1 wrote (ping-pong on the level's parity)
@@ -83,13 +86,25 @@ __device__ __forceinline__ void dwt_tile(const DwtParams &P, FwdSmem &sm, int le
   for (int ol = tid; ol < nout; ol += nt) {
     double a = 0.0, d = 0.0;
     // local sample index of tap j: 2*ol + F-1-j  (odd for even j)
-    for (int j = 0; j < F; j += 2) {
-      const int q = ol + ((F - 2 - j) >> 1);
-      const double x1 = sm.o[q], x2 = sm.e[q];
-      a = __dadd_rn(a, __dmul_rn(sm.lo[j], x1));
-      d = __dadd_rn(d, __dmul_rn(sm.hi[j], x1));
-      a = __dadd_rn(a, __dmul_rn(sm.lo[j + 1], x2));
-      d = __dadd_rn(d, __dmul_rn(sm.hi[j + 1], x2));
+    if (FT) {
+#pragma unroll
+      for (int j = 0; j < FT; j += 2) {
+        const int q = ol + ((FT - 2 - j) >> 1);
+        const double x1 = sm.o[q], x2 = sm.e[q];
+        a = __dadd_rn(a, __dmul_rn(P.tap_lo[j], x1));
+        d = __dadd_rn(d, __dmul_rn(P.tap_hi[j], x1));
+        a = __dadd_rn(a, __dmul_rn(P.tap_lo[j + 1], x2));
+        d = __dadd_rn(d, __dmul_rn(P.tap_hi[j + 1], x2));
+      }
+    } else {
+      for (int j = 0; j < F; j += 2) {
+        const int q = ol + ((F - 2 - j) >> 1);
+        const double x1 = sm.o[q], x2 = sm.e[q];
+        a = __dadd_rn(a, __dmul_rn(sm.lo[j], x1));
+        d = __dadd_rn(d, __dmul_rn(sm.hi[j], x1));
+        a = __dadd_rn(a, __dmul_rn(sm.lo[j + 1], x2));
+        d = __dadd_rn(d, __dmul_rn(sm.hi[j + 1], x2));
+      }
     }
     coefs[det_off + o0 + ol] = d;
     if (last) coefs[app_off + o0 + ol] = a;
@@ -98,10 +113,11 @@ __device__ __forceinline__ void dwt_tile(const DwtParams &P, FwdSmem &sm, int le
 }
 
 // One level, one tile per CTA: the levels with many tiles per image.
+template <int FT>
 __global__ void __launch_bounds__(DWT_THREADS) k3_dwt_level(DwtParams P) {
   __shared__ FwdSmem sm;
-  for (int i = threadIdx.x; i < P.flen; i += blockDim.x) { sm.lo[i] = P.filt[i]; sm.hi[i] = P.filt[FMAX + i]; }
-  dwt_tile<false>(P, sm, P.lev, blockIdx.x, blockIdx.y);
+  if (!FT) for (int i = threadIdx.x; i < P.flen; i += blockDim.x) { sm.lo[i] = P.filt[i]; sm.hi[i] = P.filt[FMAX + i]; }
+  dwt_tile<false, FT>(P, sm, P.lev, blockIdx.x, blockIdx.y);
 }
 
 // Levels P.lev .. P.levels of one image in ONE CTA: the deep levels are a chain of tiny dependent passes
@@ -113,7 +129,7 @@ __global__ void __launch_bounds__(DWT_THREADS) k3_dwt_tail(DwtParams P) {
     const int half = (P.N >> (lev - 1)) >> 1;
     for (int tile = 0; tile * FWD_TILE < half; tile++) {
       __syncthreads();  // shared tile reuse; also publishes the previous level's plane writes to the CTA
-      dwt_tile<true>(P, sm, lev, tile, blockIdx.x);
+      dwt_tile<true, 0>(P, sm, lev, tile, blockIdx.x);
     }
   }
 }
@@ -124,9 +140,9 @@ struct InvSmem {
 };
 
 // One tile (INV_TILE reconstructed samples) of level `lev` of image `img`.
-template <bool SAME_CTA>
+template <bool SAME_CTA, int FT>
 __device__ __forceinline__ void idwt_tile(const DwtParams &P, InvSmem &sm, int lev, int tile, size_t img) {
-  const int tid = threadIdx.x, nt = blockDim.x, F = P.flen, N = P.N;
+  const int tid = threadIdx.x, nt = blockDim.x, F = FT ? FT : P.flen, N = P.N;
   const int n = N >> (lev - 1), half = n >> 1, hmask = half - 1;
   const int32_t *Pl = (lev == 1 ? P.Q : P.Pm) + img * 2 * (size_t)N + level_off((size_t)N, lev);
   const double *vin = P.plane[lev & 1] + img * (size_t)(N >> 1);    // x^(lev+1), reconstructed by level lev+1
@@ -145,15 +161,7 @@ __device__ __forceinline__ void idwt_tile(const DwtParams &P, InvSmem &sm, int l
     sm.d[i] = coefs[det_off + ow];
   }
   __syncthreads();
-  for (int tl = tid; tl < nout; tl += nt) {
-    const int t = t0 + tl, base = t + F / 2 - 1;
-    double slo = 0.0, shi = 0.0;
-    for (int m = base & 1; m < F; m += 2) {
-      const int oi = ((base - m) >> 1) - omin;
-      slo = __dadd_rn(slo, __dmul_rn(sm.lo[m], sm.a[oi]));
-      shi = __dadd_rn(shi, __dmul_rn(sm.hi[m], sm.d[oi]));
-    }
-    double x = __dadd_rn(slo, shi);
+  auto emit = [&](int t, double x) {
     const int dst = Pl[t];
     if (lev == 1) {  // Image.decode_rbepwt: clip, no rounding (rbepwt.py:312-314)
       x = x > 255.0 ? 255.0 : (x < 0.0 ? 0.0 : x);
@@ -161,13 +169,45 @@ __device__ __forceinline__ void idwt_tile(const DwtParams &P, InvSmem &sm, int l
     } else {
       vout[dst] = x;
     }
+  };
+  if (FT) {
+    // a thread reconstructs the pair (t, t+1), t even: the two outputs use the taps of opposite parity on
+    // (nearly) the same approximation / detail samples, all tap indices are compile-time constants
+    constexpr int hh = (FT ? FT : 2) / 2 - 1, par0 = hh & 1, par1 = par0 ^ 1;
+    for (int pl = tid; 2 * pl < nout; pl += nt) {
+      const int t = t0 + 2 * pl, base = t + hh;
+      double slo0 = 0.0, shi0 = 0.0, slo1 = 0.0, shi1 = 0.0;
+#pragma unroll
+      for (int mm = 0; mm < FT; mm += 2) {
+        const int m0 = mm + par0, m1 = mm + par1;
+        const int oi0 = ((base - m0) >> 1) - omin, oi1 = ((base + 1 - m1) >> 1) - omin;
+        slo0 = __dadd_rn(slo0, __dmul_rn(P.tap_lo[m0], sm.a[oi0]));
+        shi0 = __dadd_rn(shi0, __dmul_rn(P.tap_hi[m0], sm.d[oi0]));
+        slo1 = __dadd_rn(slo1, __dmul_rn(P.tap_lo[m1], sm.a[oi1]));
+        shi1 = __dadd_rn(shi1, __dmul_rn(P.tap_hi[m1], sm.d[oi1]));
+      }
+      emit(t, __dadd_rn(slo0, shi0));
+      emit(t + 1, __dadd_rn(slo1, shi1));
+    }
+  } else {
+    for (int tl = tid; tl < nout; tl += nt) {
+      const int t = t0 + tl, base = t + F / 2 - 1;
+      double slo = 0.0, shi = 0.0;
+      for (int m = base & 1; m < F; m += 2) {
+        const int oi = ((base - m) >> 1) - omin;
+        slo = __dadd_rn(slo, __dmul_rn(sm.lo[m], sm.a[oi]));
+        shi = __dadd_rn(shi, __dmul_rn(sm.hi[m], sm.d[oi]));
+      }
+      emit(t, __dadd_rn(slo, shi));
+    }
   }
 }
 
+template <int FT>
 __global__ void __launch_bounds__(DWT_THREADS) k5_idwt_level(DwtParams P) {
   __shared__ InvSmem sm;
-  for (int i = threadIdx.x; i < P.flen; i += blockDim.x) { sm.lo[i] = P.filt[2 * FMAX + i]; sm.hi[i] = P.filt[3 * FMAX + i]; }
-  idwt_tile<false>(P, sm, P.lev, blockIdx.x, blockIdx.y);
+  if (!FT) for (int i = threadIdx.x; i < P.flen; i += blockDim.x) { sm.lo[i] = P.filt[2 * FMAX + i]; sm.hi[i] = P.filt[3 * FMAX + i]; }
+  idwt_tile<false, FT>(P, sm, P.lev, blockIdx.x, blockIdx.y);
 }
 
 // Levels P.levels down to P.lev of one image in ONE CTA (the deep levels, see k3_dwt_tail).
@@ -178,7 +218,7 @@ __global__ void __launch_bounds__(DWT_THREADS) k5_idwt_tail(DwtParams P) {
     const int n = P.N >> (lev - 1);
     for (int tile = 0; tile * INV_TILE < n; tile++) {
       __syncthreads();
-      idwt_tile<true>(P, sm, lev, tile, blockIdx.x);
+      idwt_tile<true, 0>(P, sm, lev, tile, blockIdx.x);
     }
   }
 }

@@ -111,6 +111,7 @@ struct rbepwt_ctx {
   bool has_wavelet = false;
   int flen = 0;
   DevBuf filt;
+  double h_filt[4][FT_MAX] = {};  // host copy (flen <= FT_MAX): passed to the transform kernels by value
   // state of the encoded batch
   bool has_encoding = false, has_paths = false;
   int B = 0, H = 0, W = 0, N = 0, logW = 0, levels = 0, mode = 0;
@@ -144,6 +145,32 @@ struct rbepwt_ctx {
 namespace {
 
 enum { DO_PATHS = 1, DO_DWT = 2, DO_THRESH = 4, DO_DECODE = 8 };
+
+void set_taps(const rbepwt_ctx *c, DwtParams &D, bool inverse) {
+  for (int i = 0; i < FT_MAX; i++) { D.tap_lo[i] = c->h_filt[inverse ? 2 : 0][i]; D.tap_hi[i] = c->h_filt[inverse ? 3 : 1][i]; }
+}
+
+void launch_dwt_level(const DwtParams &D, dim3 grid, cudaStream_t s) {
+  switch (D.flen) {
+    case 2: k3_dwt_level<2><<<grid, DWT_THREADS, 0, s>>>(D); break;
+    case 4: k3_dwt_level<4><<<grid, DWT_THREADS, 0, s>>>(D); break;
+    case 6: k3_dwt_level<6><<<grid, DWT_THREADS, 0, s>>>(D); break;
+    case 8: k3_dwt_level<8><<<grid, DWT_THREADS, 0, s>>>(D); break;
+    case 10: k3_dwt_level<10><<<grid, DWT_THREADS, 0, s>>>(D); break;
+    default: k3_dwt_level<0><<<grid, DWT_THREADS, 0, s>>>(D); break;
+  }
+}
+
+void launch_idwt_level(const DwtParams &D, dim3 grid, cudaStream_t s) {
+  switch (D.flen) {
+    case 2: k5_idwt_level<2><<<grid, DWT_THREADS, 0, s>>>(D); break;
+    case 4: k5_idwt_level<4><<<grid, DWT_THREADS, 0, s>>>(D); break;
+    case 6: k5_idwt_level<6><<<grid, DWT_THREADS, 0, s>>>(D); break;
+    case 8: k5_idwt_level<8><<<grid, DWT_THREADS, 0, s>>>(D); break;
+    case 10: k5_idwt_level<10><<<grid, DWT_THREADS, 0, s>>>(D); break;
+    default: k5_idwt_level<0><<<grid, DWT_THREADS, 0, s>>>(D); break;
+  }
+}
 
 struct DeviceGuard {
   int prev = -1;
@@ -439,6 +466,7 @@ int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
   D.filt = c->filt.as<double>();
   D.out_img = nullptr;
   D.flen = c->flen; D.N = N; D.levels = c->levels;
+  set_taps(c, D, false);
   double *V[2] = {sl.VA.as<double>(), sl.VB.as<double>()};
   EpwtParams E;
   size_t epwt_smem = 0;
@@ -487,7 +515,7 @@ int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
     {
       StageTimer t(c, RBEPWT_T_DWT, s);
       dim3 grid(((n >> 1) + FWD_TILE - 1) / FWD_TILE, nb);
-      k3_dwt_level<<<grid, DWT_THREADS, 0, s>>>(D);
+      launch_dwt_level(D, grid, s);
       c->launches++;
       if (c->mode == RBEPWT_PATH_EPWT && lev < c->levels && !same_paths) {
         k_plane_to_pixels<<<dim3(((n >> 1) + 255) / 256, nb), 256, 0, s>>>(V[lev & 1], D.Q, N, lev, sl.Vpix.as<double>());
@@ -518,6 +546,7 @@ int decode_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb, double *o
   D.filt = c->filt.as<double>();
   D.out_img = out_dev + (size_t)a * N;
   D.flen = c->flen; D.N = N; D.levels = c->levels;
+  set_taps(c, D, true);
   D.vin = nullptr; D.vin_stride = N;
   D.plane[0] = V[0]; D.plane[1] = V[1];
   int top = c->levels;  // deepest level still to be inverted by a per-level launch
@@ -533,7 +562,7 @@ int decode_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb, double *o
     D.lev = lev;
     const int n = N >> (lev - 1);
     dim3 grid((n + INV_TILE - 1) / INV_TILE, nb);
-    k5_idwt_level<<<grid, DWT_THREADS, 0, s>>>(D);
+    launch_idwt_level(D, grid, s);
     c->launches++;
   }
   CK(cudaGetLastError());
@@ -797,6 +826,11 @@ int rbepwt_set_wavelet(rbepwt_ctx *c, int flen, const double *dec_lo, const doub
   memcpy(&h[2 * FMAX], rec_lo, flen * 8); memcpy(&h[3 * FMAX], rec_hi, flen * 8);
   CK(cudaMemcpyAsync(c->filt.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if (flen <= FT_MAX) {
+    const double *src[4] = {dec_lo, dec_hi, rec_lo, rec_hi};
+    for (int f = 0; f < 4; f++)
+      for (int i = 0; i < FT_MAX; i++) c->h_filt[f][i] = i < flen ? src[f][i] : 0.0;
+  }
   c->flen = flen;
   c->has_wavelet = true;
   return RBEPWT_OK;
@@ -1048,13 +1082,14 @@ int rbepwt_get_level_values(rbepwt_ctx *c, int b, int level, double *vals) {
   D.filt = c->filt.as<double>();
   D.out_img = nullptr;
   D.flen = c->flen; D.N = c->N; D.levels = 31;  // never the "last" level: low-pass always goes to vout
+  set_taps(c, D, false);
   for (int lev = 1; lev < level; lev++) {
     D.lev = lev;
     D.vin = c->img_dev + (size_t)b * N;
     D.vin_stride = N;
     D.plane[0] = V[0]; D.plane[1] = V[1];
     const int half = (int)((N >> (lev - 1)) >> 1);
-    k3_dwt_level<<<dim3((half + FWD_TILE - 1) / FWD_TILE, 1), DWT_THREADS, 0, s>>>(D);
+    launch_dwt_level(D, dim3((half + FWD_TILE - 1) / FWD_TILE, 1), s);
     c->launches++;
   }
   if (level == 1) {
