@@ -49,6 +49,7 @@ struct PathParams {
   const int32_t *chunk_start, *chunk_cnt;  // chunk table of the thread-per-region kernel (regions.cuh)
   int *qmeta;
   int coop_min;  // regions of at least this many pixels get a warp of their own
+  const uint8_t *unit_lut;  // 9 x 512 unit-step table of the path mode (global memory, built once per context)
   int32_t *Q;  // [B][2N]
   int32_t *Pm;      // [B][2N] level l >= 2: position of the path point in the level's incoming order (= index into cA of level l-1)
   int32_t *posmap;  // [B][N] scratch: pixel -> position in the next level's incoming order

@@ -209,7 +209,7 @@ constexpr int TPR_MAX_RAD = 8;     // widest aligned-row window; beyond it the w
 // Unit-step table: lut[q * 512 + m] = index (di+1)*3 + (dj+1) of the winner among the neighbours present in the
 // 9-bit mask m, for pref = (q/3 - 1, q%3 - 1).  Filled by the candidate code every other path takes.
 template <int MODE>
-__device__ __forceinline__ void build_unit_lut(uint8_t *lut) {
+__device__ __forceinline__ void build_unit_lut(uint8_t *lut) {  // any block size; used once per context
   for (int e = threadIdx.x; e < TPR_LUT_ROWS * TPR_LUT_COLS; e += blockDim.x) {
     const int q = e / TPR_LUT_COLS, m = e % TPR_LUT_COLS;
     const int p0 = q / 3 - 1, p1 = q % 3 - 1;
@@ -227,6 +227,17 @@ __device__ __forceinline__ void build_unit_lut(uint8_t *lut) {
   }
 }
 
+// The tables are computed once per context (global memory, one per path mode); the path kernels copy theirs
+// into shared memory.
+template <int MODE>
+__global__ void k_build_unit_lut(uint8_t *lut) { build_unit_lut<MODE>(lut); }
+
+__device__ __forceinline__ void load_unit_lut(uint8_t *s_lut, const uint8_t *g_lut) {
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(g_lut);
+  uint32_t *dst = reinterpret_cast<uint32_t *>(s_lut);
+  for (int e = threadIdx.x; e < TPR_LUT_ROWS * TPR_LUT_COLS / 4; e += blockDim.x) dst[e] = src[e];
+}
+
 // WIDEWIN = true: the instantiation for the chunks of large bitmaps (queue classes below Q_FIRST_NARROW_CLS):
 // beyond half-width TPR_MAX_RAD it scans windows of half-width 16, 32, ... word by word instead of the whole
 // bitmap, which for a 10^4-pixel region is the difference between tens and thousands of words per far jump.
@@ -234,7 +245,7 @@ __device__ __forceinline__ void build_unit_lut(uint8_t *lut) {
 template <int MODE, bool WIDEWIN>
 __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(PathParams P) {
   __shared__ uint32_t s_arena[TPR_WARPS][TPR_ARENA_WORDS];
-  __shared__ uint8_t s_lut[TPR_LUT_ROWS * TPR_LUT_COLS];
+  __shared__ __align__(16) uint8_t s_lut[TPR_LUT_ROWS * TPR_LUT_COLS];
   const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
   uint32_t *arena = s_arena[warp];
   const int chunk_lo = WIDEWIN ? 0 : P.qmeta[QM_CHUNK_SPLIT];
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
   const int logW = P.logW, W = P.W, N = P.N, L = P.levels;
   const int Wm = W - 1;
 
-  build_unit_lut<MODE>(s_lut);
+  load_unit_lut(s_lut, P.unit_lut);
   __syncthreads();
 
   // Each warp takes its share of the chunks and retires: the grid is several waves of CTAs, so SM slots keep
@@ -589,10 +600,10 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
 template <int MODE>
 __global__ void __launch_bounds__(32) k1_paths_big(PathParams P) {
   extern __shared__ uint32_t s_big[];
-  __shared__ uint8_t s_lut[TPR_LUT_ROWS * TPR_LUT_COLS];
+  __shared__ __align__(16) uint8_t s_lut[TPR_LUT_ROWS * TPR_LUT_COLS];
   const int lane = (int)lane_id();
   if (P.qmeta[QM_NBIG] == 0) return;  // the common case: nothing oversized in this group
-  build_unit_lut<MODE>(s_lut);
+  load_unit_lut(s_lut, P.unit_lut);
   __syncthreads();
   const int nbig = P.qmeta[QM_NBIG];
   uint32_t *gs = P.gscratch + (size_t)blockIdx.x * P.gscratch_words;

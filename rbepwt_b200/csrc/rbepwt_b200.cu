@@ -110,7 +110,7 @@ struct rbepwt_ctx {
   // wavelet
   bool has_wavelet = false;
   int flen = 0;
-  DevBuf filt;
+  DevBuf filt, unit_lut;  // unit_lut: two 9 x 512 tables (euclid, chebyshev)
   double h_filt[4][FT_MAX] = {};  // host copy (flen <= FT_MAX): passed to the transform kernels by value
   // state of the encoded batch
   bool has_encoding = false, has_paths = false;
@@ -398,6 +398,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   P.chunk_cnt = sl.chunk_cnt.as<int32_t>();
   P.qmeta = sl.qmeta.as<int>();
   P.coop_min = coop_min;
+  P.unit_lut = c->unit_lut.as<uint8_t>() + (c->mode == RBEPWT_PATH_CHEB ? TPR_LUT_ROWS * TPR_LUT_COLS : 0);
   P.Q = c->Q.as<int32_t>();
   P.Pm = c->Pm.as<int32_t>();
   P.posmap = c->posmap.as<int32_t>();
@@ -755,6 +756,11 @@ int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
   CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   CK(cudaMallocHost((void **)&c->pin_err, sizeof(int)));
   CK(c->filt.ensure(4 * FMAX * sizeof(double)));
+  CK(c->unit_lut.ensure(2 * TPR_LUT_ROWS * TPR_LUT_COLS));
+  k_build_unit_lut<MODE_EUCLID><<<1, 256, 0, c->stream>>>(c->unit_lut.as<uint8_t>());
+  k_build_unit_lut<MODE_CHEB><<<1, 256, 0, c->stream>>>(c->unit_lut.as<uint8_t>() + TPR_LUT_ROWS * TPR_LUT_COLS);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
   *out = c;
   return RBEPWT_OK;
 }
@@ -768,7 +774,7 @@ void rbepwt_destroy(rbepwt_ctx *c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   for (auto *v : {&c->ev_lab, &c->ev_path, &c->ev_img, &c->ev_done})
     for (auto e : *v) cudaEventDestroy(e);
-  DevBuf *bufs[] = {&c->filt, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->img_R,
+  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->img_R,
                     &c->img_rbase, &c->img_labmin, &c->img_direct, &c->tbl, &c->slot_rid, &c->scratch_i32,
                     &c->scratch_i32b, &c->psnr_out, &c->nz_out};
   for (auto b : bufs) b->release();
