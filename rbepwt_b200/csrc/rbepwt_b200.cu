@@ -628,7 +628,9 @@ int run_pipeline(rbepwt_ctx *c, int what, long long k, const double *img_host, c
     // still arriving, which is what lets the output copy overlap the input copy.
     std::vector<int> gstart;
     {
-      const int full = Bp / Bs;
+      // device-resident inputs: nothing to overlap the path stage with, one launch over the whole chunk is the
+      // most efficient (the path kernel's long chains are amortised over more regions)
+      const int full = (!lab_host && c->opt_group == 0) ? nsub : Bp / Bs;
       int len = (lab_host && c->opt_group == 0 && !serial) ? 1 : full, first = 1;
       for (int s = 0; s < nsub;) {
         gstart.push_back(s);
