@@ -72,7 +72,12 @@ struct DevBuf {
 
 struct StageEv { int stage; int launches; cudaEvent_t a, b; };
 
-constexpr int NSLOT = 2;
+constexpr int NSLOT = 2;   // path groups in flight
+#ifndef RBEPWT_NXSLOT
+#define RBEPWT_NXSLOT 2
+#endif
+constexpr int NXSLOT = RBEPWT_NXSLOT;  // transform sub-batches in flight
+constexpr int NSLOTS = NSLOT + NXSLOT;
 #ifndef TPR_WIDE_CTAS_PER_SM
 #define TPR_WIDE_CTAS_PER_SM 5
 #endif
@@ -98,7 +103,7 @@ struct rbepwt_ctx {
   size_t smem_optin = 0;
   // internal streams: input copies + label scan, output copies, one per slot
   cudaStream_t s_in = nullptr, s_out = nullptr;
-  Slot slot[2 * NSLOT];   // [0, NSLOT): path groups, [NSLOT, 2 NSLOT): transform sub-batches
+  Slot slot[NSLOTS];      // [0, NSLOT): path groups, [NSLOT, NSLOTS): transform sub-batches
   int nslot = NSLOT;      // RBEPWT_OPT_STREAMS
   int opt_sub = 0;        // RBEPWT_OPT_SUBBATCH (0 = auto)
   int opt_group = 0;      // RBEPWT_OPT_PATHGROUP (0 = auto)
@@ -226,7 +231,7 @@ int group_images(const rbepwt_ctx *c, int nb, int N, int Bs) {
 int sync_internal(rbepwt_ctx *c) {
   CK(cudaStreamSynchronize(c->s_in));
   CK(cudaStreamSynchronize(c->s_out));
-  for (int i = 0; i < 2 * NSLOT; i++) CK(cudaStreamSynchronize(c->slot[i].s));
+  for (int i = 0; i < NSLOTS; i++) CK(cudaStreamSynchronize(c->slot[i].s));
   return RBEPWT_OK;
 }
 
@@ -235,14 +240,14 @@ int fork_streams(rbepwt_ctx *c) {
   CK(cudaEventRecord(c->ev_fork, c->stream));
   CK(cudaStreamWaitEvent(c->s_in, c->ev_fork, 0));
   CK(cudaStreamWaitEvent(c->s_out, c->ev_fork, 0));
-  for (int i = 0; i < 2 * NSLOT; i++) CK(cudaStreamWaitEvent(c->slot[i].s, c->ev_fork, 0));
+  for (int i = 0; i < NSLOTS; i++) CK(cudaStreamWaitEvent(c->slot[i].s, c->ev_fork, 0));
   return RBEPWT_OK;
 }
 
 // ... and ctx->stream continues after all of them
 int join_streams(rbepwt_ctx *c) {
-  cudaStream_t all[2 * NSLOT + 2] = {c->s_in, c->s_out};
-  for (int i = 0; i < 2 * NSLOT; i++) all[2 + i] = c->slot[i].s;
+  cudaStream_t all[NSLOTS + 2] = {c->s_in, c->s_out};
+  for (int i = 0; i < NSLOTS; i++) all[2 + i] = c->slot[i].s;
   for (cudaStream_t s : all) {
     CK(cudaEventRecord(c->ev_join, s));
     CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
@@ -252,7 +257,7 @@ int join_streams(rbepwt_ctx *c) {
 
 int check_path_error(rbepwt_ctx *c) {
   CK(cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < 2 * NSLOT; i++) {
+  for (int i = 0; i < NSLOTS; i++) {
     if (!c->slot[i].qmeta.p) continue;
     CK(cudaMemcpyAsync(c->pin_err, c->slot[i].qmeta.as<int>() + QM_ERR, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -596,7 +601,7 @@ int alloc_state(rbepwt_ctx *c, int B, int H, int W, int levels, int path_mode, u
     CK(c->tbl.ensure((size_t)Bc * 2 * N * 8));
     CK(c->slot_rid.ensure((size_t)Bc * 2 * N * 4));
   }
-  for (int i = 0; i < 2 * NSLOT; i++)
+  for (int i = 0; i < NSLOTS; i++)
     if (c->slot[i].qmeta.p) CK(cudaMemsetAsync(c->slot[i].qmeta.p, 0, QM_SIZE * 4, c->stream));
   return RBEPWT_OK;
 }
@@ -648,10 +653,11 @@ int run_pipeline(rbepwt_ctx *c, int what, long long k, const double *img_host, c
     if ((rc = need_events(c->ev_lab, ngrp)) || (rc = need_events(c->ev_path, ngrp)) || (rc = need_events(c->ev_img, nsub)) ||
         (rc = need_events(c->ev_done, nsub)))
       return rc;
-    for (int i = 0; i < c->nslot; i++) {
+    const int nx = serial ? 1 : NXSLOT;
+    for (int i = 0; i < c->nslot; i++)
       if ((what & DO_PATHS) && (rc = ensure_slot_workspace(c, c->slot[i], 0))) return rc;
+    for (int i = 0; i < nx; i++)
       if ((what & (DO_DWT | DO_DECODE)) && (rc = ensure_slot_workspace(c, c->slot[NSLOT + i], Bs))) return rc;
-    }
     if ((rc = fork_streams(c))) return rc;
     if (what & DO_PATHS)
       for (int g = 0; g < ngrp; g++)
@@ -671,7 +677,7 @@ int run_pipeline(rbepwt_ctx *c, int what, long long k, const double *img_host, c
     if (what & (DO_DWT | DO_THRESH | DO_DECODE))
       for (int s = 0; s < nsub; s++) {
         const int a = c0 + s * Bs, nb = std::min(Bs, c0 + nbc - a);
-        Slot &sl = c->slot[NSLOT + s % c->nslot];
+        Slot &sl = c->slot[NSLOT + s % nx];
         cudaStream_t st = serial ? c->slot[0].s : sl.s;
         if (what & DO_PATHS) CK(cudaStreamWaitEvent(st, c->ev_path[group_of[s]], 0));
         if ((what & DO_DWT) && img_host) CK(cudaStreamWaitEvent(st, c->ev_img[s], 0));
@@ -748,7 +754,7 @@ int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
   CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   CK(cudaStreamCreateWithPriority(&c->s_in, cudaStreamNonBlocking, prio_hi));
   CK(cudaStreamCreateWithPriority(&c->s_out, cudaStreamNonBlocking, prio_hi));
-  for (int i = 0; i < 2 * NSLOT; i++) {
+  for (int i = 0; i < NSLOTS; i++) {
     CK(cudaStreamCreateWithPriority(&c->slot[i].s, cudaStreamNonBlocking, i < NSLOT ? prio_lo : prio_hi));
     CK(cudaStreamCreateWithPriority(&c->slot[i].aux, cudaStreamNonBlocking, i < NSLOT ? prio_lo : prio_hi));
     CK(cudaEventCreateWithFlags(&c->slot[i].ev_a, cudaEventDisableTiming));
@@ -781,7 +787,7 @@ void rbepwt_destroy(rbepwt_ctx *c) {
                     &c->scratch_i32b, &c->psnr_out, &c->nz_out};
   for (auto b : bufs) b->release();
   for (auto &b : c->reg) b.release();
-  for (int i = 0; i < 2 * NSLOT; i++) {
+  for (int i = 0; i < NSLOTS; i++) {
     Slot &sl = c->slot[i];
     DevBuf *sb[] = {&sl.VA, &sl.VB, &sl.Vpix, &sl.queue, &sl.qhist, &sl.qmeta, &sl.qbins, &sl.chunk_start, &sl.chunk_cnt, &sl.gscratch};
     for (auto b : sb) b->release();
