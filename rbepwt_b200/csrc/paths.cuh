@@ -5,10 +5,13 @@
 // the point bookkeeping of RegionCollection.reduce / Region.reduce_points (1563-1584, 1349-1375).
 //
 // This file: the warp-per-region form -- one warp owns one region and walks its greedy path, the
-// lanes share the rows of the search window.  It serves the regions whose bounding-box bitmap is too
-// large for the thread-per-region kernel (paths_tpr.cuh, the common case) and the EPWT mode (one
-// region per image, values read per candidate).  The unvisited points are a bitmap over the region's
-// bounding box (shared memory; global scratch for boxes too large).
+// lanes share the rows of the search window (find_next_geo: euclid, integer keys; find_next: chebyshev
+// and EPWT, the reference's fp64 expressions).  It serves the LONG chains: regions of >= TPR_COOP_MIN
+// pixels, regions whose bounding-box bitmap is too large for a shared-memory arena, every region of a
+// small group (latency matters, not throughput), and the EPWT mode (one region per image, values read
+// per candidate).  The bulk -- hundreds of thousands of small regions per batch -- is walked thread per
+// region by paths_tpr.cuh.  The unvisited points are a bitmap over the region's bounding box (shared
+// memory; global scratch for boxes too large).
 //
 // Step rule (exactly the reference's, restated order-independently):
 //   candidates = unvisited points of the region inside the smallest square of half-width
@@ -30,9 +33,10 @@
 // positions: [ceil(a/2), ceil((a+n)/2)) at the next level), so one warp builds the region's
 // whole path pyramid, levels 1..L, without any inter-region synchronisation.
 //
-// Output: Q[level][a + t] = pixel id (row*W+col) of the t-th path point.  The transform kernels
-// address values by pixel, so the reference's per-region `permutation` lists are not needed on the
-// hot path (they are derived on demand, perm.cuh).
+// Output: Q[level][a + t] = pixel id (row*W+col) of the t-th path point, and for levels >= 2
+// Pm[level][a + t] = its place in the level's incoming order (= the reference's generating permutation
+// plus the region offset), which is what the transform kernels gather / scatter through (dwt.cuh).
+// `posmap` (pixel -> place in the next level's incoming order) links a level to the next.
 #pragma once
 #include "common.cuh"
 #include "regions.cuh"
