@@ -43,8 +43,8 @@
 // the answer is read from a 9 x 512 table in shared memory.  The table is filled at kernel start by
 // the same candidate code the generic path runs, so it cannot disagree with it.
 //
-// Three rows per trip.  For half-widths <= 15 a window row is one 32-bit word after a funnel shift
-// that puts column cj at bit 15, so a trip examines up to three rows with straight-line code; wider
+// Five rows per trip.  For half-widths <= 15 a window row is one 32-bit word after a funnel shift
+// that puts column cj at bit 15, so a trip examines up to five rows (a whole half-width-2 window); wider
 // windows (scattered regions) fall back to one bitmap word per trip.
 //
 // List mode.  From the first level at which a region keeps <= 32 points (spacing large, windows wide
@@ -192,11 +192,11 @@ __device__ unsigned long long g_tpr_stats[16 * 4 * 2 + 32];
 constexpr int TPR_LIST_MAX = 32;   // list mode from the first level with at most this many points
 constexpr int TPR_SLOT_MIN = 48;   // arena words per lane: list buffers A = [0,32), B = [32,48) ping-pong
 #ifndef TPR_ROWS_N
-#define TPR_ROWS_N 3
+#define TPR_ROWS_N 5
 #endif
 constexpr int TPR_ROWS_PER_TRIP = TPR_ROWS_N;
 #ifndef TPR_UNIT_STEPS_N
-#define TPR_UNIT_STEPS_N 2
+#define TPR_UNIT_STEPS_N 3
 #endif
 constexpr int TPR_UNIT_STEPS = TPR_UNIT_STEPS_N;  // unit steps a lane may take per trip
 // The large-bitmap instantiation walks 1..8 long chains per warp: trip overhead dominates, so a trip does more.
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
             S.reset();
           } else {
             if (rad <= TPR_MAX_RAD) {
-              // ---- up to three window rows, each one aligned word
+              // ---- up to TPR_ROWS_PER_TRIP window rows, each one aligned word
               fresh = false;
               const uint32_t wmask = ((2u << (2 * rad)) - 1u) << (15 - rad);
               if (WIDEWIN) {  // few long chains per warp: the whole window in one trip
@@ -444,13 +444,10 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
                   if (x) S.scan_row(x, i - ci, p0, p1);
                 }
               } else {
-#pragma unroll
-                for (int u = 0; u < TPR_ROWS_PER_TRIP; u++) {
-                  const bool act = i <= i1;
-                  const int ri = min(i, h - 1);
-                  const uint32_t x = act ? (row_window(bm + ri * ws, ws, cj) & wmask) : 0u;
-                  S.scan_row(x, ri - ci, p0, p1);
-                  i += act ? 1 : 0;
+#pragma unroll 1
+                for (int u = 0; u < TPR_ROWS_PER_TRIP && i <= i1; u++, i++) {  // only the rows the window has
+                  const uint32_t x = row_window(bm + i * ws, ws, cj) & wmask;
+                  if (x) S.scan_row(x, i - ci, p0, p1);
                 }
               }
               if (i > i1) {
