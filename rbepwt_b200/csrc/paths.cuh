@@ -54,6 +54,9 @@ struct PathParams {
   int *qmeta;
   int coop_min;  // regions of at least this many pixels get a warp of their own
   const uint8_t *unit_lut;  // 9 x 512 unit-step table of the path mode (global memory, built once per context)
+  uint32_t *gbm;            // [gbm_chunks][TPR_ARENA_WORDS] chunk bitmaps built by k1_bitmaps (paths_tpr.cuh)
+  int gbm_chunks;           // chunks beyond it build their bitmaps inside the path kernel
+  const uint32_t *s5_tab;   // 5x5 table step of k1_paths_tpr<MODE_EUCLID, false> (paths_tpr.cuh, S5_WORDS words)
   int32_t *Q;  // [B][2N]
   int32_t *Pm;      // [B][2N] level l >= 2: position of the path point in the level's incoming order (= index into cA of level l-1)
   int32_t *posmap;  // [B][N] scratch: pixel -> position in the next level's incoming order

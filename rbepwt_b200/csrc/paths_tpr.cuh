@@ -199,6 +199,14 @@ constexpr int TPR_ROWS_PER_TRIP = TPR_ROWS_N;
 #define TPR_UNIT_STEPS_N 3
 #endif
 constexpr int TPR_UNIT_STEPS = TPR_UNIT_STEPS_N;  // unit steps a lane may take per trip
+#ifndef TPR_S5_STEPS_N
+#define TPR_S5_STEPS_N 4
+#endif
+constexpr int TPR_S5_STEPS = TPR_S5_STEPS_N;      // 5x5 table steps a lane may take per trip
+#ifndef TPR_P2_MIN_N
+#define TPR_P2_MIN_N 1
+#endif
+constexpr int TPR_P2_MIN = TPR_P2_MIN_N;          // lanes that must be waiting before the window / list code runs
 // The large-bitmap instantiation walks 1..8 long chains per warp: trip overhead dominates, so a trip does more.
 #ifndef TPR_WIDE_UNIT_N
 #define TPR_WIDE_UNIT_N 8
@@ -227,6 +235,91 @@ __device__ __forceinline__ void build_unit_lut(uint8_t *lut) {  // any block siz
   }
 }
 
+// ---- 5x5 table step (euclid mode, small bitmaps) ---------------------------------------------------
+// The probes of half-width 1 and 2 see at most the 24 neighbours of the 5x5 window, and the key orders them by
+// d2 first: the classes d2 = 1, 2, 4, 5, 8 (4, 4, 4, 8, 4 cells).  The step is then three table reads, the
+// same instructions for every lane whatever its neighbourhood looks like:
+//   T1[row][5 window bits]  -> the row's cells as bits of a class-grouped code (A: bits 0-3, B: 4-7, C: 8-11,
+//                              D: 12-19, E: 20-23); the five rows are OR-ed;
+//   lowest set bit          -> the nearest class present and its field of the code;
+//   T2[pref][class, field]  -> the winning cell, for the 24 prefs that are themselves 5x5 offsets (the previous
+//                              step was such a step, or the level starts: 84 % of all steps of the benchmark).
+// Both tables are filled by the candidate code every other path runs (Search<MODE_EUCLID>), fp64 tie-break
+// included, so they cannot disagree with it.  The bitmap carries a margin of TPR_PAD = 2 empty rows and
+// columns, so the window never leaves it.
+constexpr int S5_T2_ROW = 320;                   // A 16 + B 16 + C 16 + D 256 + E 16 entries per pref
+constexpr int S5_T1_WORDS = 5 * 32;              // u32 [row][bits]
+constexpr int S5_CELL_WORDS = 8;                 // u8 [code bit] -> cell index (di+2)*5 + (dj+2), 24 used
+constexpr int S5_T2_WORDS = 25 * S5_T2_ROW / 4;  // u8 [pref cell][S5_T2_ROW]
+constexpr int S5_WORDS = S5_T1_WORDS + S5_CELL_WORDS + S5_T2_WORDS;
+
+// code bit of the cell (di, dj), -1 for the centre: classes by d2, cells of a class in row-major order
+__host__ __device__ constexpr int s5_code_bit(int di, int dj) {
+  const int d2 = di * di + dj * dj;
+  if (d2 == 0) return -1;
+  const int base = d2 == 1 ? 0 : d2 == 2 ? 4 : d2 == 4 ? 8 : d2 == 5 ? 12 : 20;
+  int before = 0;
+  for (int q = 0; q < (di + 2) * 5 + (dj + 2); q++) {
+    const int qi = q / 5 - 2, qj = q % 5 - 2;
+    if (qi * qi + qj * qj == d2) before++;
+  }
+  return base + before;
+}
+
+__device__ __forceinline__ void s5_field(uint32_t code, int &shift, uint32_t &fld, int &base) {
+  const int f = __ffs(code) - 1, g4 = f & ~3;
+  const bool isD = (unsigned)(f - 12) < 8u;
+  shift = isD ? 12 : g4;
+  fld = (code >> shift) & (isD ? 255u : 15u);
+  base = isD ? 48 : (f >= 20 ? 304 : g4 * 4);
+}
+
+__global__ void k_build_s5_tables(uint32_t *tab) {
+  uint8_t *cell_of_bit = reinterpret_cast<uint8_t *>(tab + S5_T1_WORDS);
+  uint8_t *t2 = reinterpret_cast<uint8_t *>(tab + S5_T1_WORDS + S5_CELL_WORDS);
+  for (int e = threadIdx.x; e < S5_T1_WORDS; e += blockDim.x) {
+    const int r = e >> 5, b = e & 31;
+    uint32_t code = 0;
+    for (int c = 0; c < 5; c++)
+      if ((b >> c) & 1) {
+        const int bit = s5_code_bit(r - 2, c - 2);
+        if (bit >= 0) code |= 1u << bit;
+      }
+    tab[e] = code;
+  }
+  for (int q = threadIdx.x; q < 32; q += blockDim.x) {
+    if (q < 25) {
+      const int bit = s5_code_bit(q / 5 - 2, q % 5 - 2);
+      if (bit >= 0) cell_of_bit[bit] = (uint8_t)q;
+    }
+    if (q >= 24) cell_of_bit[q] = 0xff;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 25 * S5_T2_ROW; e += blockDim.x) {
+    const int pid = e / S5_T2_ROW, idx = e % S5_T2_ROW;
+    const int p0 = pid / 5 - 2, p1 = pid % 5 - 2;
+    int shift, nb;
+    uint32_t fld;
+    if (idx < 48) { shift = (idx >> 4) * 4; fld = idx & 15; nb = 4; }
+    else if (idx < 304) { shift = 12; fld = idx - 48; nb = 8; }
+    else { shift = 20; fld = idx - 304; nb = 4; }
+    uint8_t v = 0xff;
+    if (pid != 12 && fld) {
+      Search<MODE_EUCLID> S;
+      S.reset();
+      for (int b = 0; b < nb; b++)
+        if ((fld >> b) & 1) {
+          const int q = cell_of_bit[shift + b];
+          S.consider(true, q / 5 - 2, q % 5 - 2, p0, p1);
+        }
+      int odi, odj, k;
+      S.finish(p0, p1, odi, odj, k);
+      v = (uint8_t)((odi + 2) * 5 + (odj + 2));
+    }
+    t2[e] = v;
+  }
+}
+
 // The tables are computed once per context (global memory, one per path mode); the path kernels copy theirs
 // into shared memory.
 template <int MODE>
@@ -238,23 +331,122 @@ __device__ __forceinline__ void load_unit_lut(uint8_t *s_lut, const uint8_t *g_l
   for (int e = threadIdx.x; e < TPR_LUT_ROWS * TPR_LUT_COLS / 4; e += blockDim.x) dst[e] = src[e];
 }
 
+// Bitmap geometry of region g in k1_paths_tpr: the bounding box with a margin of TPR_PAD on every side
+// (r0, c0 may be negative), ws words per row.
+__device__ __forceinline__ void tpr_geometry(const PathParams &P, int g, int &r0, int &c0, int &h, int &w, int &ws) {
+  r0 = (P.reg.first[g] >> P.logW) - TPR_PAD; c0 = P.reg.cmin[g] - TPR_PAD;
+  h = P.reg.rmax[g] - r0 + 1 + TPR_PAD; w = P.reg.cmax[g] - c0 + 1 + TPR_PAD; ws = (w + 31) >> 5;
+}
+
+// Cooperative bitmap build of one chunk: one ballot per bitmap word, lanes = columns; lane r holds region r's
+// geometry and its word offset `base` in `dst`.
+__device__ __forceinline__ void tpr_build_bitmaps(const PathParams &P, uint32_t *dst, int cnt, int img, int label, int r0,
+                                                  int c0, int h, int w, int ws, int base) {
+  const int lane = (int)lane_id(), logW = P.logW;
+  for (int r = 0; r < cnt; r++) {
+    const int img_r = __shfl_sync(FULL_MASK, img, r), label_r = __shfl_sync(FULL_MASK, label, r);
+    const int r0_r = __shfl_sync(FULL_MASK, r0, r), c0_r = __shfl_sync(FULL_MASK, c0, r);
+    const int h_r = __shfl_sync(FULL_MASK, h, r), w_r = __shfl_sync(FULL_MASK, w, r);
+    const int ws_r = __shfl_sync(FULL_MASK, ws, r), base_r = __shfl_sync(FULL_MASK, base, r);
+    const int32_t *lab = P.labels + (size_t)img_r * P.N;
+    const int words_r = h_r * ws_r;
+    if (ws_r == 1) {
+      // one word per row (the usual case): lane = column, the margin rows are known to be empty
+      const bool colok = lane < w_r && (unsigned)(c0_r + lane) < (unsigned)P.W;
+      const int32_t *pp = lab + c0_r + lane;
+      if (lane < 2 * TPR_PAD) dst[base_r + (lane < TPR_PAD ? lane : h_r - 2 * TPR_PAD + lane)] = 0u;
+      for (int wi = TPR_PAD; wi < h_r - TPR_PAD; wi += 8) {  // eight independent label loads in flight per lane
+        int lv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int row = r0_r + wi + u;
+          const bool ok = colok && wi + u < h_r - TPR_PAD && (unsigned)row < (unsigned)P.H;
+          lv[u] = ok ? pp[row << logW] : ~label_r;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const unsigned bits = __ballot_sync(FULL_MASK, lv[u] == label_r);
+          if (lane == 0 && wi + u < h_r - TPR_PAD) dst[base_r + wi + u] = bits;
+        }
+      }
+      continue;
+    }
+    for (int wi = 0; wi < words_r; wi += 8) {  // eight independent label loads in flight per lane
+      int lv[8];
+      bool inb[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int w_ = wi + u;
+        const int i = w_ / ws_r;
+        const int col = ((w_ - i * ws_r) << 5) + lane;
+        inb[u] = w_ < words_r && col < w_r && (unsigned)(r0_r + i) < (unsigned)P.H && (unsigned)(c0_r + col) < (unsigned)P.W;
+        lv[u] = inb[u] ? lab[((r0_r + i) << logW) + c0_r + col] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const unsigned bits = __ballot_sync(FULL_MASK, inb[u] && lv[u] == label_r);
+        if (lane == 0 && wi + u < words_r) dst[base_r + wi + u] = bits;
+      }
+    }
+  }
+}
+
+// The bitmaps of every chunk below P.gbm_chunks, built ahead of the walk by warps that do nothing else (the label
+// reads are pure memory latency; inside the path kernel they would hold a walking warp's registers and arena).
+// gbm[chunk][TPR_ARENA_WORDS]: the arena image k1_paths_tpr copies.
+__global__ void __launch_bounds__(256) k1_bitmaps(PathParams P) {
+  const int lane = (int)lane_id();
+  const int nchunks = min(P.qmeta[QM_NCHUNKS], P.gbm_chunks);
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int chunk = wid; chunk < nchunks; chunk += nw) {
+    const int qstart = P.chunk_start[chunk], cnt = P.chunk_cnt[chunk];
+    int img = 0, label = 0, r0 = 0, c0 = 0, h = 0, w = 0, ws = 0;
+    if (lane < cnt) {
+      const int g = P.queue[qstart + lane];
+      img = P.reg.img[g]; label = P.reg.label[g];
+      tpr_geometry(P, g, r0, c0, h, w, ws);
+    }
+    const int slot = lane < cnt ? max(h * ws, TPR_SLOT_MIN) : 0;
+    int inc = slot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_up_sync(FULL_MASK, inc, d);
+      if (lane >= d) inc += y;
+    }
+    tpr_build_bitmaps(P, P.gbm + (size_t)chunk * TPR_ARENA_WORDS, cnt, img, label, r0, c0, h, w, ws, inc - slot);
+  }
+}
+
 // WIDEWIN = true: the instantiation for the chunks of large bitmaps (queue classes below Q_FIRST_NARROW_CLS):
 // beyond half-width TPR_MAX_RAD it scans windows of half-width 16, 32, ... word by word instead of the whole
 // bitmap, which for a 10^4-pixel region is the difference between tens and thousands of words per far jump.
 // The common instantiation (small bitmaps) keeps the flat whole-bitmap scan and stays compact.
 template <int MODE, bool WIDEWIN>
 __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(PathParams P) {
-  __shared__ uint32_t s_arena[TPR_WARPS][TPR_ARENA_WORDS];
-  __shared__ __align__(16) uint8_t s_lut[TPR_LUT_ROWS * TPR_LUT_COLS];
+#ifdef TPR_NO_S5
+  constexpr bool S5 = false;
+#else
+  constexpr bool S5 = MODE == MODE_EUCLID && !WIDEWIN;  // the 5x5 table step replaces the unit-step table
+#endif
+  __shared__ __align__(16) uint32_t s_arena[TPR_WARPS * TPR_ARENA_WORDS + 4];  // + 1: the table step reads one word past a row
+  __shared__ __align__(16) uint8_t s_lut[S5 ? S5_WORDS * 4 : TPR_LUT_ROWS * TPR_LUT_COLS];
   const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
-  uint32_t *arena = s_arena[warp];
+  uint32_t *arena = s_arena + warp * TPR_ARENA_WORDS;
+  const uint32_t *s5_t1 = reinterpret_cast<const uint32_t *>(s_lut);
+  const uint8_t *s5_cell = s_lut + S5_T1_WORDS * 4;
+  const uint8_t *s5_t2 = s_lut + (S5_T1_WORDS + S5_CELL_WORDS) * 4;
   const int chunk_lo = WIDEWIN ? 0 : P.qmeta[QM_CHUNK_SPLIT];
   const int nchunks = (WIDEWIN ? P.qmeta[QM_CHUNK_SPLIT] : P.qmeta[QM_NCHUNKS]) - chunk_lo;
   if (nchunks <= 0) return;
   const int logW = P.logW, W = P.W, N = P.N, L = P.levels;
   const int Wm = W - 1;
 
-  load_unit_lut(s_lut, P.unit_lut);
+  if (S5) {
+    uint32_t *dst = reinterpret_cast<uint32_t *>(s_lut);
+    for (int e = threadIdx.x; e < S5_WORDS; e += blockDim.x) dst[e] = P.s5_tab[e];
+  } else {
+    load_unit_lut(s_lut, P.unit_lut);
+  }
   __syncthreads();
 
   // Each warp takes its share of the chunks and retires: the grid is several waves of CTAs, so SM slots keep
@@ -282,9 +474,9 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
       const int g = P.queue[qstart + lane];
       img = P.reg.img[g]; label = P.reg.label[g]; first = P.reg.first[g];
       size = P.reg.size[g]; off = P.reg.off[g];
-      r0 = first >> logW; c0 = P.reg.cmin[g];
-      h = P.reg.rmax[g] - r0 + 1; w = P.reg.cmax[g] - c0 + 1; ws = (w + 31) >> 5;
+      tpr_geometry(P, g, r0, c0, h, w, ws);
     }
+    const bool narrow = __all_sync(FULL_MASK, ws <= 1);     // every bitmap of the chunk has one word per row
     const int slot = mine ? max(h * ws, TPR_SLOT_MIN) : 0;  // the chunk table guarantees the sum fits
     int inc = slot;
 #pragma unroll
@@ -296,38 +488,35 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
     uint32_t *bm = arena + base;
     const float inv_ws = 1.0f / (float)max(ws, 1);
 
-    // cooperative bitmap build: one ballot per bitmap word, lanes = columns
-    for (int r = 0; r < cnt; r++) {
-      const int img_r = __shfl_sync(FULL_MASK, img, r), label_r = __shfl_sync(FULL_MASK, label, r);
-      const int r0_r = __shfl_sync(FULL_MASK, r0, r), c0_r = __shfl_sync(FULL_MASK, c0, r);
-      const int h_r = __shfl_sync(FULL_MASK, h, r), w_r = __shfl_sync(FULL_MASK, w, r);
-      const int ws_r = __shfl_sync(FULL_MASK, ws, r), base_r = __shfl_sync(FULL_MASK, base, r);
-      const int32_t *lab = P.labels + (size_t)img_r * N;
-      const int words_r = h_r * ws_r;
-      for (int wi = 0; wi < words_r; wi += 4) {  // four independent label loads in flight per lane
-        int lv[4];
-        bool inb[4];
+    if (chunk < P.gbm_chunks) {
+      // the bitmaps were built by k1_bitmaps (the same layout, in global memory): copy the chunk's words,
+      // 16 bytes per lane and load, every load in flight at once
+      const int nvec = (__shfl_sync(FULL_MASK, inc, 31) + 3) >> 2;
+      const uint4 *src = reinterpret_cast<const uint4 *>(P.gbm + (size_t)chunk * TPR_ARENA_WORDS);
+      uint4 *dst = reinterpret_cast<uint4 *>(arena);
+      for (int e0 = 0; e0 < nvec; e0 += 8 * 32) {
+        uint4 v[8];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int w_ = wi + u;
-          const int i = ws_r == 1 ? w_ : w_ / ws_r;
-          const int col = ((w_ - i * ws_r) << 5) + lane;
-          inb[u] = w_ < words_r && col < w_r;
-          lv[u] = inb[u] ? lab[((r0_r + i) << logW) + c0_r + col] : 0;
+        for (int u = 0; u < 8; u++) {
+          const int e = e0 + u * 32 + lane;
+          v[u] = e < nvec ? __ldcs(src + e) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const unsigned bits = __ballot_sync(FULL_MASK, inb[u] && lv[u] == label_r);
-          if (lane == 0 && wi + u < words_r) arena[base_r + wi + u] = bits;
+        for (int u = 0; u < 8; u++) {
+          const int e = e0 + u * 32 + lane;
+          if (e < nvec) dst[e] = v[u];
         }
       }
+    } else {
+      tpr_build_bitmaps(P, arena, cnt, img, label, r0, c0, h, w, ws, base);
     }
     __syncwarp();
 
     // every lane walks its own region; the warp advances level by level
     bool live = mine, list = false;
     int n = mine ? size : 0, a = off;
-    int si = 0, sj = (first & Wm) - c0;  // bitmap mode: start point
+    int si = TPR_PAD, sj = (first & Wm) - c0;  // bitmap mode: start point
+    const int pixbase = (r0 << logW) + c0;
     int lb = 0, sidx = 0;                // list mode: buffer offset of the level's list, index of its start point
     int32_t *Qimg = P.Q + (size_t)img * 2 * (size_t)N;
     int32_t *Pimg = P.Pm + (size_t)img * 2 * (size_t)N;
@@ -340,6 +529,8 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
       int t = n, ci = si, cj = sj, p0 = 0, p1 = 1;  // prefered_direc = (0,1)   rbepwt.py:1290
       int rad = 1, i = 0, wd = 0, i1 = 0;
       bool fresh = true;     // at the first row of a window
+      bool near = true;      // table-step variant: the step starts with the 5x5 window
+      int pid = 13;          // ... pref as a 5x5 cell index (p0+2)*5 + (p1+2), -1 when pref is a longer vector
       unsigned U = 0;        // list mode: unvisited mask
       int ncnt = 0;          // list mode: survivors appended to the other buffer
       uint32_t nmin = 0xffffffffu;
@@ -373,6 +564,66 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
         t = 1;
       }
       while (__any_sync(FULL_MASK, t < n)) {
+        if constexpr (S5) {
+        // ---- phase 1, table steps: 5x5 neighbourhood -> class-grouped code -> winner, up to TPR_S5_STEPS per trip;
+        // every lane that starts a step runs the same instructions
+#pragma unroll 1
+        for (int rep = 0; rep < TPR_S5_STEPS; rep++) {
+          const bool go = t < n && !list && near;
+          if (!__any_sync(FULL_MASK, go)) break;
+          if (go) {
+#ifdef TPR_STATS
+            atomicAdd(&g_tpr_stats[((min(lev, 16) - 1) * 4 + 0) * 2 + 1], 1ull);
+#endif
+            const int sc = cj - TPR_PAD;  // >= 0: the margin
+            const uint32_t *rp = bm + (ci - TPR_PAD) * ws + (sc >> 5);
+            const int sh = sc & 31;
+            uint32_t code = 0;
+            // the five bits straddle a word boundary only when sh > 27 (never with one word per row: cj + 2 < w <= 32)
+            if (narrow || !__any_sync(__activemask(), sh > 27)) {
+#pragma unroll
+              for (int rr = 0; rr < 5; rr++) code |= s5_t1[rr * 32 + ((rp[rr * ws] >> sh) & 31u)];
+            } else {
+#pragma unroll
+              for (int rr = 0; rr < 5; rr++)
+                code |= s5_t1[rr * 32 + (__funnelshift_r(rp[rr * ws], rp[rr * ws + 1], sh) & 31u)];
+            }
+            if (code) {
+              int shift, base, di, dj;
+              uint32_t fld;
+              s5_field(code, shift, fld, base);
+              if (pid >= 0) {
+                const int cell = s5_t2[pid * S5_T2_ROW + base + fld];
+                di = (cell * 13) >> 6;  // cell / 5 for cell < 25
+                dj = cell - 5 * di - 2;
+                di -= 2;
+                pid = cell;
+              } else {  // pref is a longer vector (the step after a jump): the class's cells through the candidate code
+                Search<MODE> T;
+                T.reset();
+                for (uint32_t u = fld; u; u &= u - 1) {
+                  const int q = s5_cell[shift + __ffs(u) - 1];
+                  const int qi = (q * 13) >> 6;
+                  T.consider(true, qi - 2, q - 5 * qi - 2, p0, p1);
+                }
+                int fk;
+                T.finish(p0, p1, di, dj, fk);
+                pid = (di + 2) * 5 + dj + 2;
+              }
+              p0 = di; p1 = dj;  // rbepwt.py:1331
+              ci += di; cj += dj;
+              bm[ci * ws + (cj >> 5)] &= ~(1u << (cj & 31));
+              Ql[t] = pixbase + (ci << logW) + cj;
+              t++;
+              rad = 4;  // where a miss of the next step starts
+            } else {  // nothing within half-width 2: the window search below, from the half-width of the last jump
+              near = false;
+              rad = max(rad, 4);
+              TPR_SET_WINDOW();
+            }
+          }
+        }
+        } else {
         // ---- phase 1, unit steps: 3x3 neighbourhood -> 9-bit mask -> table, up to TPR_UNIT_STEPS per trip
         // (half-width 1, unit pref: the state every dense stretch of a path is in)
 #pragma unroll 1
@@ -403,9 +654,19 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
             }
           }
         }
+        }
         // ---- phase 2: one unit of the other kinds
-        const bool unit_now = !list && fresh && rad == 1 && (unsigned)(p0 + 1) <= 2u && (unsigned)(p1 + 1) <= 2u;
-        if (t < n && !unit_now) {
+        const bool unit_now = S5 ? (!list && near)
+                                 : (!list && fresh && rad == 1 && (unsigned)(p0 + 1) <= 2u && (unsigned)(p1 + 1) <= 2u);
+        bool want2 = t < n && !unit_now;
+        if (S5 && TPR_P2_MIN > 1) {
+          // the other kinds wait until TPR_P2_MIN lanes want them (or no lane has a table step left): their code is long
+          // and divergent, so it is run for several lanes at once rather than in every trip for one or two
+          const int waiting = __popc(__ballot_sync(FULL_MASK, want2));
+          const bool table_left = __any_sync(FULL_MASK, t < n && unit_now);
+          want2 = want2 && (waiting >= TPR_P2_MIN || !table_left);
+        }
+        if (want2) {
           bool commit = false, expand = false;
           int fdi = 0, fdj = 0, fk = 0;
 #ifdef TPR_STATS
@@ -510,6 +771,8 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
                 ci = bi; cj = bj;
                 t++;
                 rad = 1 << fk;
+                near = true;
+                pid = max(abs(fdi), abs(fdj)) <= 2 ? (fdi + 2) * 5 + fdj + 2 : -1;
                 S.reset();
               } else if (rad > TPR_MAX_RAD &&
                          (!WIDEWIN || (ci - rad <= 0 && cj - rad <= 0 && ci + rad >= h - 1 && cj + rad >= w - 1))) {
@@ -523,63 +786,86 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
           }
         }
       }
-      // Pl[t] = place of the t-th path point in this level's incoming order (posmap was filled by the previous
-      // level's transition).  Done here, off the walk: independent loads, four in flight per lane.
-      if (lev >= 2) {
-        int tt = 0;
-        for (; tt + 4 <= n; tt += 4) {
-          const int q0 = __ldcg(Ql + tt), q1 = __ldcg(Ql + tt + 1), q2 = __ldcg(Ql + tt + 2), q3 = __ldcg(Ql + tt + 3);
-          const int v0 = __ldcg(posmap + q0), v1 = __ldcg(posmap + q1), v2 = __ldcg(posmap + q2), v3 = __ldcg(posmap + q3);
-          Pl[tt] = v0; Pl[tt + 1] = v1; Pl[tt + 2] = v2; Pl[tt + 3] = v3;
+      // ---- end of the level, one pass over the level's path Ql[0, n) (16 points per trip: four 16-byte loads, then
+      // their sixteen posmap reads, all in flight together -- this part of the kernel is pure memory latency):
+      //  * levels >= 2: Pl[t] = place of the t-th path point in this level's incoming order (posmap, filled by the
+      //    previous level's pass);
+      //  * RegionCollection.reduce: the points at even GLOBAL position a+t survive (rbepwt.py:1563-1584); they get
+      //    their place in the next level's incoming order (posmap) and are re-marked in the (all-zero) bitmap, or
+      //    become the list when at most TPR_LIST_MAX are left; the next start point is the lexicographically
+      //    smallest survivor (rbepwt.py:1035-1036).  (List mode collected its survivors during the walk.)
+      const int na = (a + 1) >> 1, nb = (a + n + 1) >> 1;
+      const int nnext = lev < L ? nb - na : 0;
+      {
+        const bool doP = lev >= 2;
+        const int smode = (!live || nnext <= 0 || list) ? 0 : (nnext <= TPR_LIST_MAX ? 2 : 1);  // 1 re-mark, 2 -> list
+        int minpix = INT32_MAX, lk = 0;
+        uint32_t mn = 0xffffffffu;
+        auto survivor = [&](int tt, int pix) {
+          posmap[pix] = (a + tt) >> 1;
+          const int pi = (pix >> logW) - r0, pj = (pix & Wm) - c0;
+          if (smode == 1) {
+            bm[pi * ws + (pj >> 5)] |= 1u << (pj & 31);
+            minpix = min(minpix, pix);
+          } else {
+            const uint32_t e = (uint32_t)(pi << 16) | (uint32_t)pj;
+            bm[lk] = e;
+            if (e < mn) { mn = e; sidx = lk; }
+            lk++;
+          }
+        };
+        const int nn = live ? n : 0;
+        // a ragged block (the head up to the 16-byte boundary, the tail): scalar loads, still all in flight together
+        auto ragged = [&](int t0, int t1) {
+          int q[16], v[16];
+#pragma unroll
+          for (int u = 0; u < 16; u++) q[u] = t0 + u < t1 ? __ldcg(Ql + t0 + u) : 0;
+          if (doP) {
+#pragma unroll
+            for (int u = 0; u < 16; u++) v[u] = t0 + u < t1 ? __ldcg(posmap + q[u]) : 0;
+#pragma unroll
+            for (int u = 0; u < 16; u++)
+              if (t0 + u < t1) Pl[t0 + u] = v[u];
+          }
+          if (smode) {
+#pragma unroll
+            for (int u = 0; u < 16; u++)
+              if (t0 + u < t1 && ((a + t0 + u) & 1) == 0) survivor(t0 + u, q[u]);
+          }
+        };
+        int tt = min(nn, (int)((4u - (unsigned)(((uintptr_t)Ql >> 2) & 3u)) & 3u));  // up to the 16-byte boundary
+        if (tt > 0) ragged(0, tt);
+        for (; tt + 16 <= nn; tt += 16) {
+          int q[16], v[16];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int4 x = __ldcg(reinterpret_cast<const int4 *>(Ql + tt) + u);
+            q[4 * u] = x.x; q[4 * u + 1] = x.y; q[4 * u + 2] = x.z; q[4 * u + 3] = x.w;
+          }
+          if (doP) {
+#pragma unroll
+            for (int u = 0; u < 16; u++) v[u] = __ldcg(posmap + q[u]);
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+              reinterpret_cast<int4 *>(Pl + tt)[u] = make_int4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+          }
+          if (smode) {
+            const int par = (a + tt) & 1;  // survivors: tt + par, tt + par + 2, ...
+#pragma unroll
+            for (int u = 0; u < 8; u++) survivor(tt + par + 2 * u, par ? q[2 * u + 1] : q[2 * u]);
+          }
         }
-        for (; tt < n; tt++) Pl[tt] = __ldcg(posmap + __ldcg(Ql + tt));
+        if (tt < nn) ragged(tt, nn);
+        if (smode == 1) { si = (minpix >> logW) - r0; sj = (minpix & Wm) - c0; }
+        if (smode == 2) { list = true; lb = 0; }
       }
       if (lev == L) break;
-      // RegionCollection.reduce: the points at even GLOBAL position a+t survive (rbepwt.py:1563-1584);
-      // the next start point is the lexicographically smallest survivor (rbepwt.py:1035-1036)
-      const int na = (a + 1) >> 1, nb = (a + n + 1) >> 1;
-      const int nnext = nb - na;
-      if (live && nnext > 0) {
-        if (list) {  // survivors were appended to the other buffer during the walk, in order: places na, na+1, ...
-          lb ^= 32; sidx = nminidx;
-          for (int k = 0; k < ncnt; k++) {
-            const uint32_t e = bm[lb + k];
-            posmap[((r0 + (int)(e >> 16)) << logW) + c0 + (int)(e & 0xffffu)] = na + k;
-          }
-        } else if (nnext <= TPR_LIST_MAX) {  // bitmap (all-zero now, dead) -> list in buffer A
-          list = true; lb = 0;
-          uint32_t mn = 0xffffffffu;
-          int k = 0;
-          for (int tt = a & 1; tt < n; tt += 2, k++) {
-            const int pix = __ldcg(Ql + tt);
-            const uint32_t e = (uint32_t)(((pix >> logW) - r0) << 16) | (uint32_t)((pix & Wm) - c0);
-            posmap[pix] = (a + tt) >> 1;
-            bm[k] = e;
-            if (e < mn) { mn = e; sidx = k; }
-          }
-        } else {  // re-mark the survivors in the (all-zero) bitmap
-          int minpix = INT32_MAX;
-          int tt = a & 1;
-          for (; tt + 6 < n; tt += 8) {  // four independent loads in flight
-            int px[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) px[u] = __ldcg(Ql + tt + 2 * u);
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const int pi = (px[u] >> logW) - r0, pj = (px[u] & Wm) - c0;
-              bm[pi * ws + (pj >> 5)] |= 1u << (pj & 31);
-              posmap[px[u]] = (a + tt + 2 * u) >> 1;
-              minpix = min(minpix, px[u]);
-            }
-          }
-          for (; tt < n; tt += 2) {
-            const int pix = __ldcg(Ql + tt);
-            const int pi = (pix >> logW) - r0, pj = (pix & Wm) - c0;
-            bm[pi * ws + (pj >> 5)] |= 1u << (pj & 31);
-            posmap[pix] = (a + tt) >> 1;
-            minpix = min(minpix, pix);
-          }
-          si = (minpix >> logW) - r0; sj = (minpix & Wm) - c0;
+      if (live && nnext > 0 && list && ncnt > 0) {
+        // list mode: survivors were appended to the other buffer during the walk, in order: places na, na+1, ...
+        lb ^= 32; sidx = nminidx;
+        for (int k = 0; k < ncnt; k++) {
+          const uint32_t e = bm[lb + k];
+          posmap[((r0 + (int)(e >> 16)) << logW) + c0 + (int)(e & 0xffffu)] = na + k;
         }
       }
       a = na; n = nnext;

@@ -92,7 +92,7 @@ struct Slot {
   cudaStream_t s = nullptr;
   cudaStream_t aux = nullptr;     // path slots: the large-bitmap path kernel runs beside the bulk one
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
-  DevBuf VA, VB, Vpix, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch;
+  DevBuf VA, VB, Vpix, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch, gbm;
 };
 
 struct rbepwt_ctx {
@@ -115,6 +115,7 @@ struct rbepwt_ctx {
   // wavelet
   bool has_wavelet = false;
   int flen = 0;
+  DevBuf s5_tab;  // tables of the 5x5 step (paths_tpr.cuh)
   DevBuf filt, unit_lut;  // unit_lut: two 9 x 512 tables (euclid, chebyshev)
   double h_filt[4][FT_MAX] = {};  // host copy (flen <= FT_MAX): passed to the transform kernels by value
   // state of the encoded batch
@@ -368,6 +369,10 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   CK(sl.queue.ensure_slack((size_t)nreg * 4));
   CK(sl.chunk_start.ensure_slack(((size_t)nreg + Q_BINS) * 4));
   CK(sl.chunk_cnt.ensure_slack(((size_t)nreg + Q_BINS) * 4));
+  // chunk bitmaps: room for the usual ~nreg/32 chunks (+ the partial chunk of every bin); more chunks than that
+  // (many large bitmaps) build theirs inside the path kernel
+  const size_t gbm_chunks = (size_t)nreg / 16 + Q_BINS;
+  CK(sl.gbm.ensure_slack(gbm_chunks * TPR_ARENA_WORDS * 4));
   CK(cudaStreamWaitEvent(s, ready, 0));
   {
     StageTimer t(c, RBEPWT_T_REGIONS, s);
@@ -404,6 +409,9 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   P.qmeta = sl.qmeta.as<int>();
   P.coop_min = coop_min;
   P.unit_lut = c->unit_lut.as<uint8_t>() + (c->mode == RBEPWT_PATH_CHEB ? TPR_LUT_ROWS * TPR_LUT_COLS : 0);
+  P.s5_tab = c->s5_tab.as<uint32_t>();
+  P.gbm = sl.gbm.as<uint32_t>();
+  P.gbm_chunks = (int)gbm_chunks;
   P.Q = c->Q.as<int32_t>();
   P.Pm = c->Pm.as<int32_t>();
   P.posmap = c->posmap.as<int32_t>();
@@ -439,6 +447,8 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   }
   {
     StageTimer t(c, RBEPWT_T_PATHS, s);
+    k1_bitmaps<<<c->sm_count * 8, 256, 0, s>>>(P);
+    c->launches++;
     // the large-bitmap chunks (few, the longest chains) run on the slot's auxiliary stream, beside the bulk
     CK(cudaEventRecord(sl.ev_a, s));
     CK(cudaStreamWaitEvent(sl.aux, sl.ev_a, 0));
@@ -767,6 +777,8 @@ int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
   CK(c->unit_lut.ensure(2 * TPR_LUT_ROWS * TPR_LUT_COLS));
   k_build_unit_lut<MODE_EUCLID><<<1, 256, 0, c->stream>>>(c->unit_lut.as<uint8_t>());
   k_build_unit_lut<MODE_CHEB><<<1, 256, 0, c->stream>>>(c->unit_lut.as<uint8_t>() + TPR_LUT_ROWS * TPR_LUT_COLS);
+  CK(c->s5_tab.ensure((size_t)S5_WORDS * 4));
+  k_build_s5_tables<<<1, 256, 0, c->stream>>>(c->s5_tab.as<uint32_t>());
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   *out = c;
@@ -782,14 +794,14 @@ void rbepwt_destroy(rbepwt_ctx *c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   for (auto *v : {&c->ev_lab, &c->ev_path, &c->ev_img, &c->ev_done})
     for (auto e : *v) cudaEventDestroy(e);
-  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->img_R,
+  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->s5_tab, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->img_R,
                     &c->img_rbase, &c->img_labmin, &c->img_direct, &c->tbl, &c->slot_rid, &c->scratch_i32,
                     &c->scratch_i32b, &c->psnr_out, &c->nz_out};
   for (auto b : bufs) b->release();
   for (auto &b : c->reg) b.release();
   for (int i = 0; i < NSLOTS; i++) {
     Slot &sl = c->slot[i];
-    DevBuf *sb[] = {&sl.VA, &sl.VB, &sl.Vpix, &sl.queue, &sl.qhist, &sl.qmeta, &sl.qbins, &sl.chunk_start, &sl.chunk_cnt, &sl.gscratch};
+    DevBuf *sb[] = {&sl.VA, &sl.VB, &sl.Vpix, &sl.queue, &sl.qhist, &sl.qmeta, &sl.qbins, &sl.chunk_start, &sl.chunk_cnt, &sl.gscratch, &sl.gbm};
     for (auto b : sb) b->release();
     cudaStreamDestroy(sl.s);
     cudaStreamDestroy(sl.aux);

@@ -409,9 +409,12 @@ __device__ __forceinline__ int region_bitmap_words(const RegionArrays &reg, int 
 }
 
 // Bitmap words used for the queue class: regions with a side above TPR_MAX_SIDE count as oversized.
+// k1_paths_tpr keeps a margin of TPR_PAD empty rows / columns around the bounding box, so that the 5x5
+// neighbourhood of any point of the region lies inside the bitmap (no bounds checks in its table step).
+constexpr int TPR_PAD = 2;
 __device__ __forceinline__ int region_class_words(const RegionArrays &reg, int g, int logW) {
-  const int h = reg.rmax[g] - (reg.first[g] >> logW) + 1;
-  const int w = reg.cmax[g] - reg.cmin[g] + 1;
+  const int h = reg.rmax[g] - (reg.first[g] >> logW) + 1 + 2 * TPR_PAD;
+  const int w = reg.cmax[g] - reg.cmin[g] + 1 + 2 * TPR_PAD;
   return (h > TPR_MAX_SIDE || w > TPR_MAX_SIDE) ? INT32_MAX : h * ((w + 31) >> 5);
 }
 
