@@ -196,11 +196,11 @@ constexpr int TPR_SLOT_MIN = 48;   // arena words per lane: list buffers A = [0,
 #endif
 constexpr int TPR_ROWS_PER_TRIP = TPR_ROWS_N;
 #ifndef TPR_UNIT_STEPS_N
-#define TPR_UNIT_STEPS_N 3
+#define TPR_UNIT_STEPS_N 4
 #endif
 constexpr int TPR_UNIT_STEPS = TPR_UNIT_STEPS_N;  // unit steps a lane may take per trip
 #ifndef TPR_S5_STEPS_N
-#define TPR_S5_STEPS_N 4
+#define TPR_S5_STEPS_N 2
 #endif
 constexpr int TPR_S5_STEPS = TPR_S5_STEPS_N;      // 5x5 table steps a lane may take per trip
 #ifndef TPR_P2_MIN_N
@@ -331,6 +331,10 @@ __device__ __forceinline__ void load_unit_lut(uint8_t *s_lut, const uint8_t *g_l
   for (int e = threadIdx.x; e < TPR_LUT_ROWS * TPR_LUT_COLS / 4; e += blockDim.x) dst[e] = src[e];
 }
 
+// Arena words of a region's slot: its bitmap, at least the two list buffers, and an ODD number, so that the slots
+// of a warp's 32 lanes start in different shared-memory banks (a stride of 48 would leave them two banks).
+__device__ __forceinline__ int tpr_slot_words(int words) { return max(words, TPR_SLOT_MIN) | 1; }
+
 // Bitmap geometry of region g in k1_paths_tpr: the bounding box with a margin of TPR_PAD on every side
 // (r0, c0 may be negative), ws words per row.
 __device__ __forceinline__ void tpr_geometry(const PathParams &P, int g, int &r0, int &c0, int &h, int &w, int &ws) {
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(256) k1_bitmaps(PathParams P) {
       img = P.reg.img[g]; label = P.reg.label[g];
       tpr_geometry(P, g, r0, c0, h, w, ws);
     }
-    const int slot = lane < cnt ? max(h * ws, TPR_SLOT_MIN) : 0;
+    const int slot = lane < cnt ? tpr_slot_words(h * ws) : 0;
     int inc = slot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -423,29 +427,39 @@ __global__ void __launch_bounds__(256) k1_bitmaps(PathParams P) {
 // The common instantiation (small bitmaps) keeps the flat whole-bitmap scan and stays compact.
 template <int MODE, bool WIDEWIN>
 __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(PathParams P) {
-#ifdef TPR_NO_S5
-  constexpr bool S5 = false;
+#ifdef TPR_TABLE5  // measured slower on the benchmark (its tables cost shared memory, hence L1): off by default
+  constexpr bool S5 = MODE == MODE_EUCLID && !WIDEWIN;  // 5x5 table steps beside the unit-step table
 #else
-  constexpr bool S5 = MODE == MODE_EUCLID && !WIDEWIN;  // the 5x5 table step replaces the unit-step table
+  constexpr bool S5 = false;
 #endif
+  constexpr bool COMPACT = !WIDEWIN;  // unit-step table without the always-empty centre bit, margin-based row fetch
   __shared__ __align__(16) uint32_t s_arena[TPR_WARPS * TPR_ARENA_WORDS + 4];  // + 1: the table step reads one word past a row
-  __shared__ __align__(16) uint8_t s_lut[S5 ? S5_WORDS * 4 : TPR_LUT_ROWS * TPR_LUT_COLS];
+  // unit-step table (table-step variant: compact, the always-empty centre bit dropped from the mask), 5x5 tables
+  constexpr int ULUT_BYTES = COMPACT ? TPR_LUT_ROWS * 256 : TPR_LUT_ROWS * TPR_LUT_COLS;
+  __shared__ __align__(16) uint8_t s_lut[ULUT_BYTES + (S5 ? S5_WORDS * 4 : 0)];
   const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
   uint32_t *arena = s_arena + warp * TPR_ARENA_WORDS;
-  const uint32_t *s5_t1 = reinterpret_cast<const uint32_t *>(s_lut);
-  const uint8_t *s5_cell = s_lut + S5_T1_WORDS * 4;
-  const uint8_t *s5_t2 = s_lut + (S5_T1_WORDS + S5_CELL_WORDS) * 4;
+  const uint8_t *s5_base = s_lut + ULUT_BYTES;
+  const uint32_t *s5_t1 = reinterpret_cast<const uint32_t *>(s5_base);
+  const uint8_t *s5_cell = s5_base + S5_T1_WORDS * 4;
+  const uint8_t *s5_t2 = s5_base + (S5_T1_WORDS + S5_CELL_WORDS) * 4;
   const int chunk_lo = WIDEWIN ? 0 : P.qmeta[QM_CHUNK_SPLIT];
   const int nchunks = (WIDEWIN ? P.qmeta[QM_CHUNK_SPLIT] : P.qmeta[QM_NCHUNKS]) - chunk_lo;
   if (nchunks <= 0) return;
   const int logW = P.logW, W = P.W, N = P.N, L = P.levels;
   const int Wm = W - 1;
 
-  if (S5) {
-    uint32_t *dst = reinterpret_cast<uint32_t *>(s_lut);
-    for (int e = threadIdx.x; e < S5_WORDS; e += blockDim.x) dst[e] = P.s5_tab[e];
+  if (COMPACT) {
+    for (int e = threadIdx.x; e < TPR_LUT_ROWS * 256; e += blockDim.x) {
+      const int q = e >> 8, m8 = e & 255;
+      s_lut[e] = P.unit_lut[q * TPR_LUT_COLS + ((m8 & 15) | ((m8 >> 4) << 5))];
+    }
   } else {
     load_unit_lut(s_lut, P.unit_lut);
+  }
+  if (S5) {
+    uint32_t *dst = reinterpret_cast<uint32_t *>(s_lut + ULUT_BYTES);
+    for (int e = threadIdx.x; e < S5_WORDS; e += blockDim.x) dst[e] = P.s5_tab[e];
   }
   __syncthreads();
 
@@ -477,7 +491,7 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
       tpr_geometry(P, g, r0, c0, h, w, ws);
     }
     const bool narrow = __all_sync(FULL_MASK, ws <= 1);     // every bitmap of the chunk has one word per row
-    const int slot = mine ? max(h * ws, TPR_SLOT_MIN) : 0;  // the chunk table guarantees the sum fits
+    const int slot = mine ? tpr_slot_words(h * ws) : 0;  // the chunk table guarantees the sum fits
     int inc = slot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -530,7 +544,7 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
       int rad = 1, i = 0, wd = 0, i1 = 0;
       bool fresh = true;     // at the first row of a window
       bool near = true;      // table-step variant: the step starts with the 5x5 window
-      int pid = 13;          // ... pref as a 5x5 cell index (p0+2)*5 + (p1+2), -1 when pref is a longer vector
+      bool ring = false;     // ... and its 3x3 neighbourhood is known to be empty (the unit-step table found nothing)
       unsigned U = 0;        // list mode: unvisited mask
       int ncnt = 0;          // list mode: survivors appended to the other buffer
       uint32_t nmin = 0xffffffffu;
@@ -565,15 +579,50 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
       }
       while (__any_sync(FULL_MASK, t < n)) {
         if constexpr (S5) {
-        // ---- phase 1, table steps: 5x5 neighbourhood -> class-grouped code -> winner, up to TPR_S5_STEPS per trip;
-        // every lane that starts a step runs the same instructions
+        // ---- phase 1a, unit steps: 3x3 neighbourhood -> 9-bit mask -> table, up to TPR_UNIT_STEPS per trip (unit pref:
+        // the state every dense stretch of a path is in).  The margin keeps the window inside the bitmap.
+#pragma unroll 1
+        for (int rep = 0; rep < TPR_UNIT_STEPS; rep++) {
+          const bool unit = t < n && !list && near && !ring && (unsigned)(p0 + 1) <= 2u && (unsigned)(p1 + 1) <= 2u;
+          if (!__any_sync(FULL_MASK, unit)) break;
+          if (unit) {
+#ifdef TPR_STATS
+            atomicAdd(&g_tpr_stats[((min(lev, 16) - 1) * 4 + 0) * 2 + 1], 1ull);
+#endif
+            const int sc = cj - 1;
+            const uint32_t *rp = bm + (ci - 1) * ws + (sc >> 5);
+            const int sh = sc & 31;
+            unsigned m;
+            // three bits straddle a word boundary only when sh > 29 (never with one word per row)
+            if (narrow || !__any_sync(__activemask(), sh > 29)) {
+              m = ((rp[0] >> sh) & 7u) | (((rp[ws] >> sh) & 7u) << 3) | (((rp[2 * ws] >> sh) & 7u) << 6);
+            } else {
+              m = (__funnelshift_r(rp[0], rp[1], sh) & 7u) | ((__funnelshift_r(rp[ws], rp[ws + 1], sh) & 7u) << 3) |
+                  ((__funnelshift_r(rp[2 * ws], rp[2 * ws + 1], sh) & 7u) << 6);
+            }
+            if (m) {
+              const int idx = s_lut[((p0 + 1) * 3 + (p1 + 1)) * 256 + ((m & 15u) | ((m >> 5) << 4))];
+              p0 = (idx * 11) >> 5;  // idx / 3 for idx < 9
+              p1 = idx - 3 * p0 - 1;
+              p0 -= 1;  // rbepwt.py:1331
+              ci += p0; cj += p1;
+              bm[ci * ws + (cj >> 5)] &= ~(1u << (cj & 31));
+              Ql[t] = pixbase + (ci << logW) + cj;
+              t++;
+            } else {
+              ring = true;  // nothing at distance 1: the 5x5 table step below
+            }
+          }
+        }
+        // ---- phase 1b, 5x5 table steps (pref not a unit step, or nothing at distance 1): neighbourhood -> class-grouped
+        // code -> winner, up to TPR_S5_STEPS per trip; every lane that takes one runs the same instructions
 #pragma unroll 1
         for (int rep = 0; rep < TPR_S5_STEPS; rep++) {
-          const bool go = t < n && !list && near;
+          const bool go = t < n && !list && near && (ring || (unsigned)(p0 + 1) > 2u || (unsigned)(p1 + 1) > 2u);
           if (!__any_sync(FULL_MASK, go)) break;
           if (go) {
 #ifdef TPR_STATS
-            atomicAdd(&g_tpr_stats[((min(lev, 16) - 1) * 4 + 0) * 2 + 1], 1ull);
+            atomicAdd(&g_tpr_stats[((min(lev, 16) - 1) * 4 + 1) * 2 + 1], 1ull);
 #endif
             const int sc = cj - TPR_PAD;  // >= 0: the margin
             const uint32_t *rp = bm + (ci - TPR_PAD) * ws + (sc >> 5);
@@ -588,16 +637,16 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
               for (int rr = 0; rr < 5; rr++)
                 code |= s5_t1[rr * 32 + (__funnelshift_r(rp[rr * ws], rp[rr * ws + 1], sh) & 31u)];
             }
+            ring = false;
             if (code) {
               int shift, base, di, dj;
               uint32_t fld;
               s5_field(code, shift, fld, base);
-              if (pid >= 0) {
-                const int cell = s5_t2[pid * S5_T2_ROW + base + fld];
+              if ((unsigned)(p0 + 2) <= 4u && (unsigned)(p1 + 2) <= 4u) {
+                const int cell = s5_t2[((p0 + 2) * 5 + p1 + 2) * S5_T2_ROW + base + fld];
                 di = (cell * 13) >> 6;  // cell / 5 for cell < 25
                 dj = cell - 5 * di - 2;
                 di -= 2;
-                pid = cell;
               } else {  // pref is a longer vector (the step after a jump): the class's cells through the candidate code
                 Search<MODE> T;
                 T.reset();
@@ -608,7 +657,6 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
                 }
                 int fk;
                 T.finish(p0, p1, di, dj, fk);
-                pid = (di + 2) * 5 + dj + 2;
               }
               p0 = di; p1 = dj;  // rbepwt.py:1331
               ci += di; cj += dj;
@@ -635,14 +683,29 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
             atomicAdd(&g_tpr_stats[((min(lev, 16) - 1) * 4 + 0) * 2 + 1], 1ull);
 #endif
             unsigned m = 0;
+            if constexpr (COMPACT) {
+              // the margin keeps the 3x3 window inside the bitmap; its three bits straddle a word boundary only
+              // when sh > 29 (never with one word per row)
+              const int sc = cj - 1;
+              const uint32_t *rp = bm + (ci - 1) * ws + (sc >> 5);
+              const int sh = sc & 31;
+              if (narrow || !__any_sync(__activemask(), sh > 29)) {
+                m = ((rp[0] >> sh) & 7u) | (((rp[ws] >> sh) & 7u) << 3) | (((rp[2 * ws] >> sh) & 7u) << 6);
+              } else {
+                m = (__funnelshift_r(rp[0], rp[1], sh) & 7u) | ((__funnelshift_r(rp[ws], rp[ws + 1], sh) & 7u) << 3) |
+                    ((__funnelshift_r(rp[2 * ws], rp[2 * ws + 1], sh) & 7u) << 6);
+              }
+            } else {
 #pragma unroll
-            for (int rr = 0; rr < 3; rr++) {
-              const int ri = ci + rr - 1;
-              const uint32_t x = (ri >= 0 && ri < h) ? row_window(bm + ri * ws, ws, cj) : 0u;
-              m |= ((x >> 14) & 7u) << (3 * rr);
+              for (int rr = 0; rr < 3; rr++) {
+                const int ri = ci + rr - 1;
+                const uint32_t x = (ri >= 0 && ri < h) ? row_window(bm + ri * ws, ws, cj) : 0u;
+                m |= ((x >> 14) & 7u) << (3 * rr);
+              }
             }
             if (m) {
-              const int idx = s_lut[((p0 + 1) * 3 + (p1 + 1)) * TPR_LUT_COLS + m];
+              const int idx = COMPACT ? s_lut[((p0 + 1) * 3 + (p1 + 1)) * 256 + ((m & 15u) | ((m >> 5) << 4))]
+                                      : s_lut[((p0 + 1) * 3 + (p1 + 1)) * TPR_LUT_COLS + m];
               p0 = idx / 3 - 1; p1 = idx % 3 - 1;  // rbepwt.py:1331
               ci += p0; cj += p1;
               bm[ci * ws + (cj >> 5)] &= ~(1u << (cj & 31));
@@ -772,7 +835,6 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
                 t++;
                 rad = 1 << fk;
                 near = true;
-                pid = max(abs(fdi), abs(fdj)) <= 2 ? (fdi + 2) * 5 + fdj + 2 : -1;
                 S.reset();
               } else if (rad > TPR_MAX_RAD &&
                          (!WIDEWIN || (ci - rad <= 0 && cj - rad <= 0 && ci + rad >= h - 1 && cj + rad >= w - 1))) {

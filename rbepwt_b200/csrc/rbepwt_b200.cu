@@ -779,6 +779,12 @@ int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
   k_build_unit_lut<MODE_CHEB><<<1, 256, 0, c->stream>>>(c->unit_lut.as<uint8_t>() + TPR_LUT_ROWS * TPR_LUT_COLS);
   CK(c->s5_tab.ensure((size_t)S5_WORDS * 4));
   k_build_s5_tables<<<1, 256, 0, c->stream>>>(c->s5_tab.as<uint32_t>());
+#ifdef TPR_TABLE5
+  // The two path-kernel instantiations of a mode run side by side (slot stream + auxiliary stream); kernels with
+  // different shared-memory carve-outs cannot share an SM, so with the table-step variant both ask for the largest.
+  CK(cudaFuncSetAttribute(k1_paths_tpr<MODE_EUCLID, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k1_paths_tpr<MODE_EUCLID, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+#endif
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   *out = c;
