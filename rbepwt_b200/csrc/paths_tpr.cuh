@@ -213,6 +213,10 @@ constexpr int TPR_P2_MIN = TPR_P2_MIN_N;          // lanes that must be waiting 
 #endif
 constexpr int TPR_UNIT_STEPS_WIDE = TPR_WIDE_UNIT_N;
 constexpr int TPR_MAX_RAD = 8;     // widest aligned-row window; beyond it the whole bitmap is scanned
+#ifndef TPR_SCAN_WORDS_N
+#define TPR_SCAN_WORDS_N 8
+#endif
+constexpr int TPR_SCAN_WORDS = TPR_SCAN_WORDS_N;  // ... that many words per trip
 
 // Unit-step table: lut[q * 512 + m] = index (di+1)*3 + (dj+1) of the winner among the neighbours present in the
 // 9-bit mask m, for pref = (q/3 - 1, q%3 - 1).  Filled by the candidate code every other path takes.
@@ -807,17 +811,17 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
                 // ---- nothing within TPR_MAX_RAD: scan the region's whole (small) bitmap, four words per trip.
                 // Ranking by (k, d2, dot) makes this equal to the remaining probes 2*TPR_MAX_RAD, ... in turn.
                 const int nwords = h * ws;
-                uint32_t b4[4];
+                uint32_t b4[TPR_SCAN_WORDS];
 #pragma unroll
-                for (int u = 0; u < 4; u++) b4[u] = wd + u < nwords ? bm[wd + u] : 0u;
+                for (int u = 0; u < TPR_SCAN_WORDS; u++) b4[u] = wd + u < nwords ? bm[wd + u] : 0u;
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+                for (int u = 0; u < TPR_SCAN_WORDS; u++)
                   if (b4[u]) {
                     const int wi = wd + u;
                     const int ri = ws == 1 ? wi : (int)(((float)wi + 0.5f) * inv_ws);  // wi / ws (wi < 2^11: exact)
                     S.scan_word(b4[u], (wi - ri * ws) << 5, ri - ci, cj, p0, p1);
                   }
-                wd += 4;
+                wd += TPR_SCAN_WORDS;
                 if (wd >= nwords) {
                   if (S.have()) { S.finish(p0, p1, fdi, fdj, fk); commit = true; }
                   else expand = true;  // the box is covered: reported as corrupt state below

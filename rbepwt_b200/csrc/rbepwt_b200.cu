@@ -545,7 +545,8 @@ int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
 
 int threshold_sub(rbepwt_ctx *c, cudaStream_t s, int a, int nb, long long k) {
   StageTimer t(c, RBEPWT_T_SELECT, s);
-  k4_threshold<<<nb * SEL_CLUSTER, SEL_THREADS, 0, s>>>(c->coefs.as<double>() + (size_t)a * c->N, c->N, k);
+  CK(cudaFuncSetAttribute(k4_threshold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_SMEM));
+  k4_threshold<<<nb * SEL_CLUSTER, SEL_THREADS, SEL_SMEM, s>>>(c->coefs.as<double>() + (size_t)a * c->N, c->N, k);
   c->launches++;
   CK(cudaGetLastError());
   return RBEPWT_OK;
