@@ -115,6 +115,21 @@ def test_large_regions_use_the_big_bitmap_path():
     assert_same_as_oracle(out, _oracle(img, lab, 16, "haar", "easypath", True, 1000), 16)
 
 
+def test_many_mid_sized_bitmaps_and_wide_regions():
+    """1024^2 tiled into 128^2 tiles of one-pixel anti-diagonal stripes: ~16k regions whose bounding-box bitmaps
+    are 100..700 words (queue classes 1-4, the windowed path kernel, more chunks than the prebuilt-bitmap buffer
+    holds, so the in-kernel bitmap build runs too), plus a band of long flat regions wider than one bitmap word."""
+    rng = np.random.default_rng(11)
+    ii, jj = np.meshgrid(np.arange(1024), np.arange(1024), indexing="ij")
+    lab = ((ii // 128) * 8 + (jj // 128)) * 256 + (ii % 128) + (jj % 128)
+    lab[:64] = 100000 + (ii[:64] // 2) * 16 + jj[:64] // 64  # 2 x 64 boxes: two words per bitmap row
+    lab = lab.astype(np.int32)
+    img = rng.uniform(0, 255, size=(1024, 1024))
+    for euclid in (True, False):
+        out = cuda_run(img, lab, 12, "haar", euclidean_distance=euclid, ncoefs=5000, with_perm=False)
+        assert_same_as_oracle(out, _oracle(img, lab, 12, "haar", "easypath", euclid, 5000), 12)
+
+
 def test_batch_equals_singles_and_threshold_properties():
     from rbepwt_b200 import synth
     import rbepwt_b200 as rb
@@ -168,6 +183,35 @@ def test_threshold_ties_keep_highest_index():
     np.testing.assert_array_equal(np.flatnonzero(got), [20, 33, 50])
     from oracle import c_oracle
     np.testing.assert_array_equal(got, c_oracle.threshold(flat, 3))
+
+
+@pytest.mark.parametrize("kind", ["one_binade", "few_values", "mixed"])
+def test_threshold_512_crowded_magnitudes_vs_oracle(kind):
+    """K4 keeps the candidates of the first digit in shared memory; these distributions overflow that buffer
+    (every CTA slice holds more same-binade keys than fit) or tie massively, so the global-memory passes and
+    the highest-index tie rule run at full size."""
+    import rbepwt_b200 as rb
+    from oracle import c_oracle
+
+    rng = np.random.default_rng({"one_binade": 1, "few_values": 2, "mixed": 3}[kind])
+    n = 512 * 512
+    if kind == "one_binade":
+        flat = rng.uniform(1.0, 1.24, n) * rng.choice([-1.0, 1.0], n)  # one quarter-binade: a single first digit
+    elif kind == "few_values":
+        flat = rng.choice([0.0, 0.5, -0.5, 3.0, -3.0, 7.25], n, p=[0.3, 0.25, 0.25, 0.1, 0.05, 0.05])
+    else:
+        flat = rng.normal(0, 2.0, n)
+        flat[rng.integers(0, n, n // 3)] = 1.5  # a third of the slice in one bin, the rest spread
+    img = np.zeros((512, 512))
+    lab = np.zeros((512, 512), np.int32)
+    c = rb.BatchCodec()
+    c.encode(img[None], lab[None], 1, "haar")
+    for k in (5, 2048, 100000, n - 7):
+        c.set_coefs(flat, 0)
+        c.threshold(k)
+        got = c.coefs(0)
+        assert np.count_nonzero(got) == min(k, np.count_nonzero(flat))
+        np.testing.assert_array_equal(got, c_oracle.threshold(flat, k))
 
 
 def test_device_pointer_path_matches_host_path():
