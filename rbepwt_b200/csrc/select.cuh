@@ -19,7 +19,10 @@ namespace cg = cooperative_groups;
 constexpr int SEL_THREADS = 1024;
 constexpr int SEL_MAXBINS = 8192;
 constexpr int SEL_CLUSTER = 8;  // CTAs per image: one thread-block cluster, histograms combined through DSMEM
-constexpr int SEL_CAND = 6144;  // candidate keys a CTA keeps in shared memory after the second pass
+#ifndef SEL_CAND_N
+#define SEL_CAND_N 6144
+#endif
+constexpr int SEL_CAND = SEL_CAND_N;  // candidate keys a CTA keeps in shared memory after the second pass
 constexpr size_t SEL_SMEM = (size_t)SEL_CAND * 8;  // dynamic shared memory of k4_threshold
 
 // One CLUSTER of SEL_CLUSTER CTAs per image.  Each CTA owns a contiguous slice of the coefficients and, in the
