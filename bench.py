@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--e2e-inflight", type=int, default=2, help="steps in flight in the end-to-end measurement")
     ap.add_argument("--sub-batch", type=int, default=0, help="images per transform sub-batch (0 = library default)")
     ap.add_argument("--path-group", type=int, default=0, help="images per path group (0 = library default)")
+    ap.add_argument("--clock-period", type=float, default=0.02, help="seconds between NVML clock samples in the timed region")
     return ap.parse_args()
 
 
@@ -251,7 +252,7 @@ def run_ours(args):
     assert int(nz.min()) == NCOEFS and int(nz.max()) == NCOEFS, nz
     psnr0 = float(codec.psnr(imgs[:1], out[:1])[0])
 
-    sampler = ClockSampler(physical_gpu_index(local))
+    sampler = ClockSampler(physical_gpu_index(local), period=args.clock_period)
     l0 = codec.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
