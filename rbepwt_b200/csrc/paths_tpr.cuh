@@ -12,9 +12,10 @@
 //
 // Lane state machine.  Lanes need windows of different size at the same time; if each lane ran its
 // whole search before the warp moved on, the warp would wait for the widest window at every step.
-// Instead one trip of the warp loop lets every lane examine ONE bitmap word of its current window;
-// a lane that exhausts its window commits the step (or doubles the window) and starts the next
-// search on the following trip, independently of its neighbours.
+// Instead one trip of the warp loop lets every lane do one bounded unit of its current search (a few
+// table steps, a few window rows or bitmap words, one list step); a lane that exhausts its window commits
+// the step (or doubles the window) and starts the next search on the following trip, independently of
+// its neighbours.
 //
 // Window guess.  The reference probes half-widths 1,2,4,... in turn.  Scanning the window of
 // half-width R once and ranking candidates by (k, dist, ...) with k = ceil(log2(Chebyshev distance))
@@ -39,18 +40,28 @@
 // has sides <= TPR_MAX_SIDE = 1024 (d2 < 2^21).  Updates are selects: all lanes execute the same instructions.
 //
 // Unit-step fast path.  When the window half-width is 1 and pref is one of the 8 unit steps (the
-// common case at level 1: 88 % of the steps), the 3x3 neighbourhood is gathered into a 9-bit mask and
-// the answer is read from a 9 x 512 table in shared memory.  The table is filled at kernel start by
-// the same candidate code the generic path runs, so it cannot disagree with it.
+// common case at level 1: 88 % of the steps), the 3x3 neighbourhood is gathered into a mask and the
+// answer is read from a table in shared memory (9 prefs x 256 masks: the centre bit is always empty).  The
+// table is filled once per context by the same candidate code the generic path runs, so it cannot disagree
+// with it.  Every bitmap carries a margin of TPR_PAD = 2 empty rows and columns around the bounding box, so
+// the fetch is three shared loads and shifts without bounds checks.
 //
 // Five rows per trip.  For half-widths <= 15 a window row is one 32-bit word after a funnel shift
 // that puts column cj at bit 15, so a trip examines up to five rows (a whole half-width-2 window); wider
-// windows (scattered regions) fall back to one bitmap word per trip.
+// windows (scattered regions) fall back to eight bitmap words per trip.
 //
 // List mode.  From the first level at which a region keeps <= 32 points (spacing large, windows wide
 // and mostly empty) the lane drops the bitmap and holds the points as a list of packed (row, col) in
 // its arena slot; a step scans the remaining points (a 32-bit unvisited mask) with the same candidate
 // code, so the cost per step is the number of points left instead of the window area.
+//
+// Memory latency kept off the walk.  The chunk's bitmaps are built from the labels by k1_bitmaps, a kernel
+// of its own (global memory, arena layout), and copied into the arena with 16-byte loads; at the end of a level
+// ONE pass over the level's path writes the incoming-order positions (levels >= 2) and re-marks the survivors,
+// 16 points per trip with every load in flight.
+//
+// 5x5 table step (-DTPR_TABLE5, off: measured slower).  The probes of half-width 1 and 2
+// resolved by three table reads with the same instructions for every lane.
 //
 // Shared memory: one arena of TPR_ARENA_WORDS words per warp holds the bounding-box bitmaps of the
 // chunk's regions (chunk table: regions.cuh; a chunk always fits).
