@@ -43,7 +43,7 @@
 // common case at level 1: 88 % of the steps), the 3x3 neighbourhood is gathered into a mask and the
 // answer is read from a table in shared memory (9 prefs x 256 masks: the centre bit is always empty).  The
 // table is filled once per context by the same candidate code the generic path runs, so it cannot disagree
-// with it.  Every bitmap carries a margin of TPR_PAD = 2 empty rows and columns around the bounding box, so
+// with it.  Every bitmap carries a margin of TPR_PAD = 1 empty row and column around the bounding box, so
 // the fetch is three shared loads and shifts without bounds checks.
 //
 // Five rows per trip.  For half-widths <= 15 a window row is one 32-bit word after a funnel shift
@@ -410,14 +410,17 @@ __device__ __forceinline__ void tpr_build_bitmaps(const PathParams &P, uint32_t 
   }
 }
 
-// The bitmaps of every chunk below P.gbm_chunks, built ahead of the walk by warps that do nothing else (the label
-// reads are pure memory latency; inside the path kernel they would hold a walking warp's registers and arena).
-// gbm[chunk][TPR_ARENA_WORDS]: the arena image k1_paths_tpr copies.
+// The bitmaps of the small-bitmap chunks (the bulk kernel's: from QM_CHUNK_SPLIT on, the first P.gbm_chunks of them),
+// built ahead of the walk by warps that do nothing else (the label reads are pure memory latency; inside the path
+// kernel they would hold a walking warp's registers and arena).  gbm[chunk - split][TPR_ARENA_WORDS]: the arena
+// image k1_paths_tpr copies.  The large-bitmap chunks of the windowed instantiation build theirs in the kernel:
+// one warp needs hundreds of dependent rounds for a 2000-word bitmap, and every path kernel would wait for it.
 __global__ void __launch_bounds__(256) k1_bitmaps(PathParams P) {
   const int lane = (int)lane_id();
-  const int nchunks = min(P.qmeta[QM_NCHUNKS], P.gbm_chunks);
+  const int split = P.qmeta[QM_CHUNK_SPLIT];
+  const int nchunks = min(P.qmeta[QM_NCHUNKS], split + P.gbm_chunks);
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  for (int chunk = wid; chunk < nchunks; chunk += nw) {
+  for (int chunk = split + wid; chunk < nchunks; chunk += nw) {
     const int qstart = P.chunk_start[chunk], cnt = P.chunk_cnt[chunk];
     int img = 0, label = 0, r0 = 0, c0 = 0, h = 0, w = 0, ws = 0;
     if (lane < cnt) {
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(256) k1_bitmaps(PathParams P) {
       const int y = __shfl_up_sync(FULL_MASK, inc, d);
       if (lane >= d) inc += y;
     }
-    tpr_build_bitmaps(P, P.gbm + (size_t)chunk * TPR_ARENA_WORDS, cnt, img, label, r0, c0, h, w, ws, inc - slot);
+    tpr_build_bitmaps(P, P.gbm + (size_t)(chunk - split) * TPR_ARENA_WORDS, cnt, img, label, r0, c0, h, w, ws, inc - slot);
   }
 }
 
@@ -517,11 +520,11 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
     uint32_t *bm = arena + base;
     const float inv_ws = 1.0f / (float)max(ws, 1);
 
-    if (chunk < P.gbm_chunks) {
+    if (!WIDEWIN && chunk - chunk_lo < P.gbm_chunks) {
       // the bitmaps were built by k1_bitmaps (the same layout, in global memory): copy the chunk's words,
       // 16 bytes per lane and load, every load in flight at once
       const int nvec = (__shfl_sync(FULL_MASK, inc, 31) + 3) >> 2;
-      const uint4 *src = reinterpret_cast<const uint4 *>(P.gbm + (size_t)chunk * TPR_ARENA_WORDS);
+      const uint4 *src = reinterpret_cast<const uint4 *>(P.gbm + (size_t)(chunk - chunk_lo) * TPR_ARENA_WORDS);
       uint4 *dst = reinterpret_cast<uint4 *>(arena);
       for (int e0 = 0; e0 < nvec; e0 += 8 * 32) {
         uint4 v[8];

@@ -1,0 +1,172 @@
+/*
+ * rbepwt_b200 -- C ABI of the B200-native RBEPWT encode -> threshold -> decode path.
+ *
+ * The reference (nareto/rbepwt) is a single Python module with no FFI of its own
+ * (SURVEY.md section 8b); this is the boundary a maintainer binds with ctypes underneath
+ * rbepwt.Image.  Each entry point names the reference code it replaces
+ * (file:line in rbepwt.py).  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative RBEPWT_E_* code on failure;
+ *     rbepwt_last_error() returns a thread-local message for the last failure.
+ *   - one context = one GPU + one CUDA stream + device-resident state of ONE encoded batch
+ *     (B images of the same H x W, levels, wavelet, path mode).  Not thread-safe per context;
+ *     use one context per host thread / per GPU.
+ *   - `flags & RBEPWT_DEVICE_PTRS`: img/labels/out pointers are DEVICE pointers on the
+ *     context's GPU (no copy is made; inputs must stay valid until the call returns);
+ *     otherwise they are HOST pointers and the call copies through the context's stream.
+ *   - images are float64 [B][H][W] row-major; labels int32 [B][H][W]; H*W must be a power
+ *     of two and 2^levels <= H*W (rbepwt.py:301-302, 1977-1978).
+ *   - calls are asynchronous on the context's stream when given device pointers; host-pointer
+ *     calls return after their copies completed.  rbepwt_sync() waits for everything.
+ */
+#ifndef RBEPWT_B200_H
+#define RBEPWT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rbepwt_ctx rbepwt_ctx;
+
+/* error codes */
+#define RBEPWT_OK 0
+#define RBEPWT_E_CUDA (-1)        /* CUDA runtime error, see rbepwt_last_error() */
+#define RBEPWT_E_NOT_POW2 (-2)    /* "Image size must be a power of 2"            rbepwt.py:301-302 */
+#define RBEPWT_E_LEVELS (-3)      /* "2^levels must be smaller or equal ..."      rbepwt.py:1977-1978 */
+#define RBEPWT_E_NO_ENCODING (-4) /* "There is no saved encoding to decode"       rbepwt.py:2057-2058 */
+#define RBEPWT_E_ARG (-5)         /* bad argument */
+#define RBEPWT_E_NO_WAVELET (-6)  /* rbepwt_set_wavelet not called */
+#define RBEPWT_E_NO_GPU (-7)      /* no usable CUDA device: there is NO CPU fallback */
+
+/* path modes: Region.easy_path distance rule                                      rbepwt.py:1301-1306 */
+#define RBEPWT_PATH_EUCLID 0 /* path_type='easypath', euclidean_distance=True  */
+#define RBEPWT_PATH_CHEB 1   /* path_type='easypath', euclidean_distance=False */
+#define RBEPWT_PATH_EPWT 2   /* path_type='epwt-easypath' (labels ignored, one region) */
+
+/* flags */
+#define RBEPWT_DEVICE_PTRS 1u /* pointer arguments are device pointers */
+#define RBEPWT_U8_WRAP 2u     /* EPWT level 1: |a-b| wraps modulo 256 like numpy uint8 scalars (rbepwt.py:1302) */
+#define RBEPWT_PATHS_FIRST_LEVEL 4u /* paths_first_level=True: Region.same_path (identity permutation) at every
+                                       level >= 2, paths are searched at level 1 only (rbepwt.py:1183-1188, 2024-2025) */
+
+/* Create a context on CUDA device `device`.  `stream` is a cudaStream_t to run on (e.g.
+ * torch's current stream) or NULL to create a private one.  Fails with RBEPWT_E_NO_GPU when
+ * there is no CUDA device -- the library has no CPU path. */
+int rbepwt_create(int device, void *stream, rbepwt_ctx **out);
+void rbepwt_destroy(rbepwt_ctx *ctx);
+const char *rbepwt_last_error(void);
+int rbepwt_sync(rbepwt_ctx *ctx);
+
+/* Filter bank of the wavelet, PyWavelets convention (pywt.Wavelet(name).filter_bank):
+ * replaces the `wavelet` argument of pywt.dwt / pywt.idwt                     rbepwt.py:2041, 2067 */
+int rbepwt_set_wavelet(rbepwt_ctx *ctx, int filter_len, const double *dec_lo, const double *dec_hi,
+                       const double *rec_lo, const double *rec_hi);
+
+/* Image.encode_rbepwt / Rbepwt.encode for a batch                     rbepwt.py:298-305, 1996-2053
+ * (+ Segmentation.compute_label_dict 840-848, Region.easy_path 1273-1347,
+ *    RegionCollection.reduce 1563-1584, pywt.dwt 2041).
+ * labels may be NULL iff path_mode == RBEPWT_PATH_EPWT. */
+int rbepwt_encode(rbepwt_ctx *ctx, const double *img, const int32_t *labels, int B, int H, int W,
+                  int levels, int path_mode, unsigned flags);
+
+/* Execution options (set between calls).
+ *   RBEPWT_OPT_STREAMS : 1 or 2 (default 2) units of each kind in flight: the batch is cut into path groups and
+ *                        transform sub-batches whose copies, path kernels and transform kernels overlap on
+ *                        internal streams; every call is still ordered on the context's stream.
+ *                        1 = all kernels on one stream (per-kernel timing).
+ *   RBEPWT_OPT_SUBBATCH: images per transform sub-batch (0 = auto: about 2^24 pixels).
+ *   RBEPWT_OPT_PATHGROUP: images per path group -- label scan + path pyramid (0 = auto: about 2^26 pixels;
+ *                        rounded to a multiple of the sub-batch). */
+#define RBEPWT_OPT_STREAMS 1
+#define RBEPWT_OPT_SUBBATCH 2
+#define RBEPWT_OPT_PATHGROUP 3
+int rbepwt_set_option(rbepwt_ctx *ctx, int option, int64_t value);
+
+/* Rbepwt.threshold_coefs(ncoefs), per image                                 rbepwt.py:2081-2112
+ * k <= 0 or k >= H*W keeps everything (reference quirk).  Ties at the k-th magnitude are
+ * unpinned in the reference; here the highest flat index survives. */
+int rbepwt_threshold(rbepwt_ctx *ctx, int64_t k);
+
+/* Rbepwt.decode + RegionCollection.expand + Image.decode_rbepwt (clip to [0,255], no rounding)
+ *                                                           rbepwt.py:2055-2079, 1586-1613, 307-317
+ * out: float64 [B][H][W]. */
+int rbepwt_decode(rbepwt_ctx *ctx, double *out_img, unsigned flags);
+
+/* encode -> threshold(k) -> decode in ONE call: the three reference calls above back to back
+ * (rbepwt.py:298, 441, 307), with the sub-batches pipelined so that, for host pointers, the input copy of
+ * one sub-batch, the kernels of the next and the output copy of the previous overlap.  Leaves the same
+ * state as the three calls (thresholded coefficients, paths).  out_img: float64 [B][H][W]. */
+int rbepwt_transcode(rbepwt_ctx *ctx, const double *img, const int32_t *labels, int B, int H, int W,
+                     int levels, int path_mode, int64_t k, double *out_img, unsigned flags);
+
+/* Decoder-side path regeneration (full_decode): build all paths from label maps alone, then
+ * decode caller-supplied coefficients (flat layout below, [B][H*W]).          rbepwt.py:106-130
+ * Only for the geometric path modes (paths do not depend on pixel values). */
+int rbepwt_full_decode(rbepwt_ctx *ctx, const double *coefs, const int32_t *labels, int B, int H,
+                       int W, int levels, int path_mode, double *out_img, unsigned flags);
+
+/* psnr(img1, img2) per image: 20 log10(255 / sqrt(mean sq err)), -1 if identical  rbepwt.py:156-162
+ * a, b: float64 [B][H][W]; out: HOST float64 [B]. */
+int rbepwt_psnr(rbepwt_ctx *ctx, const double *a, const double *b, int B, int64_t n, double *out,
+                unsigned flags);
+
+/* Image.nonzero_coefs per image; out: HOST int64 [B]                         rbepwt.py:421-432 */
+int rbepwt_nonzero_coefs(rbepwt_ctx *ctx, int64_t *out);
+
+/* Coefficients of image b in the reference's flat layout (Rbepwt.flat_wavelet, rbepwt.py:2195-2204):
+ * details[1] | details[2] | ... | details[L] | approximation, H*W doubles.  HOST pointers.
+ * set_coefs is what scripts/compute_basis_elements.py:58-81 needs (edit, then decode). */
+int rbepwt_get_coefs(rbepwt_ctx *ctx, int b, double *flat);
+int rbepwt_set_coefs(rbepwt_ctx *ctx, int b, const double *flat);
+
+/* Region bookkeeping of image b (HOST outputs).
+ *   region_count : number of regions R (label classes, in first-appearance order 840-848)
+ *   region_offsets: int32 [R+1] offsets at LEVEL 1; level l offsets are ceil(off / 2^(l-1))
+ *                  (RegionCollection.reduce keeps the even global positions, 1563-1584)
+ *   region_labels: int32 [R] label value of each region */
+int rbepwt_region_count(rbepwt_ctx *ctx, int b, int32_t *R);
+int rbepwt_region_offsets(rbepwt_ctx *ctx, int b, int32_t *off);
+int rbepwt_region_labels(rbepwt_ctx *ctx, int b, int32_t *labels);
+
+/* Paths of image b at `level` (1..L): pixel id (row*W+col) of every point of the level's
+ * concatenated signal, regions in order, each region in PATH order (Region.base_points after
+ * easy_path, 1338-1342).  level == L+1: the approximation's points in their (incoming) order.
+ * level == 0: level-1 INCOMING order (row-major inside each region).  HOST int32 [N >> (level-1)]. */
+int rbepwt_get_paths(rbepwt_ctx *ctx, int b, int level, int32_t *pix);
+/* Region.permutation of every region at `level` (1..L), concatenated: perm[off_r + t] = index in
+ * the region's incoming order of its t-th path point                          rbepwt.py:1285, 1333 */
+int rbepwt_get_perm(rbepwt_ctx *ctx, int b, int level, int32_t *perm);
+
+/* Values of image b in the INCOMING order of `level` (1..L): level 1 = pixel values in region order,
+ * level l >= 2 = the low-pass output of level l-1 (RegionCollection.values after reduce, 1578).
+ * Recomputed from the image given to rbepwt_encode, which must still be valid when device
+ * pointers were used.  HOST float64 [N >> (level-1)]. */
+int rbepwt_get_level_values(rbepwt_ctx *ctx, int b, int level, double *vals);
+
+/* Per-stage device timings (CUDA events on the context's stream) of the most recent
+ * encode / threshold / decode when enabled.  ms[RBEPWT_T_*]; returns the number of stages. */
+#define RBEPWT_T_H2D 0
+#define RBEPWT_T_REGIONS 1 /* K0: label map -> region records + work queue */
+#define RBEPWT_T_PATHS 2   /* K1: easy-path pyramid, regions whose bitmap fits a per-warp shared-memory slot */
+#define RBEPWT_T_DWT 3     /* K3: gather + analysis filter bank, all levels */
+#define RBEPWT_T_SELECT 4  /* K4: top-k radix select + zeroing */
+#define RBEPWT_T_IDWT 5    /* K5: synthesis filter bank + scatter, all levels */
+#define RBEPWT_T_D2H 6
+#define RBEPWT_T_PATHS_BIG 7 /* K1: regions with a large bounding box (one warp per CTA, whole-image bitmap) */
+#define RBEPWT_T_COUNT 8
+int rbepwt_enable_timing(rbepwt_ctx *ctx, int on);
+/* Sums the stage events recorded since the previous call (they accumulate across encode /
+ * threshold / decode calls), synchronises the stream, returns RBEPWT_T_COUNT. */
+int rbepwt_get_timings(rbepwt_ctx *ctx, float *ms, int n);
+/* Kernel launches per stage covered by the last rbepwt_get_timings call. */
+int rbepwt_get_stage_launches(rbepwt_ctx *ctx, int64_t *launches, int n);
+/* Number of kernel launches issued by this context since creation. */
+int64_t rbepwt_launch_count(rbepwt_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBEPWT_B200_H */

@@ -92,7 +92,7 @@ struct Slot {
   cudaStream_t s = nullptr;
   cudaStream_t aux = nullptr;     // path slots: the large-bitmap path kernel runs beside the bulk one
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
-  DevBuf VA, VB, Vpix, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch, gbm;
+  DevBuf VA, VB, Vpix, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch;
 };
 
 struct rbepwt_ctx {
@@ -115,7 +115,6 @@ struct rbepwt_ctx {
   // wavelet
   bool has_wavelet = false;
   int flen = 0;
-  DevBuf s5_tab;  // tables of the 5x5 step (paths_tpr.cuh)
   DevBuf filt, unit_lut;  // unit_lut: two 9 x 512 tables (euclid, chebyshev)
   double h_filt[4][FT_MAX] = {};  // host copy (flen <= FT_MAX): passed to the transform kernels by value
   // state of the encoded batch
@@ -369,10 +368,6 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   CK(sl.queue.ensure_slack((size_t)nreg * 4));
   CK(sl.chunk_start.ensure_slack(((size_t)nreg + Q_BINS) * 4));
   CK(sl.chunk_cnt.ensure_slack(((size_t)nreg + Q_BINS) * 4));
-  // chunk bitmaps: room for the usual ~nreg/32 chunks (+ the partial chunk of every bin); more chunks than that
-  // (many large bitmaps) build theirs inside the path kernel
-  const size_t gbm_chunks = (size_t)nreg / 16 + Q_BINS;
-  CK(sl.gbm.ensure_slack(gbm_chunks * TPR_ARENA_WORDS * 4));
   CK(cudaStreamWaitEvent(s, ready, 0));
   {
     StageTimer t(c, RBEPWT_T_REGIONS, s);
@@ -409,9 +404,6 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   P.qmeta = sl.qmeta.as<int>();
   P.coop_min = coop_min;
   P.unit_lut = c->unit_lut.as<uint8_t>() + (c->mode == RBEPWT_PATH_CHEB ? TPR_LUT_ROWS * TPR_LUT_COLS : 0);
-  P.s5_tab = c->s5_tab.as<uint32_t>();
-  P.gbm = sl.gbm.as<uint32_t>();
-  P.gbm_chunks = (int)gbm_chunks;
   P.Q = c->Q.as<int32_t>();
   P.Pm = c->Pm.as<int32_t>();
   P.posmap = c->posmap.as<int32_t>();
@@ -447,8 +439,6 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   }
   {
     StageTimer t(c, RBEPWT_T_PATHS, s);
-    k1_bitmaps<<<c->sm_count * 8, 256, 0, s>>>(P);
-    c->launches++;
     // the large-bitmap chunks (few, the longest chains) run on the slot's auxiliary stream, beside the bulk
     CK(cudaEventRecord(sl.ev_a, s));
     CK(cudaStreamWaitEvent(sl.aux, sl.ev_a, 0));
@@ -545,8 +535,7 @@ int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
 
 int threshold_sub(rbepwt_ctx *c, cudaStream_t s, int a, int nb, long long k) {
   StageTimer t(c, RBEPWT_T_SELECT, s);
-  CK(cudaFuncSetAttribute(k4_threshold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_SMEM));
-  k4_threshold<<<nb * SEL_CLUSTER, SEL_THREADS, SEL_SMEM, s>>>(c->coefs.as<double>() + (size_t)a * c->N, c->N, k);
+  k4_threshold<<<nb * SEL_CLUSTER, SEL_THREADS, 0, s>>>(c->coefs.as<double>() + (size_t)a * c->N, c->N, k);
   c->launches++;
   CK(cudaGetLastError());
   return RBEPWT_OK;
@@ -767,14 +756,7 @@ int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
   CK(cudaStreamCreateWithPriority(&c->s_out, cudaStreamNonBlocking, prio_hi));
   for (int i = 0; i < NSLOTS; i++) {
     CK(cudaStreamCreateWithPriority(&c->slot[i].s, cudaStreamNonBlocking, i < NSLOT ? prio_lo : prio_hi));
-    // a path slot's auxiliary stream carries the windowed path kernel: few CTAs, the longest chains of the group.
-    // It must not queue behind the bulk kernel's thousands of CTAs (measured: the stage lasts 12.5 instead of
-    // 10.7 ms when it does), so it outranks it.
-#ifdef TPR_AUX_LOW
     CK(cudaStreamCreateWithPriority(&c->slot[i].aux, cudaStreamNonBlocking, i < NSLOT ? prio_lo : prio_hi));
-#else
-    CK(cudaStreamCreateWithPriority(&c->slot[i].aux, cudaStreamNonBlocking, prio_hi));
-#endif
     CK(cudaEventCreateWithFlags(&c->slot[i].ev_a, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->slot[i].ev_b, cudaEventDisableTiming));
   }
@@ -785,14 +767,6 @@ int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
   CK(c->unit_lut.ensure(2 * TPR_LUT_ROWS * TPR_LUT_COLS));
   k_build_unit_lut<MODE_EUCLID><<<1, 256, 0, c->stream>>>(c->unit_lut.as<uint8_t>());
   k_build_unit_lut<MODE_CHEB><<<1, 256, 0, c->stream>>>(c->unit_lut.as<uint8_t>() + TPR_LUT_ROWS * TPR_LUT_COLS);
-  CK(c->s5_tab.ensure((size_t)S5_WORDS * 4));
-  k_build_s5_tables<<<1, 256, 0, c->stream>>>(c->s5_tab.as<uint32_t>());
-#ifdef TPR_TABLE5
-  // The two path-kernel instantiations of a mode run side by side (slot stream + auxiliary stream); kernels with
-  // different shared-memory carve-outs cannot share an SM, so with the table-step variant both ask for the largest.
-  CK(cudaFuncSetAttribute(k1_paths_tpr<MODE_EUCLID, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(k1_paths_tpr<MODE_EUCLID, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-#endif
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   *out = c;
@@ -808,14 +782,14 @@ void rbepwt_destroy(rbepwt_ctx *c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   for (auto *v : {&c->ev_lab, &c->ev_path, &c->ev_img, &c->ev_done})
     for (auto e : *v) cudaEventDestroy(e);
-  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->s5_tab, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->img_R,
+  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->img_R,
                     &c->img_rbase, &c->img_labmin, &c->img_direct, &c->tbl, &c->slot_rid, &c->scratch_i32,
                     &c->scratch_i32b, &c->psnr_out, &c->nz_out};
   for (auto b : bufs) b->release();
   for (auto &b : c->reg) b.release();
   for (int i = 0; i < NSLOTS; i++) {
     Slot &sl = c->slot[i];
-    DevBuf *sb[] = {&sl.VA, &sl.VB, &sl.Vpix, &sl.queue, &sl.qhist, &sl.qmeta, &sl.qbins, &sl.chunk_start, &sl.chunk_cnt, &sl.gscratch, &sl.gbm};
+    DevBuf *sb[] = {&sl.VA, &sl.VB, &sl.Vpix, &sl.queue, &sl.qhist, &sl.qmeta, &sl.qbins, &sl.chunk_start, &sl.chunk_cnt, &sl.gscratch};
     for (auto b : sb) b->release();
     cudaStreamDestroy(sl.s);
     cudaStreamDestroy(sl.aux);

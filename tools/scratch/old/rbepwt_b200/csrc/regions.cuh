@@ -384,16 +384,13 @@ __global__ void k0_single_region(int img0, int nimg, int H, int W, RegionArrays 
 // ---------------------------------------------------------------- work queue -------------
 // The path kernels pull regions from a queue ordered so that (a) regions whose bounding-box bitmap
 // does not fit a warp's shared-memory arena come first (class 0, one warp per region, paths.cuh),
-// (b) the others are grouped by bitmap size class, largest first: class c >= 1 holds the bitmaps that fit
-// the arena class_chunk_size(c) = 1, 2, 4, 8, 16, 32 at a time,
+// (b) the others are grouped by bitmap size class, largest first: class c >= 1 holds bitmaps of at most
+// TPR_ARENA_WORDS >> (Q_NCLS-1-c) words, so 32 >> (Q_NCLS-1-c) of them always fit one arena together,
 // (c) inside a class regions are sorted by pixel count, descending, in quarter-octave bins: the lanes
 // of a warp walk chains of similar length, and the longest chains start first.
 // A chunk = the regions one warp walks together (thread per region, paths_tpr.cuh).
 
-#ifndef TPR_ARENA_WORDS_N
-#define TPR_ARENA_WORDS_N 2048
-#endif
-constexpr int TPR_ARENA_WORDS = TPR_ARENA_WORDS_N;  // shared-memory words per warp of k1_paths_tpr
+constexpr int TPR_ARENA_WORDS = 2048;  // shared-memory words per warp of k1_paths_tpr
 constexpr int Q_NCLS = 7;              // class 0 = big; classes 1..6 = 1, 2, 4, 8, 16, 32 regions per chunk
 constexpr int Q_SIZE_BINS = 128;
 constexpr int Q_BINS = Q_NCLS * Q_SIZE_BINS;
@@ -412,33 +409,22 @@ __device__ __forceinline__ int region_bitmap_words(const RegionArrays &reg, int 
 }
 
 // Bitmap words used for the queue class: regions with a side above TPR_MAX_SIDE count as oversized.
-// k1_paths_tpr keeps a margin of TPR_PAD empty rows / columns around the bounding box, so that the 3x3 (5x5 with
-// the optional table step) neighbourhood of any point of the region lies inside the bitmap: no bounds checks in
-// its table steps.  The margin costs bitmap words (a 29-pixel-wide region needs a second word per row with a
-// margin of 2), which moves regions into classes with fewer lanes per warp: kept as small as the step needs.
-#ifdef TPR_TABLE5
-constexpr int TPR_PAD = 2;  // the 5x5 table step
-#else
-constexpr int TPR_PAD = 1;  // the 3x3 unit step
-#endif
 __device__ __forceinline__ int region_class_words(const RegionArrays &reg, int g, int logW) {
-  const int h = reg.rmax[g] - (reg.first[g] >> logW) + 1 + 2 * TPR_PAD;
-  const int w = reg.cmax[g] - reg.cmin[g] + 1 + 2 * TPR_PAD;
+  const int h = reg.rmax[g] - (reg.first[g] >> logW) + 1;
+  const int w = reg.cmax[g] - reg.cmin[g] + 1;
   return (h > TPR_MAX_SIDE || w > TPR_MAX_SIDE) ? INT32_MAX : h * ((w + 31) >> 5);
 }
 
-// regions per chunk of a class; a class holds the bitmaps of fewer than TPR_ARENA_WORDS / chunk size words.
-// (Intermediate chunk sizes 20, 24, 28 were measured: slower, 12.4 against 11.3 ms per 512 images.)
 __host__ __device__ __forceinline__ int class_chunk_size(int cls) { return cls == 0 ? 1 : 32 >> (Q_NCLS - 1 - cls); }
 
 __device__ __forceinline__ int queue_bin(int size, int words, int coop_min) {
   const int lg = 31 - __clz(size);                                        // size >= 1
   const int key = size >= 4 ? 4 * lg + ((size >> (lg - 2)) & 3) : size;    // <= 4*30+3, monotone in size
   int cls = 0;
-  if (words < TPR_ARENA_WORDS) {
+  if (words <= TPR_ARENA_WORDS) {
     cls = Q_NCLS - 1;
-    // slots are odd (tpr_slot_words): words | 1 <= cap - 1
-    while (cls > 1 && words >= TPR_ARENA_WORDS / class_chunk_size(cls)) cls--;
+    int cap = TPR_ARENA_WORDS >> 5;  // words per region when 32 share the arena
+    while (words > cap) { cap <<= 1; cls--; }
     if (size >= coop_min) cls = 1;  // a long chain gets a warp of its own (one region per chunk)
   }
   return cls * Q_SIZE_BINS + (Q_SIZE_BINS - 1 - key);
