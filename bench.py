@@ -372,7 +372,7 @@ def run_ours(args):
     achieved = bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9
     traffic, traffic_src = None, None
     try:  # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this run's launch size
-        with open(os.path.join(ROOT, "profiles", "r1b_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1c_traffic.json")) as f:
             tj = json.load(f)
         es = [tj[k_] for k_ in ((alg[dom][0], "k1_bitmaps") if dom == "paths" else (alg[dom][0],)) if k_ in tj]
         if es:
