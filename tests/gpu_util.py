@@ -4,31 +4,36 @@ import numpy as np
 
 
 def cuda_run(img, labels, levels, wavelet, path_type="easypath", euclidean_distance=True, ncoefs=None,
-             with_perm=True, paths_first_level=False):
+             with_perm=True, paths_first_level=False, copies=1, which=0):
+    """One image through the batch API; `copies` > 1 submits that many copies as one batch (more than 4096 regions
+    in a path group make the thread-per-region kernels walk them instead of a warp per region) and returns the
+    results of copy `which`."""
     import rbepwt_b200 as rb
 
     img = np.asarray(img)
     H, W = img.shape
     c = rb.BatchCodec()
-    c.encode(img[None], None if labels is None else np.asarray(labels)[None], levels, wavelet, path_type,
-             euclidean_distance, paths_first_level=paths_first_level)
+    imgs = np.ascontiguousarray(np.broadcast_to(img[None], (copies, H, W)))
+    labs = None if labels is None else np.ascontiguousarray(np.broadcast_to(np.asarray(labels)[None], (copies, H, W)))
+    c.encode(imgs, labs, levels, wavelet, path_type, euclidean_distance, paths_first_level=paths_first_level)
+    b = which
     out = {"perm": {}, "roff": {}, "points": {}, "codec": c}
     for lev in range(1, levels + 2):
-        out["roff"][lev] = c.region_offsets(0, lev)
-        pix = c.paths(0, lev)
+        out["roff"][lev] = c.region_offsets(b, lev)
+        pix = c.paths(b, lev)
         out["points"][lev] = np.stack([pix // W, pix % W], axis=1).astype(np.int32)
         if lev <= levels and with_perm:
-            out["perm"][lev] = c.perm(0, lev)
-    out["coefs"] = c.coefs(0)
+            out["perm"][lev] = c.perm(b, lev)
+    out["coefs"] = c.coefs(b)
     if ncoefs is not None:
         c.threshold(ncoefs)
-        th = c.coefs(0)
+        th = c.coefs(b)
         out["thresholded"] = th
         out["kept"] = np.flatnonzero(th != 0).astype(np.int64)
-        dec = c.decode()[0]
+        dec = c.decode()[b]
         out["decoded"] = dec
-        out["psnr"] = float(c.psnr(np.asarray(img, dtype=np.float64)[None], dec[None])[0])
-        out["nonzero_coefs"] = int(c.nonzero_coefs()[0])
+        out["psnr"] = float(c.psnr(imgs[b:b + 1].astype(np.float64), dec[None])[0])
+        out["nonzero_coefs"] = int(c.nonzero_coefs()[b])
     return out
 
 

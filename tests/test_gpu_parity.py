@@ -21,6 +21,22 @@ def test_cuda_reproduces_reference_golden(name):
     assert_matches_golden(out, g)
 
 
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("epwt") and "config1" not in n])
+def test_golden_through_the_thread_per_region_kernels(name):
+    """A single image's regions are each walked by a whole warp (latency); a batch with more than 4096 regions is
+    walked thread per region -- the kernel the benchmark runs.  Enough copies of the fixture to get there, then the
+    first and the last copy against what the reference produced."""
+    g = load_golden(name)
+    if g["path_type"] != "easypath":
+        pytest.skip("EPWT has its own kernel")
+    nreg = len(np.unique(g["labels"]))
+    copies = 4096 // nreg + 2
+    for which in (0, copies - 1):
+        out = cuda_run(g["img"], g["labels"], g["levels"], g["wavelet"], g["path_type"], g["euclidean_distance"],
+                       ncoefs=g["ncoefs"], paths_first_level=g["paths_first_level"], copies=copies, which=which)
+        assert_matches_golden(out, g)
+
+
 def _oracle(img, lab, levels, wavelet, ptype, euclid, k):
     from oracle import c_oracle
     import rbepwt_b200 as rb
