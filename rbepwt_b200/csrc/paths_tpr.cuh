@@ -895,47 +895,50 @@ __global__ void __launch_bounds__(TPR_WARPS * 32, TPR_MIN_CTAS) k1_paths_tpr(Pat
           }
         };
         const int nn = live ? n : 0;
+        // points per trip: 16 in the bulk instantiation; 8 in the windowed one, whose walk (with the warp-per-region
+        // code inlined) has no registers to spare -- 16 there spills in the walk (40 bytes of stack instead of 16)
+        constexpr int TB = WIDEWIN ? 8 : 16;
         // a ragged block (the head up to the 16-byte boundary, the tail): scalar loads, still all in flight together
         auto ragged = [&](int t0, int t1) {
-          int q[16], v[16];
+          int q[TB], v[TB];
 #pragma unroll
-          for (int u = 0; u < 16; u++) q[u] = t0 + u < t1 ? __ldcg(Ql + t0 + u) : 0;
+          for (int u = 0; u < TB; u++) q[u] = t0 + u < t1 ? __ldcg(Ql + t0 + u) : 0;
           if (doP) {
 #pragma unroll
-            for (int u = 0; u < 16; u++) v[u] = t0 + u < t1 ? __ldcg(posmap + q[u]) : 0;
+            for (int u = 0; u < TB; u++) v[u] = t0 + u < t1 ? __ldcg(posmap + q[u]) : 0;
 #pragma unroll
-            for (int u = 0; u < 16; u++)
+            for (int u = 0; u < TB; u++)
               if (t0 + u < t1) Pl[t0 + u] = v[u];
           }
           if (smode) {
 #pragma unroll
-            for (int u = 0; u < 16; u++)
+            for (int u = 0; u < TB; u++)
               if (t0 + u < t1 && ((a + t0 + u) & 1) == 0) survivor(t0 + u, q[u]);
           }
         };
         int tt = min(nn, (int)((4u - (unsigned)(((uintptr_t)Ql >> 2) & 3u)) & 3u));  // up to the 16-byte boundary
         if (tt > 0) ragged(0, tt);
-        for (; tt + 16 <= nn; tt += 16) {
-          int q[16], v[16];
+        for (; tt + TB <= nn; tt += TB) {
+          int q[TB], v[TB];
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
+          for (int u = 0; u < TB / 4; u++) {
             const int4 x = __ldcg(reinterpret_cast<const int4 *>(Ql + tt) + u);
             q[4 * u] = x.x; q[4 * u + 1] = x.y; q[4 * u + 2] = x.z; q[4 * u + 3] = x.w;
           }
           if (doP) {
 #pragma unroll
-            for (int u = 0; u < 16; u++) v[u] = __ldcg(posmap + q[u]);
+            for (int u = 0; u < TB; u++) v[u] = __ldcg(posmap + q[u]);
 #pragma unroll
-            for (int u = 0; u < 4; u++)
+            for (int u = 0; u < TB / 4; u++)
               reinterpret_cast<int4 *>(Pl + tt)[u] = make_int4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
           }
           if (smode) {
             const int par = (a + tt) & 1;  // survivors: tt + par, tt + par + 2, ...
 #pragma unroll
-            for (int u = 0; u < 8; u++) survivor(tt + par + 2 * u, par ? q[2 * u + 1] : q[2 * u]);
+            for (int u = 0; u < TB / 2; u++) survivor(tt + par + 2 * u, par ? q[2 * u + 1] : q[2 * u]);
           }
         }
-        if (tt < nn) ragged(tt, nn);
+        if (tt < nn) ragged(tt, nn);  // the tail: fewer than TB points
         if (smode == 1) { si = (minpix >> logW) - r0; sj = (minpix & Wm) - c0; }
         if (smode == 2) { list = true; lb = 0; }
       }
