@@ -83,3 +83,21 @@ def test_path_mode_mapping_and_guards():
     with pytest.raises(ValueError):
         rb.path_mode("zigzag")
     assert rb.ispowerof2(256 * 512) and not rb.ispowerof2(48)
+
+
+def test_bench_traffic_file_matches_bench():
+    """bench.py scales the dominant kernel's DRAM traffic from a committed ncu summary: the file it names must
+    exist and carry the entries it reads (a rename would silently null `roofline.traffic` on the GPU box)."""
+    import json
+    import re
+
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    src = open(os.path.join(root, "bench.py")).read()
+    names = re.findall(r'"(r\w+_traffic\.json)"', src)
+    assert len(names) == 1, names
+    with open(os.path.join(root, "profiles", names[0])) as f:
+        tj = json.load(f)
+    for k in ("k1_paths_tpr", "k1_bitmaps"):
+        e = tj[k]
+        assert e["dram_bytes_read"] > 0 and e["dram_bytes_write"] > 0 and e["images_per_launch"] > 0
+    assert isinstance(tj["source"], str)
