@@ -447,18 +447,20 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   }
   {
     StageTimer t(c, RBEPWT_T_PATHS, s);
-    k1_bitmaps<<<c->sm_count * 8, 256, 0, s>>>(P);
-    c->launches++;
-    // the large-bitmap chunks (few, the longest chains) run on the slot's auxiliary stream, beside the bulk
+    // the large-bitmap chunks (few, the longest chains) run on the slot's auxiliary stream, beside the bulk; they
+    // build their own bitmaps, so they start right away, under the bulk kernel's bitmap builder
     CK(cudaEventRecord(sl.ev_a, s));
     CK(cudaStreamWaitEvent(sl.aux, sl.ev_a, 0));
-    if (c->mode == RBEPWT_PATH_EUCLID) {
+    if (c->mode == RBEPWT_PATH_EUCLID)
       k1_paths_tpr<MODE_EUCLID, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, TPR_WARPS * 32, 0, sl.aux>>>(P);
-      k1_paths_tpr<MODE_EUCLID, false><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
-    } else {
+    else
       k1_paths_tpr<MODE_CHEB, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, TPR_WARPS * 32, 0, sl.aux>>>(P);
+    k1_bitmaps<<<c->sm_count * 8, 256, 0, s>>>(P);
+    c->launches++;
+    if (c->mode == RBEPWT_PATH_EUCLID)
+      k1_paths_tpr<MODE_EUCLID, false><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
+    else
       k1_paths_tpr<MODE_CHEB, false><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
-    }
     CK(cudaEventRecord(sl.ev_b, sl.aux));
     CK(cudaStreamWaitEvent(s, sl.ev_b, 0));
     c->launches += 2;
