@@ -52,6 +52,9 @@ typedef struct rbepwt_ctx rbepwt_ctx;
 #define RBEPWT_PATHS_FIRST_LEVEL 4u /* paths_first_level=True: Region.same_path (identity permutation) at every
                                        level >= 2, paths are searched at level 1 only (rbepwt.py:1183-1188, 2024-2025) */
 
+#define RBEPWT_NO_CLIP 8u /* rbepwt_decode: the values Rbepwt.decode returns (rbepwt.py:2055-2079), without the clip to
+                            [0,255] that Image.decode_rbepwt applies afterwards (rbepwt.py:313-314) */
+
 /* Create a context on CUDA device `device`.  `stream` is a cudaStream_t to run on (e.g.
  * torch's current stream) or NULL to create a private one.  Fails with RBEPWT_E_NO_GPU when
  * there is no CUDA device -- the library has no CPU path. */
@@ -92,7 +95,7 @@ int rbepwt_threshold(rbepwt_ctx *ctx, int64_t k);
 
 /* Rbepwt.decode + RegionCollection.expand + Image.decode_rbepwt (clip to [0,255], no rounding)
  *                                                           rbepwt.py:2055-2079, 1586-1613, 307-317
- * out: float64 [B][H][W]. */
+ * out: float64 [B][H][W].  flags: RBEPWT_DEVICE_PTRS, RBEPWT_NO_CLIP. */
 int rbepwt_decode(rbepwt_ctx *ctx, double *out_img, unsigned flags);
 
 /* encode -> threshold(k) -> decode in ONE call: the three reference calls above back to back
@@ -134,7 +137,9 @@ int rbepwt_region_labels(rbepwt_ctx *ctx, int b, int32_t *labels);
 /* Paths of image b at `level` (1..L): pixel id (row*W+col) of every point of the level's
  * concatenated signal, regions in order, each region in PATH order (Region.base_points after
  * easy_path, 1338-1342).  level == L+1: the approximation's points in their (incoming) order.
- * level == 0: level-1 INCOMING order (row-major inside each region).  HOST int32 [N >> (level-1)]. */
+ * level == 0: level-1 INCOMING order (row-major inside each region).  HOST int32 [N >> (level-1)].
+ * Level 0 (and rbepwt_get_perm at level 1) re-reads the LABELS given to the encoding call: with
+ * RBEPWT_DEVICE_PTRS the caller's label buffer must still be valid and unchanged. */
 int rbepwt_get_paths(rbepwt_ctx *ctx, int b, int level, int32_t *pix);
 /* Region.permutation of every region at `level` (1..L), concatenated: perm[off_r + t] = index in
  * the region's incoming order of its t-th path point                          rbepwt.py:1285, 1333 */

@@ -9,7 +9,7 @@ _lib = None
 
 E_NOT_POW2, E_LEVELS, E_NO_ENCODING, E_NO_GPU = -2, -3, -4, -7
 PATH_EUCLID, PATH_CHEB, PATH_EPWT = 0, 1, 2
-DEVICE_PTRS, U8_WRAP, PATHS_FIRST_LEVEL = 1, 2, 4
+DEVICE_PTRS, U8_WRAP, PATHS_FIRST_LEVEL, NO_CLIP = 1, 2, 4, 8
 OPT_STREAMS, OPT_SUBBATCH, OPT_PATHGROUP = 1, 2, 3
 T_NAMES = ["h2d", "regions", "paths", "dwt", "select", "idwt", "d2h", "paths_big"]
 
@@ -38,9 +38,9 @@ def lib():
         try:
             _build.build_library()
         except Exception as e:  # noqa: BLE001
-            if not os.path.isfile(path):
-                raise RbepwtError("rbepwt_b200: CUDA library is missing and could not be built (%s); "
-                                  "there is no CPU fallback" % e)
+            # never load a library older than its sources: results would silently come from stale kernels
+            raise RbepwtError("rbepwt_b200: the CUDA library is %s and could not be built (%s); there is no CPU "
+                              "fallback" % ("stale" if os.path.isfile(path) else "missing", e))
     L = ctypes.CDLL(path)
     vp, i32, i64, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint
     L.rbepwt_last_error.restype = ctypes.c_char_p

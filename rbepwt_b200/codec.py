@@ -40,6 +40,15 @@ def _ptr(x):
     return ctypes.c_void_p(x.data_ptr())
 
 
+def _labels_int32(labels):
+    """Label maps as contiguous int32; integer labels that do not survive the cast are refused (no silent wrap)."""
+    lab = np.asarray(labels)
+    lab32 = np.ascontiguousarray(lab, dtype=np.int32)
+    if lab.dtype != np.int32 and not np.array_equal(lab32, lab):
+        raise ValueError("labels must be integers representable as int32")
+    return lab32
+
+
 class BatchCodec:
     """One GPU context: encode -> threshold -> decode for a batch of same-shape images."""
 
@@ -99,6 +108,25 @@ class BatchCodec:
         _capi.check(self._lib.rbepwt_sync(self._ctx))
 
     # -- the path --------------------------------------------------------------------------
+    def _check_f64_buffer(self, x, numel, what):
+        """A buffer the C ABI reads or writes `numel` doubles through: contiguous float64 of exactly that many
+        elements, a numpy array (host path) or a CUDA tensor on this codec's device (device path).  Returns True
+        for the device path.  The library sees a raw pointer, so everything is checked here."""
+        if _is_torch_cuda(x):
+            import torch
+            if x.dtype != torch.float64 or not x.is_contiguous():
+                raise ValueError("%s must be a contiguous float64 CUDA tensor" % what)
+            if x.device.index != self.device:
+                raise ValueError("%s lives on cuda:%s, the codec on cuda:%d" % (what, x.device.index, self.device))
+            if x.numel() != numel:
+                raise ValueError("%s must hold %d elements, not %d" % (what, numel, x.numel()))
+            return True
+        if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous):
+            raise ValueError("%s must be a contiguous float64 numpy array or CUDA tensor" % what)
+        if x.size != numel:
+            raise ValueError("%s must hold %d elements, not %d" % (what, numel, x.size))
+        return False
+
     def _prep(self, imgs, labels, mode):
         dev = _is_torch_cuda(imgs)
         u8 = False
@@ -106,20 +134,18 @@ class BatchCodec:
             import torch
             if imgs.dtype != torch.float64 or not imgs.is_contiguous():
                 raise ValueError("device images must be contiguous float64")
+            if imgs.device.index != self.device:
+                raise ValueError("images live on cuda:%s, the codec on cuda:%d" % (imgs.device.index, self.device))
             if labels is not None and (not _is_torch_cuda(labels) or labels.dtype != torch.int32
-                                       or not labels.is_contiguous()):
-                raise ValueError("device labels must be contiguous int32 CUDA tensors")
+                                       or not labels.is_contiguous() or labels.device != imgs.device):
+                raise ValueError("device labels must be contiguous int32 CUDA tensors on the images' device")
             shape = tuple(imgs.shape)
         else:
             imgs = np.asarray(imgs)
             u8 = imgs.dtype == np.uint8
             imgs = np.ascontiguousarray(imgs, dtype=np.float64)
             if labels is not None:
-                lab = np.asarray(labels)
-                lab32 = np.ascontiguousarray(lab, dtype=np.int32)
-                if lab.dtype != np.int32 and not np.array_equal(lab32, lab):
-                    raise ValueError("labels must be integers representable as int32")
-                labels = lab32
+                labels = _labels_int32(labels)
             shape = imgs.shape
         if len(shape) == 2:
             shape = (1,) + tuple(shape)
@@ -171,13 +197,11 @@ class BatchCodec:
                 out = torch.empty_like(imgs)
             else:
                 out = np.empty(shape, dtype=np.float64)
-        if _is_torch_cuda(out) != dev:
+        B, H, W = shape
+        if self._check_f64_buffer(out, B * H * W, "out") != dev:
             raise ValueError("`out` must live where the inputs live")
-        if not dev and not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous):
-            raise ValueError("out must be a contiguous float64 numpy array or CUDA tensor")
         flags = (_capi.DEVICE_PTRS if dev else 0) | (_capi.U8_WRAP if (u8 and mode == _capi.PATH_EPWT) else 0)
         flags |= _capi.PATHS_FIRST_LEVEL if paths_first_level else 0
-        B, H, W = shape
         self._keep = [imgs, labels, out]
         _capi.check(self._lib.rbepwt_transcode(self._ctx, _ptr(imgs), _ptr(labels), B, H, W, int(levels), mode, int(ncoefs),
                                                _ptr(out), flags))
@@ -188,26 +212,32 @@ class BatchCodec:
         _capi.check(self._lib.rbepwt_threshold(self._ctx, int(k)))
         return self
 
-    def decode(self, out=None):
-        """Decoded images, float64 [B,H,W], clipped to [0,255].  `out` may be a torch CUDA tensor
-        (device path) or a numpy array (host path); default: a new numpy array."""
+    def decode(self, out=None, clip=True):
+        """Decoded images, float64 [B,H,W], clipped to [0,255] (Image.decode_rbepwt, rbepwt.py:313-314) unless
+        `clip` is False (what Rbepwt.decode itself returns, rbepwt.py:2055-2079).  `out` may be a torch CUDA
+        tensor (device path) or a numpy array (host path); default: a new numpy array."""
         if self.shape is None:
             raise Exception("There is no saved encoding to decode")
         if out is None:
             out = np.empty(self.shape, dtype=np.float64)
-        dev = _is_torch_cuda(out)
-        if not dev and not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous):
-            raise ValueError("out must be a contiguous float64 numpy array or CUDA tensor")
-        _capi.check(self._lib.rbepwt_decode(self._ctx, _ptr(out), _capi.DEVICE_PTRS if dev else 0))
+        B, H, W = self.shape
+        dev = self._check_f64_buffer(out, B * H * W, "out")
+        flags = (_capi.DEVICE_PTRS if dev else 0) | (0 if clip else _capi.NO_CLIP)
+        _capi.check(self._lib.rbepwt_decode(self._ctx, _ptr(out), flags))
         return out
 
     def full_decode(self, coefs, labels, levels, wavelet, path_type="easypath", euclidean_distance=True,
                     paths_first_level=False):
         """Decoder side (reference full_decode, rbepwt.py:106-130): paths regenerated from labels."""
         mode = path_mode(path_type, euclidean_distance)
-        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        labels = _labels_int32(labels)
+        if labels.ndim not in (2, 3):
+            raise ValueError("labels must be [H,W] or [B,H,W]")
         shape = labels.shape if labels.ndim == 3 else (1,) + labels.shape
-        coefs = np.ascontiguousarray(coefs, dtype=np.float64).reshape(shape[0], -1)
+        coefs = np.ascontiguousarray(coefs, dtype=np.float64)
+        if coefs.size != labels.size:
+            raise ValueError("coefs must hold B*H*W = %d values, not %d" % (labels.size, coefs.size))
+        coefs = coefs.reshape(shape[0], -1)
         self.set_wavelet(wavelet)
         out = np.empty(shape, dtype=np.float64)
         B, H, W = shape
@@ -217,13 +247,21 @@ class BatchCodec:
         return out
 
     def psnr(self, a, b):
+        """psnr(a[i], b[i]) per image (rbepwt.py:156-162); a and b are both numpy arrays or both CUDA tensors on
+        this codec's device, [B,H,W] or a single [H,W]."""
         dev = _is_torch_cuda(a)
+        if dev != _is_torch_cuda(b):
+            raise ValueError("psnr: a and b must both be numpy arrays or both CUDA tensors")
         if not dev:
             a = np.ascontiguousarray(a, dtype=np.float64)
             b = np.ascontiguousarray(b, dtype=np.float64)
         shape = tuple(a.shape)
+        if tuple(b.shape) != shape:
+            raise ValueError("psnr: a and b must have the same shape")
         B = shape[0] if len(shape) == 3 else 1
         n = int(np.prod(shape)) // B
+        self._check_f64_buffer(a, B * n, "a")
+        self._check_f64_buffer(b, B * n, "b")
         out = np.empty(B, dtype=np.float64)
         _capi.check(self._lib.rbepwt_psnr(self._ctx, _ptr(a), _ptr(b), B, n, _ptr(out), _capi.DEVICE_PTRS if dev else 0))
         return out

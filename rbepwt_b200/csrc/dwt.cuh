@@ -44,6 +44,7 @@ struct DwtParams {
   double tap_lo[FT_MAX], tap_hi[FT_MAX];  // the direction's two filters by value (constant bank) when flen <= FT_MAX
   double *out_img;     // decode, level 1: clipped image
   int flen, N, lev, levels;
+  int clip;            // decode, level 1: clip to [0,255] (Image.decode_rbepwt); 0 = Rbepwt.decode's own values
 };
 
 struct FwdSmem {
@@ -164,7 +165,7 @@ __device__ __forceinline__ void idwt_tile(const DwtParams &P, InvSmem &sm, int l
   auto emit = [&](int t, double x) {
     const int dst = Pl[t];
     if (lev == 1) {  // Image.decode_rbepwt: clip, no rounding (rbepwt.py:312-314)
-      x = x > 255.0 ? 255.0 : (x < 0.0 ? 0.0 : x);
+      if (P.clip) x = x > 255.0 ? 255.0 : (x < 0.0 ? 0.0 : x);
       P.out_img[img * (size_t)N + dst] = x;
     } else {
       vout[dst] = x;

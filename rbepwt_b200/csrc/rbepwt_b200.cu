@@ -115,13 +115,13 @@ struct rbepwt_ctx {
   // wavelet
   bool has_wavelet = false;
   int flen = 0;
-  DevBuf s5_tab;  // tables of the 5x5 step (paths_tpr.cuh)
   DevBuf filt, unit_lut;  // unit_lut: two 9 x 512 tables (euclid, chebyshev)
   double h_filt[4][FT_MAX] = {};  // host copy (flen <= FT_MAX): passed to the transform kernels by value
   // state of the encoded batch
   bool has_encoding = false, has_paths = false;
   int B = 0, H = 0, W = 0, N = 0, logW = 0, levels = 0, mode = 0;
   unsigned enc_flags = 0;
+  bool decode_noclip = false;  // RBEPWT_NO_CLIP of the decode in progress
   const int32_t *labels_dev = nullptr;  // ours (labels_own) or the caller's device pointer
   const double *img_dev = nullptr;
   DevBuf labels_own, img_own, out_own, coef_up;
@@ -271,7 +271,8 @@ int validate_shape(int B, int H, int W, int levels, int path_mode) {
   if (B < 1 || H < 1 || W < 1) return fail(RBEPWT_E_ARG, "B, H, W must be positive");
   const long long n = (long long)H * W;
   if (n & (n - 1)) return fail(RBEPWT_E_NOT_POW2, "Image size must be a power of 2");
-  if (n > (1ll << 30) || W > 32768 || H > 32768) return fail(RBEPWT_E_ARG, "image too large (H*W <= 2^30)");
+  // per-image tables hold 2 * H*W entries indexed with int
+  if (n > (1ll << 29) || W > 32768 || H > 32768) return fail(RBEPWT_E_ARG, "image too large (H*W <= 2^29, sides <= 32768)");
   if (levels < 1 || levels > 30 || (1ll << levels) > n)
     return fail(RBEPWT_E_LEVELS, "2^levels must be smaller or equal to the number of pixels in the image");
   if (path_mode < 0 || path_mode > 2) return fail(RBEPWT_E_ARG, "unknown path mode %d", path_mode);
@@ -409,7 +410,6 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   P.qmeta = sl.qmeta.as<int>();
   P.coop_min = coop_min;
   P.unit_lut = c->unit_lut.as<uint8_t>() + (c->mode == RBEPWT_PATH_CHEB ? TPR_LUT_ROWS * TPR_LUT_COLS : 0);
-  P.s5_tab = c->s5_tab.as<uint32_t>();
   P.gbm = sl.gbm.as<uint32_t>();
   P.gbm_chunks = (int)gbm_chunks;
   P.Q = c->Q.as<int32_t>();
@@ -483,7 +483,7 @@ int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
   D.coefs = c->coefs.as<double>() + (size_t)a * N;
   D.filt = c->filt.as<double>();
   D.out_img = nullptr;
-  D.flen = c->flen; D.N = N; D.levels = c->levels;
+  D.flen = c->flen; D.N = N; D.levels = c->levels; D.clip = 1;
   set_taps(c, D, false);
   double *V[2] = {sl.VA.as<double>(), sl.VB.as<double>()};
   EpwtParams E;
@@ -564,7 +564,7 @@ int decode_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb, double *o
   D.coefs = c->coefs.as<double>() + (size_t)a * N;
   D.filt = c->filt.as<double>();
   D.out_img = out_dev + (size_t)a * N;
-  D.flen = c->flen; D.N = N; D.levels = c->levels;
+  D.flen = c->flen; D.N = N; D.levels = c->levels; D.clip = c->decode_noclip ? 0 : 1;
   set_taps(c, D, true);
   D.vin = nullptr; D.vin_stride = N;
   D.plane[0] = V[0]; D.plane[1] = V[1];
@@ -744,17 +744,7 @@ extern "C" {
 
 const char *rbepwt_last_error(void) { return g_err.c_str(); }
 
-int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
-  if (!out) return fail(RBEPWT_E_ARG, "out is NULL");
-  *out = nullptr;
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev == 0)
-    return fail(RBEPWT_E_NO_GPU, "no CUDA device available (%s); rbepwt_b200 has no CPU fallback",
-                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-  if (device < 0 || device >= ndev) return fail(RBEPWT_E_ARG, "device %d out of range (%d devices)", device, ndev);
-  CK(cudaSetDevice(device));
-  rbepwt_ctx *c = new rbepwt_ctx();
+static int create_impl(rbepwt_ctx *c, int device, void *stream) {
   c->device = device;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
@@ -772,11 +762,7 @@ int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
     // a path slot's auxiliary stream carries the windowed path kernel: few CTAs, the longest chains of the group.
     // It must not queue behind the bulk kernel's thousands of CTAs (measured: the stage lasts 12.5 instead of
     // 10.7 ms when it does), so it outranks it.
-#ifdef TPR_AUX_LOW
-    CK(cudaStreamCreateWithPriority(&c->slot[i].aux, cudaStreamNonBlocking, i < NSLOT ? prio_lo : prio_hi));
-#else
     CK(cudaStreamCreateWithPriority(&c->slot[i].aux, cudaStreamNonBlocking, prio_hi));
-#endif
     CK(cudaEventCreateWithFlags(&c->slot[i].ev_a, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->slot[i].ev_b, cudaEventDisableTiming));
   }
@@ -787,16 +773,29 @@ int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
   CK(c->unit_lut.ensure(2 * TPR_LUT_ROWS * TPR_LUT_COLS));
   k_build_unit_lut<MODE_EUCLID><<<1, 256, 0, c->stream>>>(c->unit_lut.as<uint8_t>());
   k_build_unit_lut<MODE_CHEB><<<1, 256, 0, c->stream>>>(c->unit_lut.as<uint8_t>() + TPR_LUT_ROWS * TPR_LUT_COLS);
-  CK(c->s5_tab.ensure((size_t)S5_WORDS * 4));
-  k_build_s5_tables<<<1, 256, 0, c->stream>>>(c->s5_tab.as<uint32_t>());
-#ifdef TPR_TABLE5
-  // The two path-kernel instantiations of a mode run side by side (slot stream + auxiliary stream); kernels with
-  // different shared-memory carve-outs cannot share an SM, so with the table-step variant both ask for the largest.
-  CK(cudaFuncSetAttribute(k1_paths_tpr<MODE_EUCLID, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(k1_paths_tpr<MODE_EUCLID, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-#endif
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
+  return RBEPWT_OK;
+}
+
+int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
+  if (!out) return fail(RBEPWT_E_ARG, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(RBEPWT_E_NO_GPU, "no CUDA device available (%s); rbepwt_b200 has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= ndev) return fail(RBEPWT_E_ARG, "device %d out of range (%d devices)", device, ndev);
+  DeviceGuard g(device);  // the caller's current device is restored on every return path
+  rbepwt_ctx *c = new rbepwt_ctx();
+  const int rc = create_impl(c, device, stream);
+  if (rc) {  // release whatever was created (destroy tolerates the members still unset)
+    const std::string msg = g_err;
+    rbepwt_destroy(c);
+    g_err = msg;
+    return rc;
+  }
   *out = c;
   return RBEPWT_OK;
 }
@@ -804,13 +803,14 @@ int rbepwt_create(int device, void *stream, rbepwt_ctx **out) {
 void rbepwt_destroy(rbepwt_ctx *c) {
   if (!c) return;
   DeviceGuard g(c->device);
-  cudaStreamSynchronize(c->stream);
-  sync_internal(c);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (cudaStream_t st : {c->s_in, c->s_out}) if (st) cudaStreamSynchronize(st);
+  for (int i = 0; i < NSLOTS; i++) if (c->slot[i].s) cudaStreamSynchronize(c->slot[i].s);
   clear_events(c);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   for (auto *v : {&c->ev_lab, &c->ev_path, &c->ev_img, &c->ev_done})
     for (auto e : *v) cudaEventDestroy(e);
-  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->s5_tab, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->img_R,
+  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->img_R,
                     &c->img_rbase, &c->img_labmin, &c->img_direct, &c->tbl, &c->slot_rid, &c->scratch_i32,
                     &c->scratch_i32b, &c->psnr_out, &c->nz_out};
   for (auto b : bufs) b->release();
@@ -819,24 +819,27 @@ void rbepwt_destroy(rbepwt_ctx *c) {
     Slot &sl = c->slot[i];
     DevBuf *sb[] = {&sl.VA, &sl.VB, &sl.Vpix, &sl.queue, &sl.qhist, &sl.qmeta, &sl.qbins, &sl.chunk_start, &sl.chunk_cnt, &sl.gscratch, &sl.gbm};
     for (auto b : sb) b->release();
-    cudaStreamDestroy(sl.s);
-    cudaStreamDestroy(sl.aux);
-    cudaEventDestroy(sl.ev_a); cudaEventDestroy(sl.ev_b);
+    if (sl.s) cudaStreamDestroy(sl.s);
+    if (sl.aux) cudaStreamDestroy(sl.aux);
+    if (sl.ev_a) cudaEventDestroy(sl.ev_a);
+    if (sl.ev_b) cudaEventDestroy(sl.ev_b);
   }
-  cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
-  cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
   if (c->pin_R) cudaFreeHost(c->pin_R);
   if (c->pin_rbase) cudaFreeHost(c->pin_rbase);
   if (c->pin_err) cudaFreeHost(c->pin_err);
-  if (c->own_stream) cudaStreamDestroy(c->stream);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
 int rbepwt_sync(rbepwt_ctx *c) {
   if (!c) return fail(RBEPWT_E_ARG, "ctx is NULL");
   DeviceGuard g(c->device);
-  CK(cudaStreamSynchronize(c->stream));
-  return RBEPWT_OK;
+  // device-pointer calls are asynchronous: this is where a path kernel's "corrupt region state" flag surfaces
+  return check_path_error(c);
 }
 
 int rbepwt_set_option(rbepwt_ctx *c, int option, int64_t value) {
@@ -909,7 +912,9 @@ int rbepwt_decode(rbepwt_ctx *c, double *out_img, unsigned flags) {
     CK(c->out_own.ensure((size_t)c->B * c->N * 8));
     out_dev = c->out_own.as<double>();
   }
+  c->decode_noclip = (flags & RBEPWT_NO_CLIP) != 0;
   int rc = run_pipeline(c, DO_DECODE, 0, nullptr, nullptr, out_dev, host ? out_img : nullptr);
+  c->decode_noclip = false;
   if (rc) return rc;
   if (host) return check_path_error(c);
   return RBEPWT_OK;
@@ -1124,6 +1129,7 @@ int rbepwt_get_level_values(rbepwt_ctx *c, int b, int level, double *vals) {
   D.filt = c->filt.as<double>();
   D.out_img = nullptr;
   D.flen = c->flen; D.N = c->N; D.levels = 31;  // never the "last" level: low-pass always goes to vout
+  D.clip = 1;
   set_taps(c, D, false);
   for (int lev = 1; lev < level; lev++) {
     D.lev = lev;

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(K0_THREADS) k0_regions_fast(const int32_t *__r
       reg.img[g] = img;
     }
     __syncthreads();
-    if (tid == 0) s_running += total;
+    if (tid == 0) s_running += total;  // read again at the top of the next tile: the barrier below orders it
     // statistics, one update per run of equal labels inside the thread's 8 pixels (same row: 8 | W)
     if (valid) {
       const int row = p0 >> logW, col0 = p0 & (W - 1);
@@ -229,8 +229,8 @@ __global__ void __launch_bounds__(K0_THREADS) k0_regions_fast(const int32_t *__r
         i = j + 1;
       }
     }
+    __syncthreads();  // s_running of this tile is visible before the next tile's scan reads it
   }
-  __syncthreads();
   // level-1 offsets = exclusive scan of the sizes in region order
   if (tid == 0) s_running = 0;
   __syncthreads();

@@ -219,12 +219,44 @@ class RegionCollectionView:
         return iter(enumerate(self.subregions))
 
 
+class DecodedRegionCollectionView(RegionCollectionView):
+    """What Rbepwt.decode returns (rbepwt.py:2055-2079): the level-1 regions in their INCOMING order (expand
+    undoes every permutation, 1600-1608 -- row-major inside each region) carrying the DECODED values, not yet
+    clipped (the clip is Image.decode_rbepwt's, 313-314).  Values are fetched from the GPU on first access."""
+
+    def __init__(self, rb):
+        super().__init__(rb, 1)
+
+    @property
+    def values(self):
+        if self._values is None:
+            flat = self._rb._codec.decode(clip=False)[0].ravel()
+            self._values = flat[self._incoming()]
+        return self._values
+
+    @values.setter
+    def values(self, v):
+        self._values = np.asarray(v)
+
+    @property
+    def subregions(self):
+        if self._sub is None:
+            off, vals, pts = self.offsets, self.values, self._rc(self._incoming())
+            self._sub = [RegionView(pts[int(off[r]):int(off[r + 1])], vals[int(off[r]):int(off[r + 1])], None)
+                         for r in range(len(off) - 1)]
+        return self._sub
+
+
 class _LevelDict(dict):
-    """{level: RegionCollectionView}, created lazily for levels 1..L+1."""
+    """{level: RegionCollectionView} for levels 1..L+1; the views are created on first access, and every way
+    of looking at the dict (len, in, iteration, keys/values/items) sees all L+1 levels."""
 
     def __init__(self, rb):
         super().__init__()
         self._rb = rb
+
+    def _levels(self):
+        return range(1, self._rb.levels + 2)
 
     def __missing__(self, level):
         if not isinstance(level, (int, np.integer)) or not 1 <= level <= self._rb.levels + 1:
@@ -233,8 +265,26 @@ class _LevelDict(dict):
         self[int(level)] = v
         return v
 
+    def __contains__(self, level):
+        return isinstance(level, (int, np.integer)) and 1 <= level <= self._rb.levels + 1
+
+    def __len__(self):
+        return self._rb.levels + 1
+
+    def __iter__(self):
+        return iter(self._levels())
+
     def keys(self):
-        return range(1, self._rb.levels + 2)
+        return self._levels()
+
+    def values(self):
+        return [self[lev] for lev in self._levels()]
+
+    def items(self):
+        return [(lev, self[lev]) for lev in self._levels()]
+
+    def get(self, level, default=None):
+        return self[level] if level in self else default
 
 
 class Rbepwt:
@@ -342,12 +392,14 @@ class Rbepwt:
         self._refresh_mirror()
 
     def decode(self):
+        """Returns the decoded region collection like the reference (rbepwt.py:2055-2079); the clipped image is
+        kept in `decoded_img` for Image.decode_rbepwt."""
         if not self.has_encoding:
             raise Exception("There is no saved encoding to decode")  # rbepwt.py:2057-2058
         self._upload_if_mirrored()
-        self._decoded = self._codec.decode()[0]
+        self.decoded_img = self._codec.decode()[0]
         print("\n--DECODING: finished working on level 1 ")
-        return self._decoded
+        return DecodedRegionCollectionView(self)
 
     def flat_wavelet(self):
         """details[1] | ... | details[L] | approximation (rbepwt.py:2195-2204)."""
@@ -436,8 +488,8 @@ class Image:
         self.rbepwt.encode(euclidean_distance=euclidean_distance)
 
     def decode_rbepwt(self):
-        self.decoded_img = self.rbepwt.decode()  # float64, clipped to [0,255] on the GPU, not rounded
-        self.decoded_region_collection = self.rbepwt.region_collection_at_level[1]
+        self.decoded_region_collection = self.rbepwt.decode()  # decoded values by region, fetched on access
+        self.decoded_img = self.rbepwt.decoded_img  # float64, clipped to [0,255] on the GPU, not rounded (rbepwt.py:312-314)
         self.has_decoded_img = True
 
     def encode_epwt(self, levels, wavelet):

@@ -34,6 +34,23 @@ def voronoi_labels(h, w, n_seeds, seed=0, warp=3.0, shuffle_ids=True):
     return np.ascontiguousarray(lab)
 
 
+def heavytail_labels(n, n_seeds, seed=0):
+    """n x n label map with a heavy-tailed region-size distribution -- a few 10^4-pixel background regions next
+    to hundreds of small ones, which is what felzenszwalb(scale=200) produces on natural images: 85 % of the
+    Voronoi seeds crowd into three blobs covering ~15 % of the image, the rest are spread out."""
+    from scipy.spatial import cKDTree
+
+    rng = np.random.default_rng(seed)
+    centres = rng.uniform(0.15 * n, 0.85 * n, size=(3, 2))
+    ncrowd = int(0.85 * n_seeds)
+    crowd = centres[rng.integers(0, 3, size=ncrowd)] + rng.normal(0, 0.07 * n, size=(ncrowd, 2))
+    spread = rng.uniform(0, n, size=(n_seeds - ncrowd, 2))
+    pts = np.clip(np.concatenate([crowd, spread]), 0, n - 1)
+    ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    _, idx = cKDTree(pts).query(np.stack([ii.ravel(), jj.ravel()], 1))
+    return np.ascontiguousarray(idx.reshape(n, n).astype(np.int32))
+
+
 def block_labels(h, w, b):
     """Grid of b x b blocks (the label map BASELINE.md section 2 timed the reference on)."""
     ii, jj = np.meshgrid(np.arange(h) // b, np.arange(w) // b, indexing="ij")

@@ -68,6 +68,11 @@ def cases(big):
     c.append(("pfl32_euclid_bior44", img, lab, 10, "bior4.4", "easypath", True, 40, True))
     c.append(("pfl32_cheb_haar", img, noise_labels(32, 32, 6, 12), 10, "haar", "easypath", False, 40, True))
     c.append(("pfl32_epwt_db2", synth.smooth_field_image(32, 32, seed=13, sigma=2.0), None, 10, "db2", "epwt-easypath", True, 40, True))
+    # uint8 EPWT: |value[cur] - value[cand]| wraps modulo 256 at level 1 (numpy uint8 scalars, rbepwt.py:1302, 844-846)
+    c.append(("epwt16_u8_noise_haar", np.random.default_rng(14).integers(0, 256, size=(16, 16)).astype(np.uint8), None, 8,
+              "haar", "epwt-easypath", True, 32))
+    c.append(("epwt32_u8_smooth_bior44", np.round(synth.smooth_field_image(32, 32, seed=15, sigma=2.0)).astype(np.uint8), None,
+              10, "bior4.4", "epwt-easypath", True, 64))
     if big:
         img, lab = synth.config_inputs("cameraman256")  # BASELINE.json configs[0]
         c.append(("config1_cameraman256", img, lab, 16, "bior4.4", "easypath", True, 512))

@@ -16,7 +16,14 @@ def cuda_run(img, labels, levels, wavelet, path_type="easypath", euclidean_dista
     imgs = np.ascontiguousarray(np.broadcast_to(img[None], (copies, H, W)))
     labs = None if labels is None else np.ascontiguousarray(np.broadcast_to(np.asarray(labels)[None], (copies, H, W)))
     c.encode(imgs, labs, levels, wavelet, path_type, euclidean_distance, paths_first_level=paths_first_level)
-    b = which
+    return collect(c, which, imgs[which], levels, ncoefs, with_perm)
+
+
+def collect(c, b, img, levels, ncoefs=None, with_perm=True):
+    """Everything the codec holds for image `b` of its encoded batch, in the oracle's layout.  With `ncoefs` the
+    whole batch is thresholded and decoded (state changes: call it for the images of interest AFTER reading
+    whatever else is needed from the unthresholded encoding)."""
+    W = c.shape[2]
     out = {"perm": {}, "roff": {}, "points": {}, "codec": c}
     for lev in range(1, levels + 2):
         out["roff"][lev] = c.region_offsets(b, lev)
@@ -32,9 +39,26 @@ def cuda_run(img, labels, levels, wavelet, path_type="easypath", euclidean_dista
         out["kept"] = np.flatnonzero(th != 0).astype(np.int64)
         dec = c.decode()[b]
         out["decoded"] = dec
-        out["psnr"] = float(c.psnr(imgs[b:b + 1].astype(np.float64), dec[None])[0])
+        out["psnr"] = float(c.psnr(np.asarray(img, dtype=np.float64)[None], dec[None])[0])
         out["nonzero_coefs"] = int(c.nonzero_coefs()[b])
     return out
+
+
+def collect_batch(c, imgs, which, levels, ncoefs, with_perm=True):
+    """collect() for several images of ONE encoded batch: everything unthresholded first, then one threshold +
+    decode of the batch."""
+    outs = {b: collect(c, b, imgs[b], levels, None, with_perm) for b in which}
+    c.threshold(ncoefs)
+    dec = c.decode()
+    nz = c.nonzero_coefs()
+    for b, out in outs.items():
+        th = c.coefs(b)
+        out["thresholded"] = th
+        out["kept"] = np.flatnonzero(th != 0).astype(np.int64)
+        out["decoded"] = dec[b]
+        out["psnr"] = float(c.psnr(np.asarray(imgs[b], dtype=np.float64)[None], dec[b][None])[0])
+        out["nonzero_coefs"] = int(nz[b])
+    return outs
 
 
 def assert_same_as_oracle(out, orc, levels, coef_rtol=1e-12):

@@ -42,6 +42,18 @@ def test_image_facade_matches_golden():
     assert im.has_decoded_img
     assert np.max(np.abs(im.decoded_img - g["decoded"])) <= 1e-9 * 255
     assert abs(im.psnr() - g["psnr"]) < 5e-7
+    # decoded_region_collection carries the DECODED values (rbepwt.py:308-310), level-1 regions in incoming order
+    drc = im.decoded_region_collection
+    pts = drc.points
+    assert len(pts) == g["img"].size
+    rebuilt = np.zeros_like(g["decoded"])
+    for coord, value in pts.items():
+        rebuilt[coord] = value
+    assert np.max(np.abs(np.clip(rebuilt, 0, 255) - g["decoded"])) <= 1e-9 * 255
+    assert drc[0].base_points == tuple(sorted(drc[0].base_points))  # row-major inside the region
+    rcl = im.rbepwt.region_collection_at_level
+    assert len(rcl) == g["levels"] + 1 and list(rcl) == list(range(1, g["levels"] + 2)) and (g["levels"] + 1) in rcl
+    assert [k for k, _ in rcl.items()] == list(rcl.keys())
 
 
 def test_epwt_facade_and_method_quirk():
@@ -96,6 +108,36 @@ def test_full_decode_equals_fast_decode():
         fdi = rbepwt.full_decode(im.rbepwt.wavelet_details, im.rbepwt.region_collection_at_level[L + 1].values,
                                  im.label_img, g["wavelet"], "easypath")
     np.testing.assert_array_equal(fdi, im.decoded_img)
+
+
+def test_full_decode_vs_oracle_decode():
+    """rbepwt_full_decode (paths regenerated from the labels alone, rbepwt.py:106-130) against the C oracle's decode of
+    the same coefficient vectors: thresholded coefficients of the image, and arbitrary ones (the decoder must
+    not depend on having seen the image)."""
+    import rbepwt_b200 as rbepwt
+    from oracle import c_oracle
+    from rbepwt_b200 import synth
+
+    rng = np.random.default_rng(8)
+    for name, euclid in (("vor64_euclid_bior44", True), ("vor32_cheb_haar", False)):
+        g = load_golden(name)
+        fb = rbepwt.filter_bank(g["wavelet"])
+        L = g["levels"]
+        enc = c_oracle.encode(g["img"], g["labels"], L, fb, c_oracle.MODE_EUCLID if euclid else c_oracle.MODE_CHEB)
+        vecs = np.stack([g["thresholded"], rng.normal(0, 30, g["img"].size)])
+        labs = np.stack([g["labels"], g["labels"]])
+        got = rbepwt.BatchCodec().full_decode(vecs, labs, L, g["wavelet"], "easypath", euclid)
+        for i in range(2):
+            want = c_oracle.decode(enc, vecs[i], fb)
+            assert np.max(np.abs(got[i] - want)) <= 1e-9 * 255
+        assert np.max(np.abs(got[0] - g["decoded"])) <= 1e-9 * 255  # and what the reference itself decoded
+    # 512^2, the benchmark's label maps
+    lab = synth.voronoi_labels(512, 512, 1024, seed=5)
+    fb = rbepwt.filter_bank("bior4.4")
+    enc = c_oracle.encode(np.zeros((512, 512)), lab, 16, fb, c_oracle.MODE_EUCLID)
+    vec = rng.normal(0, 20, 512 * 512) * (rng.uniform(size=512 * 512) < 0.01)
+    got = rbepwt.BatchCodec().full_decode(vec[None], lab[None], 16, "bior4.4")
+    assert np.max(np.abs(got[0] - c_oracle.decode(enc, vec, fb))) <= 1e-9 * 255
 
 
 def test_guards_raise_the_reference_messages():

@@ -3,21 +3,10 @@ what Felzenszwalb produces on natural images), next to the uniform-Voronoi workl
 import sys, os, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch
-from scipy.spatial import cKDTree
 import rbepwt_b200 as rb
 from rbepwt_b200 import synth
 
-def heavytail_labels(n, nseeds, seed):
-    rng = np.random.default_rng(seed)
-    k = nseeds
-    # 85 % of the seeds crowd into three blobs covering ~15 % of the image, the rest are spread out
-    centres = rng.uniform(0.15 * n, 0.85 * n, size=(3, 2))
-    crowd = centres[rng.integers(0, 3, size=int(0.85 * k))] + rng.normal(0, 0.07 * n, size=(int(0.85 * k), 2))
-    spread = rng.uniform(0, n, size=(k - len(crowd), 2))
-    pts = np.clip(np.concatenate([crowd, spread]), 0, n - 1)
-    ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
-    _, idx = cKDTree(pts).query(np.stack([ii.ravel(), jj.ravel()], 1))
-    return idx.reshape(n, n).astype(np.int32)
+heavytail_labels = synth.heavytail_labels
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 for name, gen in (("uniform voronoi 1024", lambda s: synth.voronoi_labels(512, 512, 1024, seed=s)),
