@@ -393,8 +393,9 @@ def run_ours(args):
     # algorithmic bytes per image of each kernel family
     alg = {
         "regions": ("k0_count+k0_regions_fast+queue", 3 * 4 * N),         # three passes over the labels
-        "paths": ("k1_paths_tpr", 4 * N + 4 * S + 4 * (S - N)),            # labels in; pixel ids (all levels) + positions (levels >= 2) out
-        "paths_big": ("k1_paths_big", 4 * N + 4 * S + 4 * (S - N)),
+        "paths": ("k1_walk", 4 * N + 4 * S),                               # labels in; pixel ids (all levels) out
+        "paths_big": ("k1_paths_big", 4 * N + 4 * S),
+        "perm": ("k2_perm", 4 * S + 4 * (S - N)),                          # pixel ids in; positions (levels >= 2) out
         "dwt": ("k3_dwt_level", 4 * S + 8 * S + 8 * S),                    # paths + gathered values in, cA/cD out
         "select": ("k4_threshold", 8 * N + 8 * N),
         "idwt": ("k5_idwt_level", 4 * S + 8 * S + 8 * S),
@@ -402,7 +403,7 @@ def run_ours(args):
     kern_stages = [s for s in alg if stage_ms.get(s, 0.0) > 0.0]
     total_kernel_ms = sum(stage_ms[s] for s in kern_stages)
     dom = max(kern_stages, key=lambda s: stage_ms[s])
-    # a "launch" of the paths stage is one path group: k1_bitmaps, then the two k1_paths_tpr instantiations side by
+    # a "launch" of the paths stage is one path group: k1_bitmaps, then the two k1_walk instantiations side by
     # side (the windowed one takes the few large bitmaps) -- three kernel launches timed as one unit
     per_unit = {"paths": 3}
     dom_launches = max(stage_n.get(dom, 0) // per_unit.get(dom, 1), 1)
@@ -424,9 +425,8 @@ def run_ours(args):
                 "avg_launch_ms": dom_ms_per_launch, "launches": dom_launches,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "share_of_step": stage_ms[dom] / total_kernel_ms,
-                "note": "k1 path construction (k1_bitmaps + k1_paths_tpr, one unit per path group) is dependent chains "
-                        "(issue/latency bound: 61 % issue-active, 11 of 32 lanes per instruction, 14 % DRAM throughput in "
-                        "the ncu capture), not an HBM-bound kernel; see `kernels` for the HBM-bound ones"}
+                "note": "k1 path construction (k1_bitmaps + k1_walk, one unit per path group) is dependent chains "
+                        "(issue bound, see profiles/), not an HBM-bound kernel; see `kernels` for the HBM-bound ones"}
     kernels = {}
     for s in kern_stages:
         if stage_ms[s] < 0.01 * total_kernel_ms:

@@ -161,7 +161,8 @@ int rbepwt_get_level_values(rbepwt_ctx *ctx, int b, int level, double *vals);
 #define RBEPWT_T_IDWT 5    /* K5: synthesis filter bank + scatter, all levels */
 #define RBEPWT_T_D2H 6
 #define RBEPWT_T_PATHS_BIG 7 /* K1: regions with a large bounding box (one warp per CTA, whole-image bitmap) */
-#define RBEPWT_T_COUNT 8
+#define RBEPWT_T_PERM 8      /* K2: positions of the path points in each level's incoming order (levels >= 2) */
+#define RBEPWT_T_COUNT 9
 int rbepwt_enable_timing(rbepwt_ctx *ctx, int on);
 /* Sums the stage events recorded since the previous call (they accumulate across encode /
  * threshold / decode calls), synchronises the stream, returns RBEPWT_T_COUNT. */

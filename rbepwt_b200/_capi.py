@@ -11,7 +11,7 @@ E_NOT_POW2, E_LEVELS, E_NO_ENCODING, E_NO_GPU = -2, -3, -4, -7
 PATH_EUCLID, PATH_CHEB, PATH_EPWT = 0, 1, 2
 DEVICE_PTRS, U8_WRAP, PATHS_FIRST_LEVEL, NO_CLIP = 1, 2, 4, 8
 OPT_STREAMS, OPT_SUBBATCH, OPT_PATHGROUP = 1, 2, 3
-T_NAMES = ["h2d", "regions", "paths", "dwt", "select", "idwt", "d2h", "paths_big"]
+T_NAMES = ["h2d", "regions", "paths", "dwt", "select", "idwt", "d2h", "paths_big", "perm"]
 
 EXPORTS = [
     "rbepwt_create", "rbepwt_destroy", "rbepwt_last_error", "rbepwt_sync", "rbepwt_set_wavelet",

@@ -13,6 +13,45 @@ __host__ __device__ __forceinline__ size_t level_off(size_t n, int lev) {
   return lev <= 1 ? 0 : 2 * n - (n >> (lev - 2));
 }
 
+// Bit intrinsics callable from host code too: the per-lane logic of the path walker (walk.cuh) is __host__ __device__
+// so that tests can run it on the CPU against the oracle (tests/host_walk).
+__host__ __device__ __forceinline__ int rb_clz(uint32_t x) {
+#ifdef __CUDA_ARCH__
+  return __clz((int)x);
+#else
+  return x ? __builtin_clz(x) : 32;
+#endif
+}
+__host__ __device__ __forceinline__ int rb_ffs(uint32_t x) {  // 1-based position of the lowest set bit, 0 if none
+#ifdef __CUDA_ARCH__
+  return __ffs((int)x);
+#else
+  return __builtin_ffs((int)x);
+#endif
+}
+__host__ __device__ __forceinline__ int rb_popc(uint32_t x) {
+#ifdef __CUDA_ARCH__
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t rb_funnel_r(uint32_t lo, uint32_t hi, int sh) {  // (hi:lo) >> (sh & 31)
+#ifdef __CUDA_ARCH__
+  return __funnelshift_r(lo, hi, sh);
+#else
+  return (uint32_t)(((((unsigned long long)hi) << 32) | lo) >> (sh & 31));
+#endif
+}
+__host__ __device__ __forceinline__ double rb_dmul(double a, double b) {  // never contracted into an FMA
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  volatile double p = a * b;
+  return p;
+#endif
+}
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;

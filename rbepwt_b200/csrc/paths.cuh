@@ -10,7 +10,7 @@
 // pixels, regions whose bounding-box bitmap is too large for a shared-memory arena, every region of a
 // small group (latency matters, not throughput), and the EPWT mode (one region per image, values read
 // per candidate).  The bulk -- hundreds of thousands of small regions per batch -- is walked thread per
-// region by paths_tpr.cuh.  The unvisited points are a bitmap over the region's bounding box (shared
+// region by walk.cuh.  The unvisited points are a bitmap over the region's bounding box (shared
 // memory; global scratch for boxes too large).
 //
 // Step rule (exactly the reference's, restated order-independently):
@@ -54,9 +54,9 @@ struct PathParams {
   int *qmeta;
   int coop_min;  // regions of at least this many pixels get a warp of their own
   const uint8_t *unit_lut;  // 9 x 512 unit-step table of the path mode (global memory, built once per context)
-  uint32_t *gbm;            // [gbm_chunks][TPR_ARENA_WORDS] chunk bitmaps built by k1_bitmaps (paths_tpr.cuh)
+  const uint8_t *t2_tab;    // 5x5 step table of the euclid mode (walk.cuh, T2_BYTES)
+  uint32_t *gbm;            // [gbm_chunks][TPR_ARENA_WORDS] chunk arena images built by k1_bitmaps (walk.cuh)
   int gbm_chunks;           // chunks beyond it build their bitmaps inside the path kernel
-  const uint32_t *s5_tab;   // 5x5 table step of k1_paths_tpr<MODE_EUCLID, false> (paths_tpr.cuh, S5_WORDS words)
   int32_t *Q;  // [B][2N]
   int32_t *Pm;      // [B][2N] level l >= 2: position of the path point in the level's incoming order (= index into cA of level l-1)
   int32_t *posmap;  // [B][N] scratch: pixel -> position in the next level's incoming order
@@ -66,25 +66,25 @@ struct PathParams {
   int big_smem_words;          // dynamic shared-memory words available per CTA in the big kernel
 };
 
-constexpr int TPR_LUT_ROWS = 9, TPR_LUT_COLS = 512;  // unit-step table: 9 prefs x 512 neighbourhood masks (paths_tpr.cuh)
+constexpr int TPR_LUT_ROWS = 9, TPR_LUT_COLS = 512;  // unit-step table: 9 prefs x 512 neighbourhood masks (walk.cuh)
 constexpr int COOP_MAX_SIDE = 16384;                 // find_next_geo: integer dot products stay below 2^30
 
-__device__ __forceinline__ bool pref_ties_exactly(int p0, int p1) {
+__host__ __device__ __forceinline__ bool pref_ties_exactly(int p0, int p1) {
   if (p0 == 0 || p1 == 0) return true;
   const int a = abs(p0), b = abs(p1);
   return a == b && (a & (a - 1)) == 0;
 }
 
-__device__ __forceinline__ int probe_index(int c) { return 32 - __clz(max(c - 1, 0)); }  // ceil(log2(c)), c >= 1
+__host__ __device__ __forceinline__ int probe_index(int c) { return 32 - rb_clz((uint32_t)max(c - 1, 0)); }  // ceil(log2(c)), c >= 1
 
 // Window row as one word: bit 15 + dj  <->  column cj + dj, dj in [-15, 16]; columns outside the
 // bitmap read as 0.
-__device__ __forceinline__ uint32_t row_window(const uint32_t *row, int ws, int cj) {
+__host__ __device__ __forceinline__ uint32_t row_window(const uint32_t *row, int ws, int cj) {
   const int s = cj - 15;
   const int wlo = s >> 5;  // -1 when s < 0
   const uint32_t lo = (wlo >= 0 && wlo < ws) ? row[wlo] : 0u;
   const uint32_t hi = (wlo + 1 < ws) ? row[wlo + 1] : 0u;
-  return __funnelshift_r(lo, hi, s & 31);
+  return rb_funnel_r(lo, hi, s & 31);
 }
 
 struct Best {
@@ -96,10 +96,10 @@ struct Best {
 };
 
 // sp1 of the reference's tie-break, bit for bit.
-__device__ __forceinline__ double tie_sp1(int di, int dj, int d2, int p0, int p1) {
+__host__ __device__ __forceinline__ double tie_sp1(int di, int dj, int d2, int p0, int p1) {
   const double nrm = sqrt((double)d2);  // IEEE-correct in fp64
   const double v0 = (double)di / nrm, v1 = (double)dj / nrm;
-  double s = fma(v1, (double)p1, __dmul_rn(v0, (double)p0));
+  double s = fma(v1, (double)p1, rb_dmul(v0, (double)p0));
   if (s == 0.0) s = 0.0;  // -0.0 -> +0.0 (compares equal in the reference)
   return s;
 }
@@ -221,7 +221,7 @@ __device__ __forceinline__ bool find_next(const uint32_t *bm, int h, int w, int 
   return true;
 }
 
-// Warp-cooperative search, euclid mode, integer keys (the derivation is in paths_tpr.cuh): the lanes take the
+// Warp-cooperative search, euclid mode, integer keys (the derivation is in walk.cuh): the lanes take the
 // rows of the window, every lane keeps the best candidate of its rows as (k, d2, dot) with k = probe index
 // ceil(log2(Chebyshev distance)), three warp reductions pick the winner, and a mirror pair (equal d2 and equal dot
 // product) is settled by the cross product or -- only for a pref where the reference's fp64 expression need
@@ -239,6 +239,36 @@ struct GeoCand {
     else if (same && cdot == dot) { alt = true; adi = cdi; adj = cdj; }
   }
 };
+
+// The warp's winner among the lanes' best candidates (at least one lane has one): smallest (k, d2), then the largest
+// dot product; a mirror pair -- a second lane's best, or the first lane's own second candidate -- by the cross
+// product or, for a pref where the reference's fp64 expression need not tie exactly, by that expression.
+__device__ __forceinline__ void geo_pick(const GeoCand &b, int adi, int adj, bool alt, int p0, int p1, int &di, int &dj,
+                                         int &kmin) {
+  kmin = __reduce_min_sync(FULL_MASK, b.have ? b.k : INT32_MAX);
+  const bool s1 = b.have && b.k == kmin;
+  const int dmin = __reduce_min_sync(FULL_MASK, s1 ? b.d2 : INT32_MAX);
+  const bool s2 = s1 && b.d2 == dmin;
+  const int dotmax = __reduce_max_sync(FULL_MASK, s2 ? b.dot : INT32_MIN);
+  const unsigned tied = __ballot_sync(FULL_MASK, s2 && b.dot == dotmax);
+  const int la = __ffs(tied) - 1;
+  di = __shfl_sync(FULL_MASK, b.di, la); dj = __shfl_sync(FULL_MASK, b.dj, la);
+  const unsigned rest = tied & (tied - 1);
+  const bool alt_a = __shfl_sync(FULL_MASK, (int)alt, la) != 0;
+  if (rest || alt_a) {
+    const int lb = rest ? __ffs(rest) - 1 : la;
+    const int odi = __shfl_sync(FULL_MASK, rest ? b.di : adi, lb), odj = __shfl_sync(FULL_MASK, rest ? b.dj : adj, lb);
+    const int cb = di * p1 - dj * p0, ca = odi * p1 - odj * p0;
+    bool other_better;
+    if (pref_ties_exactly(p0, p1)) {
+      other_better = ca > cb;
+    } else {
+      const double sb = tie_sp1(di, dj, dmin, p0, p1), sa = tie_sp1(odi, odj, dmin, p0, p1);
+      other_better = sa != sb ? sa > sb : ca > cb;
+    }
+    if (other_better) { di = odi; dj = odj; }
+  }
+}
 
 __device__ __forceinline__ bool find_next_geo(const uint32_t *bm, int h, int w, int ws, int ci, int cj, int p0, int p1,
                                               int &rad, const uint8_t *lut, int &bi, int &bj) {
@@ -294,31 +324,8 @@ __device__ __forceinline__ bool find_next_geo(const uint32_t *bm, int h, int w, 
     if (__any_sync(FULL_MASK, b.have)) break;
     if (ci - rad <= 0 && cj - rad <= 0 && ci + rad >= h - 1 && cj + rad >= w - 1) return false;
   }
-  // winner: smallest (k, d2), then largest dot product
-  const int kmin = __reduce_min_sync(FULL_MASK, b.have ? b.k : INT32_MAX);
-  const bool s1 = b.have && b.k == kmin;
-  const int dmin = __reduce_min_sync(FULL_MASK, s1 ? b.d2 : INT32_MAX);
-  const bool s2 = s1 && b.d2 == dmin;
-  const int dotmax = __reduce_max_sync(FULL_MASK, s2 ? b.dot : INT32_MIN);
-  const unsigned tied = __ballot_sync(FULL_MASK, s2 && b.dot == dotmax);
-  const int la = __ffs(tied) - 1;
-  int di = __shfl_sync(FULL_MASK, b.di, la), dj = __shfl_sync(FULL_MASK, b.dj, la);
-  // the mirror partner, if any: a second lane's best, or the first lane's own second candidate
-  const unsigned rest = tied & (tied - 1);
-  const bool alt_a = __shfl_sync(FULL_MASK, (int)alt, la) != 0;
-  if (rest || alt_a) {
-    const int lb = rest ? __ffs(rest) - 1 : la;
-    const int odi = __shfl_sync(FULL_MASK, rest ? b.di : adi, lb), odj = __shfl_sync(FULL_MASK, rest ? b.dj : adj, lb);
-    const int cb = di * p1 - dj * p0, ca = odi * p1 - odj * p0;
-    bool other_better;
-    if (pref_ties_exactly(p0, p1)) {
-      other_better = ca > cb;
-    } else {
-      const double sb = tie_sp1(di, dj, dmin, p0, p1), sa = tie_sp1(odi, odj, dmin, p0, p1);
-      other_better = sa != sb ? sa > sb : ca > cb;
-    }
-    if (other_better) { di = odi; dj = odj; }
-  }
+  int di, dj, kmin;
+  geo_pick(b, adi, adj, alt, p0, p1, di, dj, kmin);
   bi = ci + di; bj = cj + dj;
   rad = 1 << kmin;
   return true;
@@ -381,7 +388,7 @@ __device__ __forceinline__ int reduce_points(uint32_t *bm, int ws, int a, int n,
       const int pix = __ldcg(Ql + t);
       const int i = (pix >> logW) - r0, j = (pix & Wm) - c0;
       atomicOr(&bm[i * ws + (j >> 5)], 1u << (j & 31));
-      posmap[pix] = (a + t) >> 1;  // the survivor's place in the next level's incoming order
+      if (posmap) posmap[pix] = (a + t) >> 1;  // EPWT: the survivor's place in the next level's incoming order
       minpix = min(minpix, pix);
     }
   }
@@ -401,8 +408,6 @@ __device__ void region_pyramid(const PathParams &P, int g, uint32_t *bm, const u
   const int h = P.reg.rmax[g] - r0 + 1, w = P.reg.cmax[g] - c0 + 1, ws = (w + 31) >> 5;
   const int32_t *lab = P.labels + (size_t)img * N;
   int32_t *Q = P.Q + (size_t)img * 2 * (size_t)N;
-  int32_t *Pm = P.Pm + (size_t)img * 2 * (size_t)N;
-  int32_t *posmap = P.posmap + (size_t)img * N;
 
   const int words = h * ws;
   for (int wi = 0; wi < words; wi += 4) {  // four independent label loads in flight per lane
@@ -426,13 +431,13 @@ __device__ void region_pyramid(const PathParams &P, int g, uint32_t *bm, const u
   int si = 0, sj = (first & (W - 1)) - c0;
   for (int lev = 1; lev <= P.levels && n > 0; lev++) {
     int32_t *Ql = Q + level_off((size_t)N, lev) + a;
-    int32_t *Pl = lev >= 2 ? Pm + level_off((size_t)N, lev) + a : nullptr;
-    if (!run_path<MODE>(bm, h, w, ws, si, sj, n, r0, c0, logW, nullptr, false, Ql, Pl, posmap, lut)) {
+    // paths only: the positions in the incoming order (Pm) of every region are computed by k2_perm (walk.cuh)
+    if (!run_path<MODE>(bm, h, w, ws, si, sj, n, r0, c0, logW, nullptr, false, Ql, nullptr, nullptr, lut)) {
       if (lane == 0) atomicExch(&P.qmeta[QM_ERR], 1);
       return;
     }
     if (lev == P.levels) break;
-    const int minpix = reduce_points(bm, ws, a, n, r0, c0, logW, Ql, posmap);
+    const int minpix = reduce_points(bm, ws, a, n, r0, c0, logW, Ql, nullptr);
     const int na = (a + 1) >> 1, nb = (a + n + 1) >> 1;
     a = na; n = nb - na;
     if (n > 0) { si = (minpix >> logW) - r0; sj = (minpix & (W - 1)) - c0; }

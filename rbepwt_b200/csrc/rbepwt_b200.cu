@@ -14,10 +14,10 @@
 #include "common.cuh"
 #include "dwt.cuh"
 #include "paths.cuh"
-#include "paths_tpr.cuh"
 #include "perm.cuh"
 #include "regions.cuh"
 #include "select.cuh"
+#include "walk.cuh"
 
 using namespace rbepwt;
 
@@ -81,7 +81,7 @@ constexpr int NSLOTS = NSLOT + NXSLOT;
 #ifndef TPR_WIDE_CTAS_PER_SM
 #define TPR_WIDE_CTAS_PER_SM 5
 #endif
-constexpr int TPR_WAVES = 8;  // k1_paths_tpr grid = this many waves of resident CTAs (see paths_tpr.cuh)
+constexpr int TPR_WAVES = 8;  // k1_walk grid = this many waves of resident CTAs (see walk.cuh)
 
 // Workspace + stream of one unit of work in flight.  The batch is cut twice: into PATH GROUPS (label scan,
 // region records, path pyramid -- large, the path kernel has a long tail and wants many regions per launch)
@@ -115,7 +115,7 @@ struct rbepwt_ctx {
   // wavelet
   bool has_wavelet = false;
   int flen = 0;
-  DevBuf filt, unit_lut;  // unit_lut: two 9 x 512 tables (euclid, chebyshev)
+  DevBuf filt, unit_lut, t2_tab;  // unit_lut: two 9 x 512 tables (euclid, chebyshev); t2_tab: the 5x5 step table (euclid)
   double h_filt[4][FT_MAX] = {};  // host copy (flen <= FT_MAX): passed to the transform kernels by value
   // state of the encoded batch
   bool has_encoding = false, has_paths = false;
@@ -368,11 +368,11 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   int rc = grow_regs(c, std::max<size_t>((size_t)c->totalR, (size_t)c->B * 2048 + 4096), (size_t)g0);
   if (rc) return rc;
   CK(sl.queue.ensure_slack((size_t)nreg * 4));
-  CK(sl.chunk_start.ensure_slack(((size_t)nreg + Q_BINS) * 4));
-  CK(sl.chunk_cnt.ensure_slack(((size_t)nreg + Q_BINS) * 4));
-  // chunk bitmaps: room for the usual ~nreg/32 chunks (+ the partial chunk of every bin); more chunks than that
-  // (many large bitmaps) build theirs inside the path kernel
-  const size_t gbm_chunks = (size_t)nreg / 16 + Q_BINS;
+  CK(sl.chunk_start.ensure_slack(((size_t)nreg + Q_NCLS) * 4));
+  CK(sl.chunk_cnt.ensure_slack(((size_t)nreg + Q_NCLS) * 4));
+  // chunk arena images: room for the usual ~nreg/32 chunks and then some; more chunks than that (many large
+  // bitmaps) build theirs inside the path kernel
+  const size_t gbm_chunks = (size_t)nreg / 16 + 64;
   CK(sl.gbm.ensure_slack(gbm_chunks * TPR_ARENA_WORDS * 4));
   CK(cudaStreamWaitEvent(s, ready, 0));
   {
@@ -394,8 +394,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     kq_hist<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, coop_min, sl.qhist.as<int>());
     kq_scan<<<1, 32, 0, s>>>(sl.qhist.as<int>(), sl.qmeta.as<int>(), sl.qbins.as<int>(), nreg);
     kq_scatter<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, coop_min, sl.qmeta.as<int>(), sl.queue.as<int32_t>());
-    kq_chunks<<<((Q_BINS - Q_SIZE_BINS) * 32 + 255) / 256, 256, 0, s>>>(sl.qbins.as<int>(), sl.chunk_start.as<int32_t>(),
-                                                                        sl.chunk_cnt.as<int32_t>());
+    kq_chunks<<<Q_NCLS - 1, 1024, 0, s>>>(sl.qbins.as<int>(), sl.chunk_start.as<int32_t>(), sl.chunk_cnt.as<int32_t>());
     c->launches += 6;
     CK(cudaGetLastError());
   }
@@ -410,6 +409,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   P.qmeta = sl.qmeta.as<int>();
   P.coop_min = coop_min;
   P.unit_lut = c->unit_lut.as<uint8_t>() + (c->mode == RBEPWT_PATH_CHEB ? TPR_LUT_ROWS * TPR_LUT_COLS : 0);
+  P.t2_tab = c->t2_tab.as<uint8_t>();
   P.gbm = sl.gbm.as<uint32_t>();
   P.gbm_chunks = (int)gbm_chunks;
   P.Q = c->Q.as<int32_t>();
@@ -430,9 +430,9 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   }
   int tpr_per_sm = 1;  // grid = TPR_WAVES waves of resident CTAs
   if (c->mode == RBEPWT_PATH_EUCLID)
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_paths_tpr<MODE_EUCLID, false>, TPR_WARPS * 32, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_walk<MODE_EUCLID, false>, WK_WARPS * 32, 0));
   else
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_paths_tpr<MODE_CHEB, false>, TPR_WARPS * 32, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_walk<MODE_CHEB, false>, WK_WARPS * 32, 0));
   const int small_ctas = c->sm_count * std::max(tpr_per_sm, 1) * TPR_WAVES;
   {
     StageTimer tb(c, RBEPWT_T_PATHS_BIG, s);
@@ -452,21 +452,28 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     CK(cudaEventRecord(sl.ev_a, s));
     CK(cudaStreamWaitEvent(sl.aux, sl.ev_a, 0));
     if (c->mode == RBEPWT_PATH_EUCLID)
-      k1_paths_tpr<MODE_EUCLID, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, TPR_WARPS * 32, 0, sl.aux>>>(P);
+      k1_walk<MODE_EUCLID, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, WK_WARPS * 32, 0, sl.aux>>>(P);
     else
-      k1_paths_tpr<MODE_CHEB, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, TPR_WARPS * 32, 0, sl.aux>>>(P);
+      k1_walk<MODE_CHEB, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, WK_WARPS * 32, 0, sl.aux>>>(P);
     k1_bitmaps<<<c->sm_count * 8, 256, 0, s>>>(P);
     c->launches++;
     if (c->mode == RBEPWT_PATH_EUCLID)
-      k1_paths_tpr<MODE_EUCLID, false><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
+      k1_walk<MODE_EUCLID, false><<<small_ctas, WK_WARPS * 32, 0, s>>>(P);
     else
-      k1_paths_tpr<MODE_CHEB, false><<<small_ctas, TPR_WARPS * 32, 0, s>>>(P);
+      k1_walk<MODE_CHEB, false><<<small_ctas, WK_WARPS * 32, 0, s>>>(P);
     CK(cudaEventRecord(sl.ev_b, sl.aux));
     CK(cudaStreamWaitEvent(s, sl.ev_b, 0));
     c->launches += 2;
-    if ((c->enc_flags & RBEPWT_PATHS_FIRST_LEVEL) && c->levels > 1) {
+  }
+  {
+    StageTimer t(c, RBEPWT_T_PERM, s);
+    if ((c->enc_flags & RBEPWT_PATHS_FIRST_LEVEL) && c->levels > 1) {  // identity permutations at the levels >= 2
       k_same_paths<<<nb, 1024, 0, s>>>(c->Q.as<int32_t>() + (size_t)a * 2 * N, c->Pm.as<int32_t>() + (size_t)a * 2 * N, N,
                                        c->levels);
+      c->launches++;
+    } else if (c->levels > 1) {  // positions in the incoming order of every level >= 2, from the paths
+      const int grid = std::max(1, std::min((nreg + K2_WARPS - 1) / K2_WARPS, c->sm_count * 16));
+      k2_perm<<<grid, K2_WARPS * 32, 0, s>>>(P, nreg);
       c->launches++;
     }
   }
@@ -773,6 +780,13 @@ static int create_impl(rbepwt_ctx *c, int device, void *stream) {
   CK(c->unit_lut.ensure(2 * TPR_LUT_ROWS * TPR_LUT_COLS));
   k_build_unit_lut<MODE_EUCLID><<<1, 256, 0, c->stream>>>(c->unit_lut.as<uint8_t>());
   k_build_unit_lut<MODE_CHEB><<<1, 256, 0, c->stream>>>(c->unit_lut.as<uint8_t>() + TPR_LUT_ROWS * TPR_LUT_COLS);
+  CK(c->t2_tab.ensure(T2_BYTES));
+  k_build_t2<<<(T2_JOBS + 255) / 256, 256, 0, c->stream>>>(c->t2_tab.as<uint8_t>());
+  // five CTAs of the path kernel per SM need more shared memory than the default carve-out offers
+  CK(cudaFuncSetAttribute(k1_walk<MODE_EUCLID, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k1_walk<MODE_EUCLID, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k1_walk<MODE_CHEB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k1_walk<MODE_CHEB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   return RBEPWT_OK;
@@ -810,7 +824,7 @@ void rbepwt_destroy(rbepwt_ctx *c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   for (auto *v : {&c->ev_lab, &c->ev_path, &c->ev_img, &c->ev_done})
     for (auto e : *v) cudaEventDestroy(e);
-  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->img_R,
+  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->t2_tab, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->img_R,
                     &c->img_rbase, &c->img_labmin, &c->img_direct, &c->tbl, &c->slot_rid, &c->scratch_i32,
                     &c->scratch_i32b, &c->psnr_out, &c->nz_out};
   for (auto b : bufs) b->release();
@@ -1183,12 +1197,12 @@ int rbepwt_get_stage_launches(rbepwt_ctx *c, int64_t *launches, int n) {
 
 int64_t rbepwt_launch_count(rbepwt_ctx *c) { return c ? c->launches : 0; }
 
-#ifdef TPR_STATS
-int rbepwt_debug_tpr_stats(rbepwt_ctx *c, unsigned long long *out, int reset) {
+#ifdef WK_STATS  // debug build only (tools/wk_stats.py): warp trips and lane units by kind of k1_walk
+int rbepwt_debug_wk_stats(rbepwt_ctx *c, unsigned long long *out, int reset) {
   DeviceGuard g(c->device);
   cudaStreamSynchronize(c->stream);
-  cudaMemcpyFromSymbol(out, g_tpr_stats, sizeof(unsigned long long) * 160);
-  if (reset) { unsigned long long z[160] = {}; cudaMemcpyToSymbol(g_tpr_stats, z, sizeof z); }
+  cudaMemcpyFromSymbol(out, g_wk_stats, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_wk_stats, z, sizeof z); }
   return 0;
 }
 #endif

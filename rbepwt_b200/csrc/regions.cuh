@@ -385,17 +385,19 @@ __global__ void k0_single_region(int img0, int nimg, int H, int W, RegionArrays 
 // The path kernels pull regions from a queue ordered so that (a) regions whose bounding-box bitmap
 // does not fit a warp's shared-memory arena come first (class 0, one warp per region, paths.cuh),
 // (b) the others are grouped by bitmap size class, largest first: class c >= 1 holds the bitmaps that fit
-// the arena class_chunk_size(c) = 1, 2, 4, 8, 16, 32 at a time,
-// (c) inside a class regions are sorted by pixel count, descending, in quarter-octave bins: the lanes
-// of a warp walk chains of similar length, and the longest chains start first.
-// A chunk = the regions one warp walks together (thread per region, paths_tpr.cuh).
+// the arena class_chunk_size(c) = 1, 2, 3, 4, 6, 8, 12, 16, 20, 24, 28, 32 at a time,
+// (c) inside a class regions are sorted by pixel count, descending, in eighth-octave bins: the lanes
+// of a warp walk chains of similar length, and the longest chains start first.  Chunks are cut from the class's
+// queue range regardless of the bins (only the last chunk of a class is partial).
+// A chunk = the regions one warp walks together (thread per region, walk.cuh).
 
 #ifndef TPR_ARENA_WORDS_N
-#define TPR_ARENA_WORDS_N 2048
+#define TPR_ARENA_WORDS_N 2080
 #endif
-constexpr int TPR_ARENA_WORDS = TPR_ARENA_WORDS_N;  // shared-memory words per warp of k1_paths_tpr
-constexpr int Q_NCLS = 7;              // class 0 = big; classes 1..6 = 1, 2, 4, 8, 16, 32 regions per chunk
-constexpr int Q_SIZE_BINS = 128;
+constexpr int TPR_ARENA_WORDS = TPR_ARENA_WORDS_N;  // shared-memory words per warp of k1_walk
+// class 0 = big; classes 1..12 = the bitmaps that fit the arena class_chunk_size(c) at a time
+constexpr int Q_NCLS = 13;
+constexpr int Q_SIZE_BINS = 256;
 constexpr int Q_BINS = Q_NCLS * Q_SIZE_BINS;
 
 #ifndef TPR_COOP_MIN_N
@@ -403,7 +405,7 @@ constexpr int Q_BINS = Q_NCLS * Q_SIZE_BINS;
 #endif
 constexpr int TPR_COOP_MIN = TPR_COOP_MIN_N;  // regions of at least this many pixels are walked by a whole warp
 constexpr int TPR_COOP_ALL_BELOW = 4096;      // ... and every region, when the whole group has at most this many
-constexpr int TPR_MAX_SIDE = 1024;     // bounding-box side limit of k1_paths_tpr (its packed candidate key)
+constexpr int TPR_MAX_SIDE = 1024;     // bounding-box side limit of k1_walk (its packed candidate key)
 
 __device__ __forceinline__ int region_bitmap_words(const RegionArrays &reg, int g, int logW) {
   const int h = reg.rmax[g] - (reg.first[g] >> logW) + 1;
@@ -411,34 +413,43 @@ __device__ __forceinline__ int region_bitmap_words(const RegionArrays &reg, int 
   return h * ((w + 31) >> 5);
 }
 
-// Bitmap words used for the queue class: regions with a side above TPR_MAX_SIDE count as oversized.
-// k1_paths_tpr keeps a margin of TPR_PAD empty rows / columns around the bounding box, so that the 3x3 (5x5 with
-// the optional table step) neighbourhood of any point of the region lies inside the bitmap: no bounds checks in
-// its table steps.  The margin costs bitmap words (a 29-pixel-wide region needs a second word per row with a
-// margin of 2), which moves regions into classes with fewer lanes per warp: kept as small as the step needs.
-#ifdef TPR_TABLE5
-constexpr int TPR_PAD = 2;  // the 5x5 table step
-#else
-constexpr int TPR_PAD = 1;  // the 3x3 unit step
+// k1_walk (walk.cuh) keeps a margin of WK_PAD = 2 empty rows / columns around the bounding box, so that the 5x5
+// neighbourhood of any point of the region lies inside the bitmap (no bounds checks in its step), and TWO planes per
+// region: the level's unvisited points and the survivors collected for the next level.
+constexpr int WK_PAD = 2;
+#ifndef WK_LIST_MAX_N
+#define WK_LIST_MAX_N 32
 #endif
+constexpr int WK_LIST_MAX = WK_LIST_MAX_N;  // list mode from the first level with at most this many points (<= 32)
+
+// Arena words of a region's slot: two bitmap planes of P words + 1 (the window fetch of a multi-word row reads one
+// word past the row's last).  P >= WK_LIST_MAX: the plane not in use holds the list of the first list-mode level.
+// The sum is odd, so the slots of a warp's lanes start in different shared-memory banks.
+__host__ __device__ __forceinline__ int wk_plane_words(int h, int ws) { return max(h * ws, WK_LIST_MAX); }
+__host__ __device__ __forceinline__ int wk_slot_words(int h, int ws) { return 2 * wk_plane_words(h, ws) + 1; }
+
+// Slot words used for the queue class: regions with a side above TPR_MAX_SIDE count as oversized.
 __device__ __forceinline__ int region_class_words(const RegionArrays &reg, int g, int logW) {
-  const int h = reg.rmax[g] - (reg.first[g] >> logW) + 1 + 2 * TPR_PAD;
-  const int w = reg.cmax[g] - reg.cmin[g] + 1 + 2 * TPR_PAD;
-  return (h > TPR_MAX_SIDE || w > TPR_MAX_SIDE) ? INT32_MAX : h * ((w + 31) >> 5);
+  const int h = reg.rmax[g] - (reg.first[g] >> logW) + 1 + 2 * WK_PAD;
+  const int w = reg.cmax[g] - reg.cmin[g] + 1 + 2 * WK_PAD;
+  return (h > TPR_MAX_SIDE || w > TPR_MAX_SIDE) ? INT32_MAX : wk_slot_words(h, (w + 31) >> 5);
 }
 
-// regions per chunk of a class; a class holds the bitmaps of fewer than TPR_ARENA_WORDS / chunk size words.
-// (Intermediate chunk sizes 20, 24, 28 were tried: no gain on the benchmark, where 3 % of the regions would use them.)
-__host__ __device__ __forceinline__ int class_chunk_size(int cls) { return cls == 0 ? 1 : 32 >> (Q_NCLS - 1 - cls); }
+// regions per chunk of a class; class c holds the slots of at most TPR_ARENA_WORDS / class_chunk_size(c) words.
+// Two planes make slots twice as large as a single bitmap, so the steps between the classes are fine: a region
+// a little too large for 32 per warp is walked 28 at a time, not 16.
+__host__ __device__ __forceinline__ int class_chunk_size(int cls) {
+  constexpr int cs[Q_NCLS] = {1, 1, 2, 3, 4, 6, 8, 12, 16, 20, 24, 28, 32};
+  return cs[cls];
+}
 
 __device__ __forceinline__ int queue_bin(int size, int words, int coop_min) {
   const int lg = 31 - __clz(size);                                        // size >= 1
-  const int key = size >= 4 ? 4 * lg + ((size >> (lg - 2)) & 3) : size;    // <= 4*30+3, monotone in size
+  const int key = size >= 8 ? 8 * lg + ((size >> (lg - 3)) & 7) : size;    // <= 8*30+7, monotone in size
   int cls = 0;
-  if (words < TPR_ARENA_WORDS) {
+  if (words <= TPR_ARENA_WORDS) {
     cls = Q_NCLS - 1;
-    // slots are odd (tpr_slot_words): words | 1 <= cap - 1
-    while (cls > 1 && words >= TPR_ARENA_WORDS / class_chunk_size(cls)) cls--;
+    while (cls > 1 && words * class_chunk_size(cls) > TPR_ARENA_WORDS) cls--;
     if (size >= coop_min) cls = 1;  // a long chain gets a warp of its own (one region per chunk)
   }
   return cls * Q_SIZE_BINS + (Q_SIZE_BINS - 1 - key);
@@ -458,37 +469,40 @@ __global__ void kq_hist(RegionArrays reg, int g0, int nreg, int logW, int coop_m
 }
 
 // qmeta: [0, Q_BINS) bin write cursors (scatter), then the named slots below.
-// qbins: [0, Q_BINS) bin start, [Q_BINS, 2 Q_BINS) bin count, [2 Q_BINS, 3 Q_BINS) first chunk of the bin.
+// qbins: per class: [0, Q_NCLS) queue start, [Q_NCLS, 2 Q_NCLS) count, [2 Q_NCLS, 3 Q_NCLS) first chunk.
 constexpr int QM_NBIG = Q_BINS, QM_NREG = Q_BINS + 1, QM_CUR_BIG = Q_BINS + 2, QM_CUR_SMALL = Q_BINS + 3,
               QM_ERR = Q_BINS + 4, QM_NCHUNKS = Q_BINS + 5, QM_CHUNK_SPLIT = Q_BINS + 6, QM_CUR_WIDE = Q_BINS + 7,
               QM_SIZE = Q_BINS + 8;
-constexpr int Q_FIRST_NARROW_CLS = 5;  // classes 1..4 (bitmaps of more than 128 words): the windowed variant of k1_paths_tpr
+constexpr int Q_FIRST_NARROW_CLS = 6;  // classes 1..5 (planes of more than 128 words: at most 6 regions per warp): the windowed variant of k1_walk
 
 __global__ void kq_scan(int *qhist, int *qmeta, int *qbins, int nreg) {
-  // one warp: exclusive scans of the bin counts (queue offsets) and of the bins' chunk counts
+  // one warp: exclusive scan of the bin counts (queue offsets); per class: queue start, count, first chunk
   const int lane = threadIdx.x;
   int acc = 0, cacc = 0;
-  for (int base = 0; base < Q_BINS; base += 32) {
-    const int b = base + lane;
-    const int cnt = qhist[b];
-    const int cls = b / Q_SIZE_BINS;
-    const int cs = class_chunk_size(cls);
-    const int nch = cls == 0 ? 0 : (cnt + cs - 1) / cs;
-    int inc = cnt, cinc = nch;
+  for (int cls = 0; cls < Q_NCLS; cls++) {
+    const int cstart = acc;
+    for (int base = cls * Q_SIZE_BINS; base < (cls + 1) * Q_SIZE_BINS; base += 32) {
+      const int b = base + lane;
+      const int cnt = qhist[b];
+      int inc = cnt;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int y = __shfl_up_sync(FULL_MASK, inc, d), cy = __shfl_up_sync(FULL_MASK, cinc, d);
-      if (lane >= d) { inc += y; cinc += cy; }
+      for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(FULL_MASK, inc, d);
+        if (lane >= d) inc += y;
+      }
+      qmeta[b] = acc + inc - cnt;
+      qhist[b] = 0;  // ready for the next group of images
+      acc += __shfl_sync(FULL_MASK, inc, 31);
     }
-    qmeta[b] = acc + inc - cnt;
-    qbins[b] = acc + inc - cnt;
-    qbins[Q_BINS + b] = cnt;
-    qbins[2 * Q_BINS + b] = cacc + cinc - nch;
-    qhist[b] = 0;  // ready for the next chunk of images
-    if (b == Q_SIZE_BINS) qmeta[QM_NBIG] = acc + inc - cnt;  // first bin of class 1
-    if (b == Q_FIRST_NARROW_CLS * Q_SIZE_BINS) qmeta[QM_CHUNK_SPLIT] = cacc + cinc - nch;  // first chunk of class 5
-    acc += __shfl_sync(FULL_MASK, inc, 31);
-    cacc += __shfl_sync(FULL_MASK, cinc, 31);
+    const int ccount = acc - cstart, cs = class_chunk_size(cls);
+    if (lane == 0) {
+      qbins[cls] = cstart;
+      qbins[Q_NCLS + cls] = ccount;
+      qbins[2 * Q_NCLS + cls] = cacc;
+      if (cls == 1) qmeta[QM_NBIG] = cstart;
+      if (cls == Q_FIRST_NARROW_CLS) qmeta[QM_CHUNK_SPLIT] = cacc;
+    }
+    if (cls >= 1) cacc += (ccount + cs - 1) / cs;
   }
   if (lane == 0) {
     qmeta[QM_NREG] = nreg;
@@ -507,15 +521,13 @@ __global__ void kq_scatter(RegionArrays reg, int g0, int nreg, int logW, int coo
   }
 }
 
-// One warp per bin of the classes >= 1: chunk table (queue offset, regions in the chunk).
+// One CTA per class >= 1: chunk table (queue offset, regions in the chunk).
 __global__ void kq_chunks(const int *qbins, int32_t *chunk_start, int32_t *chunk_cnt) {
-  const int lane = threadIdx.x & 31;
-  const int b = Q_SIZE_BINS + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (b >= Q_BINS) return;
-  const int start = qbins[b], cnt = qbins[Q_BINS + b], c0 = qbins[2 * Q_BINS + b];
-  const int cs = class_chunk_size(b / Q_SIZE_BINS);
+  const int cls = 1 + blockIdx.x;
+  const int start = qbins[cls], cnt = qbins[Q_NCLS + cls], c0 = qbins[2 * Q_NCLS + cls];
+  const int cs = class_chunk_size(cls);
   const int nch = (cnt + cs - 1) / cs;
-  for (int k = lane; k < nch; k += 32) {
+  for (int k = threadIdx.x; k < nch; k += blockDim.x) {
     chunk_start[c0 + k] = start + k * cs;
     chunk_cnt[c0 + k] = min(cs, cnt - k * cs);
   }

@@ -1,0 +1,881 @@
+// K1, thread-per-region form: every LANE of a warp owns one region and walks its greedy path pyramid
+// (all levels) alone; a warp walks up to 32 regions at once.  This is the kernel the benchmark
+// configurations spend their path time in (paths.cuh keeps the warp-per-region form for huge regions
+// and EPWT).
+//
+// Step rule = Region.easy_path (/root/reference/rbepwt.py:1273-1347): smallest square window of
+// half-width 1,2,4,... holding an unvisited point, then the lexicographic key (-dist, sp1, sp2).
+//
+// Execution shape.  A path step is a short dependent chain, while a batch holds 10^5..10^6 independent
+// regions, so the parallel axis is the region, not the window.  What bounds the kernel is the number of
+// instructions a warp issues per step, i.e. how many of its 32 lanes do useful work in an instruction.
+// Three decisions follow from that:
+//
+//  * One uniform step for (almost) every step.  The probes of half-width 1 and 2 see the 5x5 window
+//    around the current point.  Every bitmap carries a margin of WK_PAD = 2 empty rows and columns, so
+//    five shared-memory row words and shifts (no bounds checks) give the window as a 25-bit register
+//    N25, and the step is resolved from it: the classes d2 = 1, 2, 4, 5, 8 in that order are exactly
+//    "probe 1, then probe 2, nearest first" (euclid; chebyshev: ring 1, then ring 2), the first
+//    non-empty class holds the candidates, one candidate wins outright, several compete through the
+//    reference's direction tie-break.  On the benchmark 89 % of all steps end here whatever the
+//    previous step was (tools/tie_stats.c); with a unit preferred direction and a non-empty 3x3 ring
+//    the winner is read from a 9 x 256 table filled once by the same candidate code.
+//  * Lanes are not synchronised per level.  A lane that finishes a level starts the next one
+//    immediately (the region offsets of every level follow from the level-1 sizes alone), so a warp
+//    never waits for its slowest lane at each of the 16 levels, only once per chunk.
+//  * Nothing but the walk.  The survivors of a level (even GLOBAL positions, RegionCollection.reduce,
+//    rbepwt.py:1563-1584) are marked in a second bitmap plane -- or appended to a list -- at the moment
+//    they are visited; the two planes swap at the end of the level.  The kernel writes the paths as
+//    pixel ids (Q) and never reads them back; the positions in the incoming order (Pm) the transform
+//    kernels gather through are computed afterwards by k2_perm, a fully parallel kernel.
+//
+// Beyond the 5x5 window (FAR): aligned row windows of half-width 4 and 8 ranked by the packed key
+// (k = index of the first probe that would contain the candidate, d2, dot product) -- scanning the window
+// of half-width R once equals the reference's probes up to R in turn, so a search may start at the R
+// that resolved the previous jump; beyond 8 the whole (small) bitmap, or, in the WIDEWIN instantiation
+// for large bitmaps, windows of half-width 16, 32, ... word by word.
+//
+// List mode: from the first level with at most WK_LIST_MAX points the lane drops the bitmaps and holds
+// the points as a list of packed (row, col); a step scans the unvisited ones (a 32-bit mask).
+//
+// Integer tie-break (euclid): candidates compared by sp1 have the same d2, hence the same norm n, and
+// sp1 = fl(fl(dj/n)*p1 + fl(fl(di/n)*p0)) orders them like the integer dot product di*p0 + dj*p1 whenever
+// the dot products differ (they differ by >= 1/n, the rounding error is < 2^-20/n for coordinates below
+// 2^15).  Equal dot products = mirror images about pref: the fp64 expression ties exactly when pref is
+// on an axis or |p0| == |p1| a power of two (-> sp2, the integer cross product, decides), else it is
+// evaluated bit for bit.  Chebyshev compares candidates of different norms: always fp64.
+//
+// The per-lane logic (struct Walker) is __host__ __device__: tests/host_walk compiles it for the CPU and
+// checks whole pyramids against the oracle without a GPU; the kernel below only adds the warp loop.
+#pragma once
+#include "paths.cuh"
+
+namespace rbepwt {
+
+#ifndef WK_WARPS_N
+#define WK_WARPS_N 4
+#endif
+constexpr int WK_WARPS = WK_WARPS_N;
+#ifndef WK_MIN_CTAS
+#define WK_MIN_CTAS 5
+#endif
+#ifndef WK_NEAR_REPS_N
+#define WK_NEAR_REPS_N 2
+#endif
+constexpr int WK_NEAR_REPS = WK_NEAR_REPS_N;  // 5x5 steps a lane may take per trip of the warp loop
+#ifndef WK_LIST_BATCH_N
+#define WK_LIST_BATCH_N 8
+#endif
+constexpr int WK_LIST_BATCH = WK_LIST_BATCH_N;  // list-mode lanes wait for this many of their kind (or for the others to finish)
+
+// what a lane does next: a step from the 5x5 window; wait for the warp's search beyond it; commit what that search
+// found; a list-mode step; start the next level (t == n)
+enum : int { WK_DONE = 0, WK_NEAR = 1, WK_FAR = 2, WK_LIST = 3, WK_LEVEL = 4, WK_COMMIT = 5, WK_ERROR = 6 };
+
+template <int MODE>
+struct Search;
+
+// ---- euclid: packed integer keys, fp64 only for mirror pairs under a non-exact pref ----------------
+template <>
+struct Search<MODE_EUCLID> {
+  // incumbent: key = k << 21 | d2 (sides <= TPR_MAX_SIDE: d2 < 2^21, k <= 11), then the larger dot product;
+  // offsets packed (di << 16) | (dj & 0xffff)
+  unsigned key;
+  int dot, off, aoff;  // aoff: mirror partner with the same (key, dot)
+  int tag, atag;       // caller's payload of the incumbent / its mirror partner (list mode: list index)
+  bool alt;
+
+  __host__ __device__ __forceinline__ void reset() { key = 0xffffffffu; dot = 0; off = aoff = 0; tag = atag = 0; alt = false; }
+  __host__ __device__ __forceinline__ bool have() const { return key != 0xffffffffu; }
+
+  __host__ __device__ __forceinline__ void consider(bool valid, int cdi, int cdj, int p0, int p1, int ctag = 0) {
+    const int k = probe_index(max(abs(cdi), abs(cdj)));
+    const unsigned ckey = valid ? ((unsigned)k << 21) | (unsigned)(cdi * cdi + cdj * cdj) : 0xffffffffu;
+    const int cdot = cdi * p0 + cdj * p1;
+    const int coff = (int)(((unsigned)cdi << 16) | ((unsigned)cdj & 0xffffu));
+    // selects, not branches: every lane executes the same instructions
+    const bool same = ckey == key;
+    const bool lt = ckey < key || (same && cdot > dot);
+    const bool eq = valid && same && cdot == dot;  // mirror image of the incumbent about pref
+    key = lt ? ckey : key;
+    dot = lt ? cdot : dot;
+    off = lt ? coff : off;
+    tag = lt ? ctag : tag;
+    alt = lt ? false : (alt || eq);
+    aoff = eq ? coff : aoff;
+    atag = eq ? ctag : atag;
+  }
+
+  // Candidates of one row: the nearest unvisited column on the left (distance dl >= 1) and on the right
+  // (dr >= 0); the nearer one dominates the other in (k, d2), both compete only when dl == dr.
+  __host__ __device__ __forceinline__ void row_candidates(bool hl, int dl, bool hr, int dr, int rdi, int p0, int p1) {
+    if (!(hl || hr)) return;
+    const bool left_first = hl && (!hr || dl <= dr);
+    consider(true, rdi, left_first ? -dl : dr, p0, p1);
+    if (hl && hr && dl == dr) consider(true, rdi, dr, p0, p1);
+  }
+
+  // one bitmap word of row ci+rdi: columns lo..lo+31, already masked to the window
+  __host__ __device__ __forceinline__ void scan_word(uint32_t bits, int lo, int rdi, int cj, int p0, int p1) {
+    const int rel = min(cj - lo, 31);
+    const uint32_t lmask = rel < 0 ? 0u : (2u << rel) - 1u;  // columns <= cj
+    const uint32_t left = bits & lmask, right = bits & ~lmask;
+    row_candidates(left != 0u, cj - (lo + 31 - rb_clz(left)), right != 0u, lo + rb_ffs(right) - 1 - cj, rdi, p0, p1);
+  }
+
+  // one window row as an aligned word: bit 15 + dj <-> column cj + dj
+  __host__ __device__ __forceinline__ void scan_row(uint32_t x, int rdi, int p0, int p1) {
+    const uint32_t left = x & 0x7fffu, right = x >> 15;
+    row_candidates(left != 0u, rb_clz(left) - 16, right != 0u, rb_ffs(right) - 1, rdi, p0, p1);  // hb = 31 - clz -> dl = 15 - hb
+  }
+
+  __host__ __device__ __forceinline__ void finish(int p0, int p1, int &odi, int &odj, int &k) {
+    int di = off >> 16, dj = (int)(short)(off & 0xffff);
+    if (alt) {
+      const int adi = aoff >> 16, adj = (int)(short)(aoff & 0xffff);
+      const int cb = di * p1 - dj * p0, ca = adi * p1 - adj * p0;
+      bool alt_better;
+      if (pref_ties_exactly(p0, p1)) {
+        alt_better = ca > cb;
+      } else {
+        const int d2 = (int)(key & 0x1fffffu);
+        const double sb = tie_sp1(di, dj, d2, p0, p1), sa = tie_sp1(adi, adj, d2, p0, p1);
+        alt_better = sa != sb ? sa > sb : ca > cb;
+      }
+      if (alt_better) { di = adi; dj = adj; tag = atag; }
+    }
+    odi = di; odj = dj; k = (int)(key >> 21);
+  }
+};
+
+// ---- chebyshev: every point of the nearest ring competes through the fp64 sp1 ----------------------
+template <>
+struct Search<MODE_CHEB> {
+  int c, d2, di, dj, tag;
+  double sp1;
+  bool found, has_sp1;
+
+  __host__ __device__ __forceinline__ void reset() { found = false; has_sp1 = false; c = d2 = di = dj = tag = 0; sp1 = 0.0; }
+  __host__ __device__ __forceinline__ bool have() const { return found; }
+
+  __host__ __device__ __forceinline__ void consider(bool valid, int cdi, int cdj, int p0, int p1, int ctag = 0) {
+    if (!valid) return;
+    const int cc = max(abs(cdi), abs(cdj)), cd2 = cdi * cdi + cdj * cdj;
+    if (found && cc > c) return;
+    if (!found || cc < c) {
+      found = true; has_sp1 = false; c = cc; d2 = cd2; di = cdi; dj = cdj; tag = ctag;
+      return;
+    }
+    if (!has_sp1) { sp1 = tie_sp1(di, dj, d2, p0, p1); has_sp1 = true; }
+    const double s = tie_sp1(cdi, cdj, cd2, p0, p1);
+    const bool better = s != sp1 ? s > sp1 : (cdi * p1 - cdj * p0) > (di * p1 - dj * p0);
+    if (better) { sp1 = s; d2 = cd2; di = cdi; dj = cdj; tag = ctag; }
+  }
+
+  __host__ __device__ __forceinline__ void scan_word(uint32_t bits, int lo, int rdi, int cj, int p0, int p1) {
+    while (bits) {
+      const int j = lo + rb_ffs(bits) - 1;
+      bits &= bits - 1;
+      consider(true, rdi, j - cj, p0, p1);
+    }
+  }
+
+  __host__ __device__ __forceinline__ void scan_row(uint32_t x, int rdi, int p0, int p1) {
+    while (x) {
+      const int b = rb_ffs(x) - 1;
+      x &= x - 1;
+      consider(true, rdi, b - 15, p0, p1);
+    }
+  }
+
+  __host__ __device__ __forceinline__ void finish(int, int, int &odi, int &odj, int &k) {
+    odi = di; odj = dj; k = probe_index(c);
+  }
+};
+
+// Unit-step table: lut[q * 512 + m] = index (di+1)*3 + (dj+1) of the winner among the neighbours present in the
+// 9-bit mask m (bit 3*(di+1) + (dj+1)), for pref = (q/3 - 1, q%3 - 1).  Filled by the candidate code every other
+// path takes, once per context (global memory, one table per path mode); the path kernels copy theirs into shared
+// memory without the always-empty centre bit (9 x 256 bytes).
+template <int MODE>
+__host__ __device__ __forceinline__ uint8_t unit_lut_entry(int q, int m) {
+  const int p0 = q / 3 - 1, p1 = q % 3 - 1;
+  if (q == 4 || (m & 16) || !m) return 0xff;
+  Search<MODE> S;
+  S.reset();
+  for (int bpos = 0; bpos < 9; bpos++)
+    if (m & (1 << bpos)) S.consider(true, bpos / 3 - 1, bpos % 3 - 1, p0, p1);
+  int odi, odj, k;
+  S.finish(p0, p1, odi, odj, k);
+  return (uint8_t)((odi + 1) * 3 + (odj + 1));
+}
+
+constexpr int WK_LUT_BYTES = TPR_LUT_ROWS * 256;  // compact table in shared memory
+__host__ __device__ __forceinline__ int wk_lut_index(int p0, int p1, unsigned m9) {
+  return ((p0 + 1) * 3 + (p1 + 1)) * 256 + (int)((m9 & 15u) | ((m9 >> 5) << 4));
+}
+// compact index e -> index into the 9 x 512 table
+__host__ __device__ __forceinline__ int wk_lut_source(int e) {
+  const int q = e >> 8, m8 = e & 255;
+  return q * TPR_LUT_COLS + ((m8 & 15) | ((m8 >> 4) << 5));
+}
+
+// ---- 5x5 window classes: bit 5*(di+2) + (dj+2) of N25 <-> offset (di, dj) ----------------------------
+constexpr uint32_t N25_A = (1u << 7) | (1u << 11) | (1u << 13) | (1u << 17);                                      // d2 = 1
+constexpr uint32_t N25_B = (1u << 6) | (1u << 8) | (1u << 16) | (1u << 18);                                       // d2 = 2
+constexpr uint32_t N25_C = (1u << 2) | (1u << 10) | (1u << 14) | (1u << 22);                                      // d2 = 4
+constexpr uint32_t N25_D = (1u << 1) | (1u << 3) | (1u << 5) | (1u << 9) | (1u << 15) | (1u << 19) | (1u << 21) | (1u << 23);  // d2 = 5
+constexpr uint32_t N25_E = (1u << 0) | (1u << 4) | (1u << 20) | (1u << 24);                                       // d2 = 8
+constexpr uint32_t N25_RING1 = N25_A | N25_B;
+
+// 5x5 table step (euclid).  The candidates of a step are the cells of ONE class (same d2), and which of them wins
+// depends only on pref: t2[pref cell][class base + field] = winning cell, for the 24 prefs that are themselves 5x5
+// offsets (the previous step came from the 5x5 window, or the level just started: all but a few percent of the
+// steps).  `field` = the class's bits gathered into a dense index by a multiply-shift perfect hash (constants found
+// by search; wk_t2_field is checked to be injective by tests/test_host_walk.py).  The table is filled once per
+// context by the candidate code every other path takes (Search<MODE_EUCLID>, fp64 tie-break included).
+constexpr int T2_ROW = 320;              // A 16 + B 16 + C 16 + D 256 + E 16 entries per pref
+constexpr int T2_BYTES = 25 * T2_ROW;
+constexpr int T2_NCLS = 5;
+__host__ __device__ __forceinline__ uint32_t wk_t2_mask(int c) {
+  return c == 0 ? N25_A : c == 1 ? N25_B : c == 2 ? N25_C : c == 3 ? N25_D : N25_E;
+}
+__host__ __device__ __forceinline__ uint32_t wk_t2_magic(int c) {
+  return c == 0 ? 0x1121002u : c == 1 ? 0x24442045u : c == 2 ? 0x4208100u : c == 3 ? 0x24010280u : 0xc8400212u;
+}
+__host__ __device__ __forceinline__ int wk_t2_shift(int c) { return c == 3 ? 24 : 28; }
+__host__ __device__ __forceinline__ int wk_t2_base(int c) { return c == 0 ? 0 : c == 1 ? 16 : c == 2 ? 32 : c == 3 ? 48 : 304; }
+__host__ __device__ __forceinline__ int wk_t2_field(int c, uint32_t n25) {
+  return (int)(((n25 & wk_t2_mask(c)) * wk_t2_magic(c)) >> wk_t2_shift(c));
+}
+// entry for pref cell `pc` (5 * (p0 + 2) + p1 + 2) and the cells `bits` (a non-empty subset of class c's mask)
+__host__ __device__ __forceinline__ uint8_t wk_t2_entry(int pc, uint32_t bits) {
+  const int p0 = pc / 5 - 2, p1 = pc % 5 - 2;
+  if (pc == 12 || !bits) return 0xff;
+  Search<MODE_EUCLID> S;
+  S.reset();
+  for (uint32_t u = bits; u; u &= u - 1u) {
+    const int b = rb_ffs(u) - 1;
+    S.consider(true, b / 5 - 2, b % 5 - 2, p0, p1);
+  }
+  int odi, odj, k;
+  S.finish(p0, p1, odi, odj, k);
+  return (uint8_t)((odi + 2) * 5 + (odj + 2));
+}
+// the i-th subset of class c's cells, as a 25-bit window value
+__host__ __device__ __forceinline__ uint32_t wk_t2_subset(int c, int i) {
+  uint32_t m = wk_t2_mask(c), v = 0u;
+  for (int bit = 0; m; bit++, m &= m - 1u)
+    if ((i >> bit) & 1) v |= m & (0u - m);
+  return v;
+}
+// fills t2[T2_BYTES]: `job` runs over every (pref cell, class, subset)
+constexpr int T2_JOBS = 25 * (16 * 4 + 256);
+__host__ __device__ __forceinline__ void wk_t2_fill(uint8_t *t2, int job) {
+  const int pc = job / (16 * 4 + 256);
+  int r = job % (16 * 4 + 256), c;
+  if (r < 48) { c = r >> 4; r &= 15; }
+  else if (r < 304) { c = 3; r -= 48; }
+  else { c = 4; r -= 304; }
+  const uint32_t bits = wk_t2_subset(c, r);
+  t2[pc * T2_ROW + wk_t2_base(c) + wk_t2_field(c, bits)] = wk_t2_entry(pc, bits);
+}
+
+// Same-distance candidates (one class of the 5x5 window, euclid): the larger integer dot product wins, a mirror
+// pair (equal dot products) is settled like Search<MODE_EUCLID>::finish does.
+__host__ __device__ __forceinline__ bool mirror_second_wins(int di, int dj, int adi, int adj, int d2, int p0, int p1) {
+  const int cb = di * p1 - dj * p0, ca = adi * p1 - adj * p0;
+  if (pref_ties_exactly(p0, p1)) return ca > cb;
+  const double sb = tie_sp1(di, dj, d2, p0, p1), sa = tie_sp1(adi, adj, d2, p0, p1);
+  return sa != sb ? sa > sb : ca > cb;
+}
+
+// The walker of one region: all levels, one bounded unit of work per call.
+template <int MODE>
+struct Walker {
+  // the region
+  uint32_t *bm;        // its arena slot: plane at `cur` = unvisited points of the level, plane at `nxt` = survivors
+  int32_t *Qimg;       // paths of the region's image, all levels
+  const uint8_t *lut;  // chebyshev: compact unit-step table (or null)
+  const uint8_t *t2;   // euclid: 5x5 step table (or null)
+  int N, W, L;
+  int abase;           // word offset of the slot in the warp's arena
+  int h, ws;           // bitmap rows (margins included), words per row
+  int pixbase;         // pixel id of bitmap cell (0, 0): r0 * W + c0 (r0, c0 may be negative: the margin)
+  bool narrow;         // every lane of the warp has ws == 1
+  // the level
+  int kind, lev, a, n, t;
+  int ci, cj, p0, p1;
+  int cur, nxt;
+  int32_t *Qp;         // where the next path point goes
+  bool keep, tolist;   // a next level exists / its points are collected as a list
+  int ncnt, sminidx;   // list of survivors: length, index of the smallest
+  uint32_t smin;       // smallest survivor (i << 16 | j) = next start point (lexicographic min, rbepwt.py:1035-1036)
+  int pdi, pdj;        // WK_COMMIT: the step chosen (by the 5x5 window, or by the search beyond it)
+  int rq0;             // this level's plane for the warp's search beyond the window: word offset | h << 12 | ws << 23
+  uint32_t U;          // list mode: unvisited mask
+
+  __host__ __device__ __forceinline__ bool done() const { return kind == WK_DONE || kind == WK_ERROR; }
+
+  // region [a0, a0 + n0) of the level-1 signal; the level-1 bitmap is in plane 0, plane 1 is all zero;
+  // (si, sj) = its lexicographically smallest point
+  __host__ __device__ __forceinline__ void start(int a0, int n0, int si, int sj) {
+    cur = 0; nxt = wk_plane_words(h, ws);
+    lev = 1; a = a0; n = n0;
+    smin = ((uint32_t)si << 16) | (uint32_t)sj; sminidx = 0;
+    pdi = pdj = 0; U = 0u;
+    if (n <= 0) { kind = WK_DONE; return; }
+    begin_level(false);
+  }
+
+  __host__ __device__ __forceinline__ void emit() {  // the point (ci, cj) is the path's t-th
+    *Qp++ = pixbase + ci * W + cj;
+    if (keep && ((a + t) & 1) == 0) {  // even global position: survives (rbepwt.py:1570-1575)
+      const uint32_t e = ((uint32_t)ci << 16) | (uint32_t)cj;
+      if (tolist) {
+        bm[nxt + ncnt] = e;
+        if (e < smin) { smin = e; sminidx = ncnt; }
+        ncnt++;
+      } else {
+        bm[nxt + ci * ws + (cj >> 5)] |= 1u << (cj & 31);
+        smin = min(smin, e);
+      }
+    }
+  }
+
+  // lev, a, n are set; the level's points are in plane `cur` (bitmap, or list when from_list) and its start is smin
+  __host__ __device__ __forceinline__ void begin_level(bool from_list) {
+    keep = lev < L;
+    const int nnext = ((a + n + 1) >> 1) - ((a + 1) >> 1);
+    tolist = nnext <= WK_LIST_MAX;
+    Qp = Qimg + level_off((size_t)N, lev) + a;
+    uint32_t e;
+    if (from_list) {
+      e = bm[cur + sminidx];
+      U = (n >= 32 ? 0xffffffffu : (1u << n) - 1u) & ~(1u << sminidx);
+    } else {
+      e = smin;
+    }
+    ci = (int)(e >> 16); cj = (int)(e & 0xffffu);
+    rq0 = (abase + cur) | (h << 12) | (ws << 23);
+    if (!from_list) bm[cur + ci * ws + (cj >> 5)] &= ~(1u << (cj & 31));
+    ncnt = 0; sminidx = 0; smin = 0xffffffffu;
+    t = 0;
+    emit();
+    t = 1;
+    p0 = 0; p1 = 1;  // prefered_direc = (0,1)   rbepwt.py:1290
+    kind = t == n ? WK_LEVEL : (from_list ? WK_LIST : WK_NEAR);
+  }
+
+  // kind == WK_LEVEL (t == n): RegionCollection.reduce -- the region occupies [ceil(a/2), ceil((a+n)/2)) of the next level
+  __host__ __device__ __forceinline__ void next_level() {
+    const bool was_tolist = tolist;
+    const int na = (a + 1) >> 1, nb = (a + n + 1) >> 1;
+    if (!keep || nb - na <= 0) { kind = WK_DONE; return; }
+    a = na; n = nb - na; lev++;
+    const int x = cur; cur = nxt; nxt = x;  // the old plane is all zero again: every point was visited
+    begin_level(was_tolist);
+  }
+
+  // the step (di, dj) was chosen
+  __host__ __device__ __forceinline__ void commit(int di, int dj) {
+    p0 = di; p1 = dj;  // rbepwt.py:1331
+    ci += di; cj += dj;
+    bm[cur + ci * ws + (cj >> 5)] &= ~(1u << (cj & 31));
+    emit();
+    t++;
+    kind = t == n ? WK_LEVEL : WK_NEAR;
+  }
+
+  // the search beyond the 5x5 window (done for this lane by the warp, or by the host harness) found (di, dj)
+  __host__ __device__ __forceinline__ void far_found(int di, int dj) { pdi = di; pdj = dj; kind = WK_COMMIT; }
+
+  // ---- kind == WK_COMMIT: take the chosen step (lanes that chose from the window and lanes the warp searched for
+  //      commit together)
+  __host__ __device__ __forceinline__ void commit_step() { commit(pdi, pdj); }
+
+  // ---- kind == WK_NEAR: choose the step from the 5x5 window (-> WK_COMMIT), or ask for a wider search (-> WK_FAR)
+  __host__ __device__ __forceinline__ void near_select() {
+    int di = 0, dj = 0;
+    {
+      const uint32_t *rp = bm + cur + (ci - WK_PAD) * ws;
+      uint32_t n25;
+      if (narrow) {
+        const int sh = cj - WK_PAD;
+        n25 = ((rp[0] >> sh) & 31u) | (((rp[1] >> sh) & 31u) << 5) | (((rp[2] >> sh) & 31u) << 10) |
+              (((rp[3] >> sh) & 31u) << 15) | (((rp[4] >> sh) & 31u) << 20);
+      } else {
+        const int sc = cj - WK_PAD, sh = sc & 31;
+        rp += sc >> 5;
+        n25 = (rb_funnel_r(rp[0], rp[1], sh) & 31u) | ((rb_funnel_r(rp[ws], rp[ws + 1], sh) & 31u) << 5) |
+              ((rb_funnel_r(rp[2 * ws], rp[2 * ws + 1], sh) & 31u) << 10) |
+              ((rb_funnel_r(rp[3 * ws], rp[3 * ws + 1], sh) & 31u) << 15) |
+              ((rb_funnel_r(rp[4 * ws], rp[4 * ws + 1], sh) & 31u) << 20);
+      }
+      if (n25 == 0u) {  // nothing within half-width 2: probes 4, 8, ...
+        kind = WK_FAR;
+        return;
+      }
+      const uint32_t ring1 = n25 & N25_RING1;
+      if (MODE == MODE_EUCLID && t2 && (unsigned)(p0 + 2) <= 4u && (unsigned)(p1 + 2) <= 4u) {
+        // the nearest class present -> its cells as a dense field -> the winner for this pref: no loop, no branch
+        const int c = (n25 & N25_A) ? 0 : (n25 & N25_B) ? 1 : (n25 & N25_C) ? 2 : (n25 & N25_D) ? 3 : 4;
+        const int cell = t2[((p0 + 2) * 5 + p1 + 2) * T2_ROW + wk_t2_base(c) + wk_t2_field(c, n25)];
+        di = (cell * 13) >> 6;  // cell / 5 for cell < 25
+        dj = cell - 5 * di - 2;
+        di -= 2;
+      } else if (MODE != MODE_EUCLID && lut && ring1 && (unsigned)(p0 + 1) <= 2u && (unsigned)(p1 + 1) <= 2u) {
+        // unit pref, something at distance 1: the 3x3 table
+        const unsigned m9 = ((n25 >> 6) & 7u) | (((n25 >> 11) & 7u) << 3) | (((n25 >> 16) & 7u) << 6);
+        const int idx = lut[wk_lut_index(p0, p1, m9)];
+        di = (idx * 11) >> 5;  // idx / 3 for idx < 9
+        dj = idx - 3 * di - 1;
+        di -= 1;
+      } else {
+        uint32_t cls;
+        int d2 = 1;
+        if (MODE == MODE_EUCLID) {
+          cls = n25 & N25_A;
+          if (!cls) { cls = n25 & N25_B; d2 = 2; }
+          if (!cls) { cls = n25 & N25_C; d2 = 4; }
+          if (!cls) { cls = n25 & N25_D; d2 = 5; }
+          if (!cls) { cls = n25 & N25_E; d2 = 8; }
+        } else {
+          cls = ring1 ? ring1 : n25;
+        }
+        if ((cls & (cls - 1u)) == 0u) {  // one candidate
+          const int b = rb_ffs(cls) - 1;
+          di = (b * 13) >> 6;  // b / 5 for b < 25
+          dj = b - 5 * di - 2;
+          di -= 2;
+        } else if (MODE == MODE_EUCLID) {  // same distance: the larger dot product with pref, then the mirror rule
+          int bdot = INT32_MIN, adi = 0, adj = 0;
+          bool alt = false;
+          for (uint32_t u = cls; u; u &= u - 1u) {
+            const int b = rb_ffs(u) - 1;
+            const int qi = ((b * 13) >> 6) - 2, qj = b - 5 * (qi + 2) - 2;
+            const int dot = qi * p0 + qj * p1;
+            if (dot > bdot) { bdot = dot; di = qi; dj = qj; alt = false; }
+            else if (dot == bdot) { alt = true; adi = qi; adj = qj; }
+          }
+          if (alt && mirror_second_wins(di, dj, adi, adj, d2, p0, p1)) { di = adi; dj = adj; }
+        } else {
+          Search<MODE> T;
+          T.reset();
+          for (uint32_t u = cls; u; u &= u - 1u) {
+            const int b = rb_ffs(u) - 1;
+            const int qi = (b * 13) >> 6;
+            T.consider(true, qi - 2, b - 5 * qi - 2, p0, p1);
+          }
+          int fk;
+          T.finish(p0, p1, di, dj, fk);
+        }
+      }
+    }
+    pdi = di; pdj = dj;
+    kind = WK_COMMIT;
+  }
+
+  // ---- kind == WK_LIST: one whole step, candidates = the points still unvisited; then, at the end of the level,
+  //      straight on to the next one (list levels are short: 16, 8, 4, ... points)
+  __host__ __device__ __forceinline__ void list_step() {
+    Search<MODE> S;
+    S.reset();
+    for (uint32_t u = U; u; u &= u - 1u) {
+      const int idx = rb_ffs(u) - 1;
+      const uint32_t e = bm[cur + idx];
+      S.consider(true, (int)(e >> 16) - ci, (int)(e & 0xffffu) - cj, p0, p1, idx);
+    }
+    int di, dj, k;
+    S.finish(p0, p1, di, dj, k);
+    U &= ~(1u << S.tag);
+    p0 = di; p1 = dj;
+    ci += di; cj += dj;
+    emit();
+    t++;
+    if (t == n) {
+      kind = WK_LEVEL;
+      while (kind == WK_LEVEL) next_level();
+    }
+  }
+};
+
+#ifdef __CUDACC__
+
+template <int MODE>
+__global__ void k_build_unit_lut(uint8_t *lut) {  // any block size; once per context
+  for (int e = threadIdx.x; e < TPR_LUT_ROWS * TPR_LUT_COLS; e += blockDim.x)
+    lut[e] = unit_lut_entry<MODE>(e / TPR_LUT_COLS, e % TPR_LUT_COLS);
+}
+
+__global__ void k_build_t2(uint8_t *t2) {  // once per context; every slot of the table is written (the hash is a bijection)
+  for (int job = blockIdx.x * blockDim.x + threadIdx.x; job < T2_JOBS; job += gridDim.x * blockDim.x) wk_t2_fill(t2, job);
+}
+
+__device__ __forceinline__ void load_unit_lut(uint8_t *s_lut, const uint8_t *g_lut) {  // the full 9 x 512 table
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(g_lut);
+  uint32_t *dst = reinterpret_cast<uint32_t *>(s_lut);
+  for (int e = threadIdx.x; e < TPR_LUT_ROWS * TPR_LUT_COLS / 4; e += blockDim.x) dst[e] = src[e];
+}
+
+// Bitmap geometry of region g in k1_walk: the bounding box with a margin of WK_PAD on every side
+// (r0, c0 may be negative), ws words per row.
+__device__ __forceinline__ void wk_geometry(const PathParams &P, int g, int &r0, int &c0, int &h, int &w, int &ws) {
+  r0 = (P.reg.first[g] >> P.logW) - WK_PAD; c0 = P.reg.cmin[g] - WK_PAD;
+  h = P.reg.rmax[g] - r0 + 1 + WK_PAD; w = P.reg.cmax[g] - c0 + 1 + WK_PAD; ws = (w + 31) >> 5;
+}
+
+// Cooperative build of one chunk's arena image: for every region the level-1 bitmap in plane 0 (one ballot per
+// bitmap word, lanes = columns) and zeros in the rest of its slot.  Lane r holds region r's geometry and its word
+// offset `base` in `dst`; `slot` = its slot words.
+__device__ __forceinline__ void wk_build_bitmaps(const PathParams &P, uint32_t *dst, int cnt, int img, int label, int r0,
+                                                 int c0, int h, int w, int ws, int base, int slot) {
+  const int lane = (int)lane_id(), logW = P.logW;
+  for (int r = 0; r < cnt; r++) {
+    const int img_r = __shfl_sync(FULL_MASK, img, r), label_r = __shfl_sync(FULL_MASK, label, r);
+    const int r0_r = __shfl_sync(FULL_MASK, r0, r), c0_r = __shfl_sync(FULL_MASK, c0, r);
+    const int h_r = __shfl_sync(FULL_MASK, h, r), w_r = __shfl_sync(FULL_MASK, w, r);
+    const int ws_r = __shfl_sync(FULL_MASK, ws, r), base_r = __shfl_sync(FULL_MASK, base, r);
+    const int slot_r = __shfl_sync(FULL_MASK, slot, r);
+    const int32_t *lab = P.labels + (size_t)img_r * P.N;
+    const int words_r = h_r * ws_r;
+    for (int wi = 0; wi < words_r; wi += 8) {  // eight independent label loads in flight per lane
+      int lv[8];
+      bool inb[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int w_ = wi + u;
+        const int i = ws_r == 1 ? w_ : w_ / ws_r;
+        const int col = ((w_ - i * ws_r) << 5) + lane;
+        // the margin rows / columns hold no pixel of the region (they lie outside its bounding box)
+        inb[u] = w_ < words_r && i >= WK_PAD && i < h_r - WK_PAD && col >= WK_PAD && col < w_r - WK_PAD &&
+                 (unsigned)(r0_r + i) < (unsigned)P.H && (unsigned)(c0_r + col) < (unsigned)P.W;
+        lv[u] = inb[u] ? lab[((r0_r + i) << logW) + c0_r + col] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const unsigned bits = __ballot_sync(FULL_MASK, inb[u] && lv[u] == label_r);
+        if (lane == 0 && wi + u < words_r) dst[base_r + wi + u] = bits;
+      }
+    }
+    for (int q = words_r + lane; q < slot_r; q += 32) dst[base_r + q] = 0u;
+  }
+}
+
+// Chunk header shared by the bitmap builder and the walker: lane r < cnt holds region r of the chunk.
+struct WkChunkLane {
+  int g, img, label, first, size, off, r0, c0, h, w, ws, slot, base;
+};
+
+__device__ __forceinline__ WkChunkLane wk_chunk_lane(const PathParams &P, int qstart, int cnt) {
+  const int lane = (int)lane_id();
+  WkChunkLane c = {};
+  if (lane < cnt) {
+    c.g = P.queue[qstart + lane];
+    c.img = P.reg.img[c.g]; c.label = P.reg.label[c.g]; c.first = P.reg.first[c.g];
+    c.size = P.reg.size[c.g]; c.off = P.reg.off[c.g];
+    wk_geometry(P, c.g, c.r0, c.c0, c.h, c.w, c.ws);
+    c.slot = wk_slot_words(c.h, c.ws);
+  }
+  int inc = c.slot;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int y = __shfl_up_sync(FULL_MASK, inc, d);
+    if (lane >= d) inc += y;
+  }
+  c.base = inc - c.slot;
+  return c;
+}
+
+// The arena images of the small-bitmap chunks (the bulk kernel's: from QM_CHUNK_SPLIT on, the first P.gbm_chunks of
+// them), built ahead of the walk by warps that do nothing else (the label reads are pure memory latency; inside the
+// path kernel they would hold a walking warp's registers and arena).  gbm[chunk - split][TPR_ARENA_WORDS].  The
+// large-bitmap chunks of the windowed instantiation build theirs in the kernel.
+__global__ void __launch_bounds__(256) k1_bitmaps(PathParams P) {
+  const int split = P.qmeta[QM_CHUNK_SPLIT];
+  const int nchunks = min(P.qmeta[QM_NCHUNKS], split + P.gbm_chunks);
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int chunk = split + wid; chunk < nchunks; chunk += nw) {
+    const int cnt = P.chunk_cnt[chunk];
+    const WkChunkLane c = wk_chunk_lane(P, P.chunk_start[chunk], cnt);
+    wk_build_bitmaps(P, P.gbm + (size_t)(chunk - split) * TPR_ARENA_WORDS, cnt, c.img, c.label, c.r0, c.c0, c.h, c.w, c.ws,
+                     c.base, c.slot);
+  }
+}
+
+#ifdef WK_STATS  // debug build only: warp trips and lane units by kind
+__device__ unsigned long long g_wk_stats[16];  // [0] warp trips, [kind] lanes of that kind at the start of a trip
+#endif
+
+// The search beyond the 5x5 window of ONE lane's region, done by the whole warp (all arguments warp-uniform): the
+// lanes take the rows of the bitmap plane.  Euclid: a row's candidate is its nearest unvisited column on either
+// side (both when equidistant), ranked by the packed key (k << 21 | d2) and then the dot product; two warp reductions
+// pick the winner.  Rows of one or two words are scanned whole in ONE pass -- ranking by (k, d2, dot) makes that
+// equal to the reference's probes 4, 8, ... in turn; wider planes go window by window (paths.cuh, find_next_geo).
+// Chebyshev: the reference's fp64 expressions (find_next).  Returns false if the plane holds no unvisited point;
+// otherwise `step` = (di << 16) | (dj & 0xffff).
+constexpr int WK_NO_PARTNER = (int)0x80000000;
+
+template <int MODE>
+__device__ __forceinline__ bool wk_far_search(const uint32_t *plane, int h, int ws, int ci, int cj, int p0, int p1, int &step) {
+  const int lane = (int)lane_id();
+  if (MODE == MODE_EUCLID && ws <= 2) {
+    unsigned bkey = 0xffffffffu;
+    int bdot = 0, boff = 0, aoff = WK_NO_PARTNER;  // best candidate of this lane's rows, its mirror partner if any
+    const unsigned long long below = (1ull << cj) - 1ull;  // columns < cj
+    for (int i = lane; i < h; i += 32) {
+      const unsigned long long x = ws == 1 ? (unsigned long long)plane[i]
+                                           : ((unsigned long long)plane[2 * i + 1] << 32) | plane[2 * i];
+      if (!x) continue;
+      const unsigned long long left = x & below, right = x & ~below;
+      const int dl = cj - (63 - __clzll((long long)left)), dr = __ffsll((long long)right) - 1 - cj;
+      const bool use_left = left && (!right || dl <= dr);
+      const int rdi = i - ci;
+      int rdj = use_left ? -dl : dr;
+      const unsigned key = ((unsigned)probe_index(max(abs(rdi), abs(rdj))) << 21) | (unsigned)(rdi * rdi + rdj * rdj);
+      int dot = rdi * p0 + rdj * p1;
+      int partner = WK_NO_PARTNER;
+      if (left && right && dl == dr) {  // (rdi, -dl) and (rdi, +dl): same key
+        const int dot2 = rdi * p0 + dr * p1;
+        if (dot2 == dot) partner = (rdi << 16) | (dr & 0xffff);
+        if (dot2 > dot) { dot = dot2; rdj = dr; }
+      }
+      const int off = (rdi << 16) | (rdj & 0xffff);
+      if (key < bkey || (key == bkey && dot > bdot)) { bkey = key; bdot = dot; boff = off; aoff = partner; }
+      else if (key == bkey && dot == bdot) aoff = off;
+    }
+    const unsigned kmin = __reduce_min_sync(FULL_MASK, bkey);
+    if (kmin == 0xffffffffu) return false;
+    const bool sel = bkey == kmin;
+    const int dotmax = __reduce_max_sync(FULL_MASK, sel ? bdot : INT32_MIN);
+    const unsigned tied = __ballot_sync(FULL_MASK, sel && bdot == dotmax);
+    const int la = __ffs(tied) - 1;
+    step = __shfl_sync(FULL_MASK, boff, la);
+    int other = __shfl_sync(FULL_MASK, aoff, la);
+    const unsigned rest = tied & (tied - 1);
+    if (rest) other = __shfl_sync(FULL_MASK, boff, __ffs(rest) - 1);  // a mirror pair held by two lanes
+    if (other != WK_NO_PARTNER &&
+        mirror_second_wins(step >> 16, (int)(short)(step & 0xffff), other >> 16, (int)(short)(other & 0xffff),
+                           (int)(kmin & 0x1fffffu), p0, p1))
+      step = other;
+    return true;
+  }
+  int bi, bj;
+  if (MODE == MODE_EUCLID) {
+    int rad = 4;
+    if (!find_next_geo(plane, h, ws << 5, ws, ci, cj, p0, p1, rad, nullptr, bi, bj)) return false;
+  } else {
+    double curval = 0.0;
+    if (!find_next<MODE>(plane, h, ws << 5, ws, ci, cj, p0, p1, nullptr, 0, 0, 0, false, curval, bi, bj)) return false;
+  }
+  step = ((bi - ci) << 16) | ((bj - cj) & 0xffff);
+  return true;
+}
+
+// WIDEWIN = true: the instantiation for the chunks of large bitmaps (queue classes below Q_FIRST_NARROW_CLS; at most six
+// regions per warp), which builds its bitmaps itself and hands regions of at least coop_min pixels to the whole-warp
+// walker of paths.cuh.
+template <int MODE, bool WIDEWIN>
+__global__ void __launch_bounds__(WK_WARPS * 32, WK_MIN_CTAS) k1_walk(PathParams P) {
+  __shared__ __align__(16) uint32_t s_arena[WK_WARPS * TPR_ARENA_WORDS + 4];
+  // the walker's step table: euclid the 5x5 table, chebyshev the compact unit-step table
+  __shared__ __align__(16) uint8_t s_tab[MODE == MODE_EUCLID ? T2_BYTES : WK_LUT_BYTES];
+  __shared__ __align__(16) uint8_t s_lut[WIDEWIN ? TPR_LUT_ROWS * TPR_LUT_COLS : 16];  // the whole-warp walker's full table
+  const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
+  uint32_t *arena = s_arena + warp * TPR_ARENA_WORDS;
+  const int chunk_lo = WIDEWIN ? 0 : P.qmeta[QM_CHUNK_SPLIT];
+  const int nchunks = (WIDEWIN ? P.qmeta[QM_CHUNK_SPLIT] : P.qmeta[QM_NCHUNKS]) - chunk_lo;
+  if (nchunks <= 0) return;
+  if (WIDEWIN) load_unit_lut(s_lut, P.unit_lut);
+  if (MODE == MODE_EUCLID) {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(P.t2_tab);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(s_tab);
+    for (int e = threadIdx.x; e < T2_BYTES / 4; e += blockDim.x) dst[e] = src[e];
+  } else {
+    for (int e = threadIdx.x; e < WK_LUT_BYTES; e += blockDim.x) s_tab[e] = P.unit_lut[wk_lut_source(e)];
+  }
+  __syncthreads();
+
+  // Each warp takes its share of the chunks and retires: the grid is several waves of CTAs, so SM slots keep
+  // freeing up for the (higher-priority) transform kernels of other units instead of being held to the end.
+  const int share = max(1, (nchunks + (int)gridDim.x * WK_WARPS - 1) / ((int)gridDim.x * WK_WARPS));
+  for (int taken = 0; taken < share; taken++) {
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(&P.qmeta[WIDEWIN ? QM_CUR_WIDE : QM_CUR_SMALL], 1);
+    chunk = __shfl_sync(FULL_MASK, chunk, 0);
+    if (chunk >= nchunks) break;
+    chunk += chunk_lo;
+    const int qstart = P.chunk_start[chunk], cnt = P.chunk_cnt[chunk];
+    if (WIDEWIN && MODE == MODE_EUCLID && cnt == 1) {
+      // one long chain: the whole warp walks it together (paths.cuh, find_next_geo)
+      const int g = P.queue[qstart];
+      if (P.reg.size[g] >= P.coop_min) {
+        region_pyramid<MODE>(P, g, arena, s_lut);
+        __syncwarp();
+        continue;
+      }
+    }
+    const WkChunkLane c = wk_chunk_lane(P, qstart, cnt);
+    const bool mine = lane < cnt;
+    if (!WIDEWIN && chunk - chunk_lo < P.gbm_chunks) {
+      // the arena image was built by k1_bitmaps: copy the chunk's words, 16 bytes per lane and load, all in flight
+      const int total = __shfl_sync(FULL_MASK, c.base + c.slot, 31);
+      const int nvec = (total + 3) >> 2;
+      const uint4 *src = reinterpret_cast<const uint4 *>(P.gbm + (size_t)(chunk - chunk_lo) * TPR_ARENA_WORDS);
+      uint4 *dst = reinterpret_cast<uint4 *>(arena);
+      for (int e0 = 0; e0 < nvec; e0 += 8 * 32) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int e = e0 + u * 32 + lane;
+          v[u] = e < nvec ? __ldcs(src + e) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int e = e0 + u * 32 + lane;
+          if (e < nvec) dst[e] = v[u];
+        }
+      }
+    } else {
+      wk_build_bitmaps(P, arena, cnt, c.img, c.label, c.r0, c.c0, c.h, c.w, c.ws, c.base, c.slot);
+    }
+    __syncwarp();
+
+    Walker<MODE> wk;
+    wk.bm = arena + c.base;
+    wk.Qimg = P.Q + (size_t)c.img * 2 * (size_t)P.N;
+    wk.lut = MODE == MODE_EUCLID ? nullptr : s_tab;
+    wk.t2 = MODE == MODE_EUCLID ? s_tab : nullptr;
+    wk.N = P.N; wk.W = P.W; wk.L = P.levels;
+    wk.abase = c.base;
+    wk.h = c.h; wk.ws = max(c.ws, 1);
+    wk.pixbase = c.r0 * P.W + c.c0;
+    wk.narrow = __all_sync(FULL_MASK, c.ws <= 1);
+    wk.kind = WK_DONE;
+    if (mine) wk.start(c.off, c.size, WK_PAD, (c.first & (P.W - 1)) - c.c0);
+    // Every lane walks its own region through all its levels.  One round of the warp loop = one step for every lane
+    // that can take one: lanes choose their step from the 5x5 window; the warp searches beyond the window for each
+    // lane that found it empty; all of them commit together.  Lanes at the end of a level start the next; list-mode
+    // lanes take a step when enough of them are waiting (or nothing else in the warp can move).
+    while (true) {
+      const unsigned live = __ballot_sync(FULL_MASK, !wk.done());
+      if (!live) break;
+#ifdef WK_STATS
+      if (lane == 0) atomicAdd(&g_wk_stats[0], 1ull);
+      if (!wk.done()) atomicAdd(&g_wk_stats[wk.kind], 1ull);
+#endif
+      if (__any_sync(FULL_MASK, wk.kind == WK_LEVEL)) {
+        if (wk.kind == WK_LEVEL) wk.next_level();
+      }
+#pragma unroll 1
+      for (int rep = 0; rep < WK_NEAR_REPS; rep++) {
+        const bool near = wk.kind == WK_NEAR;
+        if (!__any_sync(FULL_MASK, near)) break;
+        if (near) wk.near_select();
+        unsigned farm = __ballot_sync(FULL_MASK, wk.kind == WK_FAR);
+        while (farm) {
+          const int src = __ffs(farm) - 1;
+          farm &= farm - 1;
+          // the requester's plane (word offset in the warp's arena), geometry, current point and pref, warp-uniform
+          const int pa = __shfl_sync(FULL_MASK, wk.rq0, src);
+          const int pb = __shfl_sync(FULL_MASK, wk.ci | (wk.cj << 16), src);
+          const int pc = __shfl_sync(FULL_MASK, (wk.p0 & 0xffff) | (wk.p1 << 16), src);
+          int step = 0;
+          const bool ok = wk_far_search<MODE>(arena + (pa & 0xfff), (pa >> 12) & 0x7ff, pa >> 23, pb & 0xffff, pb >> 16,
+                                              (int)(short)(pc & 0xffff), pc >> 16, step);
+          if (lane == src) {
+            if (ok) wk.far_found(step >> 16, (int)(short)(step & 0xffff));
+            else wk.kind = WK_ERROR;
+          }
+        }
+        if (wk.kind == WK_COMMIT) wk.commit_step();
+      }
+      const unsigned listm = __ballot_sync(FULL_MASK, wk.kind == WK_LIST);
+      if (listm && (__popc(listm) >= WK_LIST_BATCH || !__ballot_sync(FULL_MASK, wk.kind == WK_NEAR || wk.kind == WK_LEVEL))) {
+        if (wk.kind == WK_LIST) wk.list_step();
+      }
+    }
+    if (wk.kind == WK_ERROR) atomicExch(&P.qmeta[QM_ERR], 1);
+    __syncwarp();
+  }
+}
+
+// Big regions: one warp per CTA, bitmap in dynamic shared memory if it fits, else global scratch.
+template <int MODE>
+__global__ void __launch_bounds__(32) k1_paths_big(PathParams P) {
+  extern __shared__ uint32_t s_big[];
+  __shared__ __align__(16) uint8_t s_lut[TPR_LUT_ROWS * TPR_LUT_COLS];
+  const int lane = (int)lane_id();
+  if (P.qmeta[QM_NBIG] == 0) return;  // the common case: nothing oversized in this group
+  load_unit_lut(s_lut, P.unit_lut);
+  __syncthreads();
+  const int nbig = P.qmeta[QM_NBIG];
+  uint32_t *gs = P.gscratch + (size_t)blockIdx.x * P.gscratch_words;
+  while (true) {
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(&P.qmeta[QM_CUR_BIG], 1);
+    idx = __shfl_sync(FULL_MASK, idx, 0);
+    if (idx >= nbig) break;
+    const int g = P.queue[idx];
+    const int words = region_bitmap_words(P.reg, g, P.logW);
+    region_pyramid<MODE>(P, g, words <= P.big_smem_words ? s_big : gs, s_lut);
+    __syncwarp();
+  }
+}
+
+// K2: positions in the incoming order.  Pm[level][a + t] = place, in the level's incoming order, of the t-th point of
+// the level's path (= the reference's generating permutation + the region offset, rbepwt.py:1285, 1333), which is what
+// the transform kernels gather / scatter through.  The incoming order of level l >= 2 is the path order of level
+// l-1 subsampled at the even global positions, so with pos[pixel] = (a' + t') >> 1 for the even a' + t' of level l-1:
+// Pm_l[a + t] = pos[Q_l[a + t]].  One warp per region, level after level; pos lives in shared memory, relative to the
+// region (16 bits per cell of the bounding box), or -- bounding boxes of more than K2_CELLS cells -- in the image's
+// `posmap` in global memory.
+constexpr int K2_WARPS = 8;
+constexpr int K2_CELLS = 2560;  // 16-bit cells per warp: 5 KB
+
+__global__ void __launch_bounds__(K2_WARPS * 32) k2_perm(PathParams P, int nreg) {
+  __shared__ uint16_t s_pos[K2_WARPS][K2_CELLS];
+  const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
+  const int nw = gridDim.x * K2_WARPS;
+  const int N = P.N, logW = P.logW, Wm = P.W - 1, L = P.levels;
+  for (int q = blockIdx.x * K2_WARPS + warp; q < nreg; q += nw) {
+    const int g = P.queue[q];  // queue order: the largest regions first
+    const int img = P.reg.img[g], a1 = P.reg.off[g], n1 = P.reg.size[g];
+    const int r0 = P.reg.first[g] >> logW, c0 = P.reg.cmin[g];
+    const int hb = P.reg.rmax[g] - r0 + 1, wb = P.reg.cmax[g] - c0 + 1;
+    const bool in_smem = hb * wb <= K2_CELLS && n1 < 65536;
+    const int32_t *Qimg = P.Q + (size_t)img * 2 * (size_t)N;
+    int32_t *Pimg = P.Pm + (size_t)img * 2 * (size_t)N;
+    int32_t *posmap = P.posmap + (size_t)img * N;
+    uint16_t *pos = s_pos[warp];
+    for (int lev = 1; lev <= L; lev++) {
+      const int sh = lev - 1, add = (1 << sh) - 1;
+      const int a = (int)(((long long)a1 + add) >> sh), b = (int)(((long long)a1 + n1 + add) >> sh);
+      const int n = b - a;
+      if (n <= 0) break;
+      const int32_t *Ql = Qimg + level_off((size_t)N, lev) + a;
+      if (lev >= 2) {
+        int32_t *Pl = Pimg + level_off((size_t)N, lev) + a;
+        for (int t = lane; t < n; t += 32) {
+          const int pix = __ldcg(Ql + t);
+          Pl[t] = in_smem ? a + (int)pos[((pix >> logW) - r0) * wb + (pix & Wm) - c0] : __ldcg(posmap + pix);
+        }
+      }
+      if (lev == L) break;
+      __syncwarp();
+      const int anext = (a + 1) >> 1;
+      for (int t = 2 * lane + (a & 1); t < n; t += 64) {  // the even global positions a + t survive
+        const int pix = __ldcg(Ql + t);
+        const int place = (a + t) >> 1;
+        if (in_smem) pos[((pix >> logW) - r0) * wb + (pix & Wm) - c0] = (uint16_t)(place - anext);
+        else posmap[pix] = place;
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace rbepwt

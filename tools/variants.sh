@@ -10,6 +10,6 @@ for v in "$@"; do
 import json
 d=json.load(open("gpurun_out/var_$name.json"))
 k=d["kernels"]
-print("%-14s value %6.0f  k1 %.3f ms  k0 %.3f dwt %.3f sel %.3f idwt %.3f" % ("$name", d["value"], k["k1_paths_tpr"]["ms_per_step"], k["k0_count+k0_regions_fast+queue"]["ms_per_step"], k["k3_dwt_level"]["ms_per_step"], k["k4_threshold"]["ms_per_step"], k["k5_idwt_level"]["ms_per_step"]))
+print("%-14s value %6.0f  " % ("$name", d["value"]) + "  ".join("%s %.3f" % (n.split("+")[0], v["ms_per_step"]) for n, v in k.items()))
 PY
 done

@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Debug: build the library with -DWK_STATS into a scratch .so and print k1_walk's warp trips and lane units by
+kind for one batch of the bench workload (run on the GPU box)."""
+import ctypes, os, subprocess, sys
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+from rbepwt_b200 import build as b
+so = os.path.join(ROOT, "gpurun_out", "librbepwt_stats.so")
+extra = [a for a in sys.argv[2:] if a.startswith("-D")]
+subprocess.check_call(["nvcc"] + b.NVCC_FLAGS + ["-DWK_STATS"] + extra + ["-o", so, os.path.join(b.CSRC, "rbepwt_b200.cu")])
+b.LIB_PATH = so
+b.needs_build = lambda: False
+import numpy as np, torch
+import rbepwt_b200 as rb
+from rbepwt_b200 import synth, _capi
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+imgs, labs = synth.torch_batch(B, 512, 512, 1024, 1000, device="cuda")
+c = rb.BatchCodec()
+L = _capi.lib()
+out = (ctypes.c_ulonglong * 16)()
+c.encode(imgs, labs, 16, "bior4.4"); c.sync()
+L.rbepwt_debug_wk_stats(c._ctx, out, 1)
+c.encode(imgs, labs, 16, "bior4.4"); c.sync()
+L.rbepwt_debug_wk_stats(c._ctx, out, 1)
+v = np.array(list(out), dtype=np.float64) / B
+print("per image: warp trips %.0f | lane units: near %.0f  far %.0f  list %.0f | near units per trip %.1f (of %d x 32)"
+      % (v[0], v[1], v[2], v[3], v[1] / v[0], 4))
