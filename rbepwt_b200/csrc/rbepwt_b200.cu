@@ -473,7 +473,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
       c->launches++;
     } else if (c->levels > 1) {  // positions in the incoming order of every level >= 2, from the paths
       const int grid = std::max(1, std::min((nreg + K2_WARPS - 1) / K2_WARPS, c->sm_count * 16));
-      k2_perm<<<grid, K2_WARPS * 32, 0, s>>>(P, nreg);
+      k2_perm<<<grid, K2_WARPS * 32, 0, s>>>(P, nreg, c->mode == RBEPWT_PATH_EUCLID ? 1 : 0);
       c->launches++;
     }
   }

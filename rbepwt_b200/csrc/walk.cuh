@@ -296,6 +296,7 @@ struct Walker {
   // the region
   uint32_t *bm;        // its arena slot: plane at `cur` = unvisited points of the level, plane at `nxt` = survivors
   int32_t *Qimg;       // paths of the region's image, all levels
+  int32_t *Pimg;       // positions in the incoming order, same layout: written here for the list-mode levels only
   const uint8_t *lut;  // chebyshev: compact unit-step table (or null)
   const uint8_t *t2;   // euclid: 5x5 step table (or null)
   int N, W, L;
@@ -351,8 +352,10 @@ struct Walker {
     Qp = Qimg + level_off((size_t)N, lev) + a;
     uint32_t e;
     if (from_list) {
+      // a list holds the level's points in their incoming order: the list index IS the position k2_perm would compute
       e = bm[cur + sminidx];
       U = (n >= 32 ? 0xffffffffu : (1u << n) - 1u) & ~(1u << sminidx);
+      Pimg[Qp - Qimg] = a + sminidx;
     } else {
       e = smin;
     }
@@ -491,6 +494,7 @@ struct Walker {
     U &= ~(1u << S.tag);
     p0 = di; p1 = dj;
     ci += di; cj += dj;
+    Pimg[Qp - Qimg] = a + S.tag;
     emit();
     t++;
     if (t == n) {
@@ -622,27 +626,49 @@ __device__ __forceinline__ bool wk_far_search(const uint32_t *plane, int h, int 
   if (MODE == MODE_EUCLID && ws <= 2) {
     unsigned bkey = 0xffffffffu;
     int bdot = 0, boff = 0, aoff = WK_NO_PARTNER;  // best candidate of this lane's rows, its mirror partner if any
-    const unsigned long long below = (1ull << cj) - 1ull;  // columns < cj
-    for (int i = lane; i < h; i += 32) {
-      const unsigned long long x = ws == 1 ? (unsigned long long)plane[i]
-                                           : ((unsigned long long)plane[2 * i + 1] << 32) | plane[2 * i];
-      if (!x) continue;
-      const unsigned long long left = x & below, right = x & ~below;
-      const int dl = cj - (63 - __clzll((long long)left)), dr = __ffsll((long long)right) - 1 - cj;
-      const bool use_left = left && (!right || dl <= dr);
-      const int rdi = i - ci;
-      int rdj = use_left ? -dl : dr;
-      const unsigned key = ((unsigned)probe_index(max(abs(rdi), abs(rdj))) << 21) | (unsigned)(rdi * rdi + rdj * rdj);
-      int dot = rdi * p0 + rdj * p1;
-      int partner = WK_NO_PARTNER;
-      if (left && right && dl == dr) {  // (rdi, -dl) and (rdi, +dl): same key
-        const int dot2 = rdi * p0 + dr * p1;
-        if (dot2 == dot) partner = (rdi << 16) | (dr & 0xffff);
-        if (dot2 > dot) { dot = dot2; rdj = dr; }
+    if (ws == 1 && h <= 32) {
+      // the common case, straight-line: one row of one word per lane
+      const uint32_t x = lane < h ? plane[lane] : 0u;
+      if (x) {
+        const uint32_t below = (1u << cj) - 1u;  // columns < cj (cj <= 29: the margin)
+        const uint32_t left = x & below, right = x & ~below;
+        const int dl = cj - (31 - __clz((int)left)), dr = __ffs((int)right) - 1 - cj;
+        const bool both = left && right;
+        const bool use_left = left && (!right || dl <= dr);
+        const int rdi = lane - ci;
+        int rdj = use_left ? -dl : dr;
+        bkey = ((unsigned)probe_index(max(abs(rdi), abs(rdj))) << 21) | (unsigned)(rdi * rdi + rdj * rdj);
+        bdot = rdi * p0 + rdj * p1;
+        if (both && dl == dr) {  // (rdi, -dl) and (rdi, +dl): same key; the other one's dot product is bdot + 2 dl p1
+          const int dot2 = bdot + 2 * dr * p1;
+          if (dot2 == bdot) aoff = (rdi << 16) | (dr & 0xffff);
+          if (dot2 > bdot) { bdot = dot2; rdj = dr; }
+        }
+        boff = (rdi << 16) | (rdj & 0xffff);
       }
-      const int off = (rdi << 16) | (rdj & 0xffff);
-      if (key < bkey || (key == bkey && dot > bdot)) { bkey = key; bdot = dot; boff = off; aoff = partner; }
-      else if (key == bkey && dot == bdot) aoff = off;
+    } else {
+      const unsigned long long below = (1ull << cj) - 1ull;  // columns < cj
+      for (int i = lane; i < h; i += 32) {
+        const unsigned long long x = ws == 1 ? (unsigned long long)plane[i]
+                                             : ((unsigned long long)plane[2 * i + 1] << 32) | plane[2 * i];
+        if (!x) continue;
+        const unsigned long long left = x & below, right = x & ~below;
+        const int dl = cj - (63 - __clzll((long long)left)), dr = __ffsll((long long)right) - 1 - cj;
+        const bool use_left = left && (!right || dl <= dr);
+        const int rdi = i - ci;
+        int rdj = use_left ? -dl : dr;
+        const unsigned key = ((unsigned)probe_index(max(abs(rdi), abs(rdj))) << 21) | (unsigned)(rdi * rdi + rdj * rdj);
+        int dot = rdi * p0 + rdj * p1;
+        int partner = WK_NO_PARTNER;
+        if (left && right && dl == dr) {
+          const int dot2 = rdi * p0 + dr * p1;
+          if (dot2 == dot) partner = (rdi << 16) | (dr & 0xffff);
+          if (dot2 > dot) { dot = dot2; rdj = dr; }
+        }
+        const int off = (rdi << 16) | (rdj & 0xffff);
+        if (key < bkey || (key == bkey && dot > bdot)) { bkey = key; bdot = dot; boff = off; aoff = partner; }
+        else if (key == bkey && dot == bdot) aoff = off;
+      }
     }
     const unsigned kmin = __reduce_min_sync(FULL_MASK, bkey);
     if (kmin == 0xffffffffu) return false;
@@ -744,6 +770,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MIN_CTAS) k1_walk(PathParams
     Walker<MODE> wk;
     wk.bm = arena + c.base;
     wk.Qimg = P.Q + (size_t)c.img * 2 * (size_t)P.N;
+    wk.Pimg = P.Pm + (size_t)c.img * 2 * (size_t)P.N;
     wk.lut = MODE == MODE_EUCLID ? nullptr : s_tab;
     wk.t2 = MODE == MODE_EUCLID ? s_tab : nullptr;
     wk.N = P.N; wk.W = P.W; wk.L = P.levels;
@@ -829,11 +856,24 @@ __global__ void __launch_bounds__(32) k1_paths_big(PathParams P) {
 // l-1 subsampled at the even global positions, so with pos[pixel] = (a' + t') >> 1 for the even a' + t' of level l-1:
 // Pm_l[a + t] = pos[Q_l[a + t]].  One warp per region, level after level; pos lives in shared memory, relative to the
 // region (16 bits per cell of the bounding box), or -- bounding boxes of more than K2_CELLS cells -- in the image's
-// `posmap` in global memory.
+// `posmap` in global memory.  The thread-per-region walker already wrote the positions of its list-mode levels (at
+// most WK_LIST_MAX points: the list index is the position), so for its regions only the levels above are done here;
+// regions walked by a whole warp (paths.cuh) get every level.
 constexpr int K2_WARPS = 8;
-constexpr int K2_CELLS = 2560;  // 16-bit cells per warp: 5 KB
+constexpr int K2_CELLS = 1024;  // 16-bit cells per warp (2 KB): 64 warps per SM stay resident
+constexpr int K2_VPL = 8;       // path points per lane held in registers: a level of up to 256 points is loaded once
 
-__global__ void __launch_bounds__(K2_WARPS * 32) k2_perm(PathParams P, int nreg) {
+// the first K2_VPL * 32 points of a level's path, lane-strided; -1 beyond n
+__device__ __forceinline__ void k2_load(const int32_t *Ql, int n, int lane, int (&v)[K2_VPL]) {
+#pragma unroll
+  for (int u = 0; u < K2_VPL; u++) {
+    if (u * 32 >= n) break;
+    const int t = u * 32 + lane;
+    v[u] = t < n ? __ldcs(Ql + t) : -1;
+  }
+}
+
+__global__ void __launch_bounds__(K2_WARPS * 32) k2_perm(PathParams P, int nreg, int euclid) {
   __shared__ uint16_t s_pos[K2_WARPS][K2_CELLS];
   const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
   const int nw = gridDim.x * K2_WARPS;
@@ -844,33 +884,61 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_perm(PathParams P, int nreg)
     const int r0 = P.reg.first[g] >> logW, c0 = P.reg.cmin[g];
     const int hb = P.reg.rmax[g] - r0 + 1, wb = P.reg.cmax[g] - c0 + 1;
     const bool in_smem = hb * wb <= K2_CELLS && n1 < 65536;
+    // levels of at most `skip_below` points were done by the walker (never level 1); 0 = this region was walked by a warp
+    const bool by_warp = region_class_words(P.reg, g, logW) > TPR_ARENA_WORDS || (euclid && n1 >= P.coop_min);
+    const int skip_below = by_warp ? 0 : WK_LIST_MAX;
     const int32_t *Qimg = P.Q + (size_t)img * 2 * (size_t)N;
     int32_t *Pimg = P.Pm + (size_t)img * 2 * (size_t)N;
     int32_t *posmap = P.posmap + (size_t)img * N;
     uint16_t *pos = s_pos[warp];
+    auto cell = [&](int pix) { return ((pix >> logW) - r0) * wb + (pix & Wm) - c0; };
+    int cur[K2_VPL], nxt[K2_VPL];
+    int a = a1, n = n1;
+    if (((a + n + 1) >> 1) - ((a + 1) >> 1) <= skip_below || L < 2) continue;  // no level >= 2 to do
+    k2_load(Qimg + a, n, lane, cur);
     for (int lev = 1; lev <= L; lev++) {
-      const int sh = lev - 1, add = (1 << sh) - 1;
-      const int a = (int)(((long long)a1 + add) >> sh), b = (int)(((long long)a1 + n1 + add) >> sh);
-      const int n = b - a;
-      if (n <= 0) break;
       const int32_t *Ql = Qimg + level_off((size_t)N, lev) + a;
+      const int an = (a + 1) >> 1;
+      int nn = lev < L ? ((a + n + 1) >> 1) - an : 0;
+      if (nn <= skip_below) nn = 0;  // the next level is the walker's (or does not exist): this is the last one here
+      // the next level's path is requested before this level is processed: one memory latency per region, not per level
+      if (nn > 0) k2_load(Qimg + level_off((size_t)N, lev + 1) + an, nn, lane, nxt);
       if (lev >= 2) {
         int32_t *Pl = Pimg + level_off((size_t)N, lev) + a;
-        for (int t = lane; t < n; t += 32) {
-          const int pix = __ldcg(Ql + t);
-          Pl[t] = in_smem ? a + (int)pos[((pix >> logW) - r0) * wb + (pix & Wm) - c0] : __ldcg(posmap + pix);
+#pragma unroll
+        for (int u = 0; u < K2_VPL; u++) {
+          if (u * 32 >= n) break;
+          const int t = u * 32 + lane;
+          if (t < n) Pl[t] = in_smem ? a + (int)pos[cell(cur[u])] : __ldcg(posmap + cur[u]);
+        }
+        for (int t = K2_VPL * 32 + lane; t < n; t += 32) {
+          const int pix = __ldcs(Ql + t);
+          Pl[t] = in_smem ? a + (int)pos[cell(pix)] : __ldcg(posmap + pix);
         }
       }
-      if (lev == L) break;
+      if (nn <= 0) break;
       __syncwarp();
-      const int anext = (a + 1) >> 1;
-      for (int t = 2 * lane + (a & 1); t < n; t += 64) {  // the even global positions a + t survive
-        const int pix = __ldcg(Ql + t);
-        const int place = (a + t) >> 1;
-        if (in_smem) pos[((pix >> logW) - r0) * wb + (pix & Wm) - c0] = (uint16_t)(place - anext);
-        else posmap[pix] = place;
+      // the even global positions a + t survive: their place in the next level's incoming order
+#pragma unroll
+      for (int u = 0; u < K2_VPL; u++) {
+        if (u * 32 >= n) break;
+        const int t = u * 32 + lane;
+        if (t < n && ((a + t) & 1) == 0) {
+          const int place = (a + t) >> 1;
+          if (in_smem) pos[cell(cur[u])] = (uint16_t)(place - an);
+          else posmap[cur[u]] = place;
+        }
       }
+      for (int t = K2_VPL * 32 + lane; t < n; t += 32)
+        if (((a + t) & 1) == 0) {
+          const int pix = __ldcs(Ql + t), place = (a + t) >> 1;
+          if (in_smem) pos[cell(pix)] = (uint16_t)(place - an);
+          else posmap[pix] = place;
+        }
       __syncwarp();
+#pragma unroll
+      for (int u = 0; u < K2_VPL; u++) cur[u] = nxt[u];
+      a = an; n = nn;
     }
     __syncwarp();
   }

@@ -134,7 +134,7 @@ bool host_far(Walker<MODE> &wk) {
 }
 
 template <int MODE>
-int walk_image(const int32_t *lab, int H, int W, int levels, bool use_lut, bool literal_far, int32_t *Q, long long *steps_by_kind) {
+int walk_image(const int32_t *lab, int H, int W, int levels, bool use_lut, bool literal_far, int32_t *Q, int32_t *Pm, long long *steps_by_kind) {
   const int N = H * W;
   // regions in order of first appearance, row-major (Segmentation.compute_label_dict, rbepwt.py:840-848)
   std::unordered_map<int32_t, int> rid;
@@ -173,6 +173,7 @@ int walk_image(const int32_t *lab, int H, int W, int levels, bool use_lut, bool 
     Walker<MODE> wk;
     wk.bm = slot.data();
     wk.Qimg = Q;
+    wk.Pimg = Pm;
     wk.lut = use_lut && MODE != MODE_EUCLID ? lut.data() : nullptr;
     wk.t2 = use_lut && MODE == MODE_EUCLID ? t2.data() : nullptr;
     wk.N = N; wk.W = W; wk.L = levels;
@@ -220,9 +221,9 @@ extern "C" int hw_t2_hash_is_perfect(void) {
 }
 
 extern "C" int hw_walk_image(const int32_t *lab, int H, int W, int levels, int mode, int widewin, int use_lut, int32_t *Q,
-                             long long *steps_by_kind) {
+                             int32_t *Pm, long long *steps_by_kind) {
   std::memset(steps_by_kind, 0, 8 * sizeof(long long));
   // `widewin` selects the search beyond the 5x5 window: 1 = the reference's probes taken literally, 0 = wk_far_lane
-  if (mode == MODE_EUCLID) return walk_image<MODE_EUCLID>(lab, H, W, levels, use_lut, widewin != 0, Q, steps_by_kind);
-  return walk_image<MODE_CHEB>(lab, H, W, levels, use_lut, widewin != 0, Q, steps_by_kind);
+  if (mode == MODE_EUCLID) return walk_image<MODE_EUCLID>(lab, H, W, levels, use_lut, widewin != 0, Q, Pm, steps_by_kind);
+  return walk_image<MODE_CHEB>(lab, H, W, levels, use_lut, widewin != 0, Q, Pm, steps_by_kind);
 }

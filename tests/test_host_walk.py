@@ -31,7 +31,7 @@ def hostwalk():
         i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
         L.hw_walk_image.restype = ctypes.c_int
         L.hw_walk_image.argtypes = [i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                    i32p, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")]
+                                    i32p, i32p, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")]
         _lib = L
     return _lib
 
@@ -40,25 +40,36 @@ def host_paths(lab, levels, euclid=True, widewin=False, use_lut=True):
     lab = np.ascontiguousarray(lab, dtype=np.int32)
     H, W = lab.shape
     Q = np.full(2 * H * W, -1, dtype=np.int32)
+    Pm = np.full(2 * H * W, -1, dtype=np.int32)
     kinds = np.zeros(8, dtype=np.int64)
-    R = hostwalk().hw_walk_image(lab, H, W, levels, 0 if euclid else 1, int(widewin), int(use_lut), Q, kinds)
+    R = hostwalk().hw_walk_image(lab, H, W, levels, 0 if euclid else 1, int(widewin), int(use_lut), Q, Pm, kinds)
     assert R > 0, "walker reported corrupt region state"
-    return Q, kinds
+    return Q, Pm, kinds
 
 
 def oracle_paths(lab, levels, euclid=True):
+    """(paths as pixel ids, positions in the incoming order = region offset + generating permutation), all levels."""
     from oracle import c_oracle, pywt_port
 
     H, W = lab.shape
     enc = c_oracle.encode(np.zeros((H, W)), lab, levels, pywt_port.filter_bank("haar"),
                           c_oracle.MODE_EUCLID if euclid else c_oracle.MODE_CHEB)
-    return enc["path_pix"]
+    pos = enc["perm"].copy()
+    lo = 0
+    for lev in range(1, levels + 1):
+        nl = (H * W) >> (lev - 1)
+        roff = enc["roff"][lev - 1]
+        pos[lo:lo + nl] += np.repeat(roff[:-1], np.diff(roff))
+        lo += nl
+    return enc["path_pix"], pos
 
 
 def check(lab, levels, euclid=True, widewin=False, use_lut=True):
-    Q, kinds = host_paths(lab, levels, euclid, widewin, use_lut)
-    want = oracle_paths(lab, levels, euclid)
+    Q, Pm, kinds = host_paths(lab, levels, euclid, widewin, use_lut)
+    want, want_pos = oracle_paths(lab, levels, euclid)
     n = want.size
+    wrote = Pm[:n] >= 0  # the walker writes positions for its list-mode levels only
+    assert np.array_equal(Pm[:n][wrote], want_pos[wrote]), "list-mode positions differ from the oracle's permutation"
     if not np.array_equal(Q[:n], want):
         bad = int(np.flatnonzero(Q[:n] != want)[0])
         N, lev, lo = lab.size, 1, 0
