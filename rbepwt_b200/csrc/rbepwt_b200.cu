@@ -79,7 +79,7 @@ constexpr int NSLOT = 2;   // path groups in flight
 constexpr int NXSLOT = RBEPWT_NXSLOT;  // transform sub-batches in flight
 constexpr int NSLOTS = NSLOT + NXSLOT;
 #ifndef TPR_WIDE_CTAS_PER_SM
-#define TPR_WIDE_CTAS_PER_SM 5
+#define TPR_WIDE_CTAS_PER_SM 4
 #endif
 constexpr int TPR_WAVES = 8;  // k1_walk grid = this many waves of resident CTAs (see walk.cuh)
 
@@ -430,9 +430,9 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   }
   int tpr_per_sm = 1;  // grid = TPR_WAVES waves of resident CTAs
   if (c->mode == RBEPWT_PATH_EUCLID)
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_walk<MODE_EUCLID, false>, WK_WARPS * 32, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_walk<MODE_EUCLID, false>, WK_WARPS * 32, wk_arena_bytes(false)));
   else
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_walk<MODE_CHEB, false>, WK_WARPS * 32, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_walk<MODE_CHEB, false>, WK_WARPS * 32, wk_arena_bytes(false)));
   const int small_ctas = c->sm_count * std::max(tpr_per_sm, 1) * TPR_WAVES;
   {
     StageTimer tb(c, RBEPWT_T_PATHS_BIG, s);
@@ -452,15 +452,15 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     CK(cudaEventRecord(sl.ev_a, s));
     CK(cudaStreamWaitEvent(sl.aux, sl.ev_a, 0));
     if (c->mode == RBEPWT_PATH_EUCLID)
-      k1_walk<MODE_EUCLID, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, WK_WARPS * 32, 0, sl.aux>>>(P);
+      k1_walk<MODE_EUCLID, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, WK_WIDE_WARPS * 32, wk_arena_bytes(true), sl.aux>>>(P);
     else
-      k1_walk<MODE_CHEB, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, WK_WARPS * 32, 0, sl.aux>>>(P);
+      k1_walk<MODE_CHEB, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, WK_WIDE_WARPS * 32, wk_arena_bytes(true), sl.aux>>>(P);
     k1_bitmaps<<<c->sm_count * 8, 256, 0, s>>>(P);
     c->launches++;
     if (c->mode == RBEPWT_PATH_EUCLID)
-      k1_walk<MODE_EUCLID, false><<<small_ctas, WK_WARPS * 32, 0, s>>>(P);
+      k1_walk<MODE_EUCLID, false><<<small_ctas, WK_WARPS * 32, wk_arena_bytes(false), s>>>(P);
     else
-      k1_walk<MODE_CHEB, false><<<small_ctas, WK_WARPS * 32, 0, s>>>(P);
+      k1_walk<MODE_CHEB, false><<<small_ctas, WK_WARPS * 32, wk_arena_bytes(false), s>>>(P);
     CK(cudaEventRecord(sl.ev_b, sl.aux));
     CK(cudaStreamWaitEvent(s, sl.ev_b, 0));
     c->launches += 2;
@@ -782,7 +782,11 @@ static int create_impl(rbepwt_ctx *c, int device, void *stream) {
   k_build_unit_lut<MODE_CHEB><<<1, 256, 0, c->stream>>>(c->unit_lut.as<uint8_t>() + TPR_LUT_ROWS * TPR_LUT_COLS);
   CK(c->t2_tab.ensure(T2_BYTES));
   k_build_t2<<<(T2_JOBS + 255) / 256, 256, 0, c->stream>>>(c->t2_tab.as<uint8_t>());
-  // five CTAs of the path kernel per SM need more shared memory than the default carve-out offers
+  // the path kernels fill the SM's shared memory with their arenas
+  CK(cudaFuncSetAttribute(k1_walk<MODE_EUCLID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wk_arena_bytes(false)));
+  CK(cudaFuncSetAttribute(k1_walk<MODE_EUCLID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wk_arena_bytes(true)));
+  CK(cudaFuncSetAttribute(k1_walk<MODE_CHEB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wk_arena_bytes(false)));
+  CK(cudaFuncSetAttribute(k1_walk<MODE_CHEB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wk_arena_bytes(true)));
   CK(cudaFuncSetAttribute(k1_walk<MODE_EUCLID, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k1_walk<MODE_EUCLID, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k1_walk<MODE_CHEB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -392,7 +392,7 @@ __global__ void k0_single_region(int img0, int nimg, int H, int W, RegionArrays 
 // A chunk = the regions one warp walks together (thread per region, walk.cuh).
 
 #ifndef TPR_ARENA_WORDS_N
-#define TPR_ARENA_WORDS_N 2080
+#define TPR_ARENA_WORDS_N 2144
 #endif
 constexpr int TPR_ARENA_WORDS = TPR_ARENA_WORDS_N;  // shared-memory words per warp of k1_walk
 // class 0 = big; classes 1..12 = the bitmaps that fit the arena class_chunk_size(c) at a time

@@ -52,19 +52,24 @@
 
 namespace rbepwt {
 
+// Bulk instantiation: two large CTAs per SM, so that the step table (8 KB per CTA) costs little of the shared memory and
+// the arenas get the rest; 24 warps per SM is what the registers allow (measured: 20 warps with larger arenas 7.1 ms,
+// 24 warps 6.8 ms, 26 warps with spills 8.7 ms per 512 images).
 #ifndef WK_WARPS_N
-#define WK_WARPS_N 4
+#define WK_WARPS_N 12
 #endif
 constexpr int WK_WARPS = WK_WARPS_N;
 #ifndef WK_MIN_CTAS
-#define WK_MIN_CTAS 5
+#define WK_MIN_CTAS 2
 #endif
+constexpr int WK_WIDE_WARPS = 4;  // windowed instantiation: small CTAs (few chunks, the longest chains)
+constexpr int WK_WIDE_MIN_CTAS = 4;
 #ifndef WK_NEAR_REPS_N
-#define WK_NEAR_REPS_N 2
+#define WK_NEAR_REPS_N 4
 #endif
 constexpr int WK_NEAR_REPS = WK_NEAR_REPS_N;  // 5x5 steps a lane may take per trip of the warp loop
 #ifndef WK_LIST_BATCH_N
-#define WK_LIST_BATCH_N 8
+#define WK_LIST_BATCH_N 12
 #endif
 constexpr int WK_LIST_BATCH = WK_LIST_BATCH_N;  // list-mode lanes wait for this many of their kind (or for the others to finish)
 
@@ -295,8 +300,10 @@ template <int MODE>
 struct Walker {
   // the region
   uint32_t *bm;        // its arena slot: plane at `cur` = unvisited points of the level, plane at `nxt` = survivors
-  int32_t *Qimg;       // paths of the region's image, all levels
-  int32_t *Pimg;       // positions in the incoming order, same layout: written here for the list-mode levels only
+  int32_t *Qall;       // paths of the batch: [image][2N], levels concatenated
+  ptrdiff_t pdelta;    // positions in the incoming order live at the same offsets of another array: Pm = Q + pdelta
+                       // (written here for the list-mode levels only)
+  int img;             // the region's image
   const uint8_t *lut;  // chebyshev: compact unit-step table (or null)
   const uint8_t *t2;   // euclid: 5x5 step table (or null)
   int N, W, L;
@@ -349,13 +356,13 @@ struct Walker {
     keep = lev < L;
     const int nnext = ((a + n + 1) >> 1) - ((a + 1) >> 1);
     tolist = nnext <= WK_LIST_MAX;
-    Qp = Qimg + level_off((size_t)N, lev) + a;
+    Qp = Qall + (size_t)img * 2 * (size_t)N + level_off((size_t)N, lev) + a;
     uint32_t e;
     if (from_list) {
       // a list holds the level's points in their incoming order: the list index IS the position k2_perm would compute
       e = bm[cur + sminidx];
       U = (n >= 32 ? 0xffffffffu : (1u << n) - 1u) & ~(1u << sminidx);
-      Pimg[Qp - Qimg] = a + sminidx;
+      Qp[pdelta] = a + sminidx;
     } else {
       e = smin;
     }
@@ -494,7 +501,7 @@ struct Walker {
     U &= ~(1u << S.tag);
     p0 = di; p1 = dj;
     ci += di; cj += dj;
-    Pimg[Qp - Qimg] = a + S.tag;
+    Qp[pdelta] = a + S.tag;
     emit();
     t++;
     if (t == n) {
@@ -608,7 +615,7 @@ __global__ void __launch_bounds__(256) k1_bitmaps(PathParams P) {
 }
 
 #ifdef WK_STATS  // debug build only: warp trips and lane units by kind
-__device__ unsigned long long g_wk_stats[16];  // [0] warp trips, [kind] lanes of that kind at the start of a trip
+__device__ unsigned long long g_wk_stats[16];  // [0] warp trips, [1 + kind] lanes of that kind at the start of a trip, [10] regions of the chunk
 #endif
 
 // The search beyond the 5x5 window of ONE lane's region, done by the whole warp (all arguments warp-uniform): the
@@ -620,6 +627,31 @@ __device__ unsigned long long g_wk_stats[16];  // [0] warp trips, [kind] lanes o
 // otherwise `step` = (di << 16) | (dj & 0xffff).
 constexpr int WK_NO_PARTNER = (int)0x80000000;
 
+// The candidate of one bitmap row (x != 0, one or two words; row offset rdi from the current point): its nearest
+// unvisited column on either side of cj -- the nearer one dominates the other in (k, d2); equidistant ones share the
+// key and compete on the dot product (`partner` = the other one when the dot products tie as well).
+template <typename WORD>
+__device__ __forceinline__ void wk_row_candidate(WORD x, int cj, int rdi, int p0, int p1, unsigned &key, int &dot, int &off,
+                                                 int &partner) {
+  const WORD below = ((WORD)1 << cj) - (WORD)1;  // columns < cj
+  const WORD left = x & below, right = x & ~below;
+  int dl, dr;
+  if (sizeof(WORD) == 4) { dl = cj - (31 - __clz((int)left)); dr = __ffs((int)right) - 1 - cj; }
+  else { dl = cj - (63 - __clzll((long long)left)); dr = __ffsll((long long)right) - 1 - cj; }
+  const bool both = left && right;
+  const bool use_left = left && (!right || dl <= dr);
+  int rdj = use_left ? -dl : dr;
+  key = ((unsigned)probe_index(max(abs(rdi), abs(rdj))) << 21) | (unsigned)(rdi * rdi + rdj * rdj);
+  dot = rdi * p0 + rdj * p1;
+  partner = WK_NO_PARTNER;
+  if (both && dl == dr) {  // (rdi, -dl) and (rdi, +dl): the other one's dot product is dot + 2 dl p1
+    const int dot2 = dot + 2 * dr * p1;
+    if (dot2 == dot) partner = (rdi << 16) | (dr & 0xffff);
+    if (dot2 > dot) { dot = dot2; rdj = dr; }
+  }
+  off = (rdi << 16) | (rdj & 0xffff);
+}
+
 template <int MODE>
 __device__ __forceinline__ bool wk_far_search(const uint32_t *plane, int h, int ws, int ci, int cj, int p0, int p1, int &step) {
   const int lane = (int)lane_id();
@@ -629,43 +661,20 @@ __device__ __forceinline__ bool wk_far_search(const uint32_t *plane, int h, int 
     if (ws == 1 && h <= 32) {
       // the common case, straight-line: one row of one word per lane
       const uint32_t x = lane < h ? plane[lane] : 0u;
-      if (x) {
-        const uint32_t below = (1u << cj) - 1u;  // columns < cj (cj <= 29: the margin)
-        const uint32_t left = x & below, right = x & ~below;
-        const int dl = cj - (31 - __clz((int)left)), dr = __ffs((int)right) - 1 - cj;
-        const bool both = left && right;
-        const bool use_left = left && (!right || dl <= dr);
-        const int rdi = lane - ci;
-        int rdj = use_left ? -dl : dr;
-        bkey = ((unsigned)probe_index(max(abs(rdi), abs(rdj))) << 21) | (unsigned)(rdi * rdi + rdj * rdj);
-        bdot = rdi * p0 + rdj * p1;
-        if (both && dl == dr) {  // (rdi, -dl) and (rdi, +dl): same key; the other one's dot product is bdot + 2 dl p1
-          const int dot2 = bdot + 2 * dr * p1;
-          if (dot2 == bdot) aoff = (rdi << 16) | (dr & 0xffff);
-          if (dot2 > bdot) { bdot = dot2; rdj = dr; }
-        }
-        boff = (rdi << 16) | (rdj & 0xffff);
-      }
+      if (x) wk_row_candidate<uint32_t>(x, cj, lane - ci, p0, p1, bkey, bdot, boff, aoff);
     } else {
-      const unsigned long long below = (1ull << cj) - 1ull;  // columns < cj
       for (int i = lane; i < h; i += 32) {
-        const unsigned long long x = ws == 1 ? (unsigned long long)plane[i]
-                                             : ((unsigned long long)plane[2 * i + 1] << 32) | plane[2 * i];
-        if (!x) continue;
-        const unsigned long long left = x & below, right = x & ~below;
-        const int dl = cj - (63 - __clzll((long long)left)), dr = __ffsll((long long)right) - 1 - cj;
-        const bool use_left = left && (!right || dl <= dr);
-        const int rdi = i - ci;
-        int rdj = use_left ? -dl : dr;
-        const unsigned key = ((unsigned)probe_index(max(abs(rdi), abs(rdj))) << 21) | (unsigned)(rdi * rdi + rdj * rdj);
-        int dot = rdi * p0 + rdj * p1;
-        int partner = WK_NO_PARTNER;
-        if (left && right && dl == dr) {
-          const int dot2 = rdi * p0 + dr * p1;
-          if (dot2 == dot) partner = (rdi << 16) | (dr & 0xffff);
-          if (dot2 > dot) { dot = dot2; rdj = dr; }
+        unsigned key;
+        int dot, off, partner;
+        if (ws == 1) {
+          const uint32_t x = plane[i];
+          if (!x) continue;
+          wk_row_candidate<uint32_t>(x, cj, i - ci, p0, p1, key, dot, off, partner);
+        } else {
+          const unsigned long long x = ((unsigned long long)plane[2 * i + 1] << 32) | plane[2 * i];
+          if (!x) continue;
+          wk_row_candidate<unsigned long long>(x, cj, i - ci, p0, p1, key, dot, off, partner);
         }
-        const int off = (rdi << 16) | (rdj & 0xffff);
         if (key < bkey || (key == bkey && dot > bdot)) { bkey = key; bdot = dot; boff = off; aoff = partner; }
         else if (key == bkey && dot == bdot) aoff = off;
       }
@@ -701,9 +710,15 @@ __device__ __forceinline__ bool wk_far_search(const uint32_t *plane, int h, int 
 // WIDEWIN = true: the instantiation for the chunks of large bitmaps (queue classes below Q_FIRST_NARROW_CLS; at most six
 // regions per warp), which builds its bitmaps itself and hands regions of at least coop_min pixels to the whole-warp
 // walker of paths.cuh.
+constexpr size_t wk_arena_bytes(bool widewin) {
+  return ((size_t)(widewin ? WK_WIDE_WARPS : WK_WARPS) * TPR_ARENA_WORDS + 4) * sizeof(uint32_t);
+}
+
 template <int MODE, bool WIDEWIN>
-__global__ void __launch_bounds__(WK_WARPS * 32, WK_MIN_CTAS) k1_walk(PathParams P) {
-  __shared__ __align__(16) uint32_t s_arena[WK_WARPS * TPR_ARENA_WORDS + 4];
+__global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WIDEWIN ? WK_WIDE_MIN_CTAS : WK_MIN_CTAS)
+    k1_walk(PathParams P) {
+  constexpr int NWARPS = WIDEWIN ? WK_WIDE_WARPS : WK_WARPS;
+  extern __shared__ __align__(16) uint32_t s_arena[];  // NWARPS * TPR_ARENA_WORDS + 4 words (wk_arena_bytes)
   // the walker's step table: euclid the 5x5 table, chebyshev the compact unit-step table
   __shared__ __align__(16) uint8_t s_tab[MODE == MODE_EUCLID ? T2_BYTES : WK_LUT_BYTES];
   __shared__ __align__(16) uint8_t s_lut[WIDEWIN ? TPR_LUT_ROWS * TPR_LUT_COLS : 16];  // the whole-warp walker's full table
@@ -724,7 +739,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MIN_CTAS) k1_walk(PathParams
 
   // Each warp takes its share of the chunks and retires: the grid is several waves of CTAs, so SM slots keep
   // freeing up for the (higher-priority) transform kernels of other units instead of being held to the end.
-  const int share = max(1, (nchunks + (int)gridDim.x * WK_WARPS - 1) / ((int)gridDim.x * WK_WARPS));
+  const int share = max(1, (nchunks + (int)gridDim.x * NWARPS - 1) / ((int)gridDim.x * NWARPS));
   for (int taken = 0; taken < share; taken++) {
     int chunk = 0;
     if (lane == 0) chunk = atomicAdd(&P.qmeta[WIDEWIN ? QM_CUR_WIDE : QM_CUR_SMALL], 1);
@@ -769,8 +784,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MIN_CTAS) k1_walk(PathParams
 
     Walker<MODE> wk;
     wk.bm = arena + c.base;
-    wk.Qimg = P.Q + (size_t)c.img * 2 * (size_t)P.N;
-    wk.Pimg = P.Pm + (size_t)c.img * 2 * (size_t)P.N;
+    wk.Qall = P.Q; wk.pdelta = P.Pm - P.Q; wk.img = c.img;
     wk.lut = MODE == MODE_EUCLID ? nullptr : s_tab;
     wk.t2 = MODE == MODE_EUCLID ? s_tab : nullptr;
     wk.N = P.N; wk.W = P.W; wk.L = P.levels;
@@ -789,7 +803,8 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MIN_CTAS) k1_walk(PathParams
       if (!live) break;
 #ifdef WK_STATS
       if (lane == 0) atomicAdd(&g_wk_stats[0], 1ull);
-      if (!wk.done()) atomicAdd(&g_wk_stats[wk.kind], 1ull);
+      atomicAdd(&g_wk_stats[1 + wk.kind], 1ull);
+      if (lane == 0) atomicAdd(&g_wk_stats[10], (unsigned long long)cnt);
 #endif
       if (__any_sync(FULL_MASK, wk.kind == WK_LEVEL)) {
         if (wk.kind == WK_LEVEL) wk.next_level();

@@ -172,8 +172,7 @@ int walk_image(const int32_t *lab, int H, int W, int levels, bool use_lut, bool 
         if (lab[(r0 + i) * W + c0 + j] == label) slot[i * ws + (j >> 5)] |= 1u << (j & 31);
     Walker<MODE> wk;
     wk.bm = slot.data();
-    wk.Qimg = Q;
-    wk.Pimg = Pm;
+    wk.Qall = Q; wk.pdelta = Pm - Q; wk.img = 0;
     wk.lut = use_lut && MODE != MODE_EUCLID ? lut.data() : nullptr;
     wk.t2 = use_lut && MODE == MODE_EUCLID ? t2.data() : nullptr;
     wk.N = N; wk.W = W; wk.L = levels;

@@ -23,5 +23,6 @@ L.rbepwt_debug_wk_stats(c._ctx, out, 1)
 c.encode(imgs, labs, 16, "bior4.4"); c.sync()
 L.rbepwt_debug_wk_stats(c._ctx, out, 1)
 v = np.array(list(out), dtype=np.float64) / B
-print("per image: warp trips %.0f | lane units: near %.0f  far %.0f  list %.0f | near units per trip %.1f (of %d x 32)"
-      % (v[0], v[1], v[2], v[3], v[1] / v[0], 4))
+names = ["done", "near", "far", "list", "level", "commit", "error"]
+print("per image: warp trips %.0f, regions per chunk %.1f | lanes per trip at its start: %s"
+      % (v[0], v[10] / v[0], "  ".join("%s %.1f" % (n, v[1 + i] / v[0]) for i, n in enumerate(names))))
