@@ -727,6 +727,12 @@ __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WID
   const int chunk_lo = WIDEWIN ? 0 : P.qmeta[QM_CHUNK_SPLIT];
   const int nchunks = (WIDEWIN ? P.qmeta[QM_CHUNK_SPLIT] : P.qmeta[QM_NCHUNKS]) - chunk_lo;
   if (nchunks <= 0) return;
+  __shared__ __align__(8) unsigned long long s_mbar[NWARPS];  // one mbarrier per warp: arrival of its chunk's arena image
+  uint32_t tma_phase = 0u;
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_mbar[warp])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (WIDEWIN) load_unit_lut(s_lut, P.unit_lut);
   if (MODE == MODE_EUCLID) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(P.t2_tab);
@@ -759,17 +765,36 @@ __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WID
     const WkChunkLane c = wk_chunk_lane(P, qstart, cnt);
     const bool mine = lane < cnt;
     if (!WIDEWIN && chunk - chunk_lo < P.gbm_chunks) {
-      // the arena image was built by k1_bitmaps: copy the chunk's words, 16 bytes per lane and load, all in flight
+      // the arena image was built by k1_bitmaps: one bulk copy (TMA, 1-D) global -> shared, completion on the warp's
+      // mbarrier -- no registers, no issue slots of the walking warp spent on moving the 4..8 KB
       const int total = __shfl_sync(FULL_MASK, c.base + c.slot, 31);
+      const uint32_t *src = P.gbm + (size_t)(chunk - chunk_lo) * TPR_ARENA_WORDS;
+#ifndef WK_NO_TMA
+      const uint32_t bytes = (uint32_t)((total + 3) >> 2) * 16u;
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_mbar[warp]);
+      if (lane == 0) {
+        // what the previous chunk's walk wrote to the arena (generic proxy) is ordered before the async-proxy writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(arena)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+      }
+      uint32_t ready = 0;
+      while (!ready) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ready) : "r"(bar), "r"(tma_phase) : "memory");
+      }
+      tma_phase ^= 1u;
+#else
       const int nvec = (total + 3) >> 2;
-      const uint4 *src = reinterpret_cast<const uint4 *>(P.gbm + (size_t)(chunk - chunk_lo) * TPR_ARENA_WORDS);
+      const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
       uint4 *dst = reinterpret_cast<uint4 *>(arena);
       for (int e0 = 0; e0 < nvec; e0 += 8 * 32) {
         uint4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
           const int e = e0 + u * 32 + lane;
-          v[u] = e < nvec ? __ldcs(src + e) : make_uint4(0u, 0u, 0u, 0u);
+          v[u] = e < nvec ? __ldcs(src4 + e) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
@@ -777,6 +802,7 @@ __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WID
           if (e < nvec) dst[e] = v[u];
         }
       }
+#endif
     } else {
       wk_build_bitmaps(P, arena, cnt, c.img, c.label, c.r0, c.c0, c.h, c.w, c.ws, c.base, c.slot);
     }
