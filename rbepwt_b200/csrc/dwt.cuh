@@ -45,6 +45,8 @@ struct DwtParams {
   double *out_img;     // decode, level 1: clipped image
   int flen, N, lev, levels;
   int clip;            // decode, level 1: clip to [0,255] (Image.decode_rbepwt); 0 = Rbepwt.decode's own values
+  const unsigned long long *thr;  // decode: pending thresholds, one record of 2 words per image ({tau, flags}: select.cuh
+                                  // ThrRec) or null -- coefficients with magnitude bits below tau are read as zero
 };
 
 struct FwdSmem {
@@ -156,10 +158,15 @@ __device__ __forceinline__ void idwt_tile(const DwtParams &P, InvSmem &sm, int l
   const bool deepest = lev == P.levels;
   const size_t det_off = (size_t)N - (size_t)n;
   const size_t app_off = (size_t)N - (size_t)(N >> P.levels);
+  // a pending threshold (k4_select) is applied here, on load: tau = 0 keeps everything
+  const unsigned long long tau = (P.thr && (int)P.thr[2 * img + 1]) ? P.thr[2 * img] : 0ull;
+  auto kept = [&](double v) {
+    return ((unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull) >= tau ? v : 0.0;
+  };
   for (int i = tid; i < cnt; i += nt) {
     const int ow = (omin + i) & hmask;
-    sm.a[i] = deepest ? coefs[app_off + ow] : (SAME_CTA ? __ldcg(vin + ow) : vin[ow]);
-    sm.d[i] = coefs[det_off + ow];
+    sm.a[i] = deepest ? kept(coefs[app_off + ow]) : (SAME_CTA ? __ldcg(vin + ow) : vin[ow]);
+    sm.d[i] = kept(coefs[det_off + ow]);
   }
   __syncthreads();
   auto emit = [&](int t, double x) {

@@ -126,6 +126,8 @@ struct rbepwt_ctx {
   const double *img_dev = nullptr;
   DevBuf labels_own, img_own, out_own, coef_up;
   DevBuf Q, Pm, posmap, coefs;
+  DevBuf thr, need_exact;       // per image: pending threshold (select.cuh ThrRec), "k4_select gave up" flag
+  bool thr_pending = false;     // some image may have a threshold recorded but not yet written into its coefficients
   DevBuf reg[8];
   int totalR = 0;
   DevBuf img_R, img_rbase, img_labmin, img_direct;
@@ -490,7 +492,7 @@ int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
   D.coefs = c->coefs.as<double>() + (size_t)a * N;
   D.filt = c->filt.as<double>();
   D.out_img = nullptr;
-  D.flen = c->flen; D.N = N; D.levels = c->levels; D.clip = 1;
+  D.flen = c->flen; D.N = N; D.levels = c->levels; D.clip = 1; D.thr = nullptr;
   set_taps(c, D, false);
   double *V[2] = {sl.VA.as<double>(), sl.VB.as<double>()};
   EpwtParams E;
@@ -552,11 +554,34 @@ int transform_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb) {
   return RBEPWT_OK;
 }
 
+// K4 for images [a, a+nb): one-pass select that records the threshold (applied by the inverse transform while it
+// loads the coefficients, or written out by materialise_thresholds), then the exact in-place kernel for the images
+// the first one flagged (none, for continuous data).  The images must have no threshold pending.
 int threshold_sub(rbepwt_ctx *c, cudaStream_t s, int a, int nb, long long k) {
   StageTimer t(c, RBEPWT_T_SELECT, s);
+  if (k <= 0 || k >= (long long)c->N) return RBEPWT_OK;  // keeps everything (reference quirk)
   CK(cudaFuncSetAttribute(k4_threshold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_SMEM));
-  k4_threshold<<<nb * SEL_CLUSTER, SEL_THREADS, SEL_SMEM, s>>>(c->coefs.as<double>() + (size_t)a * c->N, c->N, k);
-  c->launches++;
+  CK(cudaFuncSetAttribute(k4_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL2_SMEM));
+  double *coefs = c->coefs.as<double>() + (size_t)a * c->N;
+  int *need = c->need_exact.as<int>() + a;
+  CK(cudaMemsetAsync(need, 0, (size_t)nb * sizeof(int), s));
+  k4_select<<<nb, SEL_THREADS, SEL2_SMEM, s>>>(coefs, c->N, k, c->thr.as<ThrRec>() + a, need);
+  k4_threshold<<<nb * SEL_CLUSTER, SEL_THREADS, SEL_SMEM, s>>>(coefs, c->N, k, need);
+  c->launches += 2;
+  c->thr_pending = true;
+  CK(cudaGetLastError());
+  return RBEPWT_OK;
+}
+
+// Pending thresholds written into the coefficients (whole batch, on the context's stream): before anything looks at or
+// replaces the coefficients, and before they are thresholded again.
+int materialise_thresholds(rbepwt_ctx *c) {
+  if (!c->thr_pending) return RBEPWT_OK;
+  const int gx = std::max(1, std::min(c->N / 1024, 64));
+  k_apply_threshold<<<dim3(gx, c->B), 256, 0, c->stream>>>(c->coefs.as<double>(), c->N, c->thr.as<ThrRec>());
+  k_clear_thresholds<<<(c->B + 255) / 256, 256, 0, c->stream>>>(c->thr.as<ThrRec>(), c->B);
+  c->launches += 2;
+  c->thr_pending = false;
   CK(cudaGetLastError());
   return RBEPWT_OK;
 }
@@ -572,6 +597,7 @@ int decode_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb, double *o
   D.filt = c->filt.as<double>();
   D.out_img = out_dev + (size_t)a * N;
   D.flen = c->flen; D.N = N; D.levels = c->levels; D.clip = c->decode_noclip ? 0 : 1;
+  D.thr = reinterpret_cast<const unsigned long long *>(c->thr.as<ThrRec>() + a);
   set_taps(c, D, true);
   D.vin = nullptr; D.vin_stride = N;
   D.plane[0] = V[0]; D.plane[1] = V[1];
@@ -606,6 +632,10 @@ int alloc_state(rbepwt_ctx *c, int B, int H, int W, int levels, int path_mode, u
   CK(c->Pm.ensure((size_t)B * 2 * N * 4));
   CK(c->posmap.ensure((size_t)B * N * 4));
   CK(c->coefs.ensure((size_t)B * N * 8));
+  CK(c->thr.ensure((size_t)B * sizeof(ThrRec)));
+  CK(c->need_exact.ensure((size_t)B * sizeof(int)));
+  CK(cudaMemsetAsync(c->thr.p, 0, (size_t)B * sizeof(ThrRec), c->stream));  // before the fork: ordered ahead of every stream
+  c->thr_pending = false;
   CK(c->img_R.ensure((size_t)B * 4)); CK(c->img_rbase.ensure((size_t)B * 4));
   CK(c->img_labmin.ensure((size_t)B * 4)); CK(c->img_direct.ensure((size_t)B * 4));
   if (B > c->pin_cap) {
@@ -828,7 +858,7 @@ void rbepwt_destroy(rbepwt_ctx *c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   for (auto *v : {&c->ev_lab, &c->ev_path, &c->ev_img, &c->ev_done})
     for (auto e : *v) cudaEventDestroy(e);
-  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->t2_tab, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->img_R,
+  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->t2_tab, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->thr, &c->need_exact, &c->img_R,
                     &c->img_rbase, &c->img_labmin, &c->img_direct, &c->tbl, &c->slot_rid, &c->scratch_i32,
                     &c->scratch_i32b, &c->psnr_out, &c->nz_out};
   for (auto b : bufs) b->release();
@@ -917,6 +947,8 @@ int rbepwt_threshold(rbepwt_ctx *c, int64_t k) {
   if (!c) return fail(RBEPWT_E_ARG, "ctx is NULL");
   if (!c->has_encoding) return fail(RBEPWT_E_NO_ENCODING, "There is no saved encoding to decode");
   DeviceGuard g(c->device);
+  int rc = materialise_thresholds(c);  // thresholding twice: the second one sees the first one's zeros
+  if (rc) return rc;
   return threshold_sub(c, c->stream, 0, c->B, (long long)k);
 }
 
@@ -1003,6 +1035,8 @@ int rbepwt_nonzero_coefs(rbepwt_ctx *c, int64_t *out) {
   if (!c || !out) return fail(RBEPWT_E_ARG, "ctx / out is NULL");
   if (!c->has_encoding) return fail(RBEPWT_E_NO_ENCODING, "There is no saved encoding to decode");
   DeviceGuard g(c->device);
+  int rc = materialise_thresholds(c);
+  if (rc) return rc;
   CK(c->nz_out.ensure((size_t)c->B * 8));
   k_nonzero<<<c->B, 256, 0, c->stream>>>(c->coefs.as<double>(), c->N, c->nz_out.as<long long>());
   c->launches++;
@@ -1023,6 +1057,7 @@ int rbepwt_get_coefs(rbepwt_ctx *c, int b, double *flat) {
   int rc = check_img(c, b, true);
   if (rc) return rc;
   DeviceGuard g(c->device);
+  if ((rc = materialise_thresholds(c))) return rc;
   CK(cudaMemcpyAsync(flat, c->coefs.as<double>() + (size_t)b * c->N, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
   return check_path_error(c);
 }
@@ -1031,6 +1066,7 @@ int rbepwt_set_coefs(rbepwt_ctx *c, int b, const double *flat) {
   int rc = check_img(c, b, true);
   if (rc) return rc;
   DeviceGuard g(c->device);
+  if ((rc = materialise_thresholds(c))) return rc;
   CK(cudaMemcpyAsync(c->coefs.as<double>() + (size_t)b * c->N, flat, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return RBEPWT_OK;
@@ -1147,7 +1183,7 @@ int rbepwt_get_level_values(rbepwt_ctx *c, int b, int level, double *vals) {
   D.filt = c->filt.as<double>();
   D.out_img = nullptr;
   D.flen = c->flen; D.N = c->N; D.levels = 31;  // never the "last" level: low-pass always goes to vout
-  D.clip = 1;
+  D.clip = 1; D.thr = nullptr;
   set_taps(c, D, false);
   for (int lev = 1; lev < level; lev++) {
     D.lev = lev;

@@ -1,4 +1,6 @@
-// K4: global top-k by |coefficient| per image (radix select on the fp64 magnitude bits) + zeroing,
+// K4: global top-k by |coefficient| per image (radix select on the fp64 magnitude bits): k4_select (one pass, the
+// threshold is recorded and applied by the inverse transform) with k4_threshold (exact multi-pass, zeroes in place)
+// behind it for the unusual cases,
 // K6: PSNR, and the non-zero count.
 //
 // Replaces Rbepwt.threshold_coefs (/root/reference/rbepwt.py:2081-2112): the reference argsorts
@@ -25,6 +27,163 @@ constexpr int SEL_CLUSTER = 8;  // CTAs per image: one thread-block cluster, his
 constexpr int SEL_CAND = SEL_CAND_N;  // candidate keys a CTA keeps in shared memory after the second pass
 constexpr size_t SEL_SMEM = (size_t)SEL_CAND * 8;  // dynamic shared memory of k4_threshold
 
+// The pending threshold of an image: the coefficients whose magnitude bits are >= tau survive.  k4_select leaves the
+// coefficients in memory untouched and records tau; the inverse transform applies it while it loads the
+// coefficients, and k_apply_threshold writes the zeros out when somebody wants to look at the coefficients.
+struct ThrRec {
+  unsigned long long tau;  // magnitude bits (sign cleared) of the k-th largest coefficient
+  int active;              // 0: nothing pending for this image
+  int pad;
+};
+
+constexpr int SEL_SAMPLE_LOG = 4;   // k4_select samples one 32-byte sector (4 coefficients) out of 16
+constexpr int SEL2_BINS = 2048;      // 11-bit digits
+constexpr int SEL2_CAND = 8192;      // candidate keys (64-bit) = sample keys (32-bit) x 2: the two share one buffer
+constexpr size_t SEL2_SMEM = (size_t)SEL2_CAND * 8;
+
+// r-th largest (r >= 1, r <= n) of n keys in shared memory by radix select, 11 bits per pass from bit `bits` - 1 down;
+// *ceq = how many keys equal it, *krem = which of them (in descending order) the r-th is: 1..ceq.  Every thread of
+// the block calls it.
+template <typename KEY>
+__device__ __forceinline__ KEY block_select_desc(const KEY *keys, int n, int r, int bits, int *s_hist, int *s_scan,
+                                                 int *s_pick, int *krem, int *ceq) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  KEY prefix = 0;
+  int done = 0;
+  while (done < bits) {
+    const int nb = min(11, bits - done), nbins = 1 << nb, shift = bits - done - nb;
+    for (int i = tid; i < nbins; i += nt) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+      const KEY key = keys[i];
+      if (done == 0 || (key >> (shift + nb)) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & (KEY)(nbins - 1))], 1);
+    }
+    __syncthreads();
+    // thread t looks at the bins nbins-1-2t and nbins-2-2t (descending digits)
+    const int b0 = nbins - 1 - 2 * tid, b1 = b0 - 1;
+    const int c0 = b0 >= 0 ? s_hist[b0] : 0, c1 = b1 >= 0 ? s_hist[b1] : 0;
+    int total;
+    const int ex = block_exclusive_scan(c0 + c1, s_scan, &total);
+    if (ex < r && ex + c0 >= r) { s_pick[0] = b0; s_pick[1] = ex; s_pick[2] = c0; }
+    else if (ex + c0 < r && ex + c0 + c1 >= r) { s_pick[0] = b1; s_pick[1] = ex + c0; s_pick[2] = c1; }
+    __syncthreads();
+    prefix = (prefix << nb) | (KEY)s_pick[0];
+    r -= s_pick[1];
+    *ceq = s_pick[2];
+    done += nb;
+    __syncthreads();  // s_pick and s_hist are rewritten by the next pass
+  }
+  *krem = r;
+  return prefix;
+}
+
+// K4, common case: ONE pass over the coefficients, one CTA per image.  A sample (1/16 of the 32-byte sectors, top 32
+// magnitude bits of each key) is held in shared memory; its order statistics of rank k/16 -+ a safety margin
+// bracket the true k-th largest with overwhelming probability.  The full pass then only counts the keys above the
+// bracket and keeps the keys inside it (a few thousand of the image's 2^18) in shared memory, where a radix select
+// over all 63 magnitude bits finds the k-th largest exactly.  Checked, not assumed: if the bracket does not contain
+// rank k, if the candidates overflow their buffer, or if ties at the k-th magnitude would have to be cut (only some
+// of them survive: the highest flat indices), the image is flagged in `need_exact` and k4_threshold -- the exact
+// multi-pass kernel below, which zeroes in place -- does it instead.
+__global__ void __launch_bounds__(SEL_THREADS) k4_select(const double *coefs_all, int N, long long k, ThrRec *rec_all,
+                                                         int *need_exact) {
+  __shared__ int s_hist[SEL2_BINS];
+  __shared__ int s_scan[33];
+  __shared__ int s_pick[3];
+  __shared__ int s_ncand;
+  extern __shared__ unsigned long long s_cand[];  // SEL2_CAND 64-bit keys; first: up to 2 * SEL2_CAND 32-bit sample keys
+  if (k <= 0 || k >= (long long)N) return;  // keeps everything (reference quirk)
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int img = blockIdx.x;
+  const unsigned long long *c = reinterpret_cast<const unsigned long long *>(coefs_all + (size_t)img * N);
+  const unsigned long long MAG = 0x7fffffffffffffffull;
+  uint32_t *s_samp = reinterpret_cast<uint32_t *>(s_cand);
+
+  // ---- A: the sample -- sector s (4 keys) of the image is sampled when s % 16 == 0 -- and the bracket [v_lo, v_hi]
+  // (top 32 magnitude bits) from its order statistics
+  uint32_t v_hi = 0xffffffffu, v_lo = 0u;
+  const int nsample = 4 * ((N >> 2) >> SEL_SAMPLE_LOG);
+  if (nsample >= 64 && nsample <= 2 * SEL2_CAND && N > SEL2_CAND) {  // (small images: everything is a candidate)
+    for (int j = tid; j < nsample; j += nt) {
+      const int i = ((j >> 2) << (2 + SEL_SAMPLE_LOG)) | (j & 3);
+      s_samp[j] = (uint32_t)((c[i] & MAG) >> 31);
+    }
+    __syncthreads();
+    // sample ranks bracketing k / 16 by ~5 standard deviations of the sampling error
+    const double ks = (double)k / (double)(1 << SEL_SAMPLE_LOG);
+    const int margin = (int)(5.0 * sqrt(ks + 1.0)) + 8;
+    const int r_hi = (int)ks - margin, r_lo = (int)ks + margin + 1;
+    int kr, ce;
+    if (r_hi >= 1) v_hi = block_select_desc<uint32_t>(s_samp, nsample, r_hi, 32, s_hist, s_scan, s_pick, &kr, &ce);
+    if (r_lo <= nsample) v_lo = block_select_desc<uint32_t>(s_samp, nsample, r_lo, 32, s_hist, s_scan, s_pick, &kr, &ce);
+  }
+  if (tid == 0) s_ncand = 0;
+  __syncthreads();  // the sample is dead: its buffer now takes the candidates
+
+  // ---- B: the one full pass: count the keys above the bracket, keep the keys inside it (eight loads in flight)
+  int cnt_hi = 0;
+  for (int i0 = 0; i0 < N; i0 += 8 * nt) {
+    unsigned long long key[8];
+    bool valid[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int i = i0 + u * nt + tid;
+      valid[u] = i < N;
+      key[u] = valid[u] ? (c[i] & MAG) : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const uint32_t top = (uint32_t)(key[u] >> 31);
+      cnt_hi += valid[u] && top > v_hi;
+      const bool hit = valid[u] && top <= v_hi && top >= v_lo;
+      const unsigned bal = __ballot_sync(FULL_MASK, hit);
+      if (bal) {
+        int at = 0;
+        if (lane_id() == 0) at = atomicAdd(&s_ncand, __popc(bal));
+        at = __shfl_sync(FULL_MASK, at, 0) + __popc(bal & ((1u << lane_id()) - 1u));
+        if (hit && at < SEL2_CAND) s_cand[at] = key[u];
+      }
+    }
+  }
+  cnt_hi = block_reduce(cnt_hi, s_scan, OpSum(), 0);
+  const int nc = s_ncand;  // (block_reduce ended with a barrier)
+  if (nc > SEL2_CAND || (long long)cnt_hi >= k || (long long)cnt_hi + nc < k) {  // uniform over the block
+    if (tid == 0) need_exact[img] = 1;
+    return;
+  }
+
+  // ---- C: the (k - cnt_hi)-th largest of the candidates, exactly
+  int krem, ceq;
+  const unsigned long long tau = block_select_desc<unsigned long long>(s_cand, nc, (int)(k - cnt_hi), 63, s_hist, s_scan,
+                                                                      s_pick, &krem, &ceq);
+  if (tid == 0) {
+    if (krem == ceq) {  // every key equal to tau survives (always, for continuous data): keep key >= tau
+      ThrRec r;
+      r.tau = tau; r.active = 1; r.pad = 0;
+      rec_all[img] = r;
+    } else {
+      need_exact[img] = 1;
+    }
+  }
+}
+
+// The pending thresholds written out: coefficients below tau become zero, the records are cleared.
+__global__ void __launch_bounds__(256) k_apply_threshold(double *coefs_all, int N, ThrRec *rec_all) {
+  const int img = blockIdx.y;
+  ThrRec *rec = rec_all + img;
+  const unsigned long long tau = rec->tau;
+  const int active = rec->active;
+  unsigned long long *c = reinterpret_cast<unsigned long long *>(coefs_all + (size_t)img * N);
+  if (active)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+      if ((c[i] & 0x7fffffffffffffffull) < tau) c[i] = 0ull;
+}
+
+__global__ void k_clear_thresholds(ThrRec *rec_all, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) { rec_all[i].tau = 0ull; rec_all[i].active = 0; rec_all[i].pad = 0; }
+}
+
 // One CLUSTER of SEL_CLUSTER CTAs per image.  Each CTA owns a contiguous slice of the coefficients and, in the
 // reduction, a contiguous slice of the digit bins.  Per radix pass: local histogram of the slice -> cluster
 // sync -> every CTA sums its bin slice over the cluster's histograms (distributed shared memory) -> cluster
@@ -35,7 +194,7 @@ constexpr size_t SEL_SMEM = (size_t)SEL_CAND * 8;  // dynamic shared memory of k
 // global memory.  (Electing one lane per bin with __match_any_sync in pass 0 was measured: slower, 1.75 against
 // 1.25 ms per 512 images.)  Then one read + write pass zeroes what is below the threshold: 3 reads + 1 write per coefficient.
 __global__ void __cluster_dims__(SEL_CLUSTER, 1, 1) __launch_bounds__(SEL_THREADS)
-    k4_threshold(double *coefs_all, int N, long long k) {
+    k4_threshold(double *coefs_all, int N, long long k, const int *need_exact) {
   __shared__ int s_hist[SEL_MAXBINS];
   __shared__ int s_tot[SEL_MAXBINS / SEL_CLUSTER];
   __shared__ int s_slice, s_ties;
@@ -44,6 +203,7 @@ __global__ void __cluster_dims__(SEL_CLUSTER, 1, 1) __launch_bounds__(SEL_THREAD
   __shared__ int s_ncand, s_over;
   extern __shared__ unsigned long long s_cand[];  // SEL_CAND keys
   if (k <= 0 || k >= (long long)N) return;  // uniform over the grid: no cluster barrier is skipped by a subset
+  if (need_exact && !need_exact[blockIdx.x / SEL_CLUSTER]) return;  // k4_select settled this image (uniform over the cluster)
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, nt = blockDim.x;
