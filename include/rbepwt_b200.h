@@ -105,6 +105,29 @@ int rbepwt_decode(rbepwt_ctx *ctx, double *out_img, unsigned flags);
 int rbepwt_transcode(rbepwt_ctx *ctx, const double *img, const int32_t *labels, int B, int H, int W,
                      int levels, int path_mode, int64_t k, double *out_img, unsigned flags);
 
+/* element types of rbepwt_transcode_ex */
+#define RBEPWT_F64 0 /* pixels: float64 (what every other entry point takes) */
+#define RBEPWT_F32 1 /* pixels: float32 */
+#define RBEPWT_U8 2  /* pixels: uint8 -- what the reference's Image.read yields for grayscale files (rbepwt.py:200-206) */
+#define RBEPWT_I32 0 /* labels: int32 */
+#define RBEPWT_U16 1 /* labels: uint16 */
+
+/* rbepwt_transcode with narrow element types and the outputs a codec needs.  The same three reference calls
+ * (rbepwt.py:298, 441, 307); what changes is what crosses the boundary:
+ *   img / labels : pixels as float64, float32 or uint8, labels as int32 or uint16 -- copied as they are and widened on
+ *                  the GPU, which is exact (the reference casts to float64 itself before pywt.dwt).  A uint8 image in
+ *                  EPWT mode implies RBEPWT_U8_WRAP, as a uint8 array does in the reference (rbepwt.py:1302).
+ *   out_img      : decoded images as float64 (bit-identical to rbepwt_transcode), float32 or uint8 (rint of the
+ *                  clipped value: what the reference's commented-out line rbepwt.py:312 would store), or NULL.
+ *   psnr_out     : HOST float64 [B], psnr(img, decoded) per image (rbepwt.py:361-368), or NULL.
+ *   kept_idx/val : HOST int32 / float64 [B][k]: the k surviving coefficients of every image as (flat index ascending,
+ *                  value) -- with the label map, the compressed representation -- or both NULL.  Needs 1 <= k < H*W.
+ * With out_img and psnr_out both NULL nothing is decoded.  Leaves the same state as rbepwt_transcode.  Synchronous
+ * whenever anything is written to host memory. */
+int rbepwt_transcode_ex(rbepwt_ctx *ctx, const void *img, int img_dtype, const void *labels, int label_dtype, int B,
+                        int H, int W, int levels, int path_mode, int64_t k, void *out_img, int out_dtype,
+                        double *psnr_out, int32_t *kept_idx, double *kept_val, unsigned flags);
+
 /* Decoder-side path regeneration (full_decode): build all paths from label maps alone, then
  * decode caller-supplied coefficients (flat layout below, [B][H*W]).          rbepwt.py:106-130
  * Only for the geometric path modes (paths do not depend on pixel values). */

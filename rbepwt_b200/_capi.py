@@ -11,11 +11,13 @@ E_NOT_POW2, E_LEVELS, E_NO_ENCODING, E_NO_GPU = -2, -3, -4, -7
 PATH_EUCLID, PATH_CHEB, PATH_EPWT = 0, 1, 2
 DEVICE_PTRS, U8_WRAP, PATHS_FIRST_LEVEL, NO_CLIP = 1, 2, 4, 8
 OPT_STREAMS, OPT_SUBBATCH, OPT_PATHGROUP = 1, 2, 3
+F64, F32, U8 = 0, 1, 2   # pixel element types of rbepwt_transcode_ex
+I32, U16 = 0, 1         # label element types
 T_NAMES = ["h2d", "regions", "paths", "dwt", "select", "idwt", "d2h", "paths_big", "perm"]
 
 EXPORTS = [
     "rbepwt_create", "rbepwt_destroy", "rbepwt_last_error", "rbepwt_sync", "rbepwt_set_wavelet",
-    "rbepwt_encode", "rbepwt_threshold", "rbepwt_decode", "rbepwt_transcode", "rbepwt_set_option",
+    "rbepwt_encode", "rbepwt_threshold", "rbepwt_decode", "rbepwt_transcode", "rbepwt_transcode_ex", "rbepwt_set_option",
     "rbepwt_full_decode", "rbepwt_psnr",
     "rbepwt_nonzero_coefs", "rbepwt_get_coefs", "rbepwt_set_coefs", "rbepwt_region_count",
     "rbepwt_region_offsets", "rbepwt_region_labels", "rbepwt_get_paths", "rbepwt_get_perm",
@@ -53,6 +55,7 @@ def lib():
     L.rbepwt_threshold.argtypes = [vp, i64]
     L.rbepwt_decode.argtypes = [vp, vp, u32]
     L.rbepwt_transcode.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i64, vp, u32]
+    L.rbepwt_transcode_ex.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i64, vp, i32, vp, vp, vp, u32]
     L.rbepwt_set_option.argtypes = [vp, i32, i64]
     L.rbepwt_full_decode.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, u32]
     L.rbepwt_psnr.argtypes = [vp, vp, vp, i32, i64, vp, u32]

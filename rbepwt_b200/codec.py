@@ -208,6 +208,84 @@ class BatchCodec:
         self.shape, self.levels, self.mode = shape, int(levels), mode
         return out
 
+    def transcode_ex(self, imgs, labels, levels, wavelet, ncoefs, path_type="easypath", euclidean_distance=True,
+                     paths_first_level=False, out=None, out_dtype=None, want_image=True, want_psnr=False, want_kept=False):
+        """encode -> threshold(ncoefs) -> decode with narrow element types and the outputs a codec needs
+        (rbepwt_transcode_ex).  Pixels may be float64, float32 or uint8, labels int32 or uint16: they cross PCIe as
+        they are and are widened (exactly) on the GPU.  Returns a dict with the requested entries:
+          'image'    decoded images [B,H,W] in `out_dtype` (float64 default; float32 / uint8 are conveniences the
+                     reference does not compute) -- `out` may supply the destination,
+          'psnr'     float64 [B], psnr(input, decoded) per image,
+          'kept_idx', 'kept_val'  int32 / float64 [B, ncoefs]: the surviving coefficients, flat index ascending.
+        With want_image and want_psnr both False nothing is decoded.  Inputs / `out`: all numpy, or all CUDA
+        tensors on this codec's device."""
+        mode = path_mode(path_type, euclidean_distance)
+        dev = _is_torch_cuda(imgs)
+        pix_codes = {"float64": _capi.F64, "float32": _capi.F32, "uint8": _capi.U8}
+        lab_codes = {"int32": _capi.I32, "uint16": _capi.U16}
+
+        def tname(x):
+            return str(x.dtype).replace("torch.", "")
+
+        if dev:
+            if tname(imgs) not in pix_codes or not imgs.is_contiguous() or imgs.device.index != self.device:
+                raise ValueError("device images must be contiguous float64 / float32 / uint8 tensors on cuda:%d" % self.device)
+            if labels is not None and (not _is_torch_cuda(labels) or tname(labels) not in lab_codes
+                                       or not labels.is_contiguous() or labels.device != imgs.device):
+                raise ValueError("device labels must be contiguous int32 / uint16 CUDA tensors on the images' device")
+        else:
+            imgs = np.ascontiguousarray(imgs)
+            if tname(imgs) not in pix_codes:
+                imgs = np.ascontiguousarray(imgs, dtype=np.float64)
+            if labels is not None:
+                labels = np.ascontiguousarray(labels)
+                if tname(labels) not in lab_codes:
+                    labels = _labels_int32(labels)
+        shape = tuple(imgs.shape)
+        if len(shape) == 2:
+            shape = (1,) + shape
+        if len(shape) != 3:
+            raise ValueError("images must be [H,W] or [B,H,W]")
+        if mode == _capi.PATH_EPWT:
+            labels = None
+        elif labels is None:
+            raise ValueError("a label map is required for path_type='easypath'")
+        elif tuple(labels.shape) not in (shape, shape[1:]):
+            raise ValueError("labels must have the shape of the images")
+        B, H, W = shape
+        self.set_wavelet(wavelet)
+        res = {}
+        out_code = _capi.F64
+        if want_image:
+            odt = np.dtype(out_dtype or (tname(out) if out is not None else "float64")).name
+            if odt not in pix_codes:
+                raise ValueError("out_dtype must be float64, float32 or uint8")
+            out_code = pix_codes[odt]
+            if out is None:
+                if dev:
+                    import torch
+                    out = torch.empty(shape, dtype=getattr(torch, odt), device=imgs.device)
+                else:
+                    out = np.empty(shape, dtype=odt)
+            if _is_torch_cuda(out) != dev or tname(out) != odt or int(np.prod(tuple(out.shape))) != B * H * W:
+                raise ValueError("`out` must live where the inputs live, hold B*H*W elements and have dtype %s" % odt)
+            if not (out.is_contiguous() if dev else out.flags.c_contiguous):
+                raise ValueError("`out` must be contiguous")
+            res["image"] = out
+        if want_psnr:
+            res["psnr"] = np.empty(B, dtype=np.float64)
+        if want_kept:
+            res["kept_idx"] = np.empty((B, int(ncoefs)), dtype=np.int32)
+            res["kept_val"] = np.empty((B, int(ncoefs)), dtype=np.float64)
+        flags = (_capi.DEVICE_PTRS if dev else 0) | (_capi.PATHS_FIRST_LEVEL if paths_first_level else 0)
+        self._keep = [imgs, labels, out]
+        _capi.check(self._lib.rbepwt_transcode_ex(
+            self._ctx, _ptr(imgs), pix_codes[tname(imgs)], _ptr(labels), lab_codes[tname(labels)] if labels is not None else 0,
+            B, H, W, int(levels), mode, int(ncoefs), _ptr(res.get("image")), out_code, _ptr(res.get("psnr")),
+            _ptr(res.get("kept_idx")), _ptr(res.get("kept_val")), flags))
+        self.shape, self.levels, self.mode = shape, int(levels), mode
+        return res
+
     def threshold(self, k):
         _capi.check(self._lib.rbepwt_threshold(self._ctx, int(k)))
         return self

@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "dwt.cuh"
+#include "io.cuh"
 #include "paths.cuh"
 #include "perm.cuh"
 #include "regions.cuh"
@@ -126,6 +127,15 @@ struct rbepwt_ctx {
   const double *img_dev = nullptr;
   DevBuf labels_own, img_own, out_own, coef_up;
   DevBuf Q, Pm, posmap, coefs;
+  // element types and extra outputs of the call in progress (rbepwt_transcode_ex; everything else: f64 / i32, none)
+  struct IoSpec {
+    int img_dtype = RBEPWT_F64, lab_dtype = RBEPWT_I32, out_dtype = RBEPWT_F64;
+    bool src_on_device = false;                  // inputs to stage are device pointers (narrow types only)
+    void *out_dst = nullptr; bool out_on_device = false;  // decoded images in out_dtype (NULL: not wanted)
+    double *psnr_host = nullptr;                 // [B]
+    int32_t *kept_idx_host = nullptr; double *kept_val_host = nullptr; long long kept_k = 0;  // [B][k]
+  } io;
+  DevBuf img_stage, lab_stage, out_stage, psnr_dev, kept_idx_dev, kept_val_dev;
   DevBuf thr, need_exact;       // per image: pending threshold (select.cuh ThrRec), "k4_select gave up" flag
   bool thr_pending = false;     // some image may have a threshold recorded but not yet written into its coefficients
   DevBuf reg[8];
@@ -310,14 +320,30 @@ int ensure_slot_workspace(rbepwt_ctx *c, Slot &sl, int nb) {  // nb = 0: no valu
 
 // Input stream, path group [a, a+nb): (host mode) copy its labels in, then scan them -- label table and
 // region count per image; the counts are read back for the host's bookkeeping.
-int stage_labels(rbepwt_ctx *c, int chunk0, int a, int nb, const int32_t *lab_host, cudaEvent_t ready) {
+size_t dtype_size(int dt_img_or_out) { return dt_img_or_out == RBEPWT_F64 ? 8 : dt_img_or_out == RBEPWT_F32 ? 4 : 1; }
+size_t label_size(int dt) { return dt == RBEPWT_I32 ? 4 : 2; }
+
+int stage_labels(rbepwt_ctx *c, int chunk0, int a, int nb, const void *lab_src, cudaEvent_t ready) {
   const size_t N = c->N;
   cudaStream_t s = c->s_in;
   if (c->mode != RBEPWT_PATH_EPWT) {
-    if (lab_host) {
+    if (lab_src) {
       StageTimer t(c, RBEPWT_T_H2D, s);
-      CK(cudaMemcpyAsync(c->labels_own.as<int32_t>() + (size_t)a * N, lab_host + (size_t)a * N, (size_t)nb * N * 4,
-                         cudaMemcpyHostToDevice, s));
+      const size_t esz = label_size(c->io.lab_dtype), cnt = (size_t)nb * N;
+      const char *src = static_cast<const char *>(lab_src) + (size_t)a * N * esz;
+      int32_t *dst = c->labels_own.as<int32_t>() + (size_t)a * N;
+      if (c->io.lab_dtype == RBEPWT_I32) {
+        CK(cudaMemcpyAsync(dst, src, cnt * 4, cudaMemcpyHostToDevice, s));
+      } else {  // narrow labels: 2 bytes per pixel over PCIe, widened on the device
+        const uint16_t *dev_src = reinterpret_cast<const uint16_t *>(src);
+        if (!c->io.src_on_device) {
+          uint16_t *stage = c->lab_stage.as<uint16_t>() + (size_t)a * N;
+          CK(cudaMemcpyAsync(stage, src, cnt * esz, cudaMemcpyHostToDevice, s));
+          dev_src = stage;
+        }
+        k_widen_labels<<<(unsigned)std::min<size_t>((cnt + 1023) / 1024, 4096), 256, 0, s>>>(dev_src, dst, cnt);
+        c->launches++;
+      }
     }
     StageTimer t(c, RBEPWT_T_REGIONS, s);
     const int T = 2 * c->N;
@@ -332,12 +358,29 @@ int stage_labels(rbepwt_ctx *c, int chunk0, int a, int nb, const int32_t *lab_ho
 }
 
 // Input stream, transform sub-batch [a, a+nb): (host mode) copy its images in.
-int stage_images(rbepwt_ctx *c, int a, int nb, const double *img_host, cudaEvent_t ready) {
+int stage_images(rbepwt_ctx *c, int a, int nb, const void *img_src, cudaEvent_t ready) {
   const size_t N = c->N;
-  StageTimer t(c, RBEPWT_T_H2D, c->s_in);
-  CK(cudaMemcpyAsync(c->img_own.as<double>() + (size_t)a * N, img_host + (size_t)a * N, (size_t)nb * N * 8,
-                     cudaMemcpyHostToDevice, c->s_in));
-  CK(cudaEventRecord(ready, c->s_in));
+  cudaStream_t s = c->s_in;
+  StageTimer t(c, RBEPWT_T_H2D, s);
+  const size_t esz = dtype_size(c->io.img_dtype), cnt = (size_t)nb * N;
+  const char *src = static_cast<const char *>(img_src) + (size_t)a * N * esz;
+  double *dst = c->img_own.as<double>() + (size_t)a * N;
+  if (c->io.img_dtype == RBEPWT_F64) {
+    CK(cudaMemcpyAsync(dst, src, cnt * 8, cudaMemcpyHostToDevice, s));
+  } else {  // uint8 / float32 pixels: 1 or 4 bytes per pixel over PCIe, widened (exactly) on the device
+    const void *dev_src = src;
+    if (!c->io.src_on_device) {
+      char *stage = c->img_stage.as<char>() + (size_t)a * N * esz;
+      CK(cudaMemcpyAsync(stage, src, cnt * esz, cudaMemcpyHostToDevice, s));
+      dev_src = stage;
+    }
+    const unsigned grid = (unsigned)std::min<size_t>((cnt + 1023) / 1024, 4096);
+    if (c->io.img_dtype == RBEPWT_U8) k_widen_pixels<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(dev_src), dst, cnt);
+    else k_widen_pixels<float><<<grid, 256, 0, s>>>(static_cast<const float *>(dev_src), dst, cnt);
+    c->launches++;
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ready, s));
   return RBEPWT_OK;
 }
 
@@ -657,13 +700,15 @@ int alloc_state(rbepwt_ctx *c, int B, int H, int W, int levels, int path_mode, u
 }
 
 // The pipeline behind encode / decode / transcode.
-//   img_host, lab_host : host inputs to copy in (NULL: inputs are already on the device)
-//   out_dev            : device destination of the decoded images (DO_DECODE)
+//   img_host, lab_host : inputs to stage -- host buffers to copy in, or (c->io.src_on_device) narrow-typed device buffers
+//                        to widen; NULL: float64 / int32 inputs already on the device
+//   out_dev            : device destination of the decoded float64 images (DO_DECODE)
 //   out_host           : host destination to copy them to (NULL: none)
+//   c->io              : narrow output type, PSNR and kept-coefficient outputs (rbepwt_transcode_ex)
 // Order on the input stream: all label groups first (the path stage needs nothing else and is the long
 // pole), then the images sub-batch by sub-batch.  With RBEPWT_OPT_STREAMS = 1 every kernel runs on one
 // stream (no overlap between kernels; copies still use their own streams).
-int run_pipeline(rbepwt_ctx *c, int what, long long k, const double *img_host, const int32_t *lab_host, double *out_dev,
+int run_pipeline(rbepwt_ctx *c, int what, long long k, const void *img_host, const void *lab_host, double *out_dev,
                  double *out_host) {
   const int B = c->B, N = c->N;
   const int Bc = chunk_images(c, B, N);
@@ -735,14 +780,52 @@ int run_pipeline(rbepwt_ctx *c, int what, long long k, const double *img_host, c
           if ((rc = transform_sub(c, sl, st, a, nb))) return rc;
         if (what & DO_THRESH)
           if ((rc = threshold_sub(c, st, a, nb, k))) return rc;
+        if ((what & DO_THRESH) && c->io.kept_idx_host) {  // the kept coefficients as (flat index, value) pairs
+          const long long kk = c->io.kept_k;
+          k_kept_pairs<<<nb, 1024, 0, st>>>(c->coefs.as<double>() + (size_t)a * N, N, c->thr.as<ThrRec>() + a, kk,
+                                            c->kept_idx_dev.as<int32_t>() + (size_t)a * kk, c->kept_val_dev.as<double>() + (size_t)a * kk);
+          c->launches++;
+        }
+        bool copy_img = false;
+        const int odt = c->io.out_dtype;
         if (what & DO_DECODE) {
           if ((rc = decode_sub(c, sl, st, a, nb, out_dev))) return rc;
-          if (out_host) {
-            CK(cudaEventRecord(c->ev_done[s], st));
-            CK(cudaStreamWaitEvent(c->s_out, c->ev_done[s], 0));
-            StageTimer t(c, RBEPWT_T_D2H, c->s_out);
+          if (c->io.psnr_host) {  // PSNR of every decoded image against its input (rbepwt.py:361-368)
+            k6_psnr<<<nb, 1024, 0, st>>>(c->img_dev + (size_t)a * N, out_dev + (size_t)a * N, (long long)N, c->psnr_dev.as<double>() + a);
+            c->launches++;
+          }
+          if (c->io.out_dst && odt != RBEPWT_F64) {  // decoded images in a narrow type: converted on the device
+            const size_t esz = dtype_size(odt), cnt = (size_t)nb * N;
+            char *dev_dst = c->io.out_on_device ? static_cast<char *>(c->io.out_dst) + (size_t)a * N * esz
+                                                : c->out_stage.as<char>() + (size_t)a * N * esz;
+            const unsigned grid = (unsigned)std::min<size_t>((cnt + 1023) / 1024, 4096);
+            if (odt == RBEPWT_U8) k_narrow_pixels<uint8_t><<<grid, 256, 0, st>>>(out_dev + (size_t)a * N, reinterpret_cast<uint8_t *>(dev_dst), cnt);
+            else k_narrow_pixels<float><<<grid, 256, 0, st>>>(out_dev + (size_t)a * N, reinterpret_cast<float *>(dev_dst), cnt);
+            c->launches++;
+          }
+          copy_img = out_host || (c->io.out_dst && odt != RBEPWT_F64 && !c->io.out_on_device);
+        }
+        const bool copy_psnr = (what & DO_DECODE) && c->io.psnr_host, copy_kept = (what & DO_THRESH) && c->io.kept_idx_host;
+        if (copy_img || copy_psnr || copy_kept) {  // this sub-batch's results leave on the output stream
+          CK(cudaEventRecord(c->ev_done[s], st));
+          CK(cudaStreamWaitEvent(c->s_out, c->ev_done[s], 0));
+          StageTimer t(c, RBEPWT_T_D2H, c->s_out);
+          if (copy_img && out_host)
             CK(cudaMemcpyAsync(out_host + (size_t)a * N, out_dev + (size_t)a * N, (size_t)nb * N * 8, cudaMemcpyDeviceToHost,
                                c->s_out));
+          else if (copy_img) {
+            const size_t esz = dtype_size(odt);
+            CK(cudaMemcpyAsync(static_cast<char *>(c->io.out_dst) + (size_t)a * N * esz, c->out_stage.as<char>() + (size_t)a * N * esz,
+                               (size_t)nb * N * esz, cudaMemcpyDeviceToHost, c->s_out));
+          }
+          if (copy_psnr)
+            CK(cudaMemcpyAsync(c->io.psnr_host + a, c->psnr_dev.as<double>() + a, (size_t)nb * 8, cudaMemcpyDeviceToHost, c->s_out));
+          if (copy_kept) {
+            const long long kk = c->io.kept_k;
+            CK(cudaMemcpyAsync(c->io.kept_idx_host + (size_t)a * kk, c->kept_idx_dev.as<int32_t>() + (size_t)a * kk,
+                               (size_t)nb * kk * 4, cudaMemcpyDeviceToHost, c->s_out));
+            CK(cudaMemcpyAsync(c->io.kept_val_host + (size_t)a * kk, c->kept_val_dev.as<double>() + (size_t)a * kk,
+                               (size_t)nb * kk * 8, cudaMemcpyDeviceToHost, c->s_out));
           }
         }
       }
@@ -752,7 +835,7 @@ int run_pipeline(rbepwt_ctx *c, int what, long long k, const double *img_host, c
 }
 
 // shared front end of encode / full_decode / transcode: validate, size the state, attach the inputs
-int begin_batch(rbepwt_ctx *c, const double *img, const int32_t *labels, int B, int H, int W, int levels, int path_mode,
+int begin_batch(rbepwt_ctx *c, const void *img, const void *labels, int B, int H, int W, int levels, int path_mode,
                 unsigned flags, bool need_img) {
   int rc = validate_shape(B, H, W, levels, path_mode);
   if (rc) return rc;
@@ -761,15 +844,20 @@ int begin_batch(rbepwt_ctx *c, const double *img, const int32_t *labels, int B, 
   if (c->evs.size() > 65536) clear_events(c);  // stage events accumulate until rbepwt_get_timings reads them
   if ((rc = alloc_state(c, B, H, W, levels, path_mode, flags))) return rc;
   const size_t n = (size_t)B * c->N;
-  if (flags & RBEPWT_DEVICE_PTRS) {
-    c->labels_dev = path_mode == RBEPWT_PATH_EPWT ? nullptr : labels;
-    c->img_dev = img;
-  } else {
-    if (path_mode != RBEPWT_PATH_EPWT) { CK(c->labels_own.ensure(n * 4)); c->labels_dev = c->labels_own.as<int32_t>(); }
-    else c->labels_dev = nullptr;
-    if (need_img) { CK(c->img_own.ensure(n * 8)); c->img_dev = c->img_own.as<double>(); }
-    else c->img_dev = nullptr;
-  }
+  const bool dev = (flags & RBEPWT_DEVICE_PTRS) != 0;
+  // inputs are used where they lie only when they are device-resident AND of the kernels' own types
+  const bool own_lab = !dev || c->io.lab_dtype != RBEPWT_I32, own_img = !dev || c->io.img_dtype != RBEPWT_F64;
+  c->io.src_on_device = dev;
+  if (path_mode == RBEPWT_PATH_EPWT) c->labels_dev = nullptr;
+  else if (own_lab) {
+    CK(c->labels_own.ensure(n * 4)); c->labels_dev = c->labels_own.as<int32_t>();
+    if (!dev && c->io.lab_dtype != RBEPWT_I32) CK(c->lab_stage.ensure(n * label_size(c->io.lab_dtype)));
+  } else c->labels_dev = static_cast<const int32_t *>(labels);
+  if (!need_img) c->img_dev = nullptr;
+  else if (own_img) {
+    CK(c->img_own.ensure(n * 8)); c->img_dev = c->img_own.as<double>();
+    if (!dev && c->io.img_dtype != RBEPWT_F64) CK(c->img_stage.ensure(n * dtype_size(c->io.img_dtype)));
+  } else c->img_dev = static_cast<const double *>(img);
   return RBEPWT_OK;
 }
 
@@ -858,7 +946,7 @@ void rbepwt_destroy(rbepwt_ctx *c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   for (auto *v : {&c->ev_lab, &c->ev_path, &c->ev_img, &c->ev_done})
     for (auto e : *v) cudaEventDestroy(e);
-  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->t2_tab, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->thr, &c->need_exact, &c->img_R,
+  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->t2_tab, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->thr, &c->need_exact, &c->img_stage, &c->lab_stage, &c->out_stage, &c->psnr_dev, &c->kept_idx_dev, &c->kept_val_dev, &c->img_R,
                     &c->img_rbase, &c->img_labmin, &c->img_direct, &c->tbl, &c->slot_rid, &c->scratch_i32,
                     &c->scratch_i32b, &c->psnr_out, &c->nz_out};
   for (auto b : bufs) b->release();
@@ -933,6 +1021,7 @@ int rbepwt_encode(rbepwt_ctx *c, const double *img, const int32_t *labels, int B
                   int path_mode, unsigned flags) {
   if (!c || !img) return fail(RBEPWT_E_ARG, "ctx / img is NULL");
   DeviceGuard g(c->device);
+  c->io = rbepwt_ctx::IoSpec();
   int rc = begin_batch(c, img, labels, B, H, W, levels, path_mode, flags, true);
   if (rc) return rc;
   const bool host = !(flags & RBEPWT_DEVICE_PTRS);
@@ -956,6 +1045,7 @@ int rbepwt_decode(rbepwt_ctx *c, double *out_img, unsigned flags) {
   if (!c || !out_img) return fail(RBEPWT_E_ARG, "ctx / out is NULL");
   if (!c->has_encoding) return fail(RBEPWT_E_NO_ENCODING, "There is no saved encoding to decode");
   DeviceGuard g(c->device);
+  c->io = rbepwt_ctx::IoSpec();
   const bool host = !(flags & RBEPWT_DEVICE_PTRS);
   double *out_dev = out_img;
   if (host) {
@@ -974,6 +1064,7 @@ int rbepwt_transcode(rbepwt_ctx *c, const double *img, const int32_t *labels, in
                      int path_mode, int64_t k, double *out_img, unsigned flags) {
   if (!c || !img || !out_img) return fail(RBEPWT_E_ARG, "ctx / img / out is NULL");
   DeviceGuard g(c->device);
+  c->io = rbepwt_ctx::IoSpec();
   int rc = begin_batch(c, img, labels, B, H, W, levels, path_mode, flags, true);
   if (rc) return rc;
   const bool host = !(flags & RBEPWT_DEVICE_PTRS);
@@ -991,6 +1082,52 @@ int rbepwt_transcode(rbepwt_ctx *c, const double *img, const int32_t *labels, in
   return RBEPWT_OK;
 }
 
+int rbepwt_transcode_ex(rbepwt_ctx *c, const void *img, int img_dtype, const void *labels, int label_dtype, int B, int H,
+                        int W, int levels, int path_mode, int64_t k, void *out_img, int out_dtype, double *psnr_out,
+                        int32_t *kept_idx, double *kept_val, unsigned flags) {
+  if (!c || !img) return fail(RBEPWT_E_ARG, "ctx / img is NULL");
+  if (img_dtype != RBEPWT_F64 && img_dtype != RBEPWT_F32 && img_dtype != RBEPWT_U8) return fail(RBEPWT_E_ARG, "unknown image element type %d", img_dtype);
+  if (out_dtype != RBEPWT_F64 && out_dtype != RBEPWT_F32 && out_dtype != RBEPWT_U8) return fail(RBEPWT_E_ARG, "unknown output element type %d", out_dtype);
+  if (label_dtype != RBEPWT_I32 && label_dtype != RBEPWT_U16) return fail(RBEPWT_E_ARG, "unknown label element type %d", label_dtype);
+  if ((kept_idx == nullptr) != (kept_val == nullptr)) return fail(RBEPWT_E_ARG, "kept_idx and kept_val go together");
+  if (kept_idx && (k < 1 || k >= (int64_t)H * W)) return fail(RBEPWT_E_ARG, "the kept-coefficient output needs 1 <= k < H*W");
+  DeviceGuard g(c->device);
+  const bool host = !(flags & RBEPWT_DEVICE_PTRS);
+  c->io = rbepwt_ctx::IoSpec();
+  c->io.img_dtype = img_dtype; c->io.lab_dtype = label_dtype; c->io.out_dtype = out_dtype;
+  // a uint8 image makes the EPWT walk compare values the way numpy uint8 scalars subtract (rbepwt.py:1302)
+  if (img_dtype == RBEPWT_U8 && path_mode == RBEPWT_PATH_EPWT) flags |= RBEPWT_U8_WRAP;
+  int rc = begin_batch(c, img, labels, B, H, W, levels, path_mode, flags, true);
+  if (rc) return rc;
+  const size_t n = (size_t)B * c->N;
+  const bool want_decode = out_img != nullptr || psnr_out != nullptr;
+  double *out_dev = nullptr;
+  double *out_host = nullptr;
+  if (want_decode) {
+    if (out_img && out_dtype == RBEPWT_F64 && !host) out_dev = static_cast<double *>(out_img);
+    else { CK(c->out_own.ensure(n * 8)); out_dev = c->out_own.as<double>(); }
+    if (out_img && out_dtype == RBEPWT_F64 && host) out_host = static_cast<double *>(out_img);
+    if (out_img && out_dtype != RBEPWT_F64) {
+      c->io.out_dst = out_img; c->io.out_on_device = !host;
+      if (host) CK(c->out_stage.ensure(n * dtype_size(out_dtype)));
+    }
+  }
+  if (psnr_out) { CK(c->psnr_dev.ensure((size_t)B * 8)); c->io.psnr_host = psnr_out; }
+  if (kept_idx) {
+    CK(c->kept_idx_dev.ensure((size_t)B * k * 4)); CK(c->kept_val_dev.ensure((size_t)B * k * 8));
+    c->io.kept_idx_host = kept_idx; c->io.kept_val_host = kept_val; c->io.kept_k = k;
+  }
+  const bool stage_img = host || img_dtype != RBEPWT_F64, stage_lab = host || label_dtype != RBEPWT_I32;
+  rc = run_pipeline(c, DO_PATHS | DO_DWT | DO_THRESH | (want_decode ? DO_DECODE : 0), (long long)k, stage_img ? img : nullptr,
+                    (stage_lab && path_mode != RBEPWT_PATH_EPWT) ? labels : nullptr, out_dev, out_host);
+  c->io = rbepwt_ctx::IoSpec();
+  if (rc) return rc;
+  c->has_paths = true;
+  c->has_encoding = true;
+  if (host || psnr_out || kept_idx) return check_path_error(c);  // anything written to host memory: synchronous
+  return RBEPWT_OK;
+}
+
 int rbepwt_full_decode(rbepwt_ctx *c, const double *coefs, const int32_t *labels, int B, int H, int W, int levels,
                        int path_mode, double *out_img, unsigned flags) {
   if (!c || !coefs || !out_img) return fail(RBEPWT_E_ARG, "ctx / coefs / out is NULL");
@@ -1000,6 +1137,7 @@ int rbepwt_full_decode(rbepwt_ctx *c, const double *coefs, const int32_t *labels
     return fail(RBEPWT_E_ARG, "full_decode needs value-independent paths (EPWT paths depend on the image)");
   }
   DeviceGuard g(c->device);
+  c->io = rbepwt_ctx::IoSpec();
   int rc = begin_batch(c, nullptr, labels, B, H, W, levels, path_mode, flags, false);
   if (rc) return rc;
   const bool host = !(flags & RBEPWT_DEVICE_PTRS);

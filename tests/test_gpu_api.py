@@ -173,3 +173,79 @@ def test_level_values_views():
     # level-2 values = level-1 low-pass
     enc = c_oracle.encode(g["img"], g["labels"], 1, rbepwt.filter_bank(g["wavelet"]), c_oracle.MODE_EUCLID)
     np.testing.assert_allclose(rc[2].values, enc["coefs"][g["img"].size // 2:], rtol=0, atol=1e-10)
+
+
+def test_transcode_ex_narrow_types_and_codec_outputs():
+    """rbepwt_transcode_ex: uint8 / float32 pixels and uint16 labels give bit-identical results to the float64 / int32
+    path on the same values (widening is exact); PSNR and the kept (index, value) pairs equal what the getters of the
+    plain path report; narrow outputs are the float64 output converted; the encode-only form decodes nothing."""
+    torch = pytest.importorskip("torch")
+    import rbepwt_b200 as rb
+    from rbepwt_b200 import synth
+
+    B, n, k = 6, 64, 300
+    labs = np.stack([synth.voronoi_labels(n, n, 20 + 3 * s, seed=50 + s, shuffle_ids=False) for s in range(B)])
+    img8 = np.stack([np.round(synth.piecewise_smooth_image(l, seed=50 + i)).astype(np.uint8) for i, l in enumerate(labs)])
+    ref = rb.BatchCodec()
+    want = ref.transcode(img8.astype(np.float64), labs, 12, "bior4.4", k)
+    want_coefs = np.stack([ref.coefs(b) for b in range(B)])
+    want_psnr = ref.psnr(img8.astype(np.float64), want)
+    c = rb.BatchCodec()
+    for pix, lab in ((img8, labs.astype(np.uint16)), (img8.astype(np.float32), labs.astype(np.int32)),
+                     (img8.astype(np.float64), labs.astype(np.uint16))):
+        r = c.transcode_ex(pix, lab, 12, "bior4.4", k, want_psnr=True, want_kept=True)
+        np.testing.assert_array_equal(r["image"], want)
+        np.testing.assert_allclose(r["psnr"], want_psnr, rtol=0, atol=1e-9)
+        for b in range(B):
+            nzi = np.flatnonzero(want_coefs[b])
+            np.testing.assert_array_equal(r["kept_idx"][b], nzi)
+            np.testing.assert_array_equal(r["kept_val"][b], want_coefs[b][nzi])
+            np.testing.assert_array_equal(c.coefs(b), want_coefs[b])  # same state as the plain call
+    # narrow outputs
+    r32 = c.transcode_ex(img8, labs.astype(np.uint16), 12, "bior4.4", k, out_dtype="float32")
+    np.testing.assert_array_equal(r32["image"], want.astype(np.float32))
+    r8 = c.transcode_ex(img8, labs.astype(np.uint16), 12, "bior4.4", k, out_dtype="uint8")
+    np.testing.assert_array_equal(r8["image"], np.rint(want).astype(np.uint8))
+    # encode-only: the compact representation, nothing decoded
+    enc = c.transcode_ex(img8, labs.astype(np.uint16), 12, "bior4.4", k, want_image=False, want_kept=True)
+    assert set(enc) == {"kept_idx", "kept_val"}
+    np.testing.assert_array_equal(enc["kept_idx"], r["kept_idx"])
+    # ... from which the decoder side rebuilds the images (full_decode: labels + coefficients)
+    flat = np.zeros((B, n * n))
+    for b in range(B):
+        flat[b, enc["kept_idx"][b]] = enc["kept_val"][b]
+    np.testing.assert_array_equal(rb.BatchCodec().full_decode(flat, labs, 12, "bior4.4"), want)
+    # device pointers, narrow types in and out
+    s = torch.cuda.Stream()
+    d = rb.BatchCodec(stream=s.cuda_stream)
+    t8, t16 = torch.from_numpy(img8).cuda(), torch.from_numpy(labs.astype(np.int32)).cuda().to(torch.uint16)
+    torch.cuda.synchronize()
+    rd = d.transcode_ex(t8, t16, 12, "bior4.4", k, out_dtype="uint8", want_psnr=True)
+    d.sync()
+    np.testing.assert_array_equal(rd["image"].cpu().numpy(), np.rint(want).astype(np.uint8))
+    np.testing.assert_allclose(rd["psnr"], want_psnr, rtol=0, atol=1e-9)
+    # uint8 EPWT wraps like the reference's uint8 arrays do (rbepwt.py:1302): same as the plain path with a uint8 array
+    g = load_golden("epwt16_u8_noise_haar")
+    re = rb.BatchCodec().transcode_ex(g["img"][None], None, g["levels"], g["wavelet"], g["ncoefs"], path_type="epwt-easypath")
+    assert np.max(np.abs(re["image"][0] - g["decoded"])) <= 1e-9 * 255
+
+
+def test_box_codec_shards_by_image():
+    """BoxCodec over every visible GPU (one here is fine: two codecs on the same device exercise the same code):
+    results in batch order, identical to one BatchCodec."""
+    torch = pytest.importorskip("torch")
+    import rbepwt_b200 as rb
+    from rbepwt_b200 import synth
+
+    B, n = 7, 64
+    labs = np.stack([synth.voronoi_labels(n, n, 25, seed=80 + s) for s in range(B)])
+    imgs = np.stack([synth.piecewise_smooth_image(l, seed=80 + i) for i, l in enumerate(labs)])
+    want = rb.BatchCodec().transcode(imgs, labs, 12, "bior4.4", 200)
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0, 0]
+    box = rb.BoxCodec(devices)
+    np.testing.assert_array_equal(box.transcode(imgs, labs, 12, "bior4.4", 200), want)
+    r = box.transcode_ex(imgs.astype(np.float32).astype(np.float64), labs.astype(np.uint16), 12, "bior4.4", 200, want_psnr=True,
+                         want_kept=True)
+    assert r["image"].shape == imgs.shape and r["psnr"].shape == (B,) and r["kept_idx"].shape == (B, 200)
+    box.close()
