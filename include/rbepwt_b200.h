@@ -45,6 +45,10 @@ typedef struct rbepwt_ctx rbepwt_ctx;
 #define RBEPWT_PATH_EUCLID 0 /* path_type='easypath', euclidean_distance=True  */
 #define RBEPWT_PATH_CHEB 1   /* path_type='easypath', euclidean_distance=False */
 #define RBEPWT_PATH_EPWT 2   /* path_type='epwt-easypath' (labels ignored, one region) */
+#define RBEPWT_PATH_GRAD 3      /* path_type='gradpath', euclidean_distance=True: Region.grad_path  rbepwt.py:1190-1271 */
+#define RBEPWT_PATH_GRAD_CHEB 4 /* path_type='gradpath', euclidean_distance=False.  Complete ties of the gradient
+                                   preference depend on CPython set order in the reference (unpinned); here the first
+                                   candidate in row-major order wins.  Every region is walked by one warp. */
 
 /* flags */
 #define RBEPWT_DEVICE_PTRS 1u /* pointer arguments are device pointers */

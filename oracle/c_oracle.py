@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 _lib = None
 
-MODE_EUCLID, MODE_CHEB, MODE_EPWT = 0, 1, 2
+MODE_EUCLID, MODE_CHEB, MODE_EPWT, MODE_GRAD_EUCLID, MODE_GRAD_CHEB = 0, 1, 2, 3, 4
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
@@ -46,6 +46,8 @@ def lib():
         L.rbo_decode.restype = ctypes.c_int
         L.rbo_decode.argtypes = [_f64p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f64p,
                                  _f64p, ctypes.c_int, _i32p, _i32p, _i32p, _f64p]
+        L.rbo_grad_tie_events.restype = ctypes.c_long
+        L.rbo_grad_tie_events.argtypes = []
         L.rbo_psnr.restype = ctypes.c_double
         L.rbo_psnr.argtypes = [_f64p, _f64p, ctypes.c_int64]
         _lib = L
@@ -57,7 +59,9 @@ def path_mode(path_type, euclidean_distance):
         return MODE_EPWT
     if path_type == "easypath":
         return MODE_EUCLID if euclidean_distance else MODE_CHEB
-    raise ValueError("oracle covers path_type 'easypath' and 'epwt-easypath' only")
+    if path_type == "gradpath":
+        return MODE_GRAD_EUCLID if euclidean_distance else MODE_GRAD_CHEB
+    raise ValueError("unknown path_type %r" % (path_type,))
 
 
 def level_offset(n, lev):
@@ -91,10 +95,14 @@ def encode(img, labels, levels, wavelet, mode, u8wrap=None, paths_first_level=Fa
         raise Exception("Image size must be a power of 2")
     if rc == -2:
         raise Exception("2^levels must be smaller or equal to the number of pixels in the image")
+    if rc == -4:
+        raise ValueError("Shape of array too small to calculate a numerical gradient, at least 2 elements are required.")
     if rc:
         raise RuntimeError("rbo_encode failed: %d" % rc)
-    return dict(R=R, H=H, W=W, levels=levels, roff=roff, inc_pix=inc_pix, path_pix=path_pix,
-                perm=perm, coefs=coefs)
+    out = dict(R=R, H=H, W=W, levels=levels, roff=roff, inc_pix=inc_pix, path_pix=path_pix, perm=perm, coefs=coefs)
+    if mode in (MODE_GRAD_EUCLID, MODE_GRAD_CHEB):
+        out["grad_tie_events"] = int(L.rbo_grad_tie_events())  # complete ties: the reference's answer is unpinned there
+    return out
 
 
 def threshold(coefs, k):

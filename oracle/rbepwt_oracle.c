@@ -37,6 +37,8 @@
 #define RBO_MODE_EUCLID 0 /* path_type='easypath', euclidean_distance=True  (rbepwt.py:1304) */
 #define RBO_MODE_CHEB 1   /* path_type='easypath', euclidean_distance=False (rbepwt.py:1306) */
 #define RBO_MODE_EPWT 2   /* path_type='epwt-easypath'                      (rbepwt.py:1302) */
+#define RBO_MODE_GRAD_EUCLID 3 /* path_type='gradpath', euclidean_distance=True  (rbepwt.py:1190-1271) */
+#define RBO_MODE_GRAD_CHEB 4   /* path_type='gradpath', euclidean_distance=False */
 
 /* ------------------------------------------------------------------ label dict ---- */
 
@@ -196,6 +198,109 @@ static void easy_path(path_ctx *c, int r, const int32_t *pix, int n, int mode, i
   }
 }
 
+/* ------------------------------------------------------------------ grad path ----- */
+
+/* Region.grad_path (rbepwt.py:1190-1271).  Same probes as easy_path; among the candidates of the first non-empty
+ * probe the smallest distance wins (euclid: np.linalg.norm of the integer offset, i.e. d2 compares; chebyshev), and
+ * equal distances are settled by the region's average gradient direction: with perp = rotate(avg_gradient, -pi/2)
+ * and v = offset / ||offset||, the larger |np.dot(v, perp)| wins, then the larger |np.dot(v, rotate(perp, -pi/2))|
+ * (rbepwt.py:1231-1247).  The sign flips of perp (1256-1259) cannot change a choice: only absolute values are compared.
+ * A COMPLETE tie (both absolute dot products bit-identical: always for two opposite offsets v and -v) keeps whichever
+ * candidate the reference's `for candidate in candidate_points` met first, i.e. CPython set order: unpinned.  Rule
+ * here: the first in row-major order wins; such events are counted so that fixtures can be chosen without any.
+ * np.dot of two 2-vectors is fma(x1, y1, x0*y0) (OpenBLAS ddot tail; checked against numpy in this container). */
+static long g_grad_tie_events = 0;
+long rbo_grad_tie_events(void) { return g_grad_tie_events; }
+
+static void rotate_mhalfpi(const double v[2], double out[2]) { /* rbepwt.py:78-82 with theta = -pi/2 */
+  const double c = 6.123233995736766e-17, s = -1.0; /* np.cos(-np.pi/2), np.sin(-np.pi/2) */
+  out[0] = fma(-s, v[1], c * v[0]);
+  out[1] = fma(c, v[1], s * v[0]);
+}
+
+static void grad_path(path_ctx *c, int r, const int32_t *pix, int n, int cheb, const double avg_grad[2],
+                      int32_t *perm, int32_t *path_pix) {
+  if (n == 0) return;
+  if (n == 1) { perm[0] = 0; path_pix[0] = pix[0]; return; }
+  const int W = c->W, H = c->H;
+  int start = 0, rmin = H, rmax = -1, cmin = W, cmax = -1;
+  for (int i = 0; i < n; i++) {
+    c->owner[pix[i]] = r;
+    c->idxmap[pix[i]] = i;
+    if (pix[i] < pix[start]) start = i;
+    int rr = pix[i] / W, cc = pix[i] % W;
+    if (rr < rmin) rmin = rr;
+    if (rr > rmax) rmax = rr;
+    if (cc < cmin) cmin = cc;
+    if (cc > cmax) cmax = cc;
+  }
+  int ci = pix[start] / W, cj = pix[start] % W;
+  c->owner[pix[start]] = -1;
+  perm[0] = start;
+  path_pix[0] = pix[start];
+  double perp[2], tmp[2];
+  rotate_mhalfpi(avg_grad, perp); /* rbepwt.py:1207 */
+  rotate_mhalfpi(perp, tmp);      /* rbepwt.py:1243 */
+  for (int t = 1; t < n; t++) {
+    int found = 0, bi = 0, bj = 0;
+    long bdist = 0;
+    double bA = 0.0, bB = 0.0;
+    for (int rad = 1; !found; rad <<= 1) {
+      int i0 = ci - rad < rmin ? rmin : ci - rad, i1 = ci + rad > rmax ? rmax : ci + rad;
+      int j0 = cj - rad < cmin ? cmin : cj - rad, j1 = cj + rad > cmax ? cmax : cj + rad;
+      for (int i = i0; i <= i1; i++)
+        for (int j = j0; j <= j1; j++) {
+          if (c->owner[i * W + j] != r) continue;
+          long di = i - ci, dj = j - cj, d2 = di * di + dj * dj;
+          long a = di < 0 ? -di : di, b = dj < 0 ? -dj : dj;
+          long dist = cheb ? (a > b ? a : b) : d2;
+          if (found && dist > bdist) continue;
+          double nrm = sqrt((double)d2);
+          double v0 = (double)di / nrm, v1 = (double)dj / nrm;
+          double A = fabs(fma(v1, perp[1], v0 * perp[0])), B = fabs(fma(v1, tmp[1], v0 * tmp[0]));
+          int better;
+          if (!found || dist < bdist) better = 1;
+          else if (A > bA) better = 1;
+          else if (A == bA && B > bB) better = 1;
+          else {
+            better = 0;
+            if (!(A < bA) && !(A == bA && B < bB)) g_grad_tie_events++; /* complete tie (or NaN direction): unpinned */
+          }
+          if (better) { found = 1; bi = i; bj = j; bdist = dist; bA = A; bB = B; }
+        }
+    }
+    int pid = bi * W + bj;
+    c->owner[pid] = -1;
+    perm[t] = c->idxmap[pid];
+    path_pix[t] = pid;
+    ci = bi; cj = bj;
+  }
+}
+
+/* Region.compute_avg_gradient (rbepwt.py:1102-1113) over np.gradient(img) (2010-2013): sums in the region's level-1
+ * point order (row-major), divided by the count, normalised by np.linalg.norm = sqrt(fma(g1, g1, g0*g0)). */
+static void region_avg_gradients(const double *img, int H, int W, const int32_t *inc_pix, const int32_t *off, int R,
+                                 double *avg /* [R][2] */) {
+  for (int r = 0; r < R; r++) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int q = off[r]; q < off[r + 1]; q++) {
+      int i = inc_pix[q] / W, j = inc_pix[q] % W;
+      double g0, g1;
+      if (i == 0) g0 = img[W + j] - img[j];
+      else if (i == H - 1) g0 = img[i * W + j] - img[(i - 1) * W + j];
+      else g0 = (img[(i + 1) * W + j] - img[(i - 1) * W + j]) / 2.0;
+      if (j == 0) g1 = img[i * W + 1] - img[i * W];
+      else if (j == W - 1) g1 = img[i * W + j] - img[i * W + j - 1];
+      else g1 = (img[i * W + j + 1] - img[i * W + j - 1]) / 2.0;
+      s0 += g0; s1 += g1;
+    }
+    const double np_ = (double)(off[r + 1] - off[r]);
+    s0 /= np_; s1 /= np_;
+    const double nrm = sqrt(fma(s1, s1, s0 * s0));
+    avg[2 * r] = s0 / nrm; avg[2 * r + 1] = s1 / nrm;
+  }
+}
+
 /* ------------------------------------------------------------------ encode -------- */
 
 static long level_len(long n, int lev) { return n >> (lev - 1); } /* lev = 1.. */
@@ -254,6 +359,13 @@ int rbo_encode(const double *img, const int32_t *labels, int H, int W, int level
   double *ca = (double *)malloc(sizeof(double) * N);
   for (int i = 0; i < N; i++) val[i] = img[inc_pix[i]];
 
+  double *avg_grad = NULL;
+  if (mode == RBO_MODE_GRAD_EUCLID || mode == RBO_MODE_GRAD_CHEB) {
+    if (H < 2 || W < 2) { free(c.owner); free(c.idxmap); free(valmap); free(val); free(sig); free(ca); return -4; } /* np.gradient needs 2 samples */
+    avg_grad = (double *)malloc(sizeof(double) * 2 * R);
+    region_avg_gradients(img, H, W, inc_pix, roff, R, avg_grad);
+    g_grad_tie_events = 0;
+  }
   long coef_off = 0;
   for (int lev = 1; lev <= levels; lev++) {
     const long nl = level_len(N, lev), lo = rbo_level_offset(N, lev);
@@ -267,6 +379,8 @@ int rbo_encode(const double *img, const int32_t *labels, int H, int W, int level
       int a = cur_off[r], n = cur_off[r + 1] - a;
       if (lev > 1 && paths_first_level) { /* Region.same_path: identity permutation (rbepwt.py:1183-1188, 2024-2025) */
         for (int t = 0; t < n; t++) { pm[a + t] = t; ppix[a + t] = ipix[a + t]; }
+      } else if (avg_grad) {
+        grad_path(&c, r, ipix + a, n, mode == RBO_MODE_GRAD_CHEB, avg_grad + 2 * r, pm + a, ppix + a);
       } else {
         easy_path(&c, r, ipix + a, n, mode, u8wrap && lev == 1, pm + a, ppix + a);
       }
@@ -283,7 +397,7 @@ int rbo_encode(const double *img, const int32_t *labels, int H, int W, int level
     }
   }
   memcpy(coefs + coef_off, val, sizeof(double) * level_len(N, levels + 1));
-  free(c.owner); free(c.idxmap); free(valmap); free(val); free(sig); free(ca);
+  free(c.owner); free(c.idxmap); free(valmap); free(val); free(sig); free(ca); free(avg_grad);
   return 0;
 }
 

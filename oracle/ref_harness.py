@@ -105,8 +105,35 @@ def make_image(img, labels=None):
     return im
 
 
+class RowMajorSet(set):
+    """A set that iterates in sorted order.  Region.grad_path resolves complete ties of its gradient preference by
+    the iteration order of a Python set of (row, col) tuples (rbepwt.py:1224), which depends on the interpreter's
+    hash-table internals: unpinned.  Binding the name `set` in the reference module's namespace to this class (the
+    source file is not touched) makes the reference's own code iterate its candidates in row-major order, the tie
+    rule the CUDA path and the C port follow; every other step of grad_path is order-independent."""
+
+    def intersection(self, *others):
+        return RowMajorSet(set.intersection(self, *others))
+
+    def __iter__(self):
+        return iter(sorted(set.__iter__(self)))
+
+
 def run_reference(img, labels, levels, wavelet, path_type="easypath",
                   euclidean_distance=True, ncoefs=None, paths_first_level=False):
+    """Reference run; path_type='gradpath' runs with the set iteration order pinned (RowMajorSet)."""
+    ref = load_reference()
+    if path_type != "gradpath":
+        return _run_reference(img, labels, levels, wavelet, path_type, euclidean_distance, ncoefs, paths_first_level)
+    ref.set = RowMajorSet
+    try:
+        return _run_reference(img, labels, levels, wavelet, path_type, euclidean_distance, ncoefs, paths_first_level)
+    finally:
+        del ref.set
+
+
+def _run_reference(img, labels, levels, wavelet, path_type="easypath",
+                   euclidean_distance=True, ncoefs=None, paths_first_level=False):
     """Encode (+ threshold + decode) with the reference; returns a dict of plain
     numpy arrays in the flat layout of SURVEY.md section 8a:
 

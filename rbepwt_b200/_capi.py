@@ -8,7 +8,7 @@ from . import build as _build
 _lib = None
 
 E_NOT_POW2, E_LEVELS, E_NO_ENCODING, E_NO_GPU = -2, -3, -4, -7
-PATH_EUCLID, PATH_CHEB, PATH_EPWT = 0, 1, 2
+PATH_EUCLID, PATH_CHEB, PATH_EPWT, PATH_GRAD, PATH_GRAD_CHEB = 0, 1, 2, 3, 4
 DEVICE_PTRS, U8_WRAP, PATHS_FIRST_LEVEL, NO_CLIP = 1, 2, 4, 8
 OPT_STREAMS, OPT_SUBBATCH, OPT_PATHGROUP = 1, 2, 3
 F64, F32, U8 = 0, 1, 2   # pixel element types of rbepwt_transcode_ex

@@ -22,9 +22,9 @@ def path_mode(path_type, euclidean_distance=True):
     if path_type == "easypath":
         return PATH_MODES[("easypath", bool(euclidean_distance))]
     if path_type == "gradpath":
-        raise NotImplementedError(
-            "path_type='gradpath' is outside the B200 hot path: its exact abs-dot ties are resolved by "
-            "CPython set iteration order in the reference and cannot be reproduced bit-exactly")
+        # Region.grad_path (rbepwt.py:1190-1271).  Complete ties of its gradient preference (two opposite offsets, always)
+        # are resolved by CPython set iteration order in the reference -- unpinned; here: first in row-major order.
+        return _capi.PATH_GRAD if euclidean_distance else _capi.PATH_GRAD_CHEB
     raise ValueError("unknown path_type %r" % (path_type,))
 
 

@@ -44,9 +44,12 @@
 namespace rbepwt {
 
 constexpr int MODE_EUCLID = 0, MODE_CHEB = 1, MODE_EPWT = 2;
+constexpr int MODE_GRAD_EUCLID = 3, MODE_GRAD_CHEB = 4;  // path_type='gradpath' (Region.grad_path, rbepwt.py:1190-1271)
+__host__ __device__ constexpr bool mode_is_grad(int mode) { return mode == MODE_GRAD_EUCLID || mode == MODE_GRAD_CHEB; }
 
 struct PathParams {
   const int32_t *labels;  // [B][N]
+  const double *img;      // [B][N] pixel values: gradpath only (the regions' average gradients)
   int H, W, logW, N, levels;
   RegionArrays reg;
   const int32_t *queue;
@@ -331,13 +334,135 @@ __device__ __forceinline__ bool find_next_geo(const uint32_t *bm, int h, int w, 
   return true;
 }
 
+// ---- gradpath (Region.grad_path, rbepwt.py:1190-1271) ------------------------------------------------------
+// Same probes as the easy path; among the candidates of the first non-empty probe the smallest distance wins
+// (euclid: d2; chebyshev), equal distances are settled by the region's average gradient: with
+// perp = rotate(avg_gradient, -pi/2), tmp = rotate(perp, -pi/2) and v = offset / ||offset||, the larger
+// A = |np.dot(v, perp)| wins, then the larger B = |np.dot(v, tmp)| (1231-1247; np.dot of 2-vectors =
+// fma(x1, y1, x0 * y0)).  The reference flips the sign of perp as it goes (1256-1259), which cannot change a
+// choice: only absolute values are compared.  A complete tie (A and B bit-identical -- always for two opposite
+// offsets -- or a NaN direction from a zero gradient) keeps whichever candidate the reference's loop over a Python
+// set met first: unpinned.  Rule here (and in the fixtures, produced by the reference with its set iteration pinned
+// to sorted order): the first candidate in row-major order.
+struct GradDir { double perp0, perp1, tmp0, tmp1; };
+
+struct GradCand {
+  int dist, i, j;  // dist < 0: none
+  double A, B;
+};
+
+// is `c` preferred to `b`?  (total order: dist asc, A desc, B desc, (i, j) asc; NaN compares as a tie)
+__device__ __forceinline__ bool grad_better(const GradCand &c, const GradCand &b) {
+  if (c.dist < 0) return false;
+  if (b.dist < 0) return true;
+  if (c.dist != b.dist) return c.dist < b.dist;
+  if (c.A > b.A) return true;
+  if (c.A < b.A) return false;
+  if (c.A == b.A) {
+    if (c.B > b.B) return true;
+    if (c.B < b.B) return false;
+  }
+  return c.i != b.i ? c.i < b.i : c.j < b.j;
+}
+
+template <bool CHEB>
+__device__ __forceinline__ bool find_next_grad(const uint32_t *bm, int h, int w, int ws, int ci, int cj, const GradDir &G,
+                                               int &bi, int &bj) {
+  const int lane = (int)lane_id();
+  GradCand b;
+  b.dist = -1; b.i = b.j = 0; b.A = b.B = 0.0;
+  for (int rad = 1;; rad <<= 1) {  // half-width 2^(k-1), k = 1,2,...   rbepwt.py:1218-1222
+    const int i0 = max(ci - rad, 0), i1 = min(ci + rad, h - 1);
+    const int j0 = max(cj - rad, 0), j1 = min(cj + rad, w - 1);
+    const int w0 = j0 >> 5, w1 = j1 >> 5;
+    for (int i = i0 + lane; i <= i1; i += 32)
+      for (int wd = w0; wd <= w1; wd++) {
+        uint32_t bits = bm[i * ws + wd];
+        const int lo = wd << 5;
+        if (lo < j0) bits &= 0xffffffffu << (j0 - lo);
+        if (lo + 31 > j1) bits &= 0xffffffffu >> (lo + 31 - j1);
+        while (bits) {
+          const int j = lo + __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int di = i - ci, dj = j - cj, d2 = di * di + dj * dj;
+          GradCand c;
+          c.dist = CHEB ? max(abs(di), abs(dj)) : d2;
+          c.i = i; c.j = j;
+          if (b.dist >= 0 && c.dist > b.dist) continue;
+          const double nrm = sqrt((double)d2);
+          const double v0 = (double)di / nrm, v1 = (double)dj / nrm;
+          c.A = fabs(fma(v1, G.perp1, rb_dmul(v0, G.perp0)));
+          c.B = fabs(fma(v1, G.tmp1, rb_dmul(v0, G.tmp0)));
+          if (grad_better(c, b)) b = c;
+        }
+      }
+    if (__any_sync(FULL_MASK, b.dist >= 0)) break;
+    if (i0 == 0 && j0 == 0 && i1 == h - 1 && j1 == w - 1) return false;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    GradCand o;
+    o.dist = __shfl_xor_sync(FULL_MASK, b.dist, d);
+    o.i = __shfl_xor_sync(FULL_MASK, b.i, d);
+    o.j = __shfl_xor_sync(FULL_MASK, b.j, d);
+    o.A = __shfl_xor_sync(FULL_MASK, b.A, d);
+    o.B = __shfl_xor_sync(FULL_MASK, b.B, d);
+    if (grad_better(o, b)) b = o;
+  }
+  bi = b.i; bj = b.j;  // identical in every lane: the order is total
+  return true;
+}
+
+// rotate(v, -pi/2) as the reference computes it (rbepwt.py:78-82): np.dot of [[c, -s], [s, c]] with v
+__device__ __forceinline__ void rotate_mhalfpi(double v0, double v1, double &o0, double &o1) {
+  const double c = 6.123233995736766e-17, s = -1.0;  // np.cos(-np.pi/2), np.sin(-np.pi/2)
+  o0 = fma(-s, v1, rb_dmul(c, v0));
+  o1 = fma(c, v1, rb_dmul(s, v0));
+}
+
+// Region.compute_avg_gradient (rbepwt.py:1102-1113) over np.gradient(img) (2010-2013) for the region whose level-1
+// bitmap is in `bm`: the sums run over the region's points in their level-1 order (row-major), so ONE lane adds them
+// up, in that order -- fp64 addition is not associative and the direction must come out bit for bit.
+__device__ __forceinline__ GradDir region_grad_dir(const double *__restrict__ img, int H, int W, const uint32_t *bm, int h, int w,
+                                                   int ws, int r0, int c0, int npoints) {
+  double s0 = 0.0, s1 = 0.0;
+  if (lane_id() == 0) {
+    for (int bi = 0; bi < h; bi++)
+      for (int wd = 0; wd < ws; wd++) {
+        uint32_t bits = bm[bi * ws + wd];
+        while (bits) {
+          const int bj = (wd << 5) + __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int i = r0 + bi, j = c0 + bj;
+          const double *p = img + (size_t)i * W + j;
+          double g0, g1;  // np.gradient: central differences inside, one-sided at the border
+          if (i == 0) g0 = __dsub_rn(p[W], p[0]);
+          else if (i == H - 1) g0 = __dsub_rn(p[0], p[-W]);
+          else g0 = __ddiv_rn(__dsub_rn(p[W], p[-W]), 2.0);
+          if (j == 0) g1 = __dsub_rn(p[1], p[0]);
+          else if (j == W - 1) g1 = __dsub_rn(p[0], p[-1]);
+          else g1 = __ddiv_rn(__dsub_rn(p[1], p[-1]), 2.0);
+          s0 = __dadd_rn(s0, g0); s1 = __dadd_rn(s1, g1);
+        }
+      }
+    s0 = __ddiv_rn(s0, (double)npoints); s1 = __ddiv_rn(s1, (double)npoints);
+    const double nrm = sqrt(fma(s1, s1, rb_dmul(s0, s0)));  // np.linalg.norm
+    s0 = __ddiv_rn(s0, nrm); s1 = __ddiv_rn(s1, nrm);
+  }
+  s0 = __shfl_sync(FULL_MASK, s0, 0); s1 = __shfl_sync(FULL_MASK, s1, 0);
+  GradDir G;
+  rotate_mhalfpi(s0, s1, G.perp0, G.perp1);
+  rotate_mhalfpi(G.perp0, G.perp1, G.tmp0, G.tmp1);
+  return G;
+}
+
 // Walk one region's path at one level.  (ci,cj) = start point (bitmap coordinates, bit still set).
 // Ql[t], t = 0..n-1, receives the pixel ids in path order.  The bitmap is all-zero afterwards.
 template <int MODE>
 __device__ __forceinline__ bool run_path(uint32_t *bm, int h, int w, int ws, int ci, int cj, int n, int r0, int c0,
                                          int logW, const double *__restrict__ vals, bool u8wrap,
                                          int32_t *__restrict__ Ql, int32_t *__restrict__ Pl, const int32_t *posmap,
-                                         const uint8_t *lut = nullptr) {
+                                         const uint8_t *lut = nullptr, const GradDir *grad = nullptr) {
   const int lane = (int)lane_id();
   const bool geo = MODE == MODE_EUCLID && h <= COOP_MAX_SIDE && w <= COOP_MAX_SIDE;
   int rad = 1;
@@ -354,6 +479,8 @@ __device__ __forceinline__ bool run_path(uint32_t *bm, int h, int w, int ws, int
     int bi, bj;
     if (geo) {
       if (!find_next_geo(bm, h, w, ws, ci, cj, p0, p1, rad, lut, bi, bj)) return false;
+    } else if (mode_is_grad(MODE)) {
+      if (!find_next_grad<MODE == MODE_GRAD_CHEB>(bm, h, w, ws, ci, cj, *grad, bi, bj)) return false;
     } else if (!find_next<MODE>(bm, h, w, ws, ci, cj, p0, p1, vals, r0, c0, logW, u8wrap, curval, bi, bj)) {
       return false;
     }
@@ -428,11 +555,13 @@ __device__ void region_pyramid(const PathParams &P, int g, uint32_t *bm, const u
     }
   }
   __syncwarp();
+  GradDir G = {0.0, 0.0, 0.0, 0.0};
+  if (mode_is_grad(MODE)) G = region_grad_dir(P.img + (size_t)img * N, P.H, W, bm, h, w, ws, r0, c0, n);
   int si = 0, sj = (first & (W - 1)) - c0;
   for (int lev = 1; lev <= P.levels && n > 0; lev++) {
     int32_t *Ql = Q + level_off((size_t)N, lev) + a;
     // paths only: the positions in the incoming order (Pm) of every region are computed by k2_perm (walk.cuh)
-    if (!run_path<MODE>(bm, h, w, ws, si, sj, n, r0, c0, logW, nullptr, false, Ql, nullptr, nullptr, lut)) {
+    if (!run_path<MODE>(bm, h, w, ws, si, sj, n, r0, c0, logW, nullptr, false, Ql, nullptr, nullptr, lut, &G)) {
       if (lane == 0) atomicExch(&P.qmeta[QM_ERR], 1);
       return;
     }

@@ -287,7 +287,9 @@ int validate_shape(int B, int H, int W, int levels, int path_mode) {
   if (n > (1ll << 29) || W > 32768 || H > 32768) return fail(RBEPWT_E_ARG, "image too large (H*W <= 2^29, sides <= 32768)");
   if (levels < 1 || levels > 30 || (1ll << levels) > n)
     return fail(RBEPWT_E_LEVELS, "2^levels must be smaller or equal to the number of pixels in the image");
-  if (path_mode < 0 || path_mode > 2) return fail(RBEPWT_E_ARG, "unknown path mode %d", path_mode);
+  if (path_mode < 0 || path_mode > RBEPWT_PATH_GRAD_CHEB) return fail(RBEPWT_E_ARG, "unknown path mode %d", path_mode);
+  if ((path_mode == RBEPWT_PATH_GRAD || path_mode == RBEPWT_PATH_GRAD_CHEB) && (H < 2 || W < 2))
+    return fail(RBEPWT_E_ARG, "Shape of array too small to calculate a numerical gradient, at least 2 elements are required.");
   return RBEPWT_OK;
 }
 
@@ -435,7 +437,8 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
                                          c->img_rbase.as<int32_t>(), c->regs());
     const int qb = std::max(1, std::min((nreg + 255) / 256, c->sm_count * 8));
     // few regions in flight (single images, small batches): every region gets its own warp -- latency, not throughput
-    coop_min = (c->mode == RBEPWT_PATH_EUCLID && nreg <= TPR_COOP_ALL_BELOW) ? 1 : TPR_COOP_MIN;
+    const bool grad = c->mode == RBEPWT_PATH_GRAD || c->mode == RBEPWT_PATH_GRAD_CHEB;  // gradpath: always warp per region
+    coop_min = (grad || (c->mode == RBEPWT_PATH_EUCLID && nreg <= TPR_COOP_ALL_BELOW)) ? 1 : TPR_COOP_MIN;
     kq_hist<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, coop_min, sl.qhist.as<int>());
     kq_scan<<<1, 32, 0, s>>>(sl.qhist.as<int>(), sl.qmeta.as<int>(), sl.qbins.as<int>(), nreg);
     kq_scatter<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, coop_min, sl.qmeta.as<int>(), sl.queue.as<int32_t>());
@@ -445,6 +448,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   }
   PathParams P;
   P.labels = c->labels_dev;
+  P.img = c->img_dev;
   P.H = c->H; P.W = c->W; P.logW = c->logW; P.N = N;
   P.levels = (c->enc_flags & RBEPWT_PATHS_FIRST_LEVEL) ? 1 : c->levels;
   P.reg = c->regs();
@@ -473,6 +477,21 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     P.gscratch = sl.gscratch.as<uint32_t>();
     P.gscratch_words = img_words;
   }
+  const bool grad_mode = c->mode == RBEPWT_PATH_GRAD || c->mode == RBEPWT_PATH_GRAD_CHEB;
+  if (grad_mode) {
+    // gradpath: regions whose bitmap exceeds a shared-memory arena in k1_paths_big, all the others one warp each
+    StageTimer t(c, RBEPWT_T_PATHS, s);
+    if (c->mode == RBEPWT_PATH_GRAD) {
+      CK(cudaFuncSetAttribute(k1_paths_big<MODE_GRAD_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      k1_paths_big<MODE_GRAD_EUCLID><<<big_ctas, 32, smem_bytes, s>>>(P);
+      k1_coop_all<MODE_GRAD_EUCLID><<<c->sm_count * 4, WK_WIDE_WARPS * 32, 0, s>>>(P);
+    } else {
+      CK(cudaFuncSetAttribute(k1_paths_big<MODE_GRAD_CHEB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      k1_paths_big<MODE_GRAD_CHEB><<<big_ctas, 32, smem_bytes, s>>>(P);
+      k1_coop_all<MODE_GRAD_CHEB><<<c->sm_count * 4, WK_WIDE_WARPS * 32, 0, s>>>(P);
+    }
+    c->launches += 2;
+  } else {
   int tpr_per_sm = 1;  // grid = TPR_WAVES waves of resident CTAs
   if (c->mode == RBEPWT_PATH_EUCLID)
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_walk<MODE_EUCLID, false>, WK_WARPS * 32, wk_arena_bytes(false)));
@@ -510,6 +529,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     CK(cudaStreamWaitEvent(s, sl.ev_b, 0));
     c->launches += 2;
   }
+  }
   {
     StageTimer t(c, RBEPWT_T_PERM, s);
     if ((c->enc_flags & RBEPWT_PATHS_FIRST_LEVEL) && c->levels > 1) {  // identity permutations at the levels >= 2
@@ -518,7 +538,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
       c->launches++;
     } else if (c->levels > 1) {  // positions in the incoming order of every level >= 2, from the paths
       const int grid = std::max(1, std::min((nreg + K2_WARPS - 1) / K2_WARPS, c->sm_count * 16));
-      k2_perm<<<grid, K2_WARPS * 32, 0, s>>>(P, nreg, c->mode == RBEPWT_PATH_EUCLID ? 1 : 0);
+      k2_perm<<<grid, K2_WARPS * 32, 0, s>>>(P, nreg, (c->mode == RBEPWT_PATH_EUCLID || grad_mode) ? 1 : 0);
       c->launches++;
     }
   }
@@ -766,6 +786,8 @@ int run_pipeline(rbepwt_ctx *c, int what, long long k, const void *img_host, con
       for (int g = 0; g < ngrp; g++) {
         Slot &sl = c->slot[g % c->nslot];
         cudaStream_t st = serial ? c->slot[0].s : sl.s;
+        if ((c->mode == RBEPWT_PATH_GRAD || c->mode == RBEPWT_PATH_GRAD_CHEB) && (what & DO_DWT) && img_host)
+          for (int sb = gstart[g]; sb < gstart[g + 1]; sb++) CK(cudaStreamWaitEvent(st, c->ev_img[sb], 0));  // gradpath reads pixel values
         if ((rc = build_regions_and_paths(c, sl, st, c0, grp_a(g), grp_nb(g), c->ev_lab[g]))) return rc;
         CK(cudaEventRecord(c->ev_path[g], st));
       }
@@ -1131,10 +1153,10 @@ int rbepwt_transcode_ex(rbepwt_ctx *c, const void *img, int img_dtype, const voi
 int rbepwt_full_decode(rbepwt_ctx *c, const double *coefs, const int32_t *labels, int B, int H, int W, int levels,
                        int path_mode, double *out_img, unsigned flags) {
   if (!c || !coefs || !out_img) return fail(RBEPWT_E_ARG, "ctx / coefs / out is NULL");
-  if (path_mode == RBEPWT_PATH_EPWT) {
+  if (path_mode == RBEPWT_PATH_EPWT || path_mode == RBEPWT_PATH_GRAD || path_mode == RBEPWT_PATH_GRAD_CHEB) {
     int rc = validate_shape(B, H, W, levels, path_mode);
     if (rc) return rc;
-    return fail(RBEPWT_E_ARG, "full_decode needs value-independent paths (EPWT paths depend on the image)");
+    return fail(RBEPWT_E_ARG, "full_decode needs value-independent paths (EPWT and gradpath paths depend on the image)");
   }
   DeviceGuard g(c->device);
   c->io = rbepwt_ctx::IoSpec();

@@ -868,6 +868,23 @@ __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WID
   }
 }
 
+// gradpath: every region of a group is walked by a whole warp (paths.cuh, region_pyramid / find_next_grad) -- the path
+// type exists for parity with the reference, not for throughput.  The queue then holds one-region chunks only.
+template <int MODE>
+__global__ void __launch_bounds__(WK_WIDE_WARPS * 32) k1_coop_all(PathParams P) {
+  __shared__ __align__(16) uint32_t s_arena[WK_WIDE_WARPS * TPR_ARENA_WORDS];
+  const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
+  const int nchunks = P.qmeta[QM_NCHUNKS];
+  while (true) {
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(&P.qmeta[QM_CUR_WIDE], 1);
+    chunk = __shfl_sync(FULL_MASK, chunk, 0);
+    if (chunk >= nchunks) break;
+    region_pyramid<MODE>(P, P.queue[P.chunk_start[chunk]], s_arena + warp * TPR_ARENA_WORDS, nullptr);
+    __syncwarp();
+  }
+}
+
 // Big regions: one warp per CTA, bitmap in dynamic shared memory if it fits, else global scratch.
 template <int MODE>
 __global__ void __launch_bounds__(32) k1_paths_big(PathParams P) {
@@ -914,7 +931,7 @@ __device__ __forceinline__ void k2_load(const int32_t *Ql, int n, int lane, int 
   }
 }
 
-__global__ void __launch_bounds__(K2_WARPS * 32) k2_perm(PathParams P, int nreg, int euclid) {
+__global__ void __launch_bounds__(K2_WARPS * 32) k2_perm(PathParams P, int nreg, int coop) {
   __shared__ uint16_t s_pos[K2_WARPS][K2_CELLS];
   const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
   const int nw = gridDim.x * K2_WARPS;
@@ -926,7 +943,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_perm(PathParams P, int nreg,
     const int hb = P.reg.rmax[g] - r0 + 1, wb = P.reg.cmax[g] - c0 + 1;
     const bool in_smem = hb * wb <= K2_CELLS && n1 < 65536;
     // levels of at most `skip_below` points were done by the walker (never level 1); 0 = this region was walked by a warp
-    const bool by_warp = region_class_words(P.reg, g, logW) > TPR_ARENA_WORDS || (euclid && n1 >= P.coop_min);
+    // (coop: the path mode hands regions of at least coop_min pixels to the whole-warp walker)
+    const bool by_warp = region_class_words(P.reg, g, logW) > TPR_ARENA_WORDS || (coop && n1 >= P.coop_min);
     const int skip_below = by_warp ? 0 : WK_LIST_MAX;
     const int32_t *Qimg = P.Q + (size_t)img * 2 * (size_t)N;
     int32_t *Pimg = P.Pm + (size_t)img * 2 * (size_t)N;

@@ -73,6 +73,18 @@ def cases(big):
               "haar", "epwt-easypath", True, 32))
     c.append(("epwt32_u8_smooth_bior44", np.round(synth.smooth_field_image(32, 32, seed=15, sigma=2.0)).astype(np.uint8), None,
               10, "bior4.4", "epwt-easypath", True, 64))
+    # gradpath (Region.grad_path, rbepwt.py:1190-1271) with the reference's set iteration pinned to row-major order
+    # (oracle/ref_harness.RowMajorSet): complete ties of the gradient preference are otherwise interpreter-dependent
+    lab = synth.voronoi_labels(16, 16, 6, seed=21)
+    img = synth.piecewise_smooth_image(lab, seed=21)
+    c.append(("grad16_euclid_haar", img, lab, 6, "haar", "gradpath", True, 30))
+    c.append(("grad16_cheb_db2", img, lab, 6, "db2", "gradpath", False, 30))
+    lab = synth.voronoi_labels(32, 32, 14, seed=22)
+    img = synth.piecewise_smooth_image(lab, seed=22)
+    c.append(("grad32_euclid_bior44", img, lab, 10, "bior4.4", "gradpath", True, 64))
+    c.append(("grad32_cheb_haar", img, noise_labels(32, 32, 4, 23), 10, "haar", "gradpath", False, 64))
+    c.append(("grad32_u8_pfl_euclid", np.round(img).astype(np.uint8), lab, 10, "haar", "gradpath", True, 64, True))
+    c.append(("grad32_flat_regions", np.full((32, 32), 7.0), lab, 10, "haar", "gradpath", True, 16))  # zero gradients: NaN directions
     if big:
         img, lab = synth.config_inputs("cameraman256")  # BASELINE.json configs[0]
         c.append(("config1_cameraman256", img, lab, 16, "bior4.4", "easypath", True, 512))

@@ -78,8 +78,7 @@ def test_path_mode_mapping_and_guards():
 
     assert rb.path_mode("easypath", True) == 0 and rb.path_mode("easypath", False) == 1
     assert rb.path_mode("epwt-easypath", True) == 2 and rb.path_mode("epwt-easypath", False) == 2
-    with pytest.raises(NotImplementedError):
-        rb.path_mode("gradpath")
+    assert rb.path_mode("gradpath", True) == 3 and rb.path_mode("gradpath", False) == 4
     with pytest.raises(ValueError):
         rb.path_mode("zigzag")
     assert rb.ispowerof2(256 * 512) and not rb.ispowerof2(48)

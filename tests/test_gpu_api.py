@@ -70,6 +70,18 @@ def test_epwt_facade_and_method_quirk():
     assert rc[2][0].base_points == tuple(map(tuple, g["points_by_level"][2]))
 
 
+def test_gradpath_facade_matches_reference_fixture():
+    g = load_golden("grad32_euclid_bior44")
+    im = _image(g)
+    with contextlib.redirect_stdout(io.StringIO()):
+        im.encode_rbepwt(g["levels"], g["wavelet"], path_type="gradpath", euclidean_distance=True)
+        assert im.rbepwt_path_type == "gradpath"
+        im.threshold_coefs(g["ncoefs"])
+        im.decode_rbepwt()
+    assert np.max(np.abs(im.decoded_img - g["decoded"])) <= 1e-9 * 255
+    assert abs(im.psnr() - g["psnr"]) < 5e-7
+
+
 def test_edit_coefficients_then_decode_like_compute_basis_elements():
     """scripts/compute_basis_elements.py:58-81: zero every array, set one coefficient, decode."""
     g = load_golden("vor32_euclid_bior44")

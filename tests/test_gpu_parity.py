@@ -102,6 +102,31 @@ def test_heavy_tailed_label_maps_vs_oracle(euclid):
     assert_same_as_oracle(one, orc[1], 16)
 
 
+@pytest.mark.parametrize("euclid", [True, False])
+def test_gradpath_vs_oracle(euclid):
+    """path_type='gradpath' (Region.grad_path, rbepwt.py:1190-1271) at 256^2 and in a batch of distinct images, against
+    the C port (itself pinned to the reference with its set iteration order fixed, tests/golden/grad*.npz): same
+    tie rule on both sides, paths bit-exact."""
+    import rbepwt_b200 as rb
+    from rbepwt_b200 import synth
+
+    img, lab = synth.config_inputs("cameraman256", seed=33)
+    out = cuda_run(img, lab, 16, "bior4.4", "gradpath", euclid, ncoefs=512)
+    assert_same_as_oracle(out, _oracle(img, lab, 16, "bior4.4", "gradpath", euclid, 512), 16)
+    rng = np.random.default_rng(9)
+    labs = np.stack([synth.voronoi_labels(64, 64, 12 + 5 * s, seed=60 + s) for s in range(4)])
+    labs[3] = rng.integers(0, 6, size=(64, 64))  # scattered classes: every step a jump
+    imgs = np.stack([synth.piecewise_smooth_image(l, seed=60 + i) for i, l in enumerate(labs)])
+    imgs[2] = np.round(imgs[2])  # quantised values: equal gradients, more ties
+    c = rb.BatchCodec()
+    c.encode(imgs, labs, 12, "haar", "gradpath", euclid)
+    outs = collect_batch(c, imgs, range(4), 12, 200)
+    for b in range(4):
+        assert_same_as_oracle(outs[b], _oracle(imgs[b], labs[b], 12, "haar", "gradpath", euclid, 200), 12)
+    with pytest.raises(Exception, match="too small to calculate a numerical gradient"):
+        rb.BatchCodec().encode(np.zeros((1, 1, 16)), np.zeros((1, 1, 16), np.int32), 2, "haar", "gradpath")
+
+
 def test_config2_512_chebyshev_vs_oracle():
     from rbepwt_b200 import synth
 
