@@ -97,6 +97,14 @@ int rbepwt_set_option(rbepwt_ctx *ctx, int option, int64_t value);
  * unpinned in the reference; here the highest flat index survives. */
 int rbepwt_threshold(rbepwt_ctx *ctx, int64_t k);
 
+/* Rbepwt.threshold_by_percentage(perc), per image and region                  rbepwt.py:2120-2192
+ * Of the n coefficients a region owns (its segment of every detail level and of the approximation) the
+ * int(min(floor(perc*n + 0.5), n)) largest in magnitude are kept, the other DETAIL coefficients zeroed; approximation
+ * coefficients take part in the ranking but always survive, which is what the reference does (its
+ * RegionCollection.update() at 2187 discards the thresholded approximation).  Ties: unpinned in the reference; here
+ * the entries later in the region's list (levels ascending, approximation last) survive. */
+int rbepwt_threshold_percentage(rbepwt_ctx *ctx, double perc);
+
 /* Rbepwt.decode + RegionCollection.expand + Image.decode_rbepwt (clip to [0,255], no rounding)
  *                                                           rbepwt.py:2055-2079, 1586-1613, 307-317
  * out: float64 [B][H][W].  flags: RBEPWT_DEVICE_PTRS, RBEPWT_NO_CLIP. */

@@ -46,6 +46,8 @@ def lib():
         L.rbo_decode.restype = ctypes.c_int
         L.rbo_decode.argtypes = [_f64p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f64p,
                                  _f64p, ctypes.c_int, _i32p, _i32p, _i32p, _f64p]
+        L.rbo_threshold_percentage.restype = ctypes.c_int
+        L.rbo_threshold_percentage.argtypes = [_f64p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _i32p, ctypes.c_double]
         L.rbo_grad_tie_events.restype = ctypes.c_long
         L.rbo_grad_tie_events.argtypes = []
         L.rbo_psnr.restype = ctypes.c_double
@@ -108,6 +110,13 @@ def encode(img, labels, levels, wavelet, mode, u8wrap=None, paths_first_level=Fa
 def threshold(coefs, k):
     out = np.array(coefs, dtype=np.float64, copy=True)
     lib().rbo_threshold(out, out.size, int(k))
+    return out
+
+
+def threshold_percentage(enc, coefs, perc):
+    """Rbepwt.threshold_by_percentage (rbepwt.py:2120-2192) on a flat coefficient vector of the encoding `enc`."""
+    out = np.array(coefs, dtype=np.float64, copy=True)
+    lib().rbo_threshold_percentage(out, enc["H"], enc["W"], enc["levels"], enc["R"], np.ascontiguousarray(enc["roff"]), float(perc))
     return out
 
 

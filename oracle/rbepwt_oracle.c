@@ -423,6 +423,51 @@ int rbo_threshold(double *coefs, int64_t n, int64_t k) {
   return 0;
 }
 
+/* Rbepwt.threshold_by_percentage(perc) (rbepwt.py:2120-2192): "keeps only perc proportion of coefficients for each
+ * region".  Region r owns, of every level l = 1..L, the detail coefficients at the positions of its level-(l+1) segment,
+ * and the approximation coefficients of its level-(L+1) segment (2124-2148); of these n_r values the
+ * int(min(floor(perc * n_r + 0.5), n_r)) largest in magnitude are kept (2155: myround), the others zeroed -- in the DETAILS
+ * only: the thresholded approximation is assigned to the level-(L+1) collection and then lost again, because
+ * RegionCollection.update() (2187, 1529-1531) rebuilds the collection's values from its sub-regions, which still hold the
+ * original ones.  So approximation coefficients take part in the ranking but are never zeroed (checked by running the
+ * reference: the fixtures).  Ties at the cut are broken by numpy's unstable argsort (unpinned); here the entry later in
+ * the region's list (levels ascending, approximation last) survives.
+ * roff: [(levels+1)][R+1] as produced by rbo_encode. */
+typedef struct { double mag; long pos; } mag_pos;
+static int cmp_mag_pos_desc(const void *a, const void *b) {
+  const mag_pos *x = (const mag_pos *)a, *y = (const mag_pos *)b;
+  if (x->mag != y->mag) return x->mag > y->mag ? -1 : 1;
+  return x->pos > y->pos ? -1 : (x->pos < y->pos ? 1 : 0);
+}
+
+int rbo_threshold_percentage(double *coefs, int H, int W, int levels, int R, const int32_t *roff, double perc) {
+  const long N = (long)H * W;
+  mag_pos *buf = (mag_pos *)malloc(sizeof(mag_pos) * (N + 1));
+  long *flat = (long *)malloc(sizeof(long) * (N + 1));
+  for (int r = 0; r < R; r++) {
+    long n = 0;
+    long det_off = 0;
+    for (int lev = 1; lev <= levels; lev++) { /* details[lev] has N >> lev entries, segment of the level-(lev+1) offsets */
+      const int32_t *o = roff + (long)lev * (R + 1);
+      for (long q = o[r]; q < o[r + 1]; q++) { flat[n] = det_off + q; n++; }
+      det_off += N >> lev;
+    }
+    const long n_det = n;
+    const int32_t *o = roff + (long)levels * (R + 1);
+    for (long q = o[r]; q < o[r + 1]; q++) { flat[n] = det_off + q; n++; }
+    if (n == 0) continue;
+    for (long i = 0; i < n; i++) { buf[i].mag = fabs(coefs[flat[i]]); buf[i].pos = i; }
+    long keep = (long)floor(perc * (double)n + 0.5);
+    if (keep > n) keep = n;
+    if (keep < 0) keep = 0;
+    qsort(buf, n, sizeof(mag_pos), cmp_mag_pos_desc);
+    for (long i = keep; i < n; i++)
+      if (buf[i].pos < n_det) coefs[flat[buf[i].pos]] = 0.0; /* approximation entries are never zeroed (see above) */
+  }
+  free(buf); free(flat);
+  return 0;
+}
+
 /* ------------------------------------------------------------------ decode -------- */
 
 int rbo_decode(const double *coefs, int H, int W, int levels, int flen, const double *rec_lo,

@@ -290,6 +290,11 @@ class BatchCodec:
         _capi.check(self._lib.rbepwt_threshold(self._ctx, int(k)))
         return self
 
+    def threshold_by_percentage(self, perc):
+        """Rbepwt.threshold_by_percentage (rbepwt.py:2120-2192): per region, keep that proportion of its coefficients."""
+        _capi.check(self._lib.rbepwt_threshold_percentage(self._ctx, float(perc)))
+        return self
+
     def decode(self, out=None, clip=True):
         """Decoded images, float64 [B,H,W], clipped to [0,255] (Image.decode_rbepwt, rbepwt.py:313-314) unless
         `clip` is False (what Rbepwt.decode itself returns, rbepwt.py:2055-2079).  `out` may be a torch CUDA

@@ -1063,6 +1063,22 @@ int rbepwt_threshold(rbepwt_ctx *c, int64_t k) {
   return threshold_sub(c, c->stream, 0, c->B, (long long)k);
 }
 
+int rbepwt_threshold_percentage(rbepwt_ctx *c, double perc) {
+  if (!c) return fail(RBEPWT_E_ARG, "ctx is NULL");
+  if (!c->has_encoding) return fail(RBEPWT_E_NO_ENCODING, "There is no saved encoding to decode");
+  if (!c->has_paths || c->totalR <= 0) return fail(RBEPWT_E_ARG, "threshold_by_percentage needs the regions of an encoding made by this context");
+  if (!(perc >= 0.0)) return fail(RBEPWT_E_ARG, "perc must be >= 0");
+  if (c->levels > PERC_MAXLEV) return fail(RBEPWT_E_ARG, "too many levels");
+  DeviceGuard g(c->device);
+  int rc = materialise_thresholds(c);
+  if (rc) return rc;
+  k4_percentage<<<c->totalR, PERC_THREADS, 0, c->stream>>>(c->coefs.as<double>(), c->N, c->levels, c->reg[7].as<int32_t>(),
+                                                         c->reg[3].as<int32_t>(), c->reg[2].as<int32_t>(), 0, perc);
+  c->launches++;
+  CK(cudaGetLastError());
+  return RBEPWT_OK;
+}
+
 int rbepwt_decode(rbepwt_ctx *c, double *out_img, unsigned flags) {
   if (!c || !out_img) return fail(RBEPWT_E_ARG, "ctx / out is NULL");
   if (!c->has_encoding) return fail(RBEPWT_E_NO_ENCODING, "There is no saved encoding to decode");

@@ -44,9 +44,9 @@ constexpr size_t SEL2_SMEM = (size_t)SEL2_CAND * 8;
 // r-th largest (r >= 1, r <= n) of n keys in shared memory by radix select, 11 bits per pass from bit `bits` - 1 down;
 // *ceq = how many keys equal it, *krem = which of them (in descending order) the r-th is: 1..ceq.  Every thread of
 // the block calls it.
-template <typename KEY>
-__device__ __forceinline__ KEY block_select_desc(const KEY *keys, int n, int r, int bits, int *s_hist, int *s_scan,
-                                                 int *s_pick, int *krem, int *ceq) {
+template <typename KEY, typename KEYFN>
+__device__ __forceinline__ KEY block_select_desc_fn(KEYFN key_at, int n, int r, int bits, int *s_hist, int *s_scan,
+                                                    int *s_pick, int *krem, int *ceq) {
   const int tid = threadIdx.x, nt = blockDim.x;
   KEY prefix = 0;
   int done = 0;
@@ -55,17 +55,27 @@ __device__ __forceinline__ KEY block_select_desc(const KEY *keys, int n, int r, 
     for (int i = tid; i < nbins; i += nt) s_hist[i] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += nt) {
-      const KEY key = keys[i];
+      const KEY key = key_at(i);
       if (done == 0 || (key >> (shift + nb)) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & (KEY)(nbins - 1))], 1);
     }
     __syncthreads();
-    // thread t looks at the bins nbins-1-2t and nbins-2-2t (descending digits)
-    const int b0 = nbins - 1 - 2 * tid, b1 = b0 - 1;
-    const int c0 = b0 >= 0 ? s_hist[b0] : 0, c1 = b1 >= 0 ? s_hist[b1] : 0;
+    // thread t looks at the bins nbins-1-pt*t .. (descending digits), pt bins each: all 2048 bins whatever the block size
+    const int pt = (SEL2_BINS + nt - 1) / nt;
+    int cnt[8];
+    int mine = 0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int b = nbins - 1 - (pt * tid + u);
+      cnt[u] = (u < pt && b >= 0) ? s_hist[b] : 0;
+      mine += cnt[u];
+    }
     int total;
-    const int ex = block_exclusive_scan(c0 + c1, s_scan, &total);
-    if (ex < r && ex + c0 >= r) { s_pick[0] = b0; s_pick[1] = ex; s_pick[2] = c0; }
-    else if (ex + c0 < r && ex + c0 + c1 >= r) { s_pick[0] = b1; s_pick[1] = ex + c0; s_pick[2] = c1; }
+    int ex = block_exclusive_scan(mine, s_scan, &total);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      if (u < pt && ex < r && ex + cnt[u] >= r) { s_pick[0] = nbins - 1 - (pt * tid + u); s_pick[1] = ex; s_pick[2] = cnt[u]; }
+      ex += cnt[u];
+    }
     __syncthreads();
     prefix = (prefix << nb) | (KEY)s_pick[0];
     r -= s_pick[1];
@@ -75,6 +85,12 @@ __device__ __forceinline__ KEY block_select_desc(const KEY *keys, int n, int r, 
   }
   *krem = r;
   return prefix;
+}
+
+template <typename KEY>
+__device__ __forceinline__ KEY block_select_desc(const KEY *keys, int n, int r, int bits, int *s_hist, int *s_scan,
+                                                 int *s_pick, int *krem, int *ceq) {
+  return block_select_desc_fn<KEY>([keys](int i) { return keys[i]; }, n, r, bits, s_hist, s_scan, s_pick, krem, ceq);
 }
 
 // K4, common case: ONE pass over the coefficients, one CTA per image.  A sample (1/16 of the 32-byte sectors, top 32
@@ -325,6 +341,86 @@ __global__ void __cluster_dims__(SEL_CLUSTER, 1, 1) __launch_bounds__(SEL_THREAD
     __syncthreads();
   }
   cluster.sync();  // s_ties stays readable until every CTA has summed it
+}
+
+// Rbepwt.threshold_by_percentage(perc) (rbepwt.py:2120-2192), one CTA per region: the region owns, of every level
+// l = 1..L, the detail coefficients at the positions of its level-(l+1) segment, and the approximation coefficients of
+// its level-(L+1) segment; of these n values the int(min(floor(perc n + 0.5), n)) largest in magnitude are kept, the
+// others zeroed -- in the details only: the reference's thresholded approximation is lost again when
+// RegionCollection.update() rebuilds the collection from its sub-regions (2187, 1529-1531), so approximation entries
+// take part in the ranking but always survive.  Ties at the cut: numpy's unstable argsort in the reference (unpinned);
+// here the entries later in the region's list (levels ascending, approximation last) survive.
+// off1 / size: the region's level-1 offset and size; level-m segment = [ceil(off1 / 2^(m-1)), ceil((off1+size) / 2^(m-1))).
+constexpr int PERC_THREADS = 256;
+constexpr int PERC_MAXLEV = 32;
+
+__global__ void __launch_bounds__(PERC_THREADS) k4_percentage(double *coefs_all, int N, int levels, const int32_t *reg_img,
+                                                              const int32_t *reg_off, const int32_t *reg_size, int g0,
+                                                              double perc) {
+  __shared__ int s_hist[SEL2_BINS];
+  __shared__ int s_scan[33];
+  __shared__ int s_pick[3];
+  __shared__ int s_pre[PERC_MAXLEV + 2];          // s_pre[q] = entries of the list before its q-th segment
+  __shared__ long long s_base[PERC_MAXLEV + 1];   // flat index of the q-th segment's first entry
+  __shared__ int s_seen;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int g = g0 + blockIdx.x;
+  const unsigned long long MAG = 0x7fffffffffffffffull;
+  unsigned long long *c = reinterpret_cast<unsigned long long *>(coefs_all + (size_t)reg_img[g] * N);
+  const long long off1 = reg_off[g], end1 = off1 + reg_size[g];
+  if (tid == 0) {
+    int acc = 0;
+    for (int q = 0; q <= levels; q++) {  // q < levels: details of level q+1; q == levels: approximation -- both on the level-(q+2) ... segment
+      const int m = q < levels ? q + 2 : levels + 1;  // segment level
+      const long long add = (1ll << (m - 1)) - 1;
+      const long long s0 = (off1 + add) >> (m - 1), s1 = (end1 + add) >> (m - 1);
+      s_pre[q] = acc;
+      s_base[q] = (q < levels ? (long long)N - ((long long)N >> q) : (long long)N - ((long long)N >> levels)) + s0;
+      acc += (int)(s1 - s0);
+    }
+    s_pre[levels + 1] = acc;
+  }
+  __syncthreads();
+  const int n = s_pre[levels + 1], n_det = s_pre[levels];
+  if (n == 0) return;
+  long long keep = (long long)floor(perc * (double)n + 0.5);
+  keep = keep > n ? n : (keep < 0 ? 0 : keep);
+  if (keep >= n) return;  // everything survives
+  auto flat_of = [&](int p) -> long long {
+    int q = 0;
+    while (p >= s_pre[q + 1]) q++;
+    return s_base[q] + (p - s_pre[q]);
+  };
+  if (keep == 0) {
+    for (int p = tid; p < n_det; p += nt) c[flat_of(p)] = 0ull;
+    return;
+  }
+  int krem, ceq;
+  const unsigned long long tau = block_select_desc_fn<unsigned long long>([&](int p) { return c[flat_of(p)] & MAG; }, n, (int)keep, 63,
+                                                                         s_hist, s_scan, s_pick, &krem, &ceq);
+  if (krem == ceq) {  // every entry equal to tau survives
+    for (int p = tid; p < n_det; p += nt) {
+      const long long f = flat_of(p);
+      if ((c[f] & MAG) < tau) c[f] = 0ull;
+    }
+    return;
+  }
+  // only `krem` of the `ceq` entries equal to tau survive: those latest in the list -- walk it from the end
+  if (tid == 0) s_seen = 0;
+  __syncthreads();
+  for (int base = ((n - 1) / nt) * nt; base >= 0; base -= nt) {
+    const int p = base + (nt - 1 - tid);  // tid order = descending list position
+    const bool valid = p < n;
+    const long long f = valid ? flat_of(p) : 0;
+    const unsigned long long key = valid ? (c[f] & MAG) : 0ull;
+    const bool tie = valid && key == tau;
+    int total;
+    const int ex = block_exclusive_scan(tie ? 1 : 0, s_scan, &total);
+    if (valid && p < n_det && (key < tau || (tie && s_seen + ex >= krem))) c[f] = 0ull;
+    __syncthreads();
+    if (tid == 0) s_seen += total;
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(256) k_nonzero(const double *coefs_all, int N, long long *out) {

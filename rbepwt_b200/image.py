@@ -391,6 +391,12 @@ class Rbepwt:
         self._codec.threshold(int(ncoefs))
         self._refresh_mirror()
 
+    def threshold_by_percentage(self, perc):
+        """Keeps only perc proportion of coefficients for each region (rbepwt.py:2120-2192)."""
+        self._upload_if_mirrored()
+        self._codec.threshold_by_percentage(perc)
+        self._refresh_mirror()
+
     def decode(self):
         """Returns the decoded region collection like the reference (rbepwt.py:2055-2079); the clipped image is
         kept in `decoded_img` for Image.decode_rbepwt."""

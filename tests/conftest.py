@@ -60,3 +60,18 @@ def assert_matches_golden(out, g, rtol=1e-9):
     assert np.max(np.abs(out["decoded"] - g["decoded"])) <= rtol * 255.0
     assert abs(out["psnr"] - g["psnr"]) < 5e-7
     assert out["nonzero_coefs"] == g["nonzero_coefs"]
+
+
+def perc_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "perc", "*.npz")))
+
+
+def load_perc(name):
+    """threshold_by_percentage fixture produced by the unmodified reference (tests/golden/make_golden.py --perc)."""
+    z = np.load(os.path.join(GOLDEN_DIR, "perc", name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    g["levels"] = int(g["levels"]); g["perc"] = float(g["perc"]); g["psnr"] = float(g["psnr"])
+    g["wavelet"] = str(g["wavelet"]); g["path_type"] = str(g["path_type"]); g["euclidean_distance"] = bool(g["euclidean_distance"])
+    if g["labels"].size == 0:
+        g["labels"] = None
+    return g

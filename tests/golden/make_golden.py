@@ -91,12 +91,53 @@ def cases(big):
     return c
 
 
+def perc_cases():
+    """Rbepwt.threshold_by_percentage (rbepwt.py:2120-2192): fixtures in tests/golden/perc/."""
+    c = []
+    lab = synth.voronoi_labels(32, 32, 9, seed=3)
+    img = synth.piecewise_smooth_image(lab, seed=3)
+    c.append(("perc32_haar_25", img, lab, 6, "haar", "easypath", True, 0.25))
+    c.append(("perc32_bior44_10", img, lab, 10, "bior4.4", "easypath", True, 0.1))
+    c.append(("perc32_cheb_db2_50", img, noise_labels(32, 32, 5, 31), 8, "db2", "easypath", False, 0.5))
+    c.append(("perc32_haar_3", img, lab, 7, "haar", "easypath", True, 0.03))
+    c.append(("perc32_haar_150", img, lab, 6, "haar", "easypath", True, 1.5))
+    c.append(("perc16_epwt_haar_20", synth.smooth_field_image(16, 16, seed=32, sigma=2.0), None, 6, "haar", "epwt-easypath", True, 0.2))
+    return c
+
+
+def make_perc(only, force):
+    import contextlib
+    import io
+
+    os.makedirs(os.path.join(HERE, "perc"), exist_ok=True)
+    for name, img, lab, levels, wav, ptype, euclid, perc in perc_cases():
+        if only and name not in only:
+            continue
+        path = os.path.join(HERE, "perc", name + ".npz")
+        if os.path.exists(path) and not force:
+            continue
+        im = ref_harness.make_image(img, lab if ptype != "epwt-easypath" else None)
+        with contextlib.redirect_stdout(io.StringIO()):
+            im.encode_rbepwt(levels, wav, path_type=ptype, euclidean_distance=euclid)
+            im.rbepwt.threshold_by_percentage(perc)
+            flat = np.asarray(im.rbepwt.flat_wavelet(), dtype=np.float64).copy()
+            im.decode_rbepwt()
+        np.savez_compressed(path, img=img, labels=(lab if lab is not None else np.zeros((0, 0), np.int32)), levels=levels,
+                            wavelet=wav, path_type=ptype, euclidean_distance=euclid, perc=perc, thresholded=flat,
+                            decoded=np.asarray(im.decoded_img, dtype=np.float64), psnr=float(im.psnr()))
+        print("%-28s kept %d" % (name, np.count_nonzero(flat)), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", nargs="*")
     ap.add_argument("--big", action="store_true")
     ap.add_argument("--force", action="store_true")
+    ap.add_argument("--perc", action="store_true", help="the threshold_by_percentage fixtures (tests/golden/perc/)")
     args = ap.parse_args()
+    if args.perc:
+        make_perc(args.only, args.force)
+        return
     for case in cases(args.big):
         name, img, lab, levels, wav, ptype, euclid, k = case[:8]
         pfl = bool(case[8]) if len(case) > 8 else False

@@ -261,3 +261,42 @@ def test_box_codec_shards_by_image():
                          want_kept=True)
     assert r["image"].shape == imgs.shape and r["psnr"].shape == (B,) and r["kept_idx"].shape == (B, 200)
     box.close()
+
+
+def test_threshold_by_percentage_matches_reference_fixtures():
+    """Rbepwt.threshold_by_percentage (rbepwt.py:2120-2192) through the facade and the batch API, against what the
+    unmodified reference produced (tests/golden/perc/), plus a 512x512 run against the C port."""
+    import rbepwt_b200 as rbepwt
+    from conftest import load_perc, perc_names
+    from oracle import c_oracle
+    from rbepwt_b200 import synth
+
+    for name in perc_names():
+        g = load_perc(name)
+        im = rbepwt.Image()
+        im.read_array(g["img"])
+        if g["labels"] is not None:
+            im.set_labels(g["labels"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            im.encode_rbepwt(g["levels"], g["wavelet"], path_type=g["path_type"], euclidean_distance=g["euclidean_distance"])
+            im.rbepwt.threshold_by_percentage(g["perc"])
+            flat = im.rbepwt.flat_wavelet()
+            im.decode_rbepwt()
+        np.testing.assert_array_equal(np.flatnonzero(flat), np.flatnonzero(g["thresholded"]), err_msg=name)
+        assert np.max(np.abs(flat - g["thresholded"])) <= 1e-9 * np.abs(g["thresholded"]).max()
+        assert np.max(np.abs(im.decoded_img - g["decoded"])) <= 1e-9 * 255
+        assert abs(im.psnr() - g["psnr"]) < 5e-7
+    img, lab = synth.config_inputs("synthetic512", seed=12)
+    fb = rbepwt.filter_bank("bior4.4")
+    enc = c_oracle.encode(img, lab, 16, fb, c_oracle.MODE_EUCLID)
+    c = rbepwt.BatchCodec()
+    c.encode(np.stack([img, img]), np.stack([lab, lab]), 16, "bior4.4")
+    c.threshold_by_percentage(0.02)
+    want = c_oracle.threshold_percentage(enc, enc["coefs"], 0.02)
+    for b in (0, 1):
+        got = c.coefs(b)
+        np.testing.assert_array_equal(np.flatnonzero(got), np.flatnonzero(want))
+    # ties at the cut: the later entries of the region's list survive (the C port's rule)
+    c.set_coefs(np.where(enc["coefs"] != 0, np.sign(enc["coefs"]) * 3.0, 0.0), 0)
+    c.threshold_by_percentage(0.3)
+    np.testing.assert_array_equal(c.coefs(0), c_oracle.threshold_percentage(enc, np.where(enc["coefs"] != 0, np.sign(enc["coefs"]) * 3.0, 0.0), 0.3))

@@ -36,3 +36,20 @@ def test_threshold_quirks():
     np.testing.assert_array_equal(c_oracle.threshold(x, 99), x)
     np.testing.assert_array_equal(c_oracle.threshold(x, 1), [0, 0, 0, 5.0, 0])  # tie: highest index
     np.testing.assert_array_equal(c_oracle.threshold(x, 3), [3.0, -5.0, 0, 5.0, 0])
+
+
+def test_oracle_threshold_by_percentage_reproduces_reference():
+    from conftest import load_perc, perc_names
+    from oracle import c_oracle, pywt_port
+
+    assert perc_names()
+    for name in perc_names():
+        g = load_perc(name)
+        fb = pywt_port.filter_bank(g["wavelet"])
+        enc = c_oracle.encode(g["img"], g["labels"], g["levels"], fb, c_oracle.path_mode(g["path_type"], g["euclidean_distance"]))
+        th = c_oracle.threshold_percentage(enc, enc["coefs"], g["perc"])
+        np.testing.assert_array_equal(np.flatnonzero(th), np.flatnonzero(g["thresholded"]), err_msg=name)
+        assert np.max(np.abs(th - g["thresholded"])) <= 1e-9 * np.abs(g["thresholded"]).max()
+        dec = c_oracle.decode(enc, th, fb)
+        assert np.max(np.abs(dec - g["decoded"])) <= 1e-9 * 255
+        assert abs(c_oracle.psnr(g["img"], dec) - g["psnr"]) < 5e-7
