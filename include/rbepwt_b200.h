@@ -97,6 +97,15 @@ int rbepwt_set_option(rbepwt_ctx *ctx, int option, int64_t value);
  * unpinned in the reference; here the highest flat index survives. */
 int rbepwt_threshold(rbepwt_ctx *ctx, int64_t k);
 
+/* The tensor-product baseline the reference compares against: Dwt.encode = pywt.wavedec2(img, wavelet, level=levels,
+ * mode='periodization')                                                            rbepwt.py:2249-2263, 318-324
+ * for a batch of square images.  The context then holds THIS encoding: rbepwt_threshold (Dwt.threshold_coefs, 2265-2298:
+ * same top-k rule and quirks), rbepwt_decode (Dwt.decode = pywt.waverec2 + the clip of Image.decode_dwt, 326-333),
+ * rbepwt_get_coefs / set_coefs / nonzero_coefs / psnr work on it; everything about paths and regions does not.
+ * Coefficient layout of get/set_coefs: one H x W pyramid per image -- level l's sub-bands are the quadrants of the
+ * top-left block of side W >> (l-1): [cA | cV ; cH | cD] in pywt's naming (see csrc/dwt2.cuh). */
+int rbepwt_dwt2_encode(rbepwt_ctx *ctx, const double *img, int B, int H, int W, int levels, unsigned flags);
+
 /* Rbepwt.threshold_by_percentage(perc), per image and region                  rbepwt.py:2120-2192
  * Of the n coefficients a region owns (its segment of every detail level and of the approximation) the
  * int(min(floor(perc*n + 0.5), n)) largest in magnitude are kept, the other DETAIL coefficients zeroed; approximation

@@ -113,3 +113,64 @@ def idwt(ca, cd, wavelet, mode="periodization"):
         s_lo[idx] = s_lo[idx] + rec_lo[m] * ca
         s_hi[idx] = s_hi[idx] + rec_hi[m] * cd
     return s_lo + s_hi
+
+
+# ---- the tensor-product baseline (class Dwt, /root/reference/rbepwt.py:2249-2298) ----------------------------------
+# pywt.wavedec2 / waverec2 with mode='periodization', restated from the two 1-D routines above: dwt2 transforms along
+# axis 0, then along axis 1 (pywt.dwtn visits the axes in order), keys 'aa', 'da' (cH), 'ad' (cV), 'dd' (cD), and the
+# next level transforms 'aa'.  PARITY UNPINNED like the 1-D routines (PyWavelets is absent here).
+
+def _dwt_axis(a, wavelet, axis):
+    lo = np.apply_along_axis(lambda v: dwt(v, wavelet)[0], axis, a)
+    hi = np.apply_along_axis(lambda v: dwt(v, wavelet)[1], axis, a)
+    return lo, hi
+
+
+def _idwt_axis(lo, hi, wavelet, axis):
+    lo, hi = np.moveaxis(lo, axis, -1), np.moveaxis(hi, axis, -1)
+    out = np.stack([idwt(l, h, wavelet) for l, h in zip(lo.reshape(-1, lo.shape[-1]), hi.reshape(-1, hi.shape[-1]))])
+    return np.moveaxis(out.reshape(lo.shape[:-1] + (2 * lo.shape[-1],)), -1, axis)
+
+
+def wavedec2(data, wavelet, level, mode="periodization"):
+    """[cA_L, (cH_L, cV_L, cD_L), ..., (cH_1, cV_1, cD_1)]"""
+    a = np.asarray(data, dtype=np.float64)
+    out = []
+    for _ in range(level):
+        lo0, hi0 = _dwt_axis(a, wavelet, 0)
+        aa, ad = _dwt_axis(lo0, wavelet, 1)
+        da, dd = _dwt_axis(hi0, wavelet, 1)
+        out.append((da, ad, dd))
+        a = aa
+    return [a] + out[::-1]
+
+
+def waverec2(coeffs, wavelet, mode="periodization"):
+    a = coeffs[0]
+    for (da, ad, dd) in coeffs[1:]:
+        lo0 = _idwt_axis(a, ad, wavelet, 1)
+        hi0 = _idwt_axis(da, dd, wavelet, 1)
+        a = _idwt_axis(lo0, hi0, wavelet, 0)
+    return a
+
+
+def dwt2_baseline(img, levels, wavelet, ncoefs):
+    """Dwt.encode -> threshold_coefs(ncoefs) -> decode + the clip of Image.decode_dwt (rbepwt.py:318-333, 2262-2298).
+    Returns (decoded image, number of non-zero coefficients, sorted magnitudes of the kept coefficients)."""
+    co = wavedec2(img, wavelet, levels)
+    flat = np.concatenate([co[0].ravel()] + [np.concatenate([h.ravel(), v.ravel(), d.ravel()]) for h, v, d in co[1:]])
+    th = np.zeros_like(flat)
+    if ncoefs <= 0 or ncoefs >= flat.size:  # the reference's `count == ncoefs` test never fires: everything is kept
+        th[:] = flat
+    else:
+        keep = np.argsort(np.abs(flat), kind="stable")[::-1][:ncoefs]
+        th[keep] = flat[keep]
+    size = co[0].size
+    new = [th[:size].reshape(co[0].shape)]
+    last = size
+    for h, v, d in co[1:]:
+        s = h.size
+        new.append((th[last:last + s].reshape(h.shape), th[last + s:last + 2 * s].reshape(v.shape), th[last + 2 * s:last + 3 * s].reshape(d.shape)))
+        last += 3 * s
+    dec = waverec2(new, wavelet)
+    return np.clip(dec, 0.0, 255.0), int(np.count_nonzero(th)), np.sort(np.abs(th[th != 0]))

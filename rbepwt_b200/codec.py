@@ -290,6 +290,29 @@ class BatchCodec:
         _capi.check(self._lib.rbepwt_threshold(self._ctx, int(k)))
         return self
 
+    def dwt2_encode(self, imgs, levels, wavelet):
+        """The tensor-product baseline (class Dwt, rbepwt.py:2249-2263): pywt.wavedec2(img, wavelet, level=levels,
+        mode='periodization') of a batch of square images.  threshold / decode / coefs / set_coefs / nonzero_coefs then
+        work on this encoding; coefs(b) is the H x W pyramid described in include/rbepwt_b200.h."""
+        dev = _is_torch_cuda(imgs)
+        if dev:
+            import torch
+            if imgs.dtype != torch.float64 or not imgs.is_contiguous() or imgs.device.index != self.device:
+                raise ValueError("device images must be contiguous float64 on cuda:%d" % self.device)
+        else:
+            imgs = np.ascontiguousarray(imgs, dtype=np.float64)
+        shape = tuple(imgs.shape)
+        if len(shape) == 2:
+            shape = (1,) + shape
+        if len(shape) != 3:
+            raise ValueError("images must be [H,W] or [B,H,W]")
+        self.set_wavelet(wavelet)
+        B, H, W = shape
+        self._keep = [imgs]
+        _capi.check(self._lib.rbepwt_dwt2_encode(self._ctx, _ptr(imgs), B, H, W, int(levels), _capi.DEVICE_PTRS if dev else 0))
+        self.shape, self.levels, self.mode = shape, int(levels), None
+        return self
+
     def threshold_by_percentage(self, perc):
         """Rbepwt.threshold_by_percentage (rbepwt.py:2120-2192): per region, keep that proportion of its coefficients."""
         _capi.check(self._lib.rbepwt_threshold_percentage(self._ctx, float(perc)))

@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "dwt.cuh"
+#include "dwt2.cuh"
 #include "io.cuh"
 #include "paths.cuh"
 #include "perm.cuh"
@@ -120,6 +121,8 @@ struct rbepwt_ctx {
   double h_filt[4][FT_MAX] = {};  // host copy (flen <= FT_MAX): passed to the transform kernels by value
   // state of the encoded batch
   bool has_encoding = false, has_paths = false;
+  bool is_dwt2 = false;  // the encoding held is the tensor-product baseline (rbepwt_dwt2_encode), not an RBEPWT one
+  DevBuf dwt2_tmp;
   int B = 0, H = 0, W = 0, N = 0, logW = 0, levels = 0, mode = 0;
   unsigned enc_flags = 0;
   bool decode_noclip = false;  // RBEPWT_NO_CLIP of the decode in progress
@@ -685,7 +688,7 @@ int decode_sub(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int a, int nb, double *o
 }
 
 int alloc_state(rbepwt_ctx *c, int B, int H, int W, int levels, int path_mode, unsigned flags) {
-  c->has_encoding = false; c->has_paths = false;
+  c->has_encoding = false; c->has_paths = false; c->is_dwt2 = false;
   c->B = B; c->H = H; c->W = W; c->N = H * W; c->logW = ilog2(W); c->levels = levels; c->mode = path_mode;
   c->enc_flags = flags;
   c->totalR = 0;
@@ -968,7 +971,7 @@ void rbepwt_destroy(rbepwt_ctx *c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   for (auto *v : {&c->ev_lab, &c->ev_path, &c->ev_img, &c->ev_done})
     for (auto e : *v) cudaEventDestroy(e);
-  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->t2_tab, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->thr, &c->need_exact, &c->img_stage, &c->lab_stage, &c->out_stage, &c->psnr_dev, &c->kept_idx_dev, &c->kept_val_dev, &c->img_R,
+  DevBuf *bufs[] = {&c->filt, &c->unit_lut, &c->t2_tab, &c->labels_own, &c->img_own, &c->out_own, &c->coef_up, &c->Q, &c->Pm, &c->posmap, &c->coefs, &c->thr, &c->need_exact, &c->dwt2_tmp, &c->img_stage, &c->lab_stage, &c->out_stage, &c->psnr_dev, &c->kept_idx_dev, &c->kept_val_dev, &c->img_R,
                     &c->img_rbase, &c->img_labmin, &c->img_direct, &c->tbl, &c->slot_rid, &c->scratch_i32,
                     &c->scratch_i32b, &c->psnr_out, &c->nz_out};
   for (auto b : bufs) b->release();
@@ -1079,11 +1082,80 @@ int rbepwt_threshold_percentage(rbepwt_ctx *c, double perc) {
   return RBEPWT_OK;
 }
 
+// ---- the tensor-product baseline (class Dwt, rbepwt.py:2249-2298): see dwt2.cuh ------------------------------------
+static int dwt2_decode(rbepwt_ctx *c, double *out_img, unsigned flags) {
+  const bool host = !(flags & RBEPWT_DEVICE_PTRS);
+  const size_t bytes = (size_t)c->B * c->N * 8;
+  int rc = materialise_thresholds(c);  // (the pending-threshold shortcut belongs to the path transform's loader)
+  if (rc) return rc;
+  double *D = out_img;
+  if (host) { CK(c->out_own.ensure(bytes)); D = c->out_own.as<double>(); }
+  CK(c->dwt2_tmp.ensure(bytes));
+  cudaStream_t s = c->stream;
+  CK(cudaMemcpyAsync(D, c->coefs.p, bytes, cudaMemcpyDeviceToDevice, s));
+  Dwt2Params P;
+  P.filt = c->filt.as<double>(); P.W = c->W; P.N = c->N; P.flen = c->flen;
+  for (int lev = c->levels; lev >= 1; lev--) {
+    P.s = c->W >> (lev - 1);
+    const dim3 grid((P.s + 255) / 256, P.s, c->B);
+    P.src = D; P.dst = c->dwt2_tmp.as<double>(); P.clip = 0;
+    k_dwt2_inv<1><<<grid, 256, 0, s>>>(P);
+    P.src = c->dwt2_tmp.as<double>(); P.dst = D; P.clip = (lev == 1 && !(flags & RBEPWT_NO_CLIP)) ? 1 : 0;
+    k_dwt2_inv<0><<<grid, 256, 0, s>>>(P);
+    c->launches += 2;
+  }
+  CK(cudaGetLastError());
+  if (host) {
+    CK(cudaMemcpyAsync(out_img, D, bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  return RBEPWT_OK;
+}
+
+int rbepwt_dwt2_encode(rbepwt_ctx *c, const double *img, int B, int H, int W, int levels, unsigned flags) {
+  if (!c || !img) return fail(RBEPWT_E_ARG, "ctx / img is NULL");
+  int rc = validate_shape(B, H, W, levels, RBEPWT_PATH_EUCLID);
+  if (rc) return rc;
+  if (H != W) return fail(RBEPWT_E_ARG, "the 2-D DWT baseline needs a square image (the reference reshapes its sub-bands as squares, rbepwt.py:2283-2296)");
+  if ((1 << levels) > W) return fail(RBEPWT_E_LEVELS, "the 2-D DWT baseline needs 2^levels <= side");
+  if (!c->has_wavelet) return fail(RBEPWT_E_NO_WAVELET, "rbepwt_set_wavelet has not been called");
+  DeviceGuard g(c->device);
+  c->io = rbepwt_ctx::IoSpec();
+  c->has_encoding = false; c->has_paths = false; c->is_dwt2 = true;
+  c->B = B; c->H = H; c->W = W; c->N = H * W; c->logW = ilog2(W); c->levels = levels; c->mode = RBEPWT_PATH_EUCLID;
+  c->enc_flags = 0; c->totalR = 0;
+  c->h_R.assign(B, 0); c->h_rbase.assign(B, 0);
+  const size_t bytes = (size_t)B * c->N * 8;
+  CK(c->coefs.ensure(bytes));
+  CK(c->dwt2_tmp.ensure(bytes));
+  CK(c->thr.ensure((size_t)B * sizeof(ThrRec)));
+  CK(c->need_exact.ensure((size_t)B * sizeof(int)));
+  cudaStream_t s = c->stream;
+  CK(cudaMemsetAsync(c->thr.p, 0, (size_t)B * sizeof(ThrRec), s));
+  c->thr_pending = false;
+  CK(cudaMemcpyAsync(c->coefs.p, img, bytes, (flags & RBEPWT_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  Dwt2Params P;
+  P.filt = c->filt.as<double>(); P.W = W; P.N = c->N; P.flen = c->flen; P.clip = 0;
+  for (int lev = 1; lev <= levels; lev++) {
+    P.s = W >> (lev - 1);
+    P.src = c->coefs.as<double>(); P.dst = c->dwt2_tmp.as<double>();
+    k_dwt2_fwd<0><<<dim3((P.s + 255) / 256, P.s / 2, B), 256, 0, s>>>(P);
+    P.src = c->dwt2_tmp.as<double>(); P.dst = c->coefs.as<double>();
+    k_dwt2_fwd<1><<<dim3((P.s / 2 + 255) / 256, P.s, B), 256, 0, s>>>(P);
+    c->launches += 2;
+  }
+  CK(cudaGetLastError());
+  c->has_encoding = true;
+  if (!(flags & RBEPWT_DEVICE_PTRS)) CK(cudaStreamSynchronize(s));
+  return RBEPWT_OK;
+}
+
 int rbepwt_decode(rbepwt_ctx *c, double *out_img, unsigned flags) {
   if (!c || !out_img) return fail(RBEPWT_E_ARG, "ctx / out is NULL");
   if (!c->has_encoding) return fail(RBEPWT_E_NO_ENCODING, "There is no saved encoding to decode");
   DeviceGuard g(c->device);
   c->io = rbepwt_ctx::IoSpec();
+  if (c->is_dwt2) return dwt2_decode(c, out_img, flags);
   const bool host = !(flags & RBEPWT_DEVICE_PTRS);
   double *out_dev = out_img;
   if (host) {

@@ -323,6 +323,7 @@ class Rbepwt:
         self._codec = _acquire_codec()
         self._codec.encode(img.img, labels, self.levels, self.wavelet, self.path_type, euclidean_distance,
                            paths_first_level=self.paths_first_level)
+        self._euclid = bool(euclidean_distance)
         self._details = self._flat = self._approx = None
         self.region_collection_at_level = _LevelDict(self)
         self.has_encoding = True
@@ -332,6 +333,31 @@ class Rbepwt:
             _release_codec(self.__dict__.pop("_codec", None))
         except Exception:  # noqa: BLE001  (interpreter shutdown)
             pass
+
+    # -- persistence (Image.save_pickle / load_pickle, rbepwt.py:447-472) ----------------------------------------
+    # The state lives on the GPU; what is pickled is what determines it: the parameters and the coefficients (with any
+    # edits and thresholding).  The paths are a function of the label map / image and are recomputed on load, the way
+    # full_decode recomputes them (rbepwt.py:106-130).
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        codec = d.pop("_codec", None)
+        d.pop("region_collection_at_level", None)
+        d["_details"] = d["_flat"] = d["_approx"] = None
+        d["_saved_flat"] = self.flat_wavelet().copy() if (self.has_encoding and codec is not None) else d.get("_saved_flat")
+        d["_saved_euclid"] = getattr(self, "_euclid", True)
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._codec = None
+
+    def _restore_gpu_state(self):
+        """After unpickling: encode again (same inputs, same paths), then put the saved coefficients back."""
+        flat = self.__dict__.pop("_saved_flat", None)
+        if flat is None or not self.has_encoding:
+            return
+        self.encode(euclidean_distance=self.__dict__.pop("_saved_euclid", True))
+        self._codec.set_coefs(flat, 0)
 
     def _level_slices(self):
         n, off, out = self.img.size, 0, {}
@@ -420,6 +446,87 @@ class Rbepwt:
         return out
 
 
+class Dwt:
+    """The tensor-product baseline (reference: class Dwt, rbepwt.py:2249-2298): pywt.wavedec2 / waverec2 with
+    mode='periodization', global top-k thresholding -- on the GPU (csrc/dwt2.cuh).  `wavelet_coefs` is PyWavelets'
+    list [cA_L, (cH_L, cV_L, cD_L), ..., (cH_1, cV_1, cD_1)]: views of a host mirror of the coefficient pyramid that is
+    created on first access and, once created, is the source of truth (uploaded before the next threshold / decode)."""
+
+    def __init__(self, img, levels, wavelet):
+        if 2 ** levels > img.size:
+            raise Exception("2^levels must be smaller or equal to the number of pixels in the image")
+        if type(img).__name__ != "Image":
+            raise Exception("First argument must be an Image instance")
+        self.img = img
+        self.levels = levels
+        self.has_encoding = False
+        self.wavelet = wavelet
+        self._codec = None
+        self._pyr = None
+
+    def encode(self):
+        _release_codec(self._codec)
+        self._codec = _acquire_codec()
+        self._codec.dwt2_encode(np.asarray(self.img.img, dtype=np.float64)[None], self.levels, self.wavelet)
+        self._pyr = None
+        self.has_encoding = True
+
+    def __del__(self):
+        try:
+            _release_codec(self.__dict__.pop("_codec", None))
+        except Exception:  # noqa: BLE001
+            pass
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        codec = d.pop("_codec", None)
+        d["_saved_pyr"] = self._pyramid().copy() if (self.has_encoding and codec is not None) else d.get("_saved_pyr")
+        d["_pyr"] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._codec = None
+
+    def _restore_gpu_state(self):
+        pyr = self.__dict__.pop("_saved_pyr", None)
+        if pyr is None or not self.has_encoding:
+            return
+        self.encode()
+        self._codec.set_coefs(pyr.ravel(), 0)
+
+    def _pyramid(self):
+        if self._pyr is None:
+            side = self.img.shape[1]
+            self._pyr = self._codec.coefs(0).reshape(-1, side)
+        return self._pyr
+
+    @property
+    def wavelet_coefs(self):
+        p = self._pyramid()
+        out = []
+        for lev in range(1, self.levels + 1):
+            h = p.shape[1] >> lev
+            out.append((p[h:2 * h, 0:h], p[0:h, h:2 * h], p[h:2 * h, h:2 * h]))  # cH ('da'), cV ('ad'), cD ('dd')
+        h = p.shape[1] >> self.levels
+        return [p[0:h, 0:h]] + out[::-1]
+
+    def _upload_if_mirrored(self):
+        if self._pyr is not None:
+            self._codec.set_coefs(np.ascontiguousarray(self._pyr).ravel(), 0)
+
+    def threshold_coefs(self, ncoefs):
+        self._upload_if_mirrored()
+        self._codec.threshold(int(ncoefs))
+        if self._pyr is not None:
+            self._pyr[...] = self._codec.coefs(0).reshape(self._pyr.shape)
+
+    def decode(self):
+        """pywt.waverec2 of the (possibly thresholded) coefficients -- not clipped (rbepwt.py:2262-2263)."""
+        self._upload_if_mirrored()
+        return self._codec.decode(clip=False)[0]
+
+
 class Image:
     """Reference facade (rbepwt.py:190-577), hot-path subset."""
 
@@ -498,6 +605,46 @@ class Image:
         self.decoded_img = self.rbepwt.decoded_img  # float64, clipped to [0,255] on the GPU, not rounded (rbepwt.py:312-314)
         self.has_decoded_img = True
 
+    def save_pickle(self, filepath):
+        """pickle.dump(self.__dict__) like the reference (rbepwt.py:447-450); the GPU-resident encoding is saved as its
+        parameters + coefficients (Rbepwt.__getstate__)."""
+        import pickle
+
+        with open(filepath, "wb") as f:
+            pickle.dump(self.__dict__, f, 3)
+
+    def load_pickle(self, filepath):
+        """rbepwt.py:452-472: restore the attributes, re-link the transform object, re-create its GPU state."""
+        import pickle
+
+        with open(filepath, "rb") as f:
+            tmpdict = pickle.load(f)
+        self.__dict__.update(tmpdict)
+        self.has_segmentation = hasattr(self, "label_img")
+        self.has_decoded_img = hasattr(self, "decoded_img")
+        if hasattr(self, "dwt"):
+            self.dwt.img = self
+            self.dwt._restore_gpu_state()
+        if hasattr(self, "rbepwt"):
+            self.rbepwt.img = self
+            self.rbepwt._restore_gpu_state()
+            if self.has_decoded_img and hasattr(self, "decoded_region_collection"):
+                self.decoded_region_collection._rb = self.rbepwt
+
+    def encode_dwt(self, levels, wavelet):
+        """The 2-D DWT baseline (rbepwt.py:318-324)."""
+        self.method = "dwt"
+        if not ispowerof2(self.img.size):
+            raise Exception("Image size must be a power of 2")
+        self.dwt = Dwt(self, levels, wavelet)
+        self.dwt_levels = levels
+        self.dwt.encode()
+
+    def decode_dwt(self):
+        """rbepwt.py:326-333: waverec2, then the clip to [0,255]."""
+        self.decoded_img = np.clip(self.dwt.decode(), 0.0, 255.0)
+        self.has_decoded_img = True
+
     def encode_epwt(self, levels, wavelet):
         self.method = "epwt"
         self.encode_rbepwt(levels, wavelet, "epwt-easypath")  # note: leaves method == 'rbepwt' (rbepwt.py:335-337)
@@ -509,20 +656,22 @@ class Image:
         if self.method in ("epwt", "rbepwt"):
             self.rbepwt.threshold_coefs(ncoefs)
         elif self.method == "dwt":
-            raise NotImplementedError("the tensor-product DWT baseline is outside the B200 hot path")
+            self.dwt.threshold_coefs(ncoefs)
 
     def psnr(self, filtered=False):
         """PSNR of the decoded image vs. the original (rbepwt.py:361-368)."""
         if filtered:
             raise NotImplementedError("Image.filter is outside the B200 hot path")
-        v = float(self.rbepwt._codec.psnr(np.asarray(self.img, dtype=np.float64)[None], self.decoded_img[None])[0])
+        codec = self.dwt._codec if self.method == "dwt" else self.rbepwt._codec
+        v = float(codec.psnr(np.asarray(self.img, dtype=np.float64)[None], self.decoded_img[None])[0])
         return -1 if v == -1.0 else v
 
     def nonzero_coefs(self):
         if self.method in ("rbepwt", "epwt"):
             self.rbepwt._upload_if_mirrored()
             return int(self.rbepwt._codec.nonzero_coefs()[0])
-        raise NotImplementedError("only the rbepwt / epwt methods are on the B200 hot path")
+        self.dwt._upload_if_mirrored()  # rbepwt.py:434-439
+        return int(self.dwt._codec.nonzero_coefs()[0])
 
 
 def full_decode(wavelet_details_dict, wavelet_approx, label_img, wavelet, path_type="easypath",

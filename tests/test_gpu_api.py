@@ -300,3 +300,82 @@ def test_threshold_by_percentage_matches_reference_fixtures():
     c.set_coefs(np.where(enc["coefs"] != 0, np.sign(enc["coefs"]) * 3.0, 0.0), 0)
     c.threshold_by_percentage(0.3)
     np.testing.assert_array_equal(c.coefs(0), c_oracle.threshold_percentage(enc, np.where(enc["coefs"] != 0, np.sign(enc["coefs"]) * 3.0, 0.0), 0.3))
+
+
+def test_save_and_load_pickle(tmp_path):
+    """Image.save_pickle / load_pickle (rbepwt.py:447-472): a thresholded encoding survives the round trip -- same
+    coefficients, same decoded image -- and the restored object keeps working (threshold again, decode, psnr)."""
+    import rbepwt_b200 as rbepwt
+
+    g = load_golden("vor32_cheb_haar")
+    im = _image(g)
+    with contextlib.redirect_stdout(io.StringIO()):
+        im.encode_rbepwt(g["levels"], g["wavelet"], euclidean_distance=False)
+        im.threshold_coefs(g["ncoefs"])
+        im.decode_rbepwt()
+    path = str(tmp_path / "im.pickle")
+    im.save_pickle(path)
+    flat, dec = im.rbepwt.flat_wavelet().copy(), im.decoded_img.copy()
+    del im
+    im2 = rbepwt.Image()
+    with contextlib.redirect_stdout(io.StringIO()):
+        im2.load_pickle(path)
+        assert im2.has_segmentation and im2.has_decoded_img and im2.method == "rbepwt"
+        np.testing.assert_array_equal(im2.rbepwt.flat_wavelet(), flat)
+        np.testing.assert_array_equal(im2.decoded_img, dec)
+        assert im2.nonzero_coefs() == g["nonzero_coefs"]
+        im2.decode_rbepwt()
+        np.testing.assert_array_equal(im2.decoded_img, dec)
+        assert abs(im2.psnr() - g["psnr"]) < 5e-7
+        reg = im2.rbepwt.region_collection_at_level[1][0]
+        assert reg.permutation == list(g["perm_by_level"][1][:len(reg)])
+        im2.threshold_coefs(5)
+        assert im2.nonzero_coefs() == 5
+
+
+def test_dwt2_baseline_vs_oracle(tmp_path):
+    """The tensor-product baseline (class Dwt, rbepwt.py:2249-2298) through the facade: wavedec2 coefficients,
+    top-k thresholding, waverec2 + clip against the numpy restatement (oracle/pywt_port.py); batch API; pickle."""
+    import rbepwt_b200 as rbepwt
+    from oracle import pywt_port
+    from rbepwt_b200 import synth
+
+    for n, levels, wav, k in ((64, 4, "bior4.4", 300), (32, 5, "haar", 50), (128, 3, "db3", 2000), (16, 2, "db4", 0)):
+        lab = synth.voronoi_labels(n, n, 12, seed=n)
+        img = synth.piecewise_smooth_image(lab, seed=n)
+        im = rbepwt.Image()
+        im.read_array(img)
+        im.encode_dwt(levels, wav)
+        assert im.method == "dwt" and im.dwt_levels == levels
+        want_co = pywt_port.wavedec2(img, rbepwt.filter_bank(wav), levels)
+        got_co = im.dwt.wavelet_coefs
+        assert len(got_co) == levels + 1
+        assert np.max(np.abs(got_co[0] - want_co[0])) <= 1e-9 * np.abs(want_co[0]).max()
+        for g3, w3 in zip(got_co[1:], want_co[1:]):
+            for gq, wq in zip(g3, w3):
+                assert gq.shape == wq.shape and np.max(np.abs(gq - wq)) <= 1e-9 * 255
+        im.threshold_coefs(k)
+        want_dec, want_nz, want_mags = pywt_port.dwt2_baseline(img, levels, rbepwt.filter_bank(wav), k)
+        assert im.nonzero_coefs() == want_nz
+        flat = np.concatenate([np.ravel(q) for c_ in im.dwt.wavelet_coefs for q in (c_ if isinstance(c_, tuple) else (c_,))])
+        np.testing.assert_allclose(np.sort(np.abs(flat[flat != 0])), want_mags, rtol=0, atol=1e-9 * 255)
+        im.decode_dwt()
+        assert np.max(np.abs(im.decoded_img - want_dec)) <= 1e-9 * 255
+        assert abs(im.psnr() - float(20 * np.log10(255 / np.sqrt(np.mean((img - want_dec) ** 2))))) < 5e-7
+    path = str(tmp_path / "dwt.pickle")
+    im.save_pickle(path)
+    im2 = rbepwt.Image()
+    im2.load_pickle(path)
+    im2.decode_dwt()
+    np.testing.assert_array_equal(im2.decoded_img, im.decoded_img)
+    # batch API + guards
+    imgs = np.stack([synth.noise_image(64, 64, seed=s) for s in range(3)])
+    c = rbepwt.BatchCodec()
+    c.dwt2_encode(imgs, 3, "bior4.4")
+    np.testing.assert_allclose(c.decode(), np.clip(imgs, 0, 255), rtol=0, atol=1e-9 * 255)  # perfect reconstruction
+    c.threshold(100)
+    assert list(c.nonzero_coefs()) == [100] * 3
+    with pytest.raises(Exception, match="square"):
+        c.dwt2_encode(np.zeros((1, 32, 64)), 2, "haar")
+    with pytest.raises(Exception):
+        c.threshold_by_percentage(0.5)  # regions do not exist for this encoding

@@ -53,3 +53,34 @@ def test_oracle_threshold_by_percentage_reproduces_reference():
         dec = c_oracle.decode(enc, th, fb)
         assert np.max(np.abs(dec - g["decoded"])) <= 1e-9 * 255
         assert abs(c_oracle.psnr(g["img"], dec) - g["psnr"]) < 5e-7
+
+
+def test_oracle_dwt2_baseline():
+    """The 2-D baseline's restatement (oracle/pywt_port.py wavedec2 / waverec2; reference class Dwt, rbepwt.py:2249-2298).
+    PyWavelets is not in this image, so this is pinned through what pywt documents: dwt2 = the 1-D periodized dwt (which
+    the golden fixtures pin) along axis 0 then axis 1, quadrant names (cH = high along rows, cV = high along columns),
+    the Haar closed form, orthogonality and perfect reconstruction."""
+    from oracle import pywt_port
+
+    rng = np.random.default_rng(3)
+    x = rng.uniform(0, 255, (32, 32))
+    co = pywt_port.wavedec2(x, "haar", 1)
+    a, b, c, d = x[0::2, 0::2], x[0::2, 1::2], x[1::2, 0::2], x[1::2, 1::2]
+    np.testing.assert_allclose(co[0], (a + b + c + d) / 2, atol=1e-12 * 255)
+    cH, cV, cD = co[1]
+    np.testing.assert_allclose(np.abs(cH), np.abs(a + b - c - d) / 2, atol=1e-12 * 255)  # detail along the rows axis
+    np.testing.assert_allclose(np.abs(cV), np.abs(a - b + c - d) / 2, atol=1e-12 * 255)
+    np.testing.assert_allclose(np.abs(cD), np.abs(a - b - c + d) / 2, atol=1e-12 * 255)
+    for wav, lev in (("db3", 3), ("bior4.4", 5), ("haar", 5)):
+        co = pywt_port.wavedec2(x, wav, lev)
+        assert co[0].shape == (32 >> lev, 32 >> lev) and len(co) == lev + 1
+        np.testing.assert_allclose(pywt_port.waverec2(co, wav), x, atol=1e-9 * 255)
+        if wav != "bior4.4":  # orthogonal banks keep the energy
+            e = np.sum(co[0] ** 2) + sum(np.sum(q ** 2) for t in co[1:] for q in t)
+            assert abs(e - np.sum(x ** 2)) <= 1e-9 * np.sum(x ** 2)
+    # separable: one level = 1-D dwt of every column, then of every row
+    lo = np.stack([pywt_port.dwt(x[:, j], "db3")[0] for j in range(32)], axis=1)
+    aa = np.stack([pywt_port.dwt(lo[i], "db3")[0] for i in range(16)], axis=0)
+    np.testing.assert_allclose(pywt_port.wavedec2(x, "db3", 1)[0], aa, atol=1e-12 * 255)
+    dec, nz, mags = pywt_port.dwt2_baseline(x, 3, "db3", 40)
+    assert nz == 40 and len(mags) == 40 and dec.shape == x.shape
