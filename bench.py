@@ -537,7 +537,7 @@ def run_ours(args):
         "paths_big": ("k1_paths_big", 4 * N + 4 * S),
         "perm": ("k2_perm", 4 * S + 4 * (S - N)),                          # pixel ids in; positions (levels >= 2) out
         "dwt": ("k3_dwt_level", 4 * S + 8 * S + 8 * S),                    # paths + gathered values in, cA/cD out
-        "select": ("k4_threshold", 8 * N + 8 * N),
+        "select": ("k4_select", 8 * N),                                      # one read of the coefficients (the threshold is applied by K5 on load)
         "idwt": ("k5_idwt_level", 4 * S + 8 * S + 8 * S),
     }
     kern_stages = [s for s in alg if stage_ms.get(s, 0.0) > 0.0]
@@ -552,7 +552,7 @@ def run_ours(args):
     achieved = bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9
     traffic, traffic_src = None, None
     try:  # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this run's launch size
-        with open(os.path.join(ROOT, "profiles", "r1c_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             tj = json.load(f)
         es = [tj[k_] for k_ in ((alg[dom][0], "k1_bitmaps") if dom == "paths" else (alg[dom][0],)) if k_ in tj]
         if es:

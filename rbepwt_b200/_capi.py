@@ -10,7 +10,7 @@ _lib = None
 E_NOT_POW2, E_LEVELS, E_NO_ENCODING, E_NO_GPU = -2, -3, -4, -7
 PATH_EUCLID, PATH_CHEB, PATH_EPWT, PATH_GRAD, PATH_GRAD_CHEB = 0, 1, 2, 3, 4
 DEVICE_PTRS, U8_WRAP, PATHS_FIRST_LEVEL, NO_CLIP = 1, 2, 4, 8
-OPT_STREAMS, OPT_SUBBATCH, OPT_PATHGROUP = 1, 2, 3
+OPT_STREAMS, OPT_SUBBATCH, OPT_PATHGROUP, OPT_COOP_LIMIT = 1, 2, 3, 4
 F64, F32, U8 = 0, 1, 2   # pixel element types of rbepwt_transcode_ex
 I32, U16 = 0, 1         # label element types
 T_NAMES = ["h2d", "regions", "paths", "dwt", "select", "idwt", "d2h", "paths_big", "perm"]

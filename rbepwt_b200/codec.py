@@ -174,11 +174,13 @@ class BatchCodec:
         self.shape, self.levels, self.mode = shape, int(levels), mode
         return self
 
-    def set_option(self, streams=None, sub_batch=None, path_group=None):
+    def set_option(self, streams=None, sub_batch=None, path_group=None, coop_limit=None):
         """streams: 1 (all kernels on one stream) or 2 units in flight; sub_batch / path_group: images per
         transform sub-batch / per path group (0 = auto)."""
         if path_group is not None:
             _capi.check(self._lib.rbepwt_set_option(self._ctx, _capi.OPT_PATHGROUP, int(path_group)))
+        if coop_limit is not None:
+            _capi.check(self._lib.rbepwt_set_option(self._ctx, _capi.OPT_COOP_LIMIT, int(coop_limit)))
         if streams is not None:
             _capi.check(self._lib.rbepwt_set_option(self._ctx, _capi.OPT_STREAMS, int(streams)))
         if sub_batch is not None:

@@ -31,7 +31,10 @@ constexpr int FWD_TILE = 512;   // low-pass outputs per CTA
 constexpr int INV_TILE = 1024;  // reconstructed samples per CTA
 
 constexpr int FT_MAX = 10;  // filter lengths up to this have kernels with the taps unrolled (bior4.4 = 10)
-constexpr int TAIL_MAX_POINTS = 2048;  // levels with at most this many points per image run in the tail kernels
+#ifndef RB_TAIL_MAX_POINTS
+#define RB_TAIL_MAX_POINTS 2048
+#endif
+constexpr int TAIL_MAX_POINTS = RB_TAIL_MAX_POINTS;  // levels with at most this many points per image run in the tail kernels
 
 struct DwtParams {
   const double *vin;   // level 1 of the forward transform: the images, image stride vin_stride

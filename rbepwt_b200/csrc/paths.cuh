@@ -55,7 +55,6 @@ struct PathParams {
   const int32_t *queue;
   const int32_t *chunk_start, *chunk_cnt;  // chunk table of the thread-per-region kernel (regions.cuh)
   int *qmeta;
-  int coop_min;  // regions of at least this many pixels get a warp of their own
   const uint8_t *unit_lut;  // 9 x 512 unit-step table of the path mode (global memory, built once per context)
   const uint8_t *t2_tab;    // 5x5 step table of the euclid mode (walk.cuh, T2_BYTES)
   uint32_t *gbm;            // [gbm_chunks][TPR_ARENA_WORDS] chunk arena images built by k1_bitmaps (walk.cuh)

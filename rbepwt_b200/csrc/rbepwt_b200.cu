@@ -93,7 +93,8 @@ constexpr int TPR_WAVES = 8;  // k1_walk grid = this many waves of resident CTAs
 struct Slot {
   cudaStream_t s = nullptr;
   cudaStream_t aux = nullptr;     // path slots: the large-bitmap path kernel runs beside the bulk one
-  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  cudaStream_t aux2 = nullptr;    // ... and so does the kernel of the oversized regions (k1_paths_big)
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
   DevBuf VA, VB, Vpix, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch, gbm;
 };
 
@@ -109,6 +110,7 @@ struct rbepwt_ctx {
   int nslot = NSLOT;      // RBEPWT_OPT_STREAMS
   int opt_sub = 0;        // RBEPWT_OPT_SUBBATCH (0 = auto)
   int opt_group = 0;      // RBEPWT_OPT_PATHGROUP (0 = auto)
+  int opt_coop_limit = -1;  // RBEPWT_OPT_COOP_LIMIT (-1 = auto)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<cudaEvent_t> ev_lab, ev_path, ev_img, ev_done;
   int32_t *pin_R = nullptr, *pin_rbase = nullptr;  // pinned staging, capacity pin_cap images
@@ -229,11 +231,13 @@ int chunk_images(const rbepwt_ctx *c, int B, int N) {
   return std::min(std::min(m, 1024), B);
 }
 
-// images per transform sub-batch: about 2^24 pixels -- enough CTAs per launch to fill the GPU, few enough that
-// copies and kernels of neighbouring sub-batches overlap
-int sub_images(const rbepwt_ctx *c, int nb, int N) {
+// images per transform sub-batch.  Host inputs: about 2^24 pixels -- enough CTAs per launch to fill the GPU, few enough
+// that copies and kernels of neighbouring sub-batches overlap.  Device-resident inputs: nothing to overlap with but the
+// next path group, and every launch of a small level costs its few microseconds whatever the size: about 2^26 pixels
+// (measured, 512 images of 512^2: forward + select + inverse 4.2 ms in sub-batches of 64, 2.6 ms in sub-batches of 256).
+int sub_images(const rbepwt_ctx *c, int nb, int N, bool host_inputs) {
   if (c->opt_sub > 0) return std::min(c->opt_sub, nb);
-  const int m = (int)std::max<long long>(1, (1ll << 24) / N);
+  const int m = (int)std::max<long long>(1, (1ll << (host_inputs ? 24 : 26)) / N);
   return std::min(m, nb);
 }
 
@@ -441,10 +445,13 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     const int qb = std::max(1, std::min((nreg + 255) / 256, c->sm_count * 8));
     // few regions in flight (single images, small batches): every region gets its own warp -- latency, not throughput
     const bool grad = c->mode == RBEPWT_PATH_GRAD || c->mode == RBEPWT_PATH_GRAD_CHEB;  // gradpath: always warp per region
-    coop_min = (grad || (c->mode == RBEPWT_PATH_EUCLID && nreg <= TPR_COOP_ALL_BELOW)) ? 1 : TPR_COOP_MIN;
-    kq_hist<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, coop_min, sl.qhist.as<int>());
-    kq_scan<<<1, 32, 0, s>>>(sl.qhist.as<int>(), sl.qmeta.as<int>(), sl.qbins.as<int>(), nreg);
-    kq_scatter<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, coop_min, sl.qmeta.as<int>(), sl.queue.as<int32_t>());
+    coop_min = (grad || (c->mode == RBEPWT_PATH_EUCLID && nreg <= TPR_COOP_ALL_BELOW && c->opt_coop_limit != 0)) ? 1 : TPR_COOP_MIN;
+    // coop_min > 1: kq_scan picks the threshold (the largest regions, at most coop_limit of them; only the Euclidean
+    // walker has a whole-warp variant inside k1_walk)
+    const int coop_limit = c->mode != RBEPWT_PATH_EUCLID ? 0 : (c->opt_coop_limit >= 0 ? c->opt_coop_limit : c->sm_count * COOP_PER_SM);
+    kq_hist<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, coop_min > 1 ? INT32_MAX : coop_min, sl.qhist.as<int>());
+    kq_scan<<<1, 32, 0, s>>>(sl.qhist.as<int>(), sl.qmeta.as<int>(), sl.qbins.as<int>(), nreg, coop_min, coop_limit);
+    kq_scatter<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, sl.qmeta.as<int>(), sl.queue.as<int32_t>());
     kq_chunks<<<Q_NCLS - 1, 1024, 0, s>>>(sl.qbins.as<int>(), sl.chunk_start.as<int32_t>(), sl.chunk_cnt.as<int32_t>());
     c->launches += 6;
     CK(cudaGetLastError());
@@ -459,7 +466,6 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   P.chunk_start = sl.chunk_start.as<int32_t>();
   P.chunk_cnt = sl.chunk_cnt.as<int32_t>();
   P.qmeta = sl.qmeta.as<int>();
-  P.coop_min = coop_min;
   P.unit_lut = c->unit_lut.as<uint8_t>() + (c->mode == RBEPWT_PATH_CHEB ? TPR_LUT_ROWS * TPR_LUT_COLS : 0);
   P.t2_tab = c->t2_tab.as<uint8_t>();
   P.gbm = sl.gbm.as<uint32_t>();
@@ -501,22 +507,27 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   else
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tpr_per_sm, k1_walk<MODE_CHEB, false>, WK_WARPS * 32, wk_arena_bytes(false)));
   const int small_ctas = c->sm_count * std::max(tpr_per_sm, 1) * TPR_WAVES;
+  // the oversized regions (one warp each, the longest chains of all) run beside everything else, on their own stream
+  // (RBEPWT_OPT_STREAMS = 1, per-kernel timing: in line, so that its time is its own and not the wait for an SM)
+  cudaStream_t sbig = c->nslot == 1 ? s : sl.aux2;
+  CK(cudaEventRecord(sl.ev_a, s));
+  CK(cudaStreamWaitEvent(sl.aux2, sl.ev_a, 0));
   {
-    StageTimer tb(c, RBEPWT_T_PATHS_BIG, s);
+    StageTimer tb(c, RBEPWT_T_PATHS_BIG, sbig);
     if (c->mode == RBEPWT_PATH_EUCLID) {
       CK(cudaFuncSetAttribute(k1_paths_big<MODE_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-      k1_paths_big<MODE_EUCLID><<<big_ctas, 32, smem_bytes, s>>>(P);
+      k1_paths_big<MODE_EUCLID><<<big_ctas, 32, smem_bytes, sbig>>>(P);
     } else {
       CK(cudaFuncSetAttribute(k1_paths_big<MODE_CHEB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-      k1_paths_big<MODE_CHEB><<<big_ctas, 32, smem_bytes, s>>>(P);
+      k1_paths_big<MODE_CHEB><<<big_ctas, 32, smem_bytes, sbig>>>(P);
     }
     c->launches++;
   }
+  CK(cudaEventRecord(sl.ev_c, sbig));
   {
     StageTimer t(c, RBEPWT_T_PATHS, s);
     // the large-bitmap chunks (few, the longest chains) run on the slot's auxiliary stream, beside the bulk; they
     // build their own bitmaps, so they start right away, under the bulk kernel's bitmap builder
-    CK(cudaEventRecord(sl.ev_a, s));
     CK(cudaStreamWaitEvent(sl.aux, sl.ev_a, 0));
     if (c->mode == RBEPWT_PATH_EUCLID)
       k1_walk<MODE_EUCLID, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, WK_WIDE_WARPS * 32, wk_arena_bytes(true), sl.aux>>>(P);
@@ -532,6 +543,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     CK(cudaStreamWaitEvent(s, sl.ev_b, 0));
     c->launches += 2;
   }
+  CK(cudaStreamWaitEvent(s, sl.ev_c, 0));
   }
   {
     StageTimer t(c, RBEPWT_T_PERM, s);
@@ -743,7 +755,8 @@ int run_pipeline(rbepwt_ctx *c, int what, long long k, const void *img_host, con
   };
   for (int c0 = 0; c0 < B; c0 += Bc) {
     const int nbc = std::min(Bc, B - c0);
-    const int Bs = sub_images(c, nbc, N);
+    const bool host_io = lab_host || img_host || out_host || (c->io.out_dst && !c->io.out_on_device);
+    const int Bs = sub_images(c, nbc, N, host_io);
     const int Bp = group_images(c, nbc, N, Bs);
     const int nsub = (nbc + Bs - 1) / Bs;
     // Path groups as [start, end) in sub-batches.  With host inputs the groups ramp up (1, 1, 2, 4, ...
@@ -751,9 +764,9 @@ int run_pipeline(rbepwt_ctx *c, int what, long long k, const void *img_host, con
     // still arriving, which is what lets the output copy overlap the input copy.
     std::vector<int> gstart;
     {
-      // device-resident inputs: nothing to overlap the path stage with, one launch over the whole chunk is the
-      // most efficient (the path kernel's long chains are amortised over more regions)
-      const int full = (!lab_host && c->opt_group == 0) ? nsub : Bp / Bs;
+      // device-resident inputs: groups of the full size (2^26 pixels), so that the transform of one group runs under the
+      // path kernel of the next (43.6k against 43.2k images/s with one group of 512)
+      const int full = Bp / Bs;
       int len = (lab_host && c->opt_group == 0 && !serial) ? 1 : full, first = 1;
       for (int s = 0; s < nsub;) {
         gstart.push_back(s);
@@ -913,6 +926,8 @@ static int create_impl(rbepwt_ctx *c, int device, void *stream) {
     // It must not queue behind the bulk kernel's thousands of CTAs (measured: the stage lasts 12.5 instead of
     // 10.7 ms when it does), so it outranks it.
     CK(cudaStreamCreateWithPriority(&c->slot[i].aux, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&c->slot[i].aux2, cudaStreamNonBlocking, prio_hi));
+    CK(cudaEventCreateWithFlags(&c->slot[i].ev_c, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->slot[i].ev_a, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->slot[i].ev_b, cudaEventDisableTiming));
   }
@@ -982,6 +997,8 @@ void rbepwt_destroy(rbepwt_ctx *c) {
     for (auto b : sb) b->release();
     if (sl.s) cudaStreamDestroy(sl.s);
     if (sl.aux) cudaStreamDestroy(sl.aux);
+    if (sl.aux2) cudaStreamDestroy(sl.aux2);
+    if (sl.ev_c) cudaEventDestroy(sl.ev_c);
     if (sl.ev_a) cudaEventDestroy(sl.ev_a);
     if (sl.ev_b) cudaEventDestroy(sl.ev_b);
   }
@@ -1013,6 +1030,10 @@ int rbepwt_set_option(rbepwt_ctx *c, int option, int64_t value) {
     case RBEPWT_OPT_SUBBATCH:
       if (value < 0 || value > (1 << 20)) return fail(RBEPWT_E_ARG, "RBEPWT_OPT_SUBBATCH out of range");
       c->opt_sub = (int)value;
+      return RBEPWT_OK;
+    case RBEPWT_OPT_COOP_LIMIT:
+      if (value < -1 || value > (1 << 30)) return fail(RBEPWT_E_ARG, "RBEPWT_OPT_COOP_LIMIT out of range");
+      c->opt_coop_limit = (int)value;
       return RBEPWT_OK;
     case RBEPWT_OPT_PATHGROUP:
       if (value < 0 || value > (1 << 20)) return fail(RBEPWT_E_ARG, "RBEPWT_OPT_PATHGROUP out of range");

@@ -404,6 +404,13 @@ constexpr int Q_BINS = Q_NCLS * Q_SIZE_BINS;
 #define TPR_COOP_MIN_N 2048
 #endif
 constexpr int TPR_COOP_MIN = TPR_COOP_MIN_N;  // regions of at least this many pixels are walked by a whole warp
+#ifndef COOP_PER_SM_N
+#define COOP_PER_SM_N 0
+#endif
+constexpr int COOP_PER_SM = COOP_PER_SM_N;    // ... at most this many per SM in a path group (kq_scan), the largest ones.
+// Measured (tools/coop_sweep.py, 256 images of 512^2): 0 is never worse -- heavy-tailed maps 14.5 ms per batch against 23.7
+// with every region of >= 2048 pixels on a warp of its own, Voronoi 64 seeds 22.1 against 36.6 -- so the default keeps the
+// whole-warp walker for small groups only (TPR_COOP_ALL_BELOW: latency, not throughput).
 constexpr int TPR_COOP_ALL_BELOW = 4096;      // ... and every region, when the whole group has at most this many
 constexpr int TPR_MAX_SIDE = 1024;     // bounding-box side limit of k1_walk (its packed candidate key)
 
@@ -443,9 +450,15 @@ __host__ __device__ __forceinline__ int class_chunk_size(int cls) {
   return cs[cls];
 }
 
+// eighth-octave size key (monotone in size, <= 8*30+7) and the smallest size of a key
+__device__ __forceinline__ int size_key(int size) {
+  const int lg = 31 - __clz(size);  // size >= 1
+  return size >= 8 ? 8 * lg + ((size >> (lg - 3)) & 7) : size;
+}
+__device__ __forceinline__ int key_min_size(int key) { return key >= 24 ? (8 + (key & 7)) << ((key >> 3) - 3) : key; }
+
 __device__ __forceinline__ int queue_bin(int size, int words, int coop_min) {
-  const int lg = 31 - __clz(size);                                        // size >= 1
-  const int key = size >= 8 ? 8 * lg + ((size >> (lg - 3)) & 7) : size;    // <= 8*30+7, monotone in size
+  const int key = size_key(size);
   int cls = 0;
   if (words <= TPR_ARENA_WORDS) {
     cls = Q_NCLS - 1;
@@ -472,12 +485,59 @@ __global__ void kq_hist(RegionArrays reg, int g0, int nreg, int logW, int coop_m
 // qbins: per class: [0, Q_NCLS) queue start, [Q_NCLS, 2 Q_NCLS) count, [2 Q_NCLS, 3 Q_NCLS) first chunk.
 constexpr int QM_NBIG = Q_BINS, QM_NREG = Q_BINS + 1, QM_CUR_BIG = Q_BINS + 2, QM_CUR_SMALL = Q_BINS + 3,
               QM_ERR = Q_BINS + 4, QM_NCHUNKS = Q_BINS + 5, QM_CHUNK_SPLIT = Q_BINS + 6, QM_CUR_WIDE = Q_BINS + 7,
-              QM_SIZE = Q_BINS + 8;
+              QM_COOP_SIZE = Q_BINS + 8,  // regions of at least this many pixels are walked by a whole warp (kq_scan decides)
+              QM_SIZE = Q_BINS + 9;
 constexpr int Q_FIRST_NARROW_CLS = 6;  // classes 1..5 (planes of more than 128 words: at most 6 regions per warp): the windowed variant of k1_walk
 
-__global__ void kq_scan(int *qhist, int *qmeta, int *qbins, int nreg) {
-  // one warp: exclusive scan of the bin counts (queue offsets); per class: queue start, count, first chunk
+// One warp.  First the whole-warp ("coop") threshold: kq_hist filed every region by its bitmap size alone when
+// coop_min > 1; here the LARGEST regions -- at most coop_limit of them, none smaller than coop_min -- move to class 1
+// (one region per chunk), where the windowed k1_walk hands them to the whole-warp walker.  A whole warp on one chain
+// steps it faster than a lane does, but spends ~10x the issue slots per step: it pays for the few longest chains of
+// a group (they set the kernel's tail), not for thousands of them (heavy-tailed maps: 40 regions of >= 2048 pixels
+// per image).  The threshold lies on a size-key boundary, so moving whole bins is exact.  coop_min <= 1: the host
+// asked for a warp per region (gradpath, single images), kq_hist filed them so already.
+// Then the exclusive scan of the bin counts (queue offsets); per class: queue start, count, first chunk.
+__global__ void kq_scan(int *qhist, int *qmeta, int *qbins, int nreg, int coop_min, int coop_limit) {
   const int lane = threadIdx.x;
+  int coop_size = coop_min;
+  if (coop_min > 1) {
+    constexpr int PER = Q_SIZE_BINS / 32;
+    int tot[PER], lsum = 0;
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+      int t = 0;
+      for (int cls = 2; cls < Q_NCLS; cls++) t += qhist[cls * Q_SIZE_BINS + lane * PER + u];
+      tot[u] = t;
+      lsum += t;
+    }
+    int inc = lsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_up_sync(FULL_MASK, inc, d);
+      if (lane >= d) inc += y;
+    }
+    const int kmin = size_key(coop_min);
+    int cum = inc - lsum, last = -1;
+#pragma unroll
+    for (int u = 0; u < PER; u++) {  // bin j holds the size key Q_SIZE_BINS - 1 - j: bins in descending size
+      const int j = lane * PER + u;
+      cum += tot[u];
+      if (cum <= coop_limit && Q_SIZE_BINS - 1 - j >= kmin) last = j;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) last = max(last, __shfl_xor_sync(FULL_MASK, last, d));
+    coop_size = last >= 0 ? key_min_size(Q_SIZE_BINS - 1 - last) : INT32_MAX;
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+      const int j = lane * PER + u;
+      if (j <= last && tot[u]) {
+        for (int cls = 2; cls < Q_NCLS; cls++) qhist[cls * Q_SIZE_BINS + j] = 0;
+        qhist[Q_SIZE_BINS + j] += tot[u];
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) qmeta[QM_COOP_SIZE] = coop_size;
   int acc = 0, cacc = 0;
   for (int cls = 0; cls < Q_NCLS; cls++) {
     const int cstart = acc;
@@ -513,7 +573,8 @@ __global__ void kq_scan(int *qhist, int *qmeta, int *qbins, int nreg) {
   }
 }
 
-__global__ void kq_scatter(RegionArrays reg, int g0, int nreg, int logW, int coop_min, int *qmeta, int32_t *queue) {
+__global__ void kq_scatter(RegionArrays reg, int g0, int nreg, int logW, int *qmeta, int32_t *queue) {
+  const int coop_min = qmeta[QM_COOP_SIZE];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nreg; i += gridDim.x * blockDim.x) {
     const int g = g0 + i;
     const int bin = queue_bin(reg.size[g], region_class_words(reg, g, logW), coop_min);

@@ -756,7 +756,7 @@ __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WID
     if (WIDEWIN && MODE == MODE_EUCLID && cnt == 1) {
       // one long chain: the whole warp walks it together (paths.cuh, find_next_geo)
       const int g = P.queue[qstart];
-      if (P.reg.size[g] >= P.coop_min) {
+      if (P.reg.size[g] >= P.qmeta[QM_COOP_SIZE]) {
         region_pyramid<MODE>(P, g, arena, s_lut);
         __syncwarp();
         continue;
@@ -936,6 +936,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_perm(PathParams P, int nreg,
   const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
   const int nw = gridDim.x * K2_WARPS;
   const int N = P.N, logW = P.logW, Wm = P.W - 1, L = P.levels;
+  const int coop_size = P.qmeta[QM_COOP_SIZE];
   for (int q = blockIdx.x * K2_WARPS + warp; q < nreg; q += nw) {
     const int g = P.queue[q];  // queue order: the largest regions first
     const int img = P.reg.img[g], a1 = P.reg.off[g], n1 = P.reg.size[g];
@@ -943,8 +944,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_perm(PathParams P, int nreg,
     const int hb = P.reg.rmax[g] - r0 + 1, wb = P.reg.cmax[g] - c0 + 1;
     const bool in_smem = hb * wb <= K2_CELLS && n1 < 65536;
     // levels of at most `skip_below` points were done by the walker (never level 1); 0 = this region was walked by a warp
-    // (coop: the path mode hands regions of at least coop_min pixels to the whole-warp walker)
-    const bool by_warp = region_class_words(P.reg, g, logW) > TPR_ARENA_WORDS || (coop && n1 >= P.coop_min);
+    // (coop: the path mode hands regions of at least qmeta[QM_COOP_SIZE] pixels to the whole-warp walker)
+    const bool by_warp = region_class_words(P.reg, g, logW) > TPR_ARENA_WORDS || (coop && n1 >= coop_size);
     const int skip_below = by_warp ? 0 : WK_LIST_MAX;
     const int32_t *Qimg = P.Q + (size_t)img * 2 * (size_t)N;
     int32_t *Pimg = P.Pm + (size_t)img * 2 * (size_t)N;

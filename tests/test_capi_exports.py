@@ -96,7 +96,7 @@ def test_bench_traffic_file_matches_bench():
     assert len(names) == 1, names
     with open(os.path.join(root, "profiles", names[0])) as f:
         tj = json.load(f)
-    for k in ("k1_paths_tpr", "k1_bitmaps"):
+    for k in ("k1_walk", "k1_bitmaps"):
         e = tj[k]
         assert e["dram_bytes_read"] > 0 and e["dram_bytes_write"] > 0 and e["images_per_launch"] > 0
     assert isinstance(tj["source"], str)

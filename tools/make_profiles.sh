@@ -1,15 +1,21 @@
 #!/bin/bash
 # usage (GPU box): tools/make_profiles.sh <round-tag>
 # 1. plain bench run (must exit 0), 2. ncu launch list of our kernels over one step,
-# 3. ncu --set full of one launch of each hot kernel.  Everything lands in gpurun_out/.
+# 3. ncu --set full of one launch of each hot kernel.  Everything lands in gpurun_out/;
+#    tools/summarize_profiles.py <tag> turns it into the committed profiles/<tag>_*.txt.
 tag=$1
-ARGS="--batch 512 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
+T=/tmp/prof_$tag; mkdir -p $T gpurun_out   # the .ncu-rep files stay on the box (gpurun_out/ is capped at 64 MiB): summaries travel
+ARGS="--batch 512 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-extras --parity-images 0"
 python bench.py $ARGS > gpurun_out/prof_plain_$tag.json 2> gpurun_out/prof_plain_$tag.err || { echo "plain run failed"; tail -5 gpurun_out/prof_plain_$tag.err; exit 1; }
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k[0-9q_]" -c 400 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k[0-9q_]" -c 600 --csv \
     --log-file gpurun_out/launches_$tag.csv python bench.py $ARGS > gpurun_out/ncu_list_$tag.log 2>&1
-for k in k1_paths_tpr k1_bitmaps k3_dwt_level k5_idwt_level k4_threshold k0_regions_fast k0_count; do
-  skip=2; [ $k = k1_paths_tpr ] && skip=3; [ $k = k3_dwt_level ] && skip=14; [ $k = k5_idwt_level ] && skip=20
-  ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -o gpurun_out/prof_${k}_$tag \
+# launch-skip: 3 warm-up steps; k1_walk launches twice per step (windowed instantiation first), k3/k5 7 times per
+# 64-image sub-batch (6 level launches + the tail) -- the captures land on the timed step's first launches
+for spec in k1_walk:6:2 k1_bitmaps:3:1 k2_perm:3:1 k4_select:24:1 k3_dwt_level:168:1 k5_idwt_level:174:1 k3_dwt_tail:24:1 k0_regions_fast:3:1 k0_count:3:1; do
+  IFS=: read k skip cnt <<< "$spec"
+  ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c $cnt -o $T/prof_${k}_$tag \
       python bench.py $ARGS > gpurun_out/ncu_full_${k}_$tag.log 2>&1
 done
-ls -la gpurun_out | grep $tag
+PROF_SRC=$T PROF_LAUNCHES=gpurun_out PROF_DST=gpurun_out/profiles_$tag python tools/summarize_profiles.py $tag
+cp $T/prof_k1_walk_$tag.ncu-rep gpurun_out/ 2>/dev/null
+ls -la gpurun_out/profiles_$tag

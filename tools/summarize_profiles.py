@@ -10,11 +10,13 @@ import sys
 
 tag = sys.argv[1]
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+G = os.environ.get("PROF_SRC", os.path.join(ROOT, "gpurun_out"))      # the .ncu-rep files
+GL = os.environ.get("PROF_LAUNCHES", os.path.join(ROOT, "gpurun_out"))  # the launch list
+P = os.environ.get("PROF_DST", os.path.join(ROOT, "profiles"))
 os.makedirs(P, exist_ok=True)
 
 # ---- launch list
-rows = list(csv.reader(open(os.path.join(G, "launches_%s.csv" % tag))))
+rows = list(csv.reader(open(os.path.join(GL, "launches_%s.csv" % tag))))
 for i, r in enumerate(rows):
     if "Kernel Name" in r:
         h, start = r, i
@@ -22,7 +24,7 @@ for i, r in enumerate(rows):
 kn, mv, idc, gs, bs = h.index("Kernel Name"), h.index("Metric Value"), h.index("ID"), h.index("Grid Size"), h.index("Block Size")
 data = [(int(r[idc]), r[kn].split("(")[0], float(r[mv].replace(",", "")), r[gs], r[bs]) for r in rows[start + 2:] if len(r) > mv]
 with open(os.path.join(P, "%s_launches.txt" % tag), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k[0-9q_]  python bench.py --batch 512 --steps 1 --warmup 3\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k[0-9q_]  python bench.py --batch 512 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-extras --parity-images 0\n")
     f.write("# per-launch device time (ns), cold-cache and serialised by ncu: compare SHARES, not absolutes.\n")
     f.write("# The list covers the warm-up steps, the timed step and the serial kernel-timing steps of bench.py.\n")
     agg = collections.OrderedDict()
@@ -51,7 +53,7 @@ for rep in sorted(glob.glob(os.path.join(G, "prof_*_%s.ncu-rep" % tag))):
     rr = list(csv.reader(out.splitlines()))
     hdr, units = rr[0], rr[1]
     with open(os.path.join(P, "%s_ncu_%s.txt" % (tag, name)), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -k regex:%s -s 2 -c 1  python bench.py --batch 512 --steps 1 --warmup 3\n" % name)
+        f.write("# ncu --set full --clock-control none --import-source on -k regex:%s -s <3 warm-up steps> -c 1|2  python bench.py --batch 512 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-extras --parity-images 0   (tools/make_profiles.sh)\n" % name)
         for r in rr[2:]:
             f.write("== %s  grid %s block %s\n" % (r[hdr.index("Kernel Name")], r[hdr.index("Grid Size")] if "Grid Size" in hdr else "?", r[hdr.index("Block Size")] if "Block Size" in hdr else "?"))
             for hh, u, v in zip(hdr, units, r):
@@ -59,3 +61,29 @@ for rep in sorted(glob.glob(os.path.join(G, "prof_*_%s.ncu-rep" % tag))):
                     if hh.endswith((".sum", ".ratio", "active", "elapsed")) or "pcsamp" in hh or "launch" in hh or "per_second" in hh:
                         f.write("  %-78s %-14s %s\n" % (hh, u, v))
     print("wrote", name)
+
+# ---- DRAM traffic of the hot kernels (bench.py scales roofline.traffic from this file)
+import json
+traffic = {"source": "profiles/%s_ncu_*.txt (ncu --set full, one launch each: k1_walk = both instantiations of one 512-image path group; k3/k5 = the level-1 launch of one sub-batch; tools/make_profiles.sh)" % tag}
+for rep in sorted(glob.glob(os.path.join(G, "prof_*_%s.ncu-rep" % tag))):
+    name = os.path.basename(rep)[len("prof_"):-len("_%s.ncu-rep" % tag)]
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(out.splitlines()))
+    hdr, units = rr[0], rr[1]
+    def col(r, n):
+        i = hdr.index(n)
+        v = float(r[i].replace(",", ""))
+        u = units[i]
+        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6}.get(u, 1.0)
+    e = {"dram_bytes_read": 0.0, "dram_bytes_write": 0.0, "duration_us": 0.0, "launches_summed": 0}
+    for r in rr[2:]:
+        e["dram_bytes_read"] += col(r, "dram__bytes_read.sum")
+        e["dram_bytes_write"] += col(r, "dram__bytes_write.sum")
+        e["duration_us"] += col(r, "gpu__time_duration.sum")
+        e["launches_summed"] += 1
+        gy = r[hdr.index("Grid Size")].strip("()").replace(" ", "").split(",") if "Grid Size" in hdr else []
+    e["images_per_launch"] = int(gy[1]) if name in ("k3_dwt_level", "k5_idwt_level") and len(gy) > 1 else (int(gy[0]) if name in ("k4_select", "k3_dwt_tail") else 512)
+    traffic[name] = e
+with open(os.path.join(P, "%s_traffic.json" % tag), "w") as f:
+    json.dump(traffic, f, indent=1)
+print("wrote traffic")

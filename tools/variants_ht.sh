@@ -2,7 +2,7 @@
 # usage (GPU box): tools/variants_ht.sh "<name>:<-D flags>" ...   builds each variant and times the heavy-tailed workload
 for v in "$@"; do
   name=${v%%:*}; flags=${v#*:}
-  so=gpurun_out/lib_$name.so
+  mkdir -p /tmp/var; so=/tmp/var/lib_$name.so
   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -shared --cudart static $flags -o $so rbepwt_b200/csrc/rbepwt_b200.cu || exit 1
-  echo "== $name"; RBEPWT_B200_LIB=$PWD/$so python tools/heavytail_timing.py 256 2>&1 | tail -1 | cut -c1-60,150-300
+  echo "== $name"; RBEPWT_B200_LIB=$so python tools/heavytail_timing.py 256 2>&1 | tail -1 | cut -c1-60,150-300
 done
