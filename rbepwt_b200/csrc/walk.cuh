@@ -16,10 +16,12 @@
 //    five shared-memory row words and shifts (no bounds checks) give the window as a 25-bit register
 //    N25, and the step is resolved from it: the classes d2 = 1, 2, 4, 5, 8 in that order are exactly
 //    "probe 1, then probe 2, nearest first" (euclid; chebyshev: ring 1, then ring 2), the first
-//    non-empty class holds the candidates, one candidate wins outright, several compete through the
-//    reference's direction tie-break.  On the benchmark 89 % of all steps end here whatever the
-//    previous step was (tools/tie_stats.c); with a unit preferred direction and a non-empty 3x3 ring
-//    the winner is read from a 9 x 256 table filled once by the same candidate code.
+//    non-empty class holds the candidates, and the winner among them for the current preferred
+//    direction is ONE byte of the table T2 ([25 prefs that are 5x5 offsets][320]: the class's subset,
+//    4 or 8 bits, is turned into a table slot by a multiply-shift perfect hash of N25 & class mask --
+//    no bit gathering).  The table is filled once per context by the same candidate code the other
+//    steps use (wk_t2_fill), so its entries are the reference's tie-break by construction.  On the
+//    benchmark 89 % of all steps end here (tools/tie_stats.c).
 //  * Lanes are not synchronised per level.  A lane that finishes a level starts the next one
 //    immediately (the region offsets of every level follow from the level-1 sizes alone), so a warp
 //    never waits for its slowest lane at each of the 16 levels, only once per chunk.
@@ -29,11 +31,12 @@
 //    pixel ids (Q) and never reads them back; the positions in the incoming order (Pm) the transform
 //    kernels gather through are computed afterwards by k2_perm, a fully parallel kernel.
 //
-// Beyond the 5x5 window (FAR): aligned row windows of half-width 4 and 8 ranked by the packed key
-// (k = index of the first probe that would contain the candidate, d2, dot product) -- scanning the window
-// of half-width R once equals the reference's probes up to R in turn, so a search may start at the R
-// that resolved the previous jump; beyond 8 the whole (small) bitmap, or, in the WIDEWIN instantiation
-// for large bitmaps, windows of half-width 16, 32, ... word by word.
+// Beyond the 5x5 window (FAR): the lane only flags the request; the WARP serves the requests one after the
+// other (wk_far_search: lanes = rows of the requester's bitmap plane, a row's candidate = its nearest unvisited
+// column on either side, ranked by the packed key (k = index of the first probe that would contain the candidate,
+// d2) and the dot product, two warp reductions) -- scanning the whole plane once equals the reference's probes
+// 4, 8, ... in turn.  The lane-local form of this search (kept in tests/host_walk as a second restatement) was
+// measured slower: it runs with ~3 of 32 lanes.  After the searches every lane that moved commits in one place.
 //
 // List mode: from the first level with at most WK_LIST_MAX points the lane drops the bitmaps and holds
 // the points as a list of packed (row, col); a step scans the unvisited ones (a 32-bit mask).
