@@ -36,18 +36,34 @@ def needs_build():
 
 
 def build_library(force=False, verbose=False):
+    """Several processes may get here at once (one rank per GPU under torchrun): one builds, under a file lock, into a
+    temporary file that is renamed over the library -- nobody ever dlopens a half-written file -- and the others find
+    it up to date when they get the lock."""
+    import fcntl
+
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        "-o", LIB_PATH, os.path.join(CSRC, "rbepwt_b200.cu")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building librbepwt_b200.so")
-    if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB_PATH
+            tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+                "-o", tmp, os.path.join(CSRC, "rbepwt_b200.cu")]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building librbepwt_b200.so")
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                sys.stderr.write(res.stdout + res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
