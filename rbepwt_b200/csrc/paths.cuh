@@ -106,6 +106,12 @@ __host__ __device__ __forceinline__ double tie_sp1(int di, int dj, int d2, int p
   return s;
 }
 
+// EPWT value loads: the values (the image at level 1, the previous level's approximation laid out by pixel after) are
+// read-only for the whole launch and the walk is local -- the next point is a neighbour -- so they go through L1.
+#ifndef RB_EPWT_LOAD
+#define RB_EPWT_LOAD(p) __ldg(p)
+#endif
+
 template <int MODE>
 __device__ __forceinline__ void consider(Best &b, int i, int j, int ci, int cj, int p0, int p1, double curval,
                                          const double *__restrict__ vals, int pix, bool u8wrap) {
@@ -117,7 +123,7 @@ __device__ __forceinline__ void consider(Best &b, int i, int j, int ci, int cj, 
   } else if (MODE == MODE_CHEB) {
     dist = (double)max(abs(di), abs(dj));
   } else {
-    val = __ldcg(vals + pix);
+    val = RB_EPWT_LOAD(vals + pix);
     const double dv = curval - val;
     dist = u8wrap ? (dv < 0.0 ? dv + 256.0 : dv) : fabs(dv);
   }
@@ -145,14 +151,18 @@ __device__ __forceinline__ void consider(Best &b, int i, int j, int ci, int cj, 
 // Returns false if no unvisited point exists in the whole bounding box (corrupt state).
 // curval (EPWT): in = value at the current point, out = value at the chosen point.
 template <int MODE>
+__device__ __forceinline__ void warp_arg_best(Best &b, int ci, int cj, int p0, int p1, double &curval, int &bi, int &bj);
+
+// start_rad > 0: the probes below that half-width are known to be empty (regwin.cuh)
+template <int MODE>
 __device__ __forceinline__ bool find_next(const uint32_t *bm, int h, int w, int ws, int ci, int cj, int p0, int p1,
                                           const double *__restrict__ vals, int r0, int c0, int logW, bool u8wrap,
-                                          double &curval, int &bi, int &bj) {
+                                          double &curval, int &bi, int &bj, int start_rad = 0) {
   const int lane = (int)lane_id();
   Best b;
   b.have = false; b.has_sp1 = false; b.dist = 0.0; b.val = 0.0; b.sp1 = 0.0; b.cross = 0; b.d2 = 0; b.i = 0; b.j = 0;
-  int rad0 = 1;
-  if (MODE == MODE_EPWT) {
+  int rad0 = start_rad > 0 ? start_rad : 1;
+  if (MODE == MODE_EPWT && start_rad <= 0) {
     // half-width 1, the common case of the one-region walk: one LANE per neighbour, so the eight value
     // loads (L2 latency each) are in flight together instead of one after the other inside a lane
     const int i = ci + lane / 3 - 1, j = cj + lane % 3 - 1;
@@ -184,7 +194,15 @@ __device__ __forceinline__ bool find_next(const uint32_t *bm, int h, int w, int 
     if (__any_sync(FULL_MASK, b.have)) break;
     if (i0 == 0 && j0 == 0 && i1 == h - 1 && j1 == w - 1) return false;
   }
-  // cross-lane arg-best: (dist asc, sp1 desc, cross desc, d2 asc)
+  warp_arg_best<MODE>(b, ci, cj, p0, p1, curval, bi, bj);
+  return true;
+}
+
+// The warp's winner among the lanes' best candidates (at least one lane has one):
+// cross-lane arg-best: (dist asc, sp1 desc, cross desc, d2 asc)
+template <int MODE>
+__device__ __forceinline__ void warp_arg_best(Best &b, int ci, int cj, int p0, int p1, double &curval, int &bi, int &bj) {
+  const int lane = (int)lane_id();
   unsigned tied;
   if (MODE == MODE_EPWT) {
     const unsigned long long k = b.have ? (unsigned long long)__double_as_longlong(b.dist) : ~0ull;  // dist >= 0
@@ -220,7 +238,6 @@ __device__ __forceinline__ bool find_next(const uint32_t *bm, int h, int w, int 
   bi = __shfl_sync(FULL_MASK, b.i, src);
   bj = __shfl_sync(FULL_MASK, b.j, src);
   if (MODE == MODE_EPWT) curval = __shfl_sync(FULL_MASK, b.val, src);
-  return true;
 }
 
 // Warp-cooperative search, euclid mode, integer keys (the derivation is in walk.cuh): the lanes take the
@@ -473,7 +490,7 @@ __device__ __forceinline__ bool run_path(uint32_t *bm, int h, int w, int ws, int
   __syncwarp();
   int p0 = 0, p1 = 1;  // prefered_direc = (0,1)   rbepwt.py:1290
   double curval = 0.0;
-  if (MODE == MODE_EPWT) curval = __ldcg(vals + (((r0 + ci) << logW) + c0 + cj));
+  if (MODE == MODE_EPWT) curval = RB_EPWT_LOAD(vals + (((r0 + ci) << logW) + c0 + cj));
   for (int t = 1; t < n; t++) {
     int bi, bj;
     if (geo) {
@@ -587,6 +604,11 @@ struct EpwtParams {
   int *qmeta;
 };
 
+// the walker with the bitmap window in registers (regwin.cuh)
+__device__ bool rw_run_path_epwt(uint32_t *bm, int h, int w, int ws, int ci, int cj, int n, int logW,
+                                 const double *__restrict__ vals, bool u8wrap, int32_t *__restrict__ Ql,
+                                 int32_t *__restrict__ Pl, const int32_t *posmap);
+
 __global__ void __launch_bounds__(32) k1_epwt_level(EpwtParams P) {
   extern __shared__ uint32_t s_big[];
   const int lane = (int)lane_id();
@@ -610,8 +632,13 @@ __global__ void __launch_bounds__(32) k1_epwt_level(EpwtParams P) {
     __syncwarp();
     start = reduce_points(bm, ws, 0, N >> (P.lev - 2), 0, 0, logW, Q + level_off((size_t)N, P.lev - 1), posmap);
   }
+#ifdef RB_NO_REGWIN
   const bool ok = run_path<MODE_EPWT>(bm, H, W, ws, start >> logW, start & (W - 1), n, 0, 0, logW, vals,
                                       P.u8wrap && P.lev == 1, Ql, Pl, posmap);
+#else
+  const bool ok = rw_run_path_epwt(bm, H, W, ws, start >> logW, start & (W - 1), n, logW, vals, P.u8wrap && P.lev == 1, Ql, Pl,
+                                   posmap);
+#endif
   if (!ok && lane == 0) atomicExch(&P.qmeta[QM_ERR], 1);
 }
 

@@ -1,0 +1,251 @@
+// K1, whole-warp form with the bitmap window in REGISTERS (Euclidean easy path): the walker of the long chains --
+// regions too large for a lane's arena slot (k1_paths_big), and every region of a small group (single images,
+// small batches: latency is all that matters there).
+//
+// A path step is a dependent chain, and one warp alone on a scheduler issues one instruction every ~4-6 cycles, so
+// the time of a chain is the NUMBER OF DEPENDENT INSTRUCTIONS per step (region_pyramid / find_next_geo, paths.cuh:
+// ~100, of which three shared-memory round trips).  Here lane r of the warp keeps 32 bits of bitmap row R0 + r, the
+// columns [C0, C0 + 32): a 32 x 32 window around the current point.  As long as the point stays in the window's
+// central 16 x 16 cells,
+//   * the 5x5 neighbourhood (probes 1 and 2) is five shuffles of a 5-bit slice, resolved by the same class order and
+//     table (T2) as the thread-per-region walker's step (walk.cuh);
+//   * the probes of half-width 4 and 8 are one pass over the lanes' registers (a row's nearest unvisited column on
+//     either side, ranked by (probe index, d2, dot product): wk_row_candidate) and two warp reductions;
+//   * visiting a point clears one bit of one lane's register; the bitmap in shared memory is kept in step by a
+//     fire-and-forget atomic of one lane (nothing waits for it), so that the window can be re-read at any time:
+//     when the point leaves the central cells, and by the search beyond half-width 8 (find_next_geo, from 16 on).
+// Step rule = Region.easy_path (/root/reference/rbepwt.py:1273-1347); the candidate code is shared with walk.cuh.
+#pragma once
+#include "walk.cuh"
+
+namespace rbepwt {
+
+struct RegWin {
+  uint32_t W;  // lane r: unvisited bits of bitmap row R0 + r, columns C0 .. C0 + 31 (cells outside the bitmap read 0)
+  int R0, C0;
+};
+
+__device__ __forceinline__ void rw_load(RegWin &rw, const uint32_t *bm, int h, int ws, int ci, int cj) {
+  rw.R0 = ci - 16; rw.C0 = cj - 16;
+  const int i = rw.R0 + (int)lane_id();
+  uint32_t x = 0u;
+  if ((unsigned)i < (unsigned)h) {
+    const int wq = rw.C0 >> 5, sh = rw.C0 & 31;  // arithmetic shift: floor, C0 may be negative
+    const uint32_t lo = (unsigned)wq < (unsigned)ws ? bm[i * ws + wq] : 0u;
+    const uint32_t hi = (unsigned)(wq + 1) < (unsigned)ws ? bm[i * ws + wq + 1] : 0u;
+    x = __funnelshift_r(lo, hi, sh);
+  }
+  rw.W = x;
+}
+
+// The step from a non-empty 5x5 window (euclid): the nearest class present, its winner for pref (p0, p1).
+__device__ __forceinline__ void rw_near_pick(uint32_t n25, int p0, int p1, const uint8_t *t2, int &di, int &dj) {
+  if ((unsigned)(p0 + 2) <= 4u && (unsigned)(p1 + 2) <= 4u) {
+    const int c = (n25 & N25_A) ? 0 : (n25 & N25_B) ? 1 : (n25 & N25_C) ? 2 : (n25 & N25_D) ? 3 : 4;
+    const int cell = t2[((p0 + 2) * 5 + p1 + 2) * T2_ROW + wk_t2_base(c) + wk_t2_field(c, n25)];
+    di = (cell * 13) >> 6;  // cell / 5 for cell < 25
+    dj = cell - 5 * di - 2;
+    di -= 2;
+    return;
+  }
+  // pref is a jump: the class's cells through the integer dot product, a mirror pair by the reference's rule
+  uint32_t cls = n25 & N25_A;
+  int d2 = 1;
+  if (!cls) { cls = n25 & N25_B; d2 = 2; }
+  if (!cls) { cls = n25 & N25_C; d2 = 4; }
+  if (!cls) { cls = n25 & N25_D; d2 = 5; }
+  if (!cls) { cls = n25 & N25_E; d2 = 8; }
+  int bdot = INT32_MIN, adi = 0, adj = 0;
+  bool alt = false;
+  di = dj = 0;
+  for (uint32_t u = cls; u; u &= u - 1u) {
+    const int b = __ffs(u) - 1;
+    const int qi = ((b * 13) >> 6) - 2, qj = b - 5 * (qi + 2) - 2;
+    const int dot = qi * p0 + qj * p1;
+    if (dot > bdot) { bdot = dot; di = qi; dj = qj; alt = false; }
+    else if (dot == bdot) { alt = true; adi = qi; adj = qj; }
+  }
+  if (alt && mirror_second_wins(di, dj, adi, adj, d2, p0, p1)) { di = adi; dj = adj; }
+}
+
+// Probes of half-width 4 and 8 from the register window ((wi, wj) = the point's window coordinates, 8 <= wi, wj <= 23):
+// one pass, candidates ranked by (k, d2) and the dot product.  false: nothing within half-width 8.
+__device__ __forceinline__ bool rw_probe8(const RegWin &rw, int wi, int wj, int p0, int p1, int &di, int &dj) {
+  const int lane = (int)lane_id();
+  const int rdi = lane - wi;
+  const uint32_t x = abs(rdi) <= 8 ? (rw.W & (0x1ffffu << (wj - 8))) : 0u;
+  unsigned bkey = 0xffffffffu;
+  int bdot = 0, boff = 0, aoff = WK_NO_PARTNER;
+  if (x) wk_row_candidate<uint32_t>(x, wj, rdi, p0, p1, bkey, bdot, boff, aoff);
+  const unsigned kmin = __reduce_min_sync(FULL_MASK, bkey);
+  if (kmin == 0xffffffffu) return false;
+  const bool sel = bkey == kmin;
+  const int dotmax = __reduce_max_sync(FULL_MASK, sel ? bdot : INT32_MIN);
+  const unsigned tied = __ballot_sync(FULL_MASK, sel && bdot == dotmax);
+  const int la = __ffs(tied) - 1;
+  int step = __shfl_sync(FULL_MASK, boff, la);
+  int other = __shfl_sync(FULL_MASK, aoff, la);
+  const unsigned rest = tied & (tied - 1);
+  if (rest) other = __shfl_sync(FULL_MASK, boff, __ffs(rest) - 1);  // a mirror pair held by two lanes
+  if (other != WK_NO_PARTNER &&
+      mirror_second_wins(step >> 16, (int)(short)(step & 0xffff), other >> 16, (int)(short)(other & 0xffff),
+                         (int)(kmin & 0x1fffffu), p0, p1))
+    step = other;
+  di = step >> 16; dj = (int)(short)(step & 0xffff);
+  return true;
+}
+
+// One level's path of one region.  (ci, cj) = start point (bitmap coordinates, bit still set); Ql[t], t = 0..n-1,
+// receives the pixel ids in path order.  The bitmap is all-zero afterwards.
+__device__ __forceinline__ bool rw_run_path(uint32_t *bm, int h, int w, int ws, int ci, int cj, int n, int r0, int c0, int logW,
+                                            int32_t *__restrict__ Ql, const uint8_t *t2) {
+  const int lane = (int)lane_id();
+  int myq = 0;
+  if (lane == 0) {
+    myq = ((r0 + ci) << logW) + c0 + cj;
+    bm[ci * ws + (cj >> 5)] &= ~(1u << (cj & 31));
+  }
+  __syncwarp();
+  RegWin rw;
+  rw_load(rw, bm, h, ws, ci, cj);
+  int p0 = 0, p1 = 1;  // prefered_direc = (0,1)   rbepwt.py:1290
+  for (int t = 1; t < n; t++) {
+    int wi = ci - rw.R0, wj = cj - rw.C0;
+    if ((unsigned)(wi - 8) > 15u || (unsigned)(wj - 8) > 15u) {  // left the central cells: a fresh window
+      __syncwarp();  // lane 0's updates of the bitmap before everybody's reads
+      rw_load(rw, bm, h, ws, ci, cj);
+      wi = wj = 16;
+    }
+    const uint32_t s5 = (rw.W >> (wj - 2)) & 31u;
+    const uint32_t n25 = __shfl_sync(FULL_MASK, s5, wi - 2) | (__shfl_sync(FULL_MASK, s5, wi - 1) << 5) |
+                         (__shfl_sync(FULL_MASK, s5, wi) << 10) | (__shfl_sync(FULL_MASK, s5, wi + 1) << 15) |
+                         (__shfl_sync(FULL_MASK, s5, wi + 2) << 20);
+    int di, dj;
+    if (n25) {
+      rw_near_pick(n25, p0, p1, t2, di, dj);
+    } else if (!rw_probe8(rw, wi, wj, p0, p1, di, dj)) {
+      int rad = 16, bi, bj;
+      __syncwarp();
+      if (!find_next_geo(bm, h, w, ws, ci, cj, p0, p1, rad, nullptr, bi, bj)) return false;
+      di = bi - ci; dj = bj - cj;
+    }
+    ci += di; cj += dj;
+    const int ti = wi + di, tj = wj + dj;
+    if (lane == ti && (unsigned)tj < 32u) rw.W &= ~(1u << tj);
+    if (lane == 0) atomicAnd(&bm[ci * ws + (cj >> 5)], ~(1u << (cj & 31)));
+    if ((t & 31) == lane) myq = ((r0 + ci) << logW) + c0 + cj;
+    if ((t & 31) == 31) Ql[t - 31 + lane] = myq;  // coalesced flush of 32 path points
+    p0 = di; p1 = dj;  // rbepwt.py:1331
+  }
+  if (lane < (n & 31)) Ql[(n & ~31) + lane] = myq;
+  __syncwarp();
+  return true;
+}
+
+// EPWT (rbepwt.py:1296-1306 with the value distance): the same window, the candidates of probe 1 (the 3x3 ring) or, when
+// that is empty, probe 2 (the rest of the 5x5 window) one per lane -- their values are loaded together (L1: the walk is
+// local) -- and the warp's arg-best of paths.cuh; beyond half-width 2 the search of paths.cuh from half-width 4 on.
+// The whole image is one region (r0 = c0 = 0).  Pl[t] = posmap[Ql[t]] (levels >= 2), as run_path does.
+__device__ bool rw_run_path_epwt(uint32_t *bm, int h, int w, int ws, int ci, int cj, int n, int logW,
+                                 const double *__restrict__ vals, bool u8wrap, int32_t *__restrict__ Ql,
+                                 int32_t *__restrict__ Pl, const int32_t *posmap) {
+  const int lane = (int)lane_id();
+  int myq = 0;
+  if (lane == 0) {
+    myq = (ci << logW) + cj;
+    bm[ci * ws + (cj >> 5)] &= ~(1u << (cj & 31));
+  }
+  __syncwarp();
+  RegWin rw;
+  rw_load(rw, bm, h, ws, ci, cj);
+  int p0 = 0, p1 = 1;
+  double curval = RB_EPWT_LOAD(vals + ((ci << logW) + cj));
+  const int ldi = ((lane * 13) >> 6) - 2, ldj = lane - 5 * (ldi + 2) - 2;  // this lane's cell of the 5x5 window (lane < 25)
+  for (int t = 1; t < n; t++) {
+    int wi = ci - rw.R0, wj = cj - rw.C0;
+    if ((unsigned)(wi - 2) > 27u || (unsigned)(wj - 2) > 27u) {
+      __syncwarp();
+      rw_load(rw, bm, h, ws, ci, cj);
+      wi = wj = 16;
+    }
+    const uint32_t s5 = (rw.W >> (wj - 2)) & 31u;
+    const uint32_t n25 = __shfl_sync(FULL_MASK, s5, wi - 2) | (__shfl_sync(FULL_MASK, s5, wi - 1) << 5) |
+                         (__shfl_sync(FULL_MASK, s5, wi) << 10) | (__shfl_sync(FULL_MASK, s5, wi + 1) << 15) |
+                         (__shfl_sync(FULL_MASK, s5, wi + 2) << 20);
+    int bi, bj;
+    if (n25) {
+      const uint32_t cm = (n25 & N25_RING1) ? (n25 & N25_RING1) : n25;
+      Best b;
+      b.have = false; b.has_sp1 = false; b.dist = 0.0; b.val = 0.0; b.sp1 = 0.0; b.cross = 0; b.d2 = 0; b.i = 0; b.j = 0;
+      if ((cm >> lane) & 1u)
+        consider<MODE_EPWT>(b, ci + ldi, cj + ldj, ci, cj, p0, p1, curval, vals, ((ci + ldi) << logW) + cj + ldj, u8wrap);
+      warp_arg_best<MODE_EPWT>(b, ci, cj, p0, p1, curval, bi, bj);
+    } else {
+      __syncwarp();
+      if (!find_next<MODE_EPWT>(bm, h, w, ws, ci, cj, p0, p1, vals, 0, 0, logW, u8wrap, curval, bi, bj, 4)) return false;
+    }
+    const int di = bi - ci, dj = bj - cj;
+    ci = bi; cj = bj;
+    const int ti = wi + di, tj = wj + dj;
+    if (lane == ti && (unsigned)tj < 32u) rw.W &= ~(1u << tj);
+    if (lane == 0) atomicAnd(&bm[ci * ws + (cj >> 5)], ~(1u << (cj & 31)));
+    if ((t & 31) == lane) myq = (ci << logW) + cj;
+    if ((t & 31) == 31) {
+      Ql[t - 31 + lane] = myq;
+      if (Pl) Pl[t - 31 + lane] = __ldcg(posmap + myq);
+    }
+    p0 = di; p1 = dj;
+  }
+  if (lane < (n & 31)) {
+    Ql[(n & ~31) + lane] = myq;
+    if (Pl) Pl[(n & ~31) + lane] = __ldcg(posmap + myq);
+  }
+  __syncwarp();
+  return true;
+}
+
+// The whole pyramid of one region (paths only: the positions in the incoming order are k2_perm's).
+__device__ void region_pyramid_rw(const PathParams &P, int g, uint32_t *bm, const uint8_t *t2) {
+  const int lane = (int)lane_id();
+  const int logW = P.logW, W = P.W, N = P.N;
+  const int img = P.reg.img[g], label = P.reg.label[g], first = P.reg.first[g];
+  int n = P.reg.size[g], a = P.reg.off[g];
+  const int r0 = first >> logW, c0 = P.reg.cmin[g];
+  const int h = P.reg.rmax[g] - r0 + 1, w = P.reg.cmax[g] - c0 + 1, ws = (w + 31) >> 5;
+  const int32_t *lab = P.labels + (size_t)img * N;
+  int32_t *Q = P.Q + (size_t)img * 2 * (size_t)N;
+  const int words = h * ws;
+  for (int wi = 0; wi < words; wi += 4) {  // four independent label loads in flight per lane
+    int lv[4];
+    bool inb[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int w_ = wi + u;
+      const int i = ws == 1 ? w_ : w_ / ws;
+      const int col = ((w_ - i * ws) << 5) + lane;
+      inb[u] = w_ < words && col < w;
+      lv[u] = inb[u] ? lab[((r0 + i) << logW) + c0 + col] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const unsigned bits = __ballot_sync(FULL_MASK, inb[u] && lv[u] == label);
+      if (lane == 0 && wi + u < words) bm[wi + u] = bits;
+    }
+  }
+  __syncwarp();
+  int si = 0, sj = (first & (W - 1)) - c0;
+  for (int lev = 1; lev <= P.levels && n > 0; lev++) {
+    int32_t *Ql = Q + level_off((size_t)N, lev) + a;
+    if (!rw_run_path(bm, h, w, ws, si, sj, n, r0, c0, logW, Ql, t2)) {
+      if (lane == 0) atomicExch(&P.qmeta[QM_ERR], 1);
+      return;
+    }
+    if (lev == P.levels) break;
+    const int minpix = reduce_points(bm, ws, a, n, r0, c0, logW, Ql, nullptr);
+    const int na = (a + 1) >> 1, nb = (a + n + 1) >> 1;
+    a = na; n = nb - na;
+    if (n > 0) { si = (minpix >> logW) - r0; sj = (minpix & (W - 1)) - c0; }
+  }
+}
+
+}  // namespace rbepwt

@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(256) k1_bitmaps(PathParams P) {
 }
 
 #ifdef WK_STATS  // debug build only: warp trips and lane units by kind
-__device__ unsigned long long g_wk_stats[16];  // [0] warp trips, [1 + kind] lanes of that kind at the start of a trip, [10] regions of the chunk
+__device__ unsigned long long g_wk_stats[16];  // [0] warp trips, [1 + kind] lanes of that kind at the start of a trip, [10] regions of the chunk, [11]/[12] searches beyond the window served (planes of <= 2 / more words per row), [13] bitmap-mode steps, [14] trips of the windowed instantiation
 #endif
 
 // The search beyond the 5x5 window of ONE lane's region, done by the whole warp (all arguments warp-uniform): the
@@ -629,6 +629,9 @@ __device__ unsigned long long g_wk_stats[16];  // [0] warp trips, [1 + kind] lan
 // Chebyshev: the reference's fp64 expressions (find_next).  Returns false if the plane holds no unvisited point;
 // otherwise `step` = (di << 16) | (dj & 0xffff).
 constexpr int WK_NO_PARTNER = (int)0x80000000;
+#ifndef WK_FAR_RAD0
+#define WK_FAR_RAD0 8
+#endif
 
 // The candidate of one bitmap row (x != 0, one or two words; row offset rdi from the current point): its nearest
 // unvisited column on either side of cj -- the nearer one dominates the other in (k, d2); equidistant ones share the
@@ -700,7 +703,8 @@ __device__ __forceinline__ bool wk_far_search(const uint32_t *plane, int h, int 
   }
   int bi, bj;
   if (MODE == MODE_EUCLID) {
-    int rad = 4;
+    // half-width 8 at once: ranked by (k, d2, dot) one pass over the 17 rows equals the probes 4 and 8 in turn
+    int rad = WK_FAR_RAD0;
     if (!find_next_geo(plane, h, ws << 5, ws, ci, cj, p0, p1, rad, nullptr, bi, bj)) return false;
   } else {
     double curval = 0.0;
@@ -709,6 +713,9 @@ __device__ __forceinline__ bool wk_far_search(const uint32_t *plane, int h, int 
   step = ((bi - ci) << 16) | ((bj - cj) & 0xffff);
   return true;
 }
+
+// the whole-warp walker with the bitmap window in registers (regwin.cuh, included at the end of this file)
+__device__ void region_pyramid_rw(const PathParams &P, int g, uint32_t *bm, const uint8_t *t2);
 
 // WIDEWIN = true: the instantiation for the chunks of large bitmaps (queue classes below Q_FIRST_NARROW_CLS; at most six
 // regions per warp), which builds its bitmaps itself and hands regions of at least coop_min pixels to the whole-warp
@@ -760,7 +767,11 @@ __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WID
       // one long chain: the whole warp walks it together (paths.cuh, find_next_geo)
       const int g = P.queue[qstart];
       if (P.reg.size[g] >= P.qmeta[QM_COOP_SIZE]) {
+#ifdef RB_NO_REGWIN
         region_pyramid<MODE>(P, g, arena, s_lut);
+#else
+        region_pyramid_rw(P, g, arena, s_tab);
+#endif
         __syncwarp();
         continue;
       }
@@ -834,6 +845,7 @@ __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WID
       if (lane == 0) atomicAdd(&g_wk_stats[0], 1ull);
       atomicAdd(&g_wk_stats[1 + wk.kind], 1ull);
       if (lane == 0) atomicAdd(&g_wk_stats[10], (unsigned long long)cnt);
+      if (lane == 0 && WIDEWIN) atomicAdd(&g_wk_stats[14], 1ull);
 #endif
       if (__any_sync(FULL_MASK, wk.kind == WK_LEVEL)) {
         if (wk.kind == WK_LEVEL) wk.next_level();
@@ -851,6 +863,9 @@ __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WID
           const int pa = __shfl_sync(FULL_MASK, wk.rq0, src);
           const int pb = __shfl_sync(FULL_MASK, wk.ci | (wk.cj << 16), src);
           const int pc = __shfl_sync(FULL_MASK, (wk.p0 & 0xffff) | (wk.p1 << 16), src);
+#ifdef WK_STATS
+          if (lane == 0) atomicAdd(&g_wk_stats[(pa >> 23) <= 2 ? 11 : 12], 1ull);
+#endif
           int step = 0;
           const bool ok = wk_far_search<MODE>(arena + (pa & 0xfff), (pa >> 12) & 0x7ff, pa >> 23, pb & 0xffff, pb >> 16,
                                               (int)(short)(pc & 0xffff), pc >> 16, step);
@@ -859,6 +874,9 @@ __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WID
             else wk.kind = WK_ERROR;
           }
         }
+#ifdef WK_STATS
+        if (wk.kind == WK_COMMIT) atomicAdd(&g_wk_stats[13], 1ull);
+#endif
         if (wk.kind == WK_COMMIT) wk.commit_step();
       }
       const unsigned listm = __ballot_sync(FULL_MASK, wk.kind == WK_LIST);
@@ -892,10 +910,15 @@ __global__ void __launch_bounds__(WK_WIDE_WARPS * 32) k1_coop_all(PathParams P) 
 template <int MODE>
 __global__ void __launch_bounds__(32) k1_paths_big(PathParams P) {
   extern __shared__ uint32_t s_big[];
-  __shared__ __align__(16) uint8_t s_lut[TPR_LUT_ROWS * TPR_LUT_COLS];
+  __shared__ __align__(16) uint8_t s_lut[MODE == MODE_EUCLID ? T2_BYTES : TPR_LUT_ROWS * TPR_LUT_COLS];
   const int lane = (int)lane_id();
   if (P.qmeta[QM_NBIG] == 0) return;  // the common case: nothing oversized in this group
-  load_unit_lut(s_lut, P.unit_lut);
+  if (MODE == MODE_EUCLID) {
+    for (int e = threadIdx.x; e < T2_BYTES / 4; e += blockDim.x)
+      reinterpret_cast<uint32_t *>(s_lut)[e] = reinterpret_cast<const uint32_t *>(P.t2_tab)[e];
+  } else {
+    load_unit_lut(s_lut, P.unit_lut);
+  }
   __syncthreads();
   const int nbig = P.qmeta[QM_NBIG];
   uint32_t *gs = P.gscratch + (size_t)blockIdx.x * P.gscratch_words;
@@ -906,7 +929,8 @@ __global__ void __launch_bounds__(32) k1_paths_big(PathParams P) {
     if (idx >= nbig) break;
     const int g = P.queue[idx];
     const int words = region_bitmap_words(P.reg, g, P.logW);
-    region_pyramid<MODE>(P, g, words <= P.big_smem_words ? s_big : gs, s_lut);
+    if (MODE == MODE_EUCLID) region_pyramid_rw(P, g, words <= P.big_smem_words ? s_big : gs, s_lut);
+    else region_pyramid<MODE>(P, g, words <= P.big_smem_words ? s_big : gs, s_lut);
     __syncwarp();
   }
 }
@@ -1010,3 +1034,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_perm(PathParams P, int nreg,
 #endif  // __CUDACC__
 
 }  // namespace rbepwt
+
+#ifdef __CUDACC__
+#include "regwin.cuh"
+#endif
