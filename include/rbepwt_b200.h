@@ -87,10 +87,9 @@ int rbepwt_encode(rbepwt_ctx *ctx, const double *img, const int32_t *labels, int
  *   RBEPWT_OPT_SUBBATCH: images per transform sub-batch (0 = auto: about 2^24 pixels).
  *   RBEPWT_OPT_PATHGROUP: images per path group -- label scan + path pyramid (0 = auto: about 2^26 pixels;
  *                        rounded to a multiple of the sub-batch).
- *   RBEPWT_OPT_COOP_LIMIT: how many regions of a path group (the largest ones, of >= 2048 pixels) get a whole warp
- *                        instead of one lane of the path kernel (-1 = auto: none, except in groups of at most 4096 regions,
- *                        where every region gets one; 0 = never).  A tuning knob:
- *                        results do not depend on it. */
+ *   RBEPWT_OPT_COOP_LIMIT: how many regions of a path group (the largest ones, of >= 2048 pixels) are walked by a whole
+ *                        warp instead of one lane of the path kernel (-1 = auto: 4 per SM, and every region of a group
+ *                        of at most 4096 regions; 0 = none).  A tuning knob: results do not depend on it. */
 #define RBEPWT_OPT_STREAMS 1
 #define RBEPWT_OPT_SUBBATCH 2
 #define RBEPWT_OPT_PATHGROUP 3

@@ -418,7 +418,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     c->totalR += c->h_R[a + i];
   }
   const int nreg = c->totalR - g0;
-  int coop_min = TPR_COOP_MIN;
+  bool coop_all = false;  // every region of the group walked by a whole warp (k1_coop_all)
   int rc = grow_regs(c, std::max<size_t>((size_t)c->totalR, (size_t)c->B * 2048 + 4096), (size_t)g0);
   if (rc) return rc;
   CK(sl.queue.ensure_slack((size_t)nreg * 4));
@@ -443,13 +443,14 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
                                          c->img_labmin.as<int32_t>(), c->img_direct.as<int32_t>(),
                                          c->img_rbase.as<int32_t>(), c->regs());
     const int qb = std::max(1, std::min((nreg + 255) / 256, c->sm_count * 8));
-    // few regions in flight (single images, small batches): every region gets its own warp -- latency, not throughput
-    const bool grad = c->mode == RBEPWT_PATH_GRAD || c->mode == RBEPWT_PATH_GRAD_CHEB;  // gradpath: always warp per region
-    coop_min = (grad || (c->mode == RBEPWT_PATH_EUCLID && nreg <= TPR_COOP_ALL_BELOW && c->opt_coop_limit != 0)) ? 1 : TPR_COOP_MIN;
-    // coop_min > 1: kq_scan picks the threshold (the largest regions, at most coop_limit of them; only the Euclidean
-    // walker has a whole-warp variant inside k1_walk)
+    // few regions in flight (single images, small batches): every region gets its own warp -- latency, not throughput;
+    // gradpath: always.  Otherwise (euclid) the largest regions of the group do, kq_scan picks the threshold.
+    // RBEPWT_OPT_COOP_LIMIT: how many (-1 = auto: COOP_PER_SM per SM; 0 = none, and no small-group rule either)
+    const bool grad = c->mode == RBEPWT_PATH_GRAD || c->mode == RBEPWT_PATH_GRAD_CHEB;
+    coop_all = grad || (c->mode == RBEPWT_PATH_EUCLID && nreg <= TPR_COOP_ALL_BELOW && c->opt_coop_limit != 0);
+    const int coop_min = coop_all ? 1 : TPR_COOP_MIN;
     const int coop_limit = c->mode != RBEPWT_PATH_EUCLID ? 0 : (c->opt_coop_limit >= 0 ? c->opt_coop_limit : c->sm_count * COOP_PER_SM);
-    kq_hist<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, coop_min > 1 ? INT32_MAX : coop_min, sl.qhist.as<int>());
+    kq_hist<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, coop_all ? 1 : INT32_MAX, sl.qhist.as<int>());
     kq_scan<<<1, 32, 0, s>>>(sl.qhist.as<int>(), sl.qmeta.as<int>(), sl.qbins.as<int>(), nreg, coop_min, coop_limit);
     kq_scatter<<<qb, 256, 0, s>>>(c->regs(), g0, nreg, c->logW, sl.qmeta.as<int>(), sl.queue.as<int32_t>());
     kq_chunks<<<Q_NCLS - 1, 1024, 0, s>>>(sl.qbins.as<int>(), sl.chunk_start.as<int32_t>(), sl.chunk_cnt.as<int32_t>());
@@ -468,6 +469,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   P.qmeta = sl.qmeta.as<int>();
   P.unit_lut = c->unit_lut.as<uint8_t>() + (c->mode == RBEPWT_PATH_CHEB ? TPR_LUT_ROWS * TPR_LUT_COLS : 0);
   P.t2_tab = c->t2_tab.as<uint8_t>();
+  P.coop = c->mode != RBEPWT_PATH_CHEB ? 1 : 0;
   P.gbm = sl.gbm.as<uint32_t>();
   P.gbm_chunks = (int)gbm_chunks;
   P.Q = c->Q.as<int32_t>();
@@ -487,18 +489,27 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     P.gscratch_words = img_words;
   }
   const bool grad_mode = c->mode == RBEPWT_PATH_GRAD || c->mode == RBEPWT_PATH_GRAD_CHEB;
-  if (grad_mode) {
-    // gradpath: regions whose bitmap exceeds a shared-memory arena in k1_paths_big, all the others one warp each
+  if (coop_all) {
+    // regions whose bitmap exceeds a shared-memory arena in k1_paths_big (own stream), all the others one warp each
     StageTimer t(c, RBEPWT_T_PATHS, s);
+    cudaStream_t sbig = c->nslot == 1 ? s : sl.aux2;
+    CK(cudaEventRecord(sl.ev_a, s));
+    CK(cudaStreamWaitEvent(sl.aux2, sl.ev_a, 0));
     if (c->mode == RBEPWT_PATH_GRAD) {
       CK(cudaFuncSetAttribute(k1_paths_big<MODE_GRAD_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-      k1_paths_big<MODE_GRAD_EUCLID><<<big_ctas, 32, smem_bytes, s>>>(P);
-      k1_coop_all<MODE_GRAD_EUCLID><<<c->sm_count * 4, WK_WIDE_WARPS * 32, 0, s>>>(P);
-    } else {
+      k1_paths_big<MODE_GRAD_EUCLID><<<big_ctas, 32, smem_bytes, sbig>>>(P);
+      k1_coop_all<MODE_GRAD_EUCLID><<<c->sm_count * 4, COOP_WARPS * 32, 0, s>>>(P);
+    } else if (c->mode == RBEPWT_PATH_GRAD_CHEB) {
       CK(cudaFuncSetAttribute(k1_paths_big<MODE_GRAD_CHEB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-      k1_paths_big<MODE_GRAD_CHEB><<<big_ctas, 32, smem_bytes, s>>>(P);
-      k1_coop_all<MODE_GRAD_CHEB><<<c->sm_count * 4, WK_WIDE_WARPS * 32, 0, s>>>(P);
+      k1_paths_big<MODE_GRAD_CHEB><<<big_ctas, 32, smem_bytes, sbig>>>(P);
+      k1_coop_all<MODE_GRAD_CHEB><<<c->sm_count * 4, COOP_WARPS * 32, 0, s>>>(P);
+    } else {
+      CK(cudaFuncSetAttribute(k1_paths_big<MODE_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      k1_paths_big<MODE_EUCLID><<<big_ctas, 32, smem_bytes, sbig>>>(P);
+      k1_coop_all<MODE_EUCLID><<<c->sm_count * 4, COOP_WARPS * 32, 0, s>>>(P);
     }
+    CK(cudaEventRecord(sl.ev_c, sbig));
+    CK(cudaStreamWaitEvent(s, sl.ev_c, 0));
     c->launches += 2;
   } else {
   int tpr_per_sm = 1;  // grid = TPR_WAVES waves of resident CTAs
@@ -521,6 +532,10 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
       CK(cudaFuncSetAttribute(k1_paths_big<MODE_CHEB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
       k1_paths_big<MODE_CHEB><<<big_ctas, 32, smem_bytes, sbig>>>(P);
     }
+    c->launches++;
+  }
+  if (c->mode == RBEPWT_PATH_EUCLID) {  // the group's largest regions, a warp each (class 1), beside the lane walkers
+    k1_coop_all<MODE_EUCLID><<<c->sm_count * 4, COOP_WARPS * 32, 0, sbig>>>(P);
     c->launches++;
   }
   CK(cudaEventRecord(sl.ev_c, sbig));

@@ -400,18 +400,19 @@ constexpr int Q_NCLS = 13;
 constexpr int Q_SIZE_BINS = 256;
 constexpr int Q_BINS = Q_NCLS * Q_SIZE_BINS;
 
+// Whole-warp walking (k1_coop_all) of regions that would fit a lane's slot: the largest regions of a group, at least
+// TPR_COOP_MIN pixels each and at most COOP_PER_SM per SM of them (kq_scan), and every region of a small group.
+// Measured (tools/coop_sweep.py, 256 images of 512^2): EVERY region of >= 2048 pixels on a warp of its own is 1.6x slower on
+// heavy-tailed maps (40 such regions per image) -- a warp on one chain spends ~10x the issue slots per step.
 #ifndef TPR_COOP_MIN_N
 #define TPR_COOP_MIN_N 2048
 #endif
-constexpr int TPR_COOP_MIN = TPR_COOP_MIN_N;  // regions of at least this many pixels are walked by a whole warp
+constexpr int TPR_COOP_MIN = TPR_COOP_MIN_N;
 #ifndef COOP_PER_SM_N
-#define COOP_PER_SM_N 0
+#define COOP_PER_SM_N 4
 #endif
-constexpr int COOP_PER_SM = COOP_PER_SM_N;    // ... at most this many per SM in a path group (kq_scan), the largest ones.
-// Measured (tools/coop_sweep.py, 256 images of 512^2): 0 is never worse -- heavy-tailed maps 14.5 ms per batch against 23.7
-// with every region of >= 2048 pixels on a warp of its own, Voronoi 64 seeds 22.1 against 36.6 -- so the default keeps the
-// whole-warp walker for small groups only (TPR_COOP_ALL_BELOW: latency, not throughput).
-constexpr int TPR_COOP_ALL_BELOW = 4096;      // ... and every region, when the whole group has at most this many
+constexpr int COOP_PER_SM = COOP_PER_SM_N;
+constexpr int TPR_COOP_ALL_BELOW = 4096;      // every region gets a warp when the whole group has at most this many regions
 constexpr int TPR_MAX_SIDE = 1024;     // bounding-box side limit of k1_walk (its packed candidate key)
 
 __device__ __forceinline__ int region_bitmap_words(const RegionArrays &reg, int g, int logW) {
@@ -457,6 +458,13 @@ __device__ __forceinline__ int size_key(int size) {
 }
 __device__ __forceinline__ int key_min_size(int key) { return key >= 24 ? (8 + (key & 7)) << ((key >> 3) - 3) : key; }
 
+// Is a region of `words` slot words and `size` pixels walked by a whole warp?  (coop: the path mode has a whole-warp
+// kernel for regions that fit an arena: euclid and gradpath)  Oversized bitmaps always are (k1_paths_big); of the
+// others, with coop, class 1: the slots that fit the arena only one at a time, and the regions of >= coop_size pixels.
+__device__ __forceinline__ bool walked_by_warp(int size, int words, int coop_size, bool coop) {
+  return words > TPR_ARENA_WORDS || (coop && (2 * words > TPR_ARENA_WORDS || size >= coop_size));
+}
+
 __device__ __forceinline__ int queue_bin(int size, int words, int coop_min) {
   const int key = size_key(size);
   int cls = 0;
@@ -486,16 +494,18 @@ __global__ void kq_hist(RegionArrays reg, int g0, int nreg, int logW, int coop_m
 constexpr int QM_NBIG = Q_BINS, QM_NREG = Q_BINS + 1, QM_CUR_BIG = Q_BINS + 2, QM_CUR_SMALL = Q_BINS + 3,
               QM_ERR = Q_BINS + 4, QM_NCHUNKS = Q_BINS + 5, QM_CHUNK_SPLIT = Q_BINS + 6, QM_CUR_WIDE = Q_BINS + 7,
               QM_COOP_SIZE = Q_BINS + 8,  // regions of at least this many pixels are walked by a whole warp (kq_scan decides)
-              QM_SIZE = Q_BINS + 9;
+              QM_CLS1_CHUNKS = Q_BINS + 9,  // chunks (= regions) of class 1: the first chunks of the table
+              QM_CUR_COOP = Q_BINS + 10,    // k1_coop_all's chunk cursor
+              QM_SIZE = Q_BINS + 11;
 constexpr int Q_FIRST_NARROW_CLS = 6;  // classes 1..5 (planes of more than 128 words: at most 6 regions per warp): the windowed variant of k1_walk
 
-// One warp.  First the whole-warp ("coop") threshold: kq_hist filed every region by its bitmap size alone when
-// coop_min > 1; here the LARGEST regions -- at most coop_limit of them, none smaller than coop_min -- move to class 1
-// (one region per chunk), where the windowed k1_walk hands them to the whole-warp walker.  A whole warp on one chain
-// steps it faster than a lane does, but spends ~10x the issue slots per step: it pays for the few longest chains of
-// a group (they set the kernel's tail), not for thousands of them (heavy-tailed maps: 40 regions of >= 2048 pixels
-// per image).  The threshold lies on a size-key boundary, so moving whole bins is exact.  coop_min <= 1: the host
-// asked for a warp per region (gradpath, single images), kq_hist filed them so already.
+// One warp.  First the whole-warp threshold: kq_hist filed every region by its bitmap size alone when coop_min > 1; here
+// the LARGEST regions -- at most coop_limit of them, none smaller than coop_min -- move to class 1 (one region per chunk),
+// which k1_coop_all walks with a whole warp each (regwin.cuh).  A whole warp steps a chain about twice as fast as a lane
+// does, and the longest chain of a group is what its path stage lasts; but a warp spends ~10x the issue slots per step,
+// so this pays for the few longest chains only, not for thousands of them.  The threshold lies on a size-key boundary,
+// so moving whole bins is exact.  coop_min <= 1: the host asked for a warp per region (gradpath, small groups), kq_hist
+// filed them so already.
 // Then the exclusive scan of the bin counts (queue offsets); per class: queue start, count, first chunk.
 __global__ void kq_scan(int *qhist, int *qmeta, int *qbins, int nreg, int coop_min, int coop_limit) {
   const int lane = threadIdx.x;
@@ -559,7 +569,7 @@ __global__ void kq_scan(int *qhist, int *qmeta, int *qbins, int nreg, int coop_m
       qbins[cls] = cstart;
       qbins[Q_NCLS + cls] = ccount;
       qbins[2 * Q_NCLS + cls] = cacc;
-      if (cls == 1) qmeta[QM_NBIG] = cstart;
+      if (cls == 1) { qmeta[QM_NBIG] = cstart; qmeta[QM_CLS1_CHUNKS] = ccount; }
       if (cls == Q_FIRST_NARROW_CLS) qmeta[QM_CHUNK_SPLIT] = cacc;
     }
     if (cls >= 1) cacc += (ccount + cs - 1) / cs;
@@ -569,6 +579,7 @@ __global__ void kq_scan(int *qhist, int *qmeta, int *qbins, int nreg, int coop_m
     qmeta[QM_CUR_BIG] = 0;
     qmeta[QM_CUR_SMALL] = 0;
     qmeta[QM_CUR_WIDE] = 0;
+    qmeta[QM_CUR_COOP] = 0;
     qmeta[QM_NCHUNKS] = cacc;
   }
 }

@@ -65,8 +65,15 @@ constexpr int WK_WARPS = WK_WARPS_N;
 #ifndef WK_MIN_CTAS
 #define WK_MIN_CTAS 2
 #endif
-constexpr int WK_WIDE_WARPS = 4;  // windowed instantiation: small CTAs (few chunks, the longest chains)
-constexpr int WK_WIDE_MIN_CTAS = 4;
+#ifndef WK_WIDE_WARPS_N
+#define WK_WIDE_WARPS_N 4
+#endif
+constexpr int WK_WIDE_WARPS = WK_WIDE_WARPS_N;  // windowed instantiation: small CTAs (few chunks, the longest chains)
+constexpr int COOP_WARPS = 4;                   // k1_coop_all: warps (= regions in flight) per CTA
+#ifndef WK_WIDE_MIN_CTAS_N
+#define WK_WIDE_MIN_CTAS_N 4
+#endif
+constexpr int WK_WIDE_MIN_CTAS = WK_WIDE_MIN_CTAS_N;  // measured on heavy-tailed maps: 4 x 4 warps 17.9k, 5 x 4 17.6k, 2 x 12 15.0k images/s
 #ifndef WK_NEAR_REPS_N
 #define WK_NEAR_REPS_N 4
 #endif
@@ -718,8 +725,7 @@ __device__ __forceinline__ bool wk_far_search(const uint32_t *plane, int h, int 
 __device__ void region_pyramid_rw(const PathParams &P, int g, uint32_t *bm, const uint8_t *t2);
 
 // WIDEWIN = true: the instantiation for the chunks of large bitmaps (queue classes below Q_FIRST_NARROW_CLS; at most six
-// regions per warp), which builds its bitmaps itself and hands regions of at least coop_min pixels to the whole-warp
-// walker of paths.cuh.
+// regions per warp), which builds its bitmaps itself.
 constexpr size_t wk_arena_bytes(bool widewin) {
   return ((size_t)(widewin ? WK_WIDE_WARPS : WK_WARPS) * TPR_ARENA_WORDS + 4) * sizeof(uint32_t);
 }
@@ -731,10 +737,10 @@ __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WID
   extern __shared__ __align__(16) uint32_t s_arena[];  // NWARPS * TPR_ARENA_WORDS + 4 words (wk_arena_bytes)
   // the walker's step table: euclid the 5x5 table, chebyshev the compact unit-step table
   __shared__ __align__(16) uint8_t s_tab[MODE == MODE_EUCLID ? T2_BYTES : WK_LUT_BYTES];
-  __shared__ __align__(16) uint8_t s_lut[WIDEWIN ? TPR_LUT_ROWS * TPR_LUT_COLS : 16];  // the whole-warp walker's full table
   const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
   uint32_t *arena = s_arena + warp * TPR_ARENA_WORDS;
-  const int chunk_lo = WIDEWIN ? 0 : P.qmeta[QM_CHUNK_SPLIT];
+  // chunk table: class 1 (k1_coop_all's when the path mode has one: P.coop), classes 2..5 (windowed), 6.. (bulk)
+  const int chunk_lo = WIDEWIN ? (P.coop ? P.qmeta[QM_CLS1_CHUNKS] : 0) : P.qmeta[QM_CHUNK_SPLIT];
   const int nchunks = (WIDEWIN ? P.qmeta[QM_CHUNK_SPLIT] : P.qmeta[QM_NCHUNKS]) - chunk_lo;
   if (nchunks <= 0) return;
   __shared__ __align__(8) unsigned long long s_mbar[NWARPS];  // one mbarrier per warp: arrival of its chunk's arena image
@@ -743,7 +749,6 @@ __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WID
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_mbar[warp])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (WIDEWIN) load_unit_lut(s_lut, P.unit_lut);
   if (MODE == MODE_EUCLID) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(P.t2_tab);
     uint32_t *dst = reinterpret_cast<uint32_t *>(s_tab);
@@ -763,19 +768,6 @@ __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WID
     if (chunk >= nchunks) break;
     chunk += chunk_lo;
     const int qstart = P.chunk_start[chunk], cnt = P.chunk_cnt[chunk];
-    if (WIDEWIN && MODE == MODE_EUCLID && cnt == 1) {
-      // one long chain: the whole warp walks it together (paths.cuh, find_next_geo)
-      const int g = P.queue[qstart];
-      if (P.reg.size[g] >= P.qmeta[QM_COOP_SIZE]) {
-#ifdef RB_NO_REGWIN
-        region_pyramid<MODE>(P, g, arena, s_lut);
-#else
-        region_pyramid_rw(P, g, arena, s_tab);
-#endif
-        __syncwarp();
-        continue;
-      }
-    }
     const WkChunkLane c = wk_chunk_lane(P, qstart, cnt);
     const bool mine = lane < cnt;
     if (!WIDEWIN && chunk - chunk_lo < P.gbm_chunks) {
@@ -889,19 +881,29 @@ __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WID
   }
 }
 
-// gradpath: every region of a group is walked by a whole warp (paths.cuh, region_pyramid / find_next_grad) -- the path
-// type exists for parity with the reference, not for throughput.  The queue then holds one-region chunks only.
+// Every region of a group walked by a whole warp, one region per chunk.  Euclid: small groups (single images, small
+// batches -- latency is all that matters there), through the register-window walker (regwin.cuh).  gradpath (paths.cuh,
+// region_pyramid / find_next_grad): always -- the path type exists for parity with the reference, not for throughput.
 template <int MODE>
-__global__ void __launch_bounds__(WK_WIDE_WARPS * 32) k1_coop_all(PathParams P) {
-  __shared__ __align__(16) uint32_t s_arena[WK_WIDE_WARPS * TPR_ARENA_WORDS];
+__global__ void __launch_bounds__(COOP_WARPS * 32) k1_coop_all(PathParams P) {
+  __shared__ __align__(16) uint32_t s_arena[COOP_WARPS * TPR_ARENA_WORDS];
+  __shared__ __align__(16) uint8_t s_t2[MODE == MODE_EUCLID ? T2_BYTES : 16];
   const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
-  const int nchunks = P.qmeta[QM_NCHUNKS];
+  const int nchunks = P.qmeta[QM_CLS1_CHUNKS];  // class 1 = the regions walked by a warp (all of them in a small group)
+  if (nchunks == 0) return;
+  if (MODE == MODE_EUCLID) {
+    for (int e = threadIdx.x; e < T2_BYTES / 4; e += blockDim.x)
+      reinterpret_cast<uint32_t *>(s_t2)[e] = reinterpret_cast<const uint32_t *>(P.t2_tab)[e];
+    __syncthreads();
+  }
   while (true) {
     int chunk = 0;
-    if (lane == 0) chunk = atomicAdd(&P.qmeta[QM_CUR_WIDE], 1);
+    if (lane == 0) chunk = atomicAdd(&P.qmeta[QM_CUR_COOP], 1);
     chunk = __shfl_sync(FULL_MASK, chunk, 0);
     if (chunk >= nchunks) break;
-    region_pyramid<MODE>(P, P.queue[P.chunk_start[chunk]], s_arena + warp * TPR_ARENA_WORDS, nullptr);
+    const int g = P.queue[P.chunk_start[chunk]];
+    if (MODE == MODE_EUCLID) region_pyramid_rw(P, g, s_arena + warp * TPR_ARENA_WORDS, s_t2);
+    else region_pyramid<MODE>(P, g, s_arena + warp * TPR_ARENA_WORDS, nullptr);
     __syncwarp();
   }
 }
@@ -972,7 +974,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_perm(PathParams P, int nreg,
     const bool in_smem = hb * wb <= K2_CELLS && n1 < 65536;
     // levels of at most `skip_below` points were done by the walker (never level 1); 0 = this region was walked by a warp
     // (coop: the path mode hands regions of at least qmeta[QM_COOP_SIZE] pixels to the whole-warp walker)
-    const bool by_warp = region_class_words(P.reg, g, logW) > TPR_ARENA_WORDS || (coop && n1 >= coop_size);
+    const bool by_warp = walked_by_warp(n1, region_class_words(P.reg, g, logW), coop_size, coop != 0);
     const int skip_below = by_warp ? 0 : WK_LIST_MAX;
     const int32_t *Qimg = P.Q + (size_t)img * 2 * (size_t)N;
     int32_t *Pimg = P.Pm + (size_t)img * 2 * (size_t)N;

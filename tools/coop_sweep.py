@@ -7,7 +7,7 @@ import rbepwt_b200 as rb
 from rbepwt_b200 import synth
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-LIMITS = [0, -1] if len(sys.argv) > 2 else [0, 148, 592, 2368, 1 << 30]
+LIMITS = [0, -1] if len(sys.argv) > 2 else [0, 74, 148, 296, 592, 1184, 2368]
 fams = [("voronoi 1024", lambda s: synth.voronoi_labels(512, 512, 1024, seed=s)),
         ("voronoi 256", lambda s: synth.voronoi_labels(512, 512, 256, seed=s)),
         ("voronoi 64", lambda s: synth.voronoi_labels(512, 512, 64, seed=s)),
