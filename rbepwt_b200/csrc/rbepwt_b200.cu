@@ -81,7 +81,7 @@ constexpr int NSLOT = 2;   // path groups in flight
 constexpr int NXSLOT = RBEPWT_NXSLOT;  // transform sub-batches in flight
 constexpr int NSLOTS = NSLOT + NXSLOT;
 #ifndef TPR_WIDE_CTAS_PER_SM
-#define TPR_WIDE_CTAS_PER_SM 4
+#define TPR_WIDE_CTAS_PER_SM 3
 #endif
 constexpr int TPR_WAVES = 8;  // k1_walk grid = this many waves of resident CTAs (see walk.cuh)
 

@@ -385,7 +385,7 @@ __global__ void k0_single_region(int img0, int nimg, int H, int W, RegionArrays 
 // The path kernels pull regions from a queue ordered so that (a) regions whose bounding-box bitmap
 // does not fit a warp's shared-memory arena come first (class 0, one warp per region, paths.cuh),
 // (b) the others are grouped by bitmap size class, largest first: class c >= 1 holds the bitmaps that fit
-// the arena class_chunk_size(c) = 1, 2, 3, 4, 6, 8, 12, 16, 20, 24, 28, 32 at a time,
+// its kernel's arena class_chunk_size(c) at a time (1; 4, 6, 8, 12 in the windowed kernel's; 8, ..., 32 in the bulk kernel's),
 // (c) inside a class regions are sorted by pixel count, descending, in eighth-octave bins: the lanes
 // of a warp walk chains of similar length, and the longest chains start first.  Chunks are cut from the class's
 // queue range regardless of the bins (only the last chunk of a class is partial).
@@ -443,13 +443,22 @@ __device__ __forceinline__ int region_class_words(const RegionArrays &reg, int g
   return (h > TPR_MAX_SIDE || w > TPR_MAX_SIDE) ? INT32_MAX : wk_slot_words(h, (w + 31) >> 5);
 }
 
-// regions per chunk of a class; class c holds the slots of at most TPR_ARENA_WORDS / class_chunk_size(c) words.
-// Two planes make slots twice as large as a single bitmap, so the steps between the classes are fine: a region
-// a little too large for 32 per warp is walked 28 at a time, not 16.
+// Regions per chunk of a class.  Classes 6..12 (the bulk instantiation of k1_walk, arenas of TPR_ARENA_WORDS): the slots
+// of at most TPR_ARENA_WORDS / size words; two planes make slots twice as large as a single bitmap, so the steps between
+// the classes are fine: a region a little too large for 32 per warp is walked 28 at a time, not 16.  Classes 2..5 (the
+// windowed instantiation, fewer warps with arenas of TPR_WIDE_ARENA_WORDS): the slots of at most TPR_WIDE_ARENA_WORDS /
+// size words.  Class 1: the larger slots that still fit TPR_ARENA_WORDS, one per chunk (walked by a whole warp where the
+// path mode has such a kernel).
+#ifndef TPR_WIDE_ARENA_WORDS_N
+#define TPR_WIDE_ARENA_WORDS_N 4096
+#endif
+constexpr int TPR_WIDE_ARENA_WORDS = TPR_WIDE_ARENA_WORDS_N;
 __host__ __device__ __forceinline__ int class_chunk_size(int cls) {
-  constexpr int cs[Q_NCLS] = {1, 1, 2, 3, 4, 6, 8, 12, 16, 20, 24, 28, 32};
+  constexpr int cs[Q_NCLS] = {1, 1, 4, 6, 8, 12, 8, 12, 16, 20, 24, 28, 32};
   return cs[cls];
 }
+__host__ __device__ __forceinline__ int class_arena_words(int cls) { return cls < 6 ? TPR_WIDE_ARENA_WORDS : TPR_ARENA_WORDS; }
+static_assert(TPR_WIDE_ARENA_WORDS / 12 >= TPR_ARENA_WORDS / 8, "class 5 must take over where class 6 ends");
 
 // eighth-octave size key (monotone in size, <= 8*30+7) and the smallest size of a key
 __device__ __forceinline__ int size_key(int size) {
@@ -462,7 +471,7 @@ __device__ __forceinline__ int key_min_size(int key) { return key >= 24 ? (8 + (
 // kernel for regions that fit an arena: euclid and gradpath)  Oversized bitmaps always are (k1_paths_big); of the
 // others, with coop, class 1: the slots that fit the arena only one at a time, and the regions of >= coop_size pixels.
 __device__ __forceinline__ bool walked_by_warp(int size, int words, int coop_size, bool coop) {
-  return words > TPR_ARENA_WORDS || (coop && (2 * words > TPR_ARENA_WORDS || size >= coop_size));
+  return words > TPR_ARENA_WORDS || (coop && (words * class_chunk_size(2) > TPR_WIDE_ARENA_WORDS || size >= coop_size));
 }
 
 __device__ __forceinline__ int queue_bin(int size, int words, int coop_min) {
@@ -470,7 +479,7 @@ __device__ __forceinline__ int queue_bin(int size, int words, int coop_min) {
   int cls = 0;
   if (words <= TPR_ARENA_WORDS) {
     cls = Q_NCLS - 1;
-    while (cls > 1 && words * class_chunk_size(cls) > TPR_ARENA_WORDS) cls--;
+    while (cls > 1 && words * class_chunk_size(cls) > class_arena_words(cls)) cls--;
     if (size >= coop_min) cls = 1;  // a long chain gets a warp of its own (one region per chunk)
   }
   return cls * Q_SIZE_BINS + (Q_SIZE_BINS - 1 - key);
@@ -497,7 +506,7 @@ constexpr int QM_NBIG = Q_BINS, QM_NREG = Q_BINS + 1, QM_CUR_BIG = Q_BINS + 2, Q
               QM_CLS1_CHUNKS = Q_BINS + 9,  // chunks (= regions) of class 1: the first chunks of the table
               QM_CUR_COOP = Q_BINS + 10,    // k1_coop_all's chunk cursor
               QM_SIZE = Q_BINS + 11;
-constexpr int Q_FIRST_NARROW_CLS = 6;  // classes 1..5 (planes of more than 128 words: at most 6 regions per warp): the windowed variant of k1_walk
+constexpr int Q_FIRST_NARROW_CLS = 6;  // classes 1..5 (slots of more than TPR_ARENA_WORDS / 8 words): the windowed variant of k1_walk
 
 // One warp.  First the whole-warp threshold: kq_hist filed every region by its bitmap size alone when coop_min > 1; here
 // the LARGEST regions -- at most coop_limit of them, none smaller than coop_min -- move to class 1 (one region per chunk),

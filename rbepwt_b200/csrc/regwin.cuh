@@ -38,15 +38,30 @@ __device__ __forceinline__ void rw_load(RegWin &rw, const uint32_t *bm, int h, i
   rw.W = x;
 }
 
+// The window's bits back into the bitmap (bits are only ever cleared, so this is an AND; lanes own distinct rows).
+__device__ __forceinline__ void rw_store(const RegWin &rw, uint32_t *bm, int h, int ws) {
+  const int i = rw.R0 + (int)lane_id();
+  if ((unsigned)i < (unsigned)h) {
+    const int wq = rw.C0 >> 5, sh = rw.C0 & 31;
+    const uint32_t keep_lo = (1u << sh) - 1u;  // columns of word wq to the left of the window
+    if ((unsigned)wq < (unsigned)ws) bm[i * ws + wq] &= (rw.W << sh) | keep_lo;
+    if (sh && (unsigned)(wq + 1) < (unsigned)ws) bm[i * ws + wq + 1] &= (rw.W >> (32 - sh)) | ~keep_lo;
+  }
+}
+
 // The step from a non-empty 5x5 window (euclid): the nearest class present, its winner for pref (p0, p1).
-__device__ __forceinline__ void rw_near_pick(uint32_t n25, int p0, int p1, const uint8_t *t2, int &di, int &dj) {
-  if ((unsigned)(p0 + 2) <= 4u && (unsigned)(p1 + 2) <= 4u) {
-    const int c = (n25 & N25_A) ? 0 : (n25 & N25_B) ? 1 : (n25 & N25_C) ? 2 : (n25 & N25_D) ? 3 : 4;
-    const int cell = t2[((p0 + 2) * 5 + p1 + 2) * T2_ROW + wk_t2_base(c) + wk_t2_field(c, n25)];
-    di = (cell * 13) >> 6;  // cell / 5 for cell < 25
-    dj = cell - 5 * di - 2;
-    di -= 2;
-    return;
+// `pc` = the preferred direction as a cell of the 5x5 window ((p0 + 2) * 5 + p1 + 2), or -1 when it is a jump; returns the
+// chosen cell (which is the next step's pc).
+__device__ __forceinline__ int rw_near_pick(uint32_t n25, int pc, int p0, int p1, const uint8_t *t2) {
+  if (pc >= 0) {
+    // every lane holds the same n25: the class tests are uniform branches, the hash constants immediates
+    int slot;
+    if (n25 & N25_A) slot = wk_t2_base(0) + wk_t2_field(0, n25);
+    else if (n25 & N25_B) slot = wk_t2_base(1) + wk_t2_field(1, n25);
+    else if (n25 & N25_C) slot = wk_t2_base(2) + wk_t2_field(2, n25);
+    else if (n25 & N25_D) slot = wk_t2_base(3) + wk_t2_field(3, n25);
+    else slot = wk_t2_base(4) + wk_t2_field(4, n25);
+    return t2[pc * T2_ROW + slot];
   }
   // pref is a jump: the class's cells through the integer dot product, a mirror pair by the reference's rule
   uint32_t cls = n25 & N25_A;
@@ -55,9 +70,8 @@ __device__ __forceinline__ void rw_near_pick(uint32_t n25, int p0, int p1, const
   if (!cls) { cls = n25 & N25_C; d2 = 4; }
   if (!cls) { cls = n25 & N25_D; d2 = 5; }
   if (!cls) { cls = n25 & N25_E; d2 = 8; }
-  int bdot = INT32_MIN, adi = 0, adj = 0;
+  int bdot = INT32_MIN, di = 0, dj = 0, adi = 0, adj = 0;
   bool alt = false;
-  di = dj = 0;
   for (uint32_t u = cls; u; u &= u - 1u) {
     const int b = __ffs(u) - 1;
     const int qi = ((b * 13) >> 6) - 2, qj = b - 5 * (qi + 2) - 2;
@@ -66,6 +80,7 @@ __device__ __forceinline__ void rw_near_pick(uint32_t n25, int p0, int p1, const
     else if (dot == bdot) { alt = true; adi = qi; adj = qj; }
   }
   if (alt && mirror_second_wins(di, dj, adi, adj, d2, p0, p1)) { di = adi; dj = adj; }
+  return (di + 2) * 5 + dj + 2;
 }
 
 // Probes of half-width 4 and 8 from the register window ((wi, wj) = the point's window coordinates, 8 <= wi, wj <= 23):
@@ -96,24 +111,26 @@ __device__ __forceinline__ bool rw_probe8(const RegWin &rw, int wi, int wj, int 
 }
 
 // One level's path of one region.  (ci, cj) = start point (bitmap coordinates, bit still set); Ql[t], t = 0..n-1,
-// receives the pixel ids in path order.  The bitmap is all-zero afterwards.
+// receives the pixel ids in path order.  The bitmap is all-zero afterwards.  Loop-carried state: the point's window
+// coordinates (wi, wj), its pixel id, the preferred direction; lane t mod 32 stores path point t.
 __device__ __forceinline__ bool rw_run_path(uint32_t *bm, int h, int w, int ws, int ci, int cj, int n, int r0, int c0, int logW,
                                             int32_t *__restrict__ Ql, const uint8_t *t2) {
   const int lane = (int)lane_id();
-  int myq = 0;
+  int pix = ((r0 + ci) << logW) + c0 + cj;
   if (lane == 0) {
-    myq = ((r0 + ci) << logW) + c0 + cj;
+    Ql[0] = pix;
     bm[ci * ws + (cj >> 5)] &= ~(1u << (cj & 31));
   }
   __syncwarp();
   RegWin rw;
   rw_load(rw, bm, h, ws, ci, cj);
-  int p0 = 0, p1 = 1;  // prefered_direc = (0,1)   rbepwt.py:1290
+  int wi = 16, wj = 16;
+  int p0 = 0, p1 = 1, pc = 2 * 5 + 3;  // prefered_direc = (0,1)   rbepwt.py:1290
   for (int t = 1; t < n; t++) {
-    int wi = ci - rw.R0, wj = cj - rw.C0;
     if ((unsigned)(wi - 8) > 15u || (unsigned)(wj - 8) > 15u) {  // left the central cells: a fresh window
-      __syncwarp();  // lane 0's updates of the bitmap before everybody's reads
-      rw_load(rw, bm, h, ws, ci, cj);
+      rw_store(rw, bm, h, ws);
+      __syncwarp();
+      rw_load(rw, bm, h, ws, rw.R0 + wi, rw.C0 + wj);
       wi = wj = 16;
     }
     const uint32_t s5 = (rw.W >> (wj - 2)) & 31u;
@@ -122,22 +139,36 @@ __device__ __forceinline__ bool rw_run_path(uint32_t *bm, int h, int w, int ws, 
                          (__shfl_sync(FULL_MASK, s5, wi + 2) << 20);
     int di, dj;
     if (n25) {
-      rw_near_pick(n25, p0, p1, t2, di, dj);
-    } else if (!rw_probe8(rw, wi, wj, p0, p1, di, dj)) {
-      int rad = 16, bi, bj;
-      __syncwarp();
-      if (!find_next_geo(bm, h, w, ws, ci, cj, p0, p1, rad, nullptr, bi, bj)) return false;
-      di = bi - ci; dj = bj - cj;
+      pc = rw_near_pick(n25, pc, p0, p1, t2);
+      di = (pc * 13) >> 6;  // pc / 5 for pc < 25
+      dj = pc - 5 * di - 2;
+      di -= 2;
+      wi += di; wj += dj;
+      rw.W &= ~((lane == wi ? 1u : 0u) << wj);
+    } else {
+      if (!rw_probe8(rw, wi, wj, p0, p1, di, dj)) {
+        const int ci_ = rw.R0 + wi, cj_ = rw.C0 + wj;
+        int rad = 16, bi, bj;
+        rw_store(rw, bm, h, ws);
+        __syncwarp();
+        if (!find_next_geo(bm, h, w, ws, ci_, cj_, p0, p1, rad, nullptr, bi, bj)) return false;
+        di = bi - ci_; dj = bj - cj_;
+      }
+      pc = -1;
+      wi += di; wj += dj;
+      if ((unsigned)wi < 32u && (unsigned)wj < 32u) {
+        rw.W &= ~((lane == wi ? 1u : 0u) << wj);
+      } else {  // a jump out of the window: the bit in the bitmap itself, then a fresh window (the check above)
+        const int ni = rw.R0 + wi, nj = rw.C0 + wj;
+        if (lane == 0) bm[ni * ws + (nj >> 5)] &= ~(1u << (nj & 31));
+        __syncwarp();
+      }
     }
-    ci += di; cj += dj;
-    const int ti = wi + di, tj = wj + dj;
-    if (lane == ti && (unsigned)tj < 32u) rw.W &= ~(1u << tj);
-    if (lane == 0) atomicAnd(&bm[ci * ws + (cj >> 5)], ~(1u << (cj & 31)));
-    if ((t & 31) == lane) myq = ((r0 + ci) << logW) + c0 + cj;
-    if ((t & 31) == 31) Ql[t - 31 + lane] = myq;  // coalesced flush of 32 path points
+    pix += (di << logW) + dj;
+    if (lane == (t & 31)) Ql[t] = pix;
     p0 = di; p1 = dj;  // rbepwt.py:1331
   }
-  if (lane < (n & 31)) Ql[(n & ~31) + lane] = myq;
+  rw_store(rw, bm, h, ws);
   __syncwarp();
   return true;
 }
@@ -150,48 +181,53 @@ __device__ bool rw_run_path_epwt(uint32_t *bm, int h, int w, int ws, int ci, int
                                  const double *__restrict__ vals, bool u8wrap, int32_t *__restrict__ Ql,
                                  int32_t *__restrict__ Pl, const int32_t *posmap) {
   const int lane = (int)lane_id();
-  int myq = 0;
-  if (lane == 0) {
-    myq = (ci << logW) + cj;
-    bm[ci * ws + (cj >> 5)] &= ~(1u << (cj & 31));
-  }
+  int pix = (ci << logW) + cj;
+  int myq = pix;  // lane t mod 32 holds path point t until the warp flushes 32 of them
+  if (lane == 0) bm[ci * ws + (cj >> 5)] &= ~(1u << (cj & 31));
   __syncwarp();
   RegWin rw;
   rw_load(rw, bm, h, ws, ci, cj);
+  int wi = 16, wj = 16;
   int p0 = 0, p1 = 1;
-  double curval = RB_EPWT_LOAD(vals + ((ci << logW) + cj));
+  double curval = RB_EPWT_LOAD(vals + pix);
   const int ldi = ((lane * 13) >> 6) - 2, ldj = lane - 5 * (ldi + 2) - 2;  // this lane's cell of the 5x5 window (lane < 25)
+  const int lpix = (ldi << logW) + ldj;
   for (int t = 1; t < n; t++) {
-    int wi = ci - rw.R0, wj = cj - rw.C0;
     if ((unsigned)(wi - 2) > 27u || (unsigned)(wj - 2) > 27u) {
+      rw_store(rw, bm, h, ws);
       __syncwarp();
-      rw_load(rw, bm, h, ws, ci, cj);
+      rw_load(rw, bm, h, ws, rw.R0 + wi, rw.C0 + wj);
       wi = wj = 16;
     }
     const uint32_t s5 = (rw.W >> (wj - 2)) & 31u;
     const uint32_t n25 = __shfl_sync(FULL_MASK, s5, wi - 2) | (__shfl_sync(FULL_MASK, s5, wi - 1) << 5) |
                          (__shfl_sync(FULL_MASK, s5, wi) << 10) | (__shfl_sync(FULL_MASK, s5, wi + 1) << 15) |
                          (__shfl_sync(FULL_MASK, s5, wi + 2) << 20);
+    const int ci_ = rw.R0 + wi, cj_ = rw.C0 + wj;
     int bi, bj;
     if (n25) {
       const uint32_t cm = (n25 & N25_RING1) ? (n25 & N25_RING1) : n25;
       Best b;
       b.have = false; b.has_sp1 = false; b.dist = 0.0; b.val = 0.0; b.sp1 = 0.0; b.cross = 0; b.d2 = 0; b.i = 0; b.j = 0;
-      if ((cm >> lane) & 1u)
-        consider<MODE_EPWT>(b, ci + ldi, cj + ldj, ci, cj, p0, p1, curval, vals, ((ci + ldi) << logW) + cj + ldj, u8wrap);
-      warp_arg_best<MODE_EPWT>(b, ci, cj, p0, p1, curval, bi, bj);
+      if ((cm >> lane) & 1u) consider<MODE_EPWT>(b, ci_ + ldi, cj_ + ldj, ci_, cj_, p0, p1, curval, vals, pix + lpix, u8wrap);
+      warp_arg_best<MODE_EPWT>(b, ci_, cj_, p0, p1, curval, bi, bj);
     } else {
+      rw_store(rw, bm, h, ws);
       __syncwarp();
-      if (!find_next<MODE_EPWT>(bm, h, w, ws, ci, cj, p0, p1, vals, 0, 0, logW, u8wrap, curval, bi, bj, 4)) return false;
+      if (!find_next<MODE_EPWT>(bm, h, w, ws, ci_, cj_, p0, p1, vals, 0, 0, logW, u8wrap, curval, bi, bj, 4)) return false;
     }
-    const int di = bi - ci, dj = bj - cj;
-    ci = bi; cj = bj;
-    const int ti = wi + di, tj = wj + dj;
-    if (lane == ti && (unsigned)tj < 32u) rw.W &= ~(1u << tj);
-    if (lane == 0) atomicAnd(&bm[ci * ws + (cj >> 5)], ~(1u << (cj & 31)));
-    if ((t & 31) == lane) myq = (ci << logW) + cj;
-    if ((t & 31) == 31) {
-      Ql[t - 31 + lane] = myq;
+    const int di = bi - ci_, dj = bj - cj_;
+    wi += di; wj += dj;
+    if ((unsigned)wi < 32u && (unsigned)wj < 32u) {
+      rw.W &= ~((lane == wi ? 1u : 0u) << wj);
+    } else {
+      if (lane == 0) bm[bi * ws + (bj >> 5)] &= ~(1u << (bj & 31));
+      __syncwarp();
+    }
+    pix = (bi << logW) + bj;
+    if ((t & 31) == lane) myq = pix;
+    if ((t & 31) == 31) {  // coalesced flush of 32 path points (+ their positions in the incoming order: a load the
+      Ql[t - 31 + lane] = myq;  // store waits for, so not once per step)
       if (Pl) Pl[t - 31 + lane] = __ldcg(posmap + myq);
     }
     p0 = di; p1 = dj;
@@ -200,6 +236,7 @@ __device__ bool rw_run_path_epwt(uint32_t *bm, int h, int w, int ws, int ci, int
     Ql[(n & ~31) + lane] = myq;
     if (Pl) Pl[(n & ~31) + lane] = __ldcg(posmap + myq);
   }
+  rw_store(rw, bm, h, ws);
   __syncwarp();
   return true;
 }

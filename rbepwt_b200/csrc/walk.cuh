@@ -71,7 +71,7 @@ constexpr int WK_WARPS = WK_WARPS_N;
 constexpr int WK_WIDE_WARPS = WK_WIDE_WARPS_N;  // windowed instantiation: small CTAs (few chunks, the longest chains)
 constexpr int COOP_WARPS = 4;                   // k1_coop_all: warps (= regions in flight) per CTA
 #ifndef WK_WIDE_MIN_CTAS_N
-#define WK_WIDE_MIN_CTAS_N 4
+#define WK_WIDE_MIN_CTAS_N 3
 #endif
 constexpr int WK_WIDE_MIN_CTAS = WK_WIDE_MIN_CTAS_N;  // measured on heavy-tailed maps: 4 x 4 warps 17.9k, 5 x 4 17.6k, 2 x 12 15.0k images/s
 #ifndef WK_NEAR_REPS_N
@@ -330,7 +330,7 @@ struct Walker {
   int ncnt, sminidx;   // list of survivors: length, index of the smallest
   uint32_t smin;       // smallest survivor (i << 16 | j) = next start point (lexicographic min, rbepwt.py:1035-1036)
   int pdi, pdj;        // WK_COMMIT: the step chosen (by the 5x5 window, or by the search beyond it)
-  int rq0;             // this level's plane for the warp's search beyond the window: word offset | h << 12 | ws << 23
+  int rq0;             // this level's plane for the warp's search beyond the window: word offset | h << 13 | ws << 24
   uint32_t U;          // list mode: unvisited mask
 
   __host__ __device__ __forceinline__ bool done() const { return kind == WK_DONE || kind == WK_ERROR; }
@@ -377,7 +377,7 @@ struct Walker {
       e = smin;
     }
     ci = (int)(e >> 16); cj = (int)(e & 0xffffu);
-    rq0 = (abase + cur) | (h << 12) | (ws << 23);
+    rq0 = (abase + cur) | (h << 13) | (ws << 24);
     if (!from_list) bm[cur + ci * ws + (cj >> 5)] &= ~(1u << (cj & 31));
     ncnt = 0; sminidx = 0; smin = 0xffffffffu;
     t = 0;
@@ -726,19 +726,22 @@ __device__ void region_pyramid_rw(const PathParams &P, int g, uint32_t *bm, cons
 
 // WIDEWIN = true: the instantiation for the chunks of large bitmaps (queue classes below Q_FIRST_NARROW_CLS; at most six
 // regions per warp), which builds its bitmaps itself.
+constexpr int wk_arena_words(bool widewin) { return widewin ? TPR_WIDE_ARENA_WORDS : TPR_ARENA_WORDS; }
 constexpr size_t wk_arena_bytes(bool widewin) {
-  return ((size_t)(widewin ? WK_WIDE_WARPS : WK_WARPS) * TPR_ARENA_WORDS + 4) * sizeof(uint32_t);
+  return ((size_t)(widewin ? WK_WIDE_WARPS : WK_WARPS) * wk_arena_words(widewin) + 4) * sizeof(uint32_t);
 }
+static_assert(TPR_WIDE_ARENA_WORDS <= 8192 && TPR_MAX_SIDE + 2 * WK_PAD < 2048, "Walker::rq0 packs the plane offset in 13 bits, h in 11");
 
 template <int MODE, bool WIDEWIN>
 __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WIDEWIN ? WK_WIDE_MIN_CTAS : WK_MIN_CTAS)
     k1_walk(PathParams P) {
   constexpr int NWARPS = WIDEWIN ? WK_WIDE_WARPS : WK_WARPS;
-  extern __shared__ __align__(16) uint32_t s_arena[];  // NWARPS * TPR_ARENA_WORDS + 4 words (wk_arena_bytes)
+  extern __shared__ __align__(16) uint32_t s_arena[];  // NWARPS * wk_arena_words(WIDEWIN) + 4 words (wk_arena_bytes)
   // the walker's step table: euclid the 5x5 table, chebyshev the compact unit-step table
   __shared__ __align__(16) uint8_t s_tab[MODE == MODE_EUCLID ? T2_BYTES : WK_LUT_BYTES];
   const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
-  uint32_t *arena = s_arena + warp * TPR_ARENA_WORDS;
+  constexpr int ARENA = WIDEWIN ? TPR_WIDE_ARENA_WORDS : TPR_ARENA_WORDS;
+  uint32_t *arena = s_arena + warp * ARENA;
   // chunk table: class 1 (k1_coop_all's when the path mode has one: P.coop), classes 2..5 (windowed), 6.. (bulk)
   const int chunk_lo = WIDEWIN ? (P.coop ? P.qmeta[QM_CLS1_CHUNKS] : 0) : P.qmeta[QM_CHUNK_SPLIT];
   const int nchunks = (WIDEWIN ? P.qmeta[QM_CHUNK_SPLIT] : P.qmeta[QM_NCHUNKS]) - chunk_lo;
@@ -856,10 +859,10 @@ __global__ void __launch_bounds__((WIDEWIN ? WK_WIDE_WARPS : WK_WARPS) * 32, WID
           const int pb = __shfl_sync(FULL_MASK, wk.ci | (wk.cj << 16), src);
           const int pc = __shfl_sync(FULL_MASK, (wk.p0 & 0xffff) | (wk.p1 << 16), src);
 #ifdef WK_STATS
-          if (lane == 0) atomicAdd(&g_wk_stats[(pa >> 23) <= 2 ? 11 : 12], 1ull);
+          if (lane == 0) atomicAdd(&g_wk_stats[(pa >> 24) <= 2 ? 11 : 12], 1ull);
 #endif
           int step = 0;
-          const bool ok = wk_far_search<MODE>(arena + (pa & 0xfff), (pa >> 12) & 0x7ff, pa >> 23, pb & 0xffff, pb >> 16,
+          const bool ok = wk_far_search<MODE>(arena + (pa & 0x1fff), (pa >> 13) & 0x7ff, pa >> 24, pb & 0xffff, pb >> 16,
                                               (int)(short)(pc & 0xffff), pc >> 16, step);
           if (lane == src) {
             if (ok) wk.far_found(step >> 16, (int)(short)(step & 0xffff));
