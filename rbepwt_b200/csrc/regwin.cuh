@@ -207,10 +207,31 @@ __device__ bool rw_run_path_epwt(uint32_t *bm, int h, int w, int ws, int ci, int
     int bi, bj;
     if (n25) {
       const uint32_t cm = (n25 & N25_RING1) ? (n25 & N25_RING1) : n25;
-      Best b;
-      b.have = false; b.has_sp1 = false; b.dist = 0.0; b.val = 0.0; b.sp1 = 0.0; b.cross = 0; b.d2 = 0; b.i = 0; b.j = 0;
-      if ((cm >> lane) & 1u) consider<MODE_EPWT>(b, ci_ + ldi, cj_ + ldj, ci_, cj_, p0, p1, curval, vals, pix + lpix, u8wrap);
-      warp_arg_best<MODE_EPWT>(b, ci_, cj_, p0, p1, curval, bi, bj);
+      const bool has = (cm >> lane) & 1u;  // this lane's cell is a candidate (cm < 2^25: lanes 25..31 never are)
+      // the value distance as an orderable 64-bit key (dist >= 0), smallest over the warp; one winner is the common case
+      double val = 0.0;
+      unsigned hi = 0xffffffffu, lo = 0xffffffffu;
+      if (has) {
+        val = RB_EPWT_LOAD(vals + pix + lpix);
+        const double dv = curval - val;
+        const double dist = u8wrap ? (dv < 0.0 ? dv + 256.0 : dv) : fabs(dv);  // rbepwt.py:1302 (uint8 arithmetic wraps)
+        const unsigned long long k = (unsigned long long)__double_as_longlong(dist);
+        hi = (unsigned)(k >> 32); lo = (unsigned)k;
+      }
+      const unsigned mh = __reduce_min_sync(FULL_MASK, hi);
+      const unsigned ml = __reduce_min_sync(FULL_MASK, hi == mh ? lo : 0xffffffffu);
+      const unsigned tied = __ballot_sync(FULL_MASK, has && hi == mh && lo == ml);
+      if ((tied & (tied - 1u)) == 0u) {
+        const int cell = __ffs(tied) - 1;
+        const int wdi = ((cell * 13) >> 6) - 2;
+        bi = ci_ + wdi; bj = cj_ + cell - 5 * (wdi + 2) - 2;
+        curval = __shfl_sync(FULL_MASK, val, cell);
+      } else {  // equal value distances: the reference's direction tie-break (paths.cuh)
+        Best b;
+        b.have = false; b.has_sp1 = false; b.dist = 0.0; b.val = 0.0; b.sp1 = 0.0; b.cross = 0; b.d2 = 0; b.i = 0; b.j = 0;
+        if (has) consider<MODE_EPWT>(b, ci_ + ldi, cj_ + ldj, ci_, cj_, p0, p1, curval, vals, pix + lpix, u8wrap);
+        warp_arg_best<MODE_EPWT>(b, ci_, cj_, p0, p1, curval, bi, bj);
+      }
     } else {
       rw_store(rw, bm, h, ws);
       __syncwarp();
