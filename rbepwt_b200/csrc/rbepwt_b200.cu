@@ -1529,6 +1529,15 @@ int rbepwt_debug_wk_stats(rbepwt_ctx *c, unsigned long long *out, int reset) {
   if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_wk_stats, z, sizeof z); }
   return 0;
 }
+// the named queue slots (qmeta[Q_BINS ..]) and the per-class table (qbins) of path slot `slot` after the last group it ran
+int rbepwt_debug_queue(rbepwt_ctx *c, int slot, int *out) {
+  DeviceGuard g(c->device);
+  sync_internal(c);
+  cudaStreamSynchronize(c->stream);
+  cudaMemcpy(out, c->slot[slot].qmeta.as<int>() + Q_BINS, (QM_SIZE - Q_BINS) * sizeof(int), cudaMemcpyDeviceToHost);
+  cudaMemcpy(out + 16, c->slot[slot].qbins.as<int>(), 3 * Q_NCLS * sizeof(int), cudaMemcpyDeviceToHost);
+  return 0;
+}
 #endif
 
 }  // extern "C"

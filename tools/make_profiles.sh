@@ -9,13 +9,14 @@ ARGS="--batch 512 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-extras --
 python bench.py $ARGS > gpurun_out/prof_plain_$tag.json 2> gpurun_out/prof_plain_$tag.err || { echo "plain run failed"; tail -5 gpurun_out/prof_plain_$tag.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k[0-9q_]" -c 600 --csv \
     --log-file gpurun_out/launches_$tag.csv python bench.py $ARGS > gpurun_out/ncu_list_$tag.log 2>&1
-# launch-skip: 3 warm-up steps; k1_walk launches twice per step (windowed instantiation first), k3/k5 7 times per
-# 64-image sub-batch (6 level launches + the tail) -- the captures land on the timed step's first launches
-for spec in k1_walk:6:2 k1_bitmaps:3:1 k2_perm:3:1 k4_select:24:1 k3_dwt_level:168:1 k5_idwt_level:174:1 k3_dwt_tail:24:1 k0_regions_fast:3:1 k0_count:3:1; do
+# launch-skip: 3 warm-up steps.  Per step (512 device-resident images = 2 path groups and 2 transform sub-batches of 256):
+# k1_walk launches 4 times (per group: the windowed instantiation, then the bulk one), k3/k5 14 times (per sub-batch the 7
+# level launches; the tail kernel has its own name), everything else twice -- the captures land on the timed step's first launches
+for spec in k1_walk:12:2 k1_bitmaps:6:1 k1_coop_all:6:1 k2_perm:6:1 k4_select:6:1 k3_dwt_level:42:1 k5_idwt_level:48:1 k3_dwt_tail:6:1 k0_regions_fast:6:1 k0_count:6:1; do
   IFS=: read k skip cnt <<< "$spec"
   ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c $cnt -o $T/prof_${k}_$tag \
       python bench.py $ARGS > gpurun_out/ncu_full_${k}_$tag.log 2>&1
 done
-PROF_SRC=$T PROF_LAUNCHES=gpurun_out PROF_DST=gpurun_out/profiles_$tag python tools/summarize_profiles.py $tag
+PROF_GROUP=256 PROF_SRC=$T PROF_LAUNCHES=gpurun_out PROF_DST=gpurun_out/profiles_$tag python tools/summarize_profiles.py $tag
 cp $T/prof_k1_walk_$tag.ncu-rep gpurun_out/ 2>/dev/null
 ls -la gpurun_out/profiles_$tag

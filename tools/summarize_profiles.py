@@ -64,7 +64,7 @@ for rep in sorted(glob.glob(os.path.join(G, "prof_*_%s.ncu-rep" % tag))):
 
 # ---- DRAM traffic of the hot kernels (bench.py scales roofline.traffic from this file)
 import json
-traffic = {"source": "profiles/%s_ncu_*.txt (ncu --set full, one launch each: k1_walk = both instantiations of one 512-image path group; k3/k5 = the level-1 launch of one sub-batch; tools/make_profiles.sh)" % tag}
+traffic = {"source": "profiles/%s_ncu_*.txt (ncu --set full, one launch each: k1_walk = both instantiations of one 256-image path group; k3/k5 = the level-1 launch of one sub-batch; tools/make_profiles.sh)" % tag}
 for rep in sorted(glob.glob(os.path.join(G, "prof_*_%s.ncu-rep" % tag))):
     name = os.path.basename(rep)[len("prof_"):-len("_%s.ncu-rep" % tag)]
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -82,7 +82,7 @@ for rep in sorted(glob.glob(os.path.join(G, "prof_*_%s.ncu-rep" % tag))):
         e["duration_us"] += col(r, "gpu__time_duration.sum")
         e["launches_summed"] += 1
         gy = r[hdr.index("Grid Size")].strip("()").replace(" ", "").split(",") if "Grid Size" in hdr else []
-    e["images_per_launch"] = int(gy[1]) if name in ("k3_dwt_level", "k5_idwt_level") and len(gy) > 1 else (int(gy[0]) if name in ("k4_select", "k3_dwt_tail") else 512)
+    e["images_per_launch"] = int(gy[1]) if name in ("k3_dwt_level", "k5_idwt_level") and len(gy) > 1 else (int(gy[0]) if name in ("k4_select", "k3_dwt_tail") else int(os.environ.get("PROF_GROUP", "256")))
     traffic[name] = e
 with open(os.path.join(P, "%s_traffic.json" % tag), "w") as f:
     json.dump(traffic, f, indent=1)
