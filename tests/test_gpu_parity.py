@@ -100,6 +100,17 @@ def test_heavy_tailed_label_maps_vs_oracle(euclid):
         assert_same_as_oracle(outs[b], orc[b % 2], 16)
     one = cuda_run(imgs[1], labs[1], 16, "bior4.4", euclidean_distance=euclid, ncoefs=2048)
     assert_same_as_oracle(one, orc[1], 16)
+    # who is walked by a whole warp is a tuning decision (RBEPWT_OPT_COOP_LIMIT: the largest n regions of the group;
+    # default 4 per SM): the results must not depend on it -- none, a handful (the threshold falls inside the size
+    # distribution), everything of >= 2048 pixels
+    for lim in (0, 7, 1 << 20):
+        c2 = rb.BatchCodec()
+        c2.set_option(coop_limit=lim)
+        c2.encode(bi, bl, 16, "bior4.4", euclidean_distance=euclid)
+        outs2 = collect_batch(c2, bi, (1, 8), 16, 2048)
+        for b in (1, 8):
+            assert_same_as_oracle(outs2[b], orc[b % 2], 16)
+        c2.close()
 
 
 @pytest.mark.parametrize("euclid", [True, False])
