@@ -560,6 +560,27 @@ __device__ __forceinline__ void wk_build_bitmaps(const PathParams &P, uint32_t *
     const int slot_r = __shfl_sync(FULL_MASK, slot, r);
     const int32_t *lab = P.labels + (size_t)img_r * P.N;
     const int words_r = h_r * ws_r;
+    if (ws_r == 1 && h_r <= 32) {
+      // the common shape (one word per row, at most 32 rows): lane = column for the loads and ballots, lane = row for
+      // the result, which leaves as ONE coalesced store; per row an add, a load, a compare, a ballot and a select.
+      // The rows and columns of the bounding box lie inside the image; the margin rows / columns stay zero.
+      const bool cok = lane >= WK_PAD && lane < w_r - WK_PAD;
+      const int32_t *p = lab + ((r0_r + WK_PAD) << logW) + c0_r + lane;
+      const int nrows = h_r - 2 * WK_PAD;
+      uint32_t mine = 0u;
+      for (int i0 = 0; i0 < nrows; i0 += 8) {  // eight independent label loads in flight per lane
+        int lv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) lv[u] = (cok && i0 + u < nrows) ? p[(size_t)(i0 + u) << logW] : ~label_r;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const unsigned bits = __ballot_sync(FULL_MASK, lv[u] == label_r);
+          mine = lane == i0 + u + WK_PAD ? bits : mine;
+        }
+      }
+      for (int q = lane; q < slot_r; q += 32) dst[base_r + q] = q < h_r ? mine : 0u;
+      continue;
+    }
     for (int wi = 0; wi < words_r; wi += 8) {  // eight independent label loads in flight per lane
       int lv[8];
       bool inb[8];
