@@ -57,6 +57,8 @@ struct PathParams {
   int *qmeta;
   const uint8_t *unit_lut;  // 9 x 512 unit-step table of the path mode (global memory, built once per context)
   const uint8_t *t2_tab;    // 5x5 step table of the euclid mode (walk.cuh, T2_BYTES)
+  int32_t *slot_of;         // [nreg] word offset of a region's slot in gbm, -1: its chunk builds its own (kq_slots)
+  int g0, nreg;             // the path group's regions: [g0, g0 + nreg)
   int coop;                 // the path mode has a whole-warp kernel for class 1 (k1_coop_all): euclid, gradpath
   uint32_t *gbm;            // [gbm_chunks][TPR_ARENA_WORDS] chunk arena images built by k1_bitmaps (walk.cuh)
   int gbm_chunks;           // chunks beyond it build their bitmaps inside the path kernel

@@ -95,7 +95,7 @@ struct Slot {
   cudaStream_t aux = nullptr;     // path slots: the large-bitmap path kernel runs beside the bulk one
   cudaStream_t aux2 = nullptr;    // ... and so does the kernel of the oversized regions (k1_paths_big)
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
-  DevBuf VA, VB, Vpix, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch, gbm;
+  DevBuf VA, VB, Vpix, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch, gbm, slot_of;
 };
 
 struct rbepwt_ctx {
@@ -428,6 +428,7 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   // bitmaps) build theirs inside the path kernel
   const size_t gbm_chunks = (size_t)nreg / 16 + 64;
   CK(sl.gbm.ensure_slack(gbm_chunks * TPR_ARENA_WORDS * 4));
+  CK(sl.slot_of.ensure_slack((size_t)nreg * 4));
   CK(cudaStreamWaitEvent(s, ready, 0));
   {
     StageTimer t(c, RBEPWT_T_REGIONS, s);
@@ -471,6 +472,8 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
   P.t2_tab = c->t2_tab.as<uint8_t>();
   P.coop = c->mode != RBEPWT_PATH_CHEB ? 1 : 0;
   P.gbm = sl.gbm.as<uint32_t>();
+  P.slot_of = sl.slot_of.as<int32_t>();
+  P.g0 = g0; P.nreg = nreg;
   P.gbm_chunks = (int)gbm_chunks;
   P.Q = c->Q.as<int32_t>();
   P.Pm = c->Pm.as<int32_t>();
@@ -548,8 +551,10 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
       k1_walk<MODE_EUCLID, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, WK_WIDE_WARPS * 32, wk_arena_bytes(true), sl.aux>>>(P);
     else
       k1_walk<MODE_CHEB, true><<<c->sm_count * TPR_WIDE_CTAS_PER_SM, WK_WIDE_WARPS * 32, wk_arena_bytes(true), sl.aux>>>(P);
+    CK(cudaMemsetAsync(P.slot_of, 0xff, (size_t)nreg * 4, s));
+    kq_slots<<<c->sm_count * 4, 256, 0, s>>>(P);
     k1_bitmaps<<<c->sm_count * 8, 256, 0, s>>>(P);
-    c->launches++;
+    c->launches += 2;
     if (c->mode == RBEPWT_PATH_EUCLID)
       k1_walk<MODE_EUCLID, false><<<small_ctas, WK_WARPS * 32, wk_arena_bytes(false), s>>>(P);
     else
@@ -1008,7 +1013,7 @@ void rbepwt_destroy(rbepwt_ctx *c) {
   for (auto &b : c->reg) b.release();
   for (int i = 0; i < NSLOTS; i++) {
     Slot &sl = c->slot[i];
-    DevBuf *sb[] = {&sl.VA, &sl.VB, &sl.Vpix, &sl.queue, &sl.qhist, &sl.qmeta, &sl.qbins, &sl.chunk_start, &sl.chunk_cnt, &sl.gscratch, &sl.gbm};
+    DevBuf *sb[] = {&sl.VA, &sl.VB, &sl.Vpix, &sl.queue, &sl.qhist, &sl.qmeta, &sl.qbins, &sl.chunk_start, &sl.chunk_cnt, &sl.gscratch, &sl.gbm, &sl.slot_of};
     for (auto b : sb) b->release();
     if (sl.s) cudaStreamDestroy(sl.s);
     if (sl.aux) cudaStreamDestroy(sl.aux);

@@ -546,61 +546,66 @@ __device__ __forceinline__ void wk_geometry(const PathParams &P, int g, int &r0,
   h = P.reg.rmax[g] - r0 + 1 + WK_PAD; w = P.reg.cmax[g] - c0 + 1 + WK_PAD; ws = (w + 31) >> 5;
 }
 
-// Cooperative build of one chunk's arena image: for every region the level-1 bitmap in plane 0 (one ballot per
-// bitmap word, lanes = columns) and zeros in the rest of its slot.  Lane r holds region r's geometry and its word
-// offset `base` in `dst`; `slot` = its slot words.
+// Cooperative build of ONE region's slot of an arena image (all arguments warp-uniform): the level-1 bitmap in plane 0
+// (one ballot per bitmap word, lanes = columns) and zeros in the rest of the slot.  dst = the slot's first word.
+__device__ __forceinline__ void wk_build_one(const PathParams &P, uint32_t *dst, int img_r, int label_r, int r0_r, int c0_r,
+                                             int h_r, int w_r, int ws_r, int slot_r) {
+  const int lane = (int)lane_id(), logW = P.logW;
+  const int32_t *lab = P.labels + (size_t)img_r * P.N;
+  const int words_r = h_r * ws_r;
+  if (ws_r == 1 && h_r <= 32) {
+    // the common shape (one word per row, at most 32 rows): lane = column for the loads and ballots, lane = row for
+    // the result, which leaves as ONE coalesced store; per row an add, a load, a compare, a ballot and a select.
+    // The rows and columns of the bounding box lie inside the image; the margin rows / columns stay zero.
+    const bool cok = lane >= WK_PAD && lane < w_r - WK_PAD;
+    const int32_t *p = lab + ((r0_r + WK_PAD) << logW) + c0_r + lane;
+    const int nrows = h_r - 2 * WK_PAD;
+    uint32_t mine = 0u;
+    for (int i0 = 0; i0 < nrows; i0 += 8) {  // eight independent label loads in flight per lane
+      int lv[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) lv[u] = (cok && i0 + u < nrows) ? p[(size_t)(i0 + u) << logW] : ~label_r;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const unsigned bits = __ballot_sync(FULL_MASK, lv[u] == label_r);
+        mine = lane == i0 + u + WK_PAD ? bits : mine;
+      }
+    }
+    for (int q = lane; q < slot_r; q += 32) dst[q] = q < h_r ? mine : 0u;
+    return;
+  }
+  for (int wi = 0; wi < words_r; wi += 8) {  // eight independent label loads in flight per lane
+    int lv[8];
+    bool inb[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int w_ = wi + u;
+      const int i = ws_r == 1 ? w_ : w_ / ws_r;
+      const int col = ((w_ - i * ws_r) << 5) + lane;
+      // the margin rows / columns hold no pixel of the region (they lie outside its bounding box)
+      inb[u] = w_ < words_r && i >= WK_PAD && i < h_r - WK_PAD && col >= WK_PAD && col < w_r - WK_PAD &&
+               (unsigned)(r0_r + i) < (unsigned)P.H && (unsigned)(c0_r + col) < (unsigned)P.W;
+      lv[u] = inb[u] ? lab[((r0_r + i) << logW) + c0_r + col] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const unsigned bits = __ballot_sync(FULL_MASK, inb[u] && lv[u] == label_r);
+      if (lane == 0 && wi + u < words_r) dst[wi + u] = bits;
+    }
+  }
+  for (int q = words_r + lane; q < slot_r; q += 32) dst[q] = 0u;
+}
+
+// One chunk's arena image: lane r holds region r's geometry and its word offset `base` in `dst`; `slot` = its slot words.
 __device__ __forceinline__ void wk_build_bitmaps(const PathParams &P, uint32_t *dst, int cnt, int img, int label, int r0,
                                                  int c0, int h, int w, int ws, int base, int slot) {
-  const int lane = (int)lane_id(), logW = P.logW;
   for (int r = 0; r < cnt; r++) {
     const int img_r = __shfl_sync(FULL_MASK, img, r), label_r = __shfl_sync(FULL_MASK, label, r);
     const int r0_r = __shfl_sync(FULL_MASK, r0, r), c0_r = __shfl_sync(FULL_MASK, c0, r);
     const int h_r = __shfl_sync(FULL_MASK, h, r), w_r = __shfl_sync(FULL_MASK, w, r);
     const int ws_r = __shfl_sync(FULL_MASK, ws, r), base_r = __shfl_sync(FULL_MASK, base, r);
     const int slot_r = __shfl_sync(FULL_MASK, slot, r);
-    const int32_t *lab = P.labels + (size_t)img_r * P.N;
-    const int words_r = h_r * ws_r;
-    if (ws_r == 1 && h_r <= 32) {
-      // the common shape (one word per row, at most 32 rows): lane = column for the loads and ballots, lane = row for
-      // the result, which leaves as ONE coalesced store; per row an add, a load, a compare, a ballot and a select.
-      // The rows and columns of the bounding box lie inside the image; the margin rows / columns stay zero.
-      const bool cok = lane >= WK_PAD && lane < w_r - WK_PAD;
-      const int32_t *p = lab + ((r0_r + WK_PAD) << logW) + c0_r + lane;
-      const int nrows = h_r - 2 * WK_PAD;
-      uint32_t mine = 0u;
-      for (int i0 = 0; i0 < nrows; i0 += 8) {  // eight independent label loads in flight per lane
-        int lv[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) lv[u] = (cok && i0 + u < nrows) ? p[(size_t)(i0 + u) << logW] : ~label_r;
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          const unsigned bits = __ballot_sync(FULL_MASK, lv[u] == label_r);
-          mine = lane == i0 + u + WK_PAD ? bits : mine;
-        }
-      }
-      for (int q = lane; q < slot_r; q += 32) dst[base_r + q] = q < h_r ? mine : 0u;
-      continue;
-    }
-    for (int wi = 0; wi < words_r; wi += 8) {  // eight independent label loads in flight per lane
-      int lv[8];
-      bool inb[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const int w_ = wi + u;
-        const int i = ws_r == 1 ? w_ : w_ / ws_r;
-        const int col = ((w_ - i * ws_r) << 5) + lane;
-        // the margin rows / columns hold no pixel of the region (they lie outside its bounding box)
-        inb[u] = w_ < words_r && i >= WK_PAD && i < h_r - WK_PAD && col >= WK_PAD && col < w_r - WK_PAD &&
-                 (unsigned)(r0_r + i) < (unsigned)P.H && (unsigned)(c0_r + col) < (unsigned)P.W;
-        lv[u] = inb[u] ? lab[((r0_r + i) << logW) + c0_r + col] : 0;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const unsigned bits = __ballot_sync(FULL_MASK, inb[u] && lv[u] == label_r);
-        if (lane == 0 && wi + u < words_r) dst[base_r + wi + u] = bits;
-      }
-    }
-    for (int q = words_r + lane; q < slot_r; q += 32) dst[base_r + q] = 0u;
+    wk_build_one(P, dst + base_r, img_r, label_r, r0_r, c0_r, h_r, w_r, ws_r, slot_r);
   }
 }
 
@@ -633,15 +638,31 @@ __device__ __forceinline__ WkChunkLane wk_chunk_lane(const PathParams &P, int qs
 // them), built ahead of the walk by warps that do nothing else (the label reads are pure memory latency; inside the
 // path kernel they would hold a walking warp's registers and arena).  gbm[chunk - split][TPR_ARENA_WORDS].  The
 // large-bitmap chunks of the windowed instantiation build theirs in the kernel.
-__global__ void __launch_bounds__(256) k1_bitmaps(PathParams P) {
+// Two kernels.  kq_slots: a warp per chunk writes, for every region of the chunk, where its slot lies in gbm (-1 for
+// the regions of other chunks: the buffer is preset).  k1_bitmaps: a warp per region IN REGION ORDER, i.e. image by
+// image and, inside an image, in first-appearance (row-major) order -- the warps running at the same time read the
+// label rows of a handful of images, which stay in L2: a chunk's regions come from 32 different images, and building
+// chunk by chunk fetched every bounding-box row from DRAM (3.3x the label bytes).
+__global__ void __launch_bounds__(256) kq_slots(PathParams P) {
   const int split = P.qmeta[QM_CHUNK_SPLIT];
   const int nchunks = min(P.qmeta[QM_NCHUNKS], split + P.gbm_chunks);
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   for (int chunk = split + wid; chunk < nchunks; chunk += nw) {
     const int cnt = P.chunk_cnt[chunk];
     const WkChunkLane c = wk_chunk_lane(P, P.chunk_start[chunk], cnt);
-    wk_build_bitmaps(P, P.gbm + (size_t)(chunk - split) * TPR_ARENA_WORDS, cnt, c.img, c.label, c.r0, c.c0, c.h, c.w, c.ws,
-                     c.base, c.slot);
+    if ((int)lane_id() < cnt) P.slot_of[c.g - P.g0] = (chunk - split) * TPR_ARENA_WORDS + c.base;
+  }
+}
+
+__global__ void __launch_bounds__(256) k1_bitmaps(PathParams P) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int i = wid; i < P.nreg; i += nw) {
+    const int so = P.slot_of[i];
+    if (so < 0) continue;
+    const int g = P.g0 + i;
+    int r0, c0, h, w, ws;
+    wk_geometry(P, g, r0, c0, h, w, ws);
+    wk_build_one(P, P.gbm + so, P.reg.img[g], P.reg.label[g], r0, c0, h, w, ws, wk_slot_words(h, ws));
   }
 }
 
