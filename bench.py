@@ -570,9 +570,9 @@ def run_ours(args):
     kern_stages = [s for s in alg if stage_ms.get(s, 0.0) > 0.0]
     total_kernel_ms = sum(stage_ms[s] for s in kern_stages)
     dom = max(kern_stages, key=lambda s: stage_ms[s])
-    # a "launch" of the paths stage is one path group: k1_bitmaps, then the two k1_walk instantiations side by
-    # side (the windowed one takes the few large bitmaps) -- three kernel launches timed as one unit
-    per_unit = {"paths": 3}
+    # a "launch" of the paths stage is one path group: kq_slots + k1_bitmaps, then the two k1_walk instantiations side by
+    # side (the windowed one takes the few large bitmaps) -- four kernel launches timed as one unit
+    per_unit = {"paths": 4}
     dom_launches = max(stage_n.get(dom, 0) // per_unit.get(dom, 1), 1)
     dom_ms_per_launch = stage_ms[dom] / dom_launches
     bytes_per_launch = alg[dom][1] * B * K / dom_launches
