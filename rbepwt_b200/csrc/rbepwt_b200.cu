@@ -96,6 +96,11 @@ struct Slot {
   cudaStream_t aux2 = nullptr;    // ... and so does the kernel of the oversized regions (k1_paths_big)
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
   DevBuf VA, VB, Vpix, queue, qhist, qmeta, qbins, chunk_start, chunk_cnt, gscratch, gbm, slot_of;
+  // a path group between its two phases (build_regions_and_paths): kernel parameters and launch shapes
+  PathParams P;
+  int p_nreg = 0, p_big_ctas = 0;
+  size_t p_smem_bytes = 0;
+  bool p_coop_all = false;
 };
 
 struct rbepwt_ctx {
@@ -113,7 +118,7 @@ struct rbepwt_ctx {
   int opt_coop_limit = -1;  // RBEPWT_OPT_COOP_LIMIT (-1 = auto)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<cudaEvent_t> ev_lab, ev_path, ev_img, ev_done;
-  int32_t *pin_R = nullptr, *pin_rbase = nullptr;  // pinned staging, capacity pin_cap images
+  int32_t *pin_R = nullptr, *pin_rbase = nullptr, *pin_direct = nullptr;  // pinned staging, capacity pin_cap images
   int *pin_err = nullptr;
   int pin_cap = 0;
   // wavelet
@@ -361,6 +366,7 @@ int stage_labels(rbepwt_ctx *c, int chunk0, int a, int nb, const void *lab_src, 
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c->pin_R + a, c->img_R.as<int32_t>() + a, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c->pin_direct + a, c->img_direct.as<int32_t>() + a, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
   }
   CK(cudaEventRecord(ready, s));
   return RBEPWT_OK;
@@ -393,11 +399,19 @@ int stage_images(rbepwt_ctx *c, int a, int nb, const void *img_src, cudaEvent_t 
   return RBEPWT_OK;
 }
 
-// K0 (region records, work queue) + K1 (path pyramid) of one path group on stream s (workspace: sl).
+// K0 (region records, work queue) + K1 (path pyramid) of one path group on stream s (workspace: sl), in two phases:
+//   PHASE_REGIONS: label scan results -> region records, the size-sorted queue;
+//   PHASE_WALK   : the chunk arena images, the path kernels and the positions (k2_perm).
+// run_pipeline enqueues the first phase of EVERY group of a chunk before any second phase: the first phase is latency /
+// atomics bound and its groups overlap well with each other, but its 1024-thread CTAs cannot get onto an SM while walk
+// CTAs fill it -- enqueued after walk(g) it waited ~3 ms for the walk to drain (tools/pipe_stages.py) and delayed
+// walk(g+1) by its whole length.
 // EPWT: one region per image; its paths depend on the level's values and are built in transform_sub().
-int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0, int a, int nb, cudaEvent_t ready) {
+enum { PHASE_REGIONS = 1, PHASE_WALK = 2 };
+int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0, int a, int nb, cudaEvent_t ready, int phases) {
   const int N = c->N, T = 2 * N;
   if (c->mode == RBEPWT_PATH_EPWT) {
+    if (!(phases & PHASE_REGIONS)) return RBEPWT_OK;
     int rc = grow_regs(c, (size_t)c->B, (size_t)a);
     if (rc) return rc;
     CK(cudaStreamWaitEvent(s, ready, 0));
@@ -410,8 +424,11 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     CK(cudaGetLastError());
     return RBEPWT_OK;
   }
+  if (phases & PHASE_REGIONS) {
   CK(cudaEventSynchronize(ready));  // the host needs the sub-batch's region counts
   const int g0 = c->totalR;
+  bool any_general = false;  // an image the shared-memory sweep cannot take (sparse label values, > 4096 regions, ...)
+  for (int i = 0; i < nb; i++) any_general |= !k0_fast_eligible(c->pin_direct[a + i], c->pin_R[a + i], c->logW);
   for (int i = 0; i < nb; i++) {
     c->h_R[a + i] = c->pin_R[a + i];
     c->h_rbase[a + i] = c->pin_rbase[a + i] = c->totalR;
@@ -438,11 +455,12 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
                                                     c->tbl.as<unsigned long long>() + (size_t)(a - chunk0) * T, T,
                                                     c->img_R.as<int32_t>(), c->img_labmin.as<int32_t>(),
                                                     c->img_direct.as<int32_t>(), c->img_rbase.as<int32_t>(), c->regs());
-    k0_regions<<<nb * K0_CLUSTER, K0_THREADS, 0, s>>>(c->labels_dev, a, N, c->logW,
-                                         c->tbl.as<unsigned long long>() + (size_t)(a - chunk0) * T,
-                                         c->slot_rid.as<int32_t>() + (size_t)(a - chunk0) * T, T, c->img_R.as<int32_t>(),
-                                         c->img_labmin.as<int32_t>(), c->img_direct.as<int32_t>(),
-                                         c->img_rbase.as<int32_t>(), c->regs());
+    if (any_general)  // (a cluster launch of 1024-thread CTAs waits for eight free SMs: not worth an empty launch)
+      k0_regions<<<nb * K0_CLUSTER, K0_THREADS, 0, s>>>(c->labels_dev, a, N, c->logW,
+                                           c->tbl.as<unsigned long long>() + (size_t)(a - chunk0) * T,
+                                           c->slot_rid.as<int32_t>() + (size_t)(a - chunk0) * T, T, c->img_R.as<int32_t>(),
+                                           c->img_labmin.as<int32_t>(), c->img_direct.as<int32_t>(),
+                                           c->img_rbase.as<int32_t>(), c->regs());
     const int qb = std::max(1, std::min((nreg + 255) / 256, c->sm_count * 8));
     // few regions in flight (single images, small batches): every region gets its own warp -- latency, not throughput;
     // gradpath: always.  Otherwise (euclid) the largest regions of the group do, kq_scan picks the threshold.
@@ -491,6 +509,14 @@ int build_regions_and_paths(rbepwt_ctx *c, Slot &sl, cudaStream_t s, int chunk0,
     P.gscratch = sl.gscratch.as<uint32_t>();
     P.gscratch_words = img_words;
   }
+  sl.P = P; sl.p_nreg = nreg; sl.p_big_ctas = big_ctas; sl.p_smem_bytes = smem_bytes; sl.p_coop_all = coop_all;
+  }  // PHASE_REGIONS
+  if (!(phases & PHASE_WALK)) return RBEPWT_OK;
+  sl.P.reg = c->regs();  // another group's first phase may have grown (moved) the region arrays since this group's
+  const PathParams &P = sl.P;
+  const int nreg = sl.p_nreg, big_ctas = sl.p_big_ctas;
+  const size_t smem_bytes = sl.p_smem_bytes;
+  const bool coop_all = sl.p_coop_all;
   const bool grad_mode = c->mode == RBEPWT_PATH_GRAD || c->mode == RBEPWT_PATH_GRAD_CHEB;
   if (coop_all) {
     // regions whose bitmap exceeds a shared-memory arena in k1_paths_big (own stream), all the others one warp each
@@ -739,9 +765,11 @@ int alloc_state(rbepwt_ctx *c, int B, int H, int W, int levels, int path_mode, u
   if (B > c->pin_cap) {
     if (c->pin_R) cudaFreeHost(c->pin_R);
     if (c->pin_rbase) cudaFreeHost(c->pin_rbase);
-    c->pin_R = c->pin_rbase = nullptr; c->pin_cap = 0;
+    if (c->pin_direct) cudaFreeHost(c->pin_direct);
+    c->pin_R = c->pin_rbase = c->pin_direct = nullptr; c->pin_cap = 0;
     CK(cudaMallocHost((void **)&c->pin_R, (size_t)B * 4));
     CK(cudaMallocHost((void **)&c->pin_rbase, (size_t)B * 4));
+    CK(cudaMallocHost((void **)&c->pin_direct, (size_t)B * 4));
     c->pin_cap = B;
   }
   const int Bc = chunk_images(c, B, c->N);
@@ -818,15 +846,27 @@ int run_pipeline(rbepwt_ctx *c, int what, long long k, const void *img_host, con
         const int a = c0 + s * Bs, nb = std::min(Bs, c0 + nbc - a);
         if ((rc = stage_images(c, a, nb, img_host, c->ev_img[s]))) return rc;
       }
-    if (what & DO_PATHS)
-      for (int g = 0; g < ngrp; g++) {
+    if (what & DO_PATHS) {
+      auto run_phase = [&](int g, int phases) -> int {
         Slot &sl = c->slot[g % c->nslot];
         cudaStream_t st = serial ? c->slot[0].s : sl.s;
-        if ((c->mode == RBEPWT_PATH_GRAD || c->mode == RBEPWT_PATH_GRAD_CHEB) && (what & DO_DWT) && img_host)
+        if ((phases & PHASE_REGIONS) && (c->mode == RBEPWT_PATH_GRAD || c->mode == RBEPWT_PATH_GRAD_CHEB) && (what & DO_DWT) && img_host)
           for (int sb = gstart[g]; sb < gstart[g + 1]; sb++) CK(cudaStreamWaitEvent(st, c->ev_img[sb], 0));  // gradpath reads pixel values
-        if ((rc = build_regions_and_paths(c, sl, st, c0, grp_a(g), grp_nb(g), c->ev_lab[g]))) return rc;
-        CK(cudaEventRecord(c->ev_path[g], st));
+        int rc2 = build_regions_and_paths(c, sl, st, c0, grp_a(g), grp_nb(g), c->ev_lab[g], phases);
+        if (rc2) return rc2;
+        if (phases & PHASE_WALK) CK(cudaEventRecord(c->ev_path[g], st));
+        return RBEPWT_OK;
+      };
+      // regions(0), regions(1), walk(0), regions(2), walk(1), ...: the first phase runs one group ahead (two path slots:
+      // a slot's next group is enqueued on the slot's stream after its previous group's walk, so nothing is overwritten).
+      // One stream (RBEPWT_OPT_STREAMS = 1): group after group.
+      for (int g = 0; g < ngrp; g++) {
+        if (serial) { if ((rc = run_phase(g, PHASE_REGIONS | PHASE_WALK))) return rc; continue; }
+        if ((rc = run_phase(g, PHASE_REGIONS))) return rc;
+        if (g >= 1 && (rc = run_phase(g - 1, PHASE_WALK))) return rc;
       }
+      if (!serial && (rc = run_phase(ngrp - 1, PHASE_WALK))) return rc;
+    }
     if (what & (DO_DWT | DO_THRESH | DO_DECODE))
       for (int s = 0; s < nsub; s++) {
         const int a = c0 + s * Bs, nb = std::min(Bs, c0 + nbc - a);
@@ -1028,6 +1068,7 @@ void rbepwt_destroy(rbepwt_ctx *c) {
   if (c->s_out) cudaStreamDestroy(c->s_out);
   if (c->pin_R) cudaFreeHost(c->pin_R);
   if (c->pin_rbase) cudaFreeHost(c->pin_rbase);
+  if (c->pin_direct) cudaFreeHost(c->pin_direct);
   if (c->pin_err) cudaFreeHost(c->pin_err);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
