@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k[0-9q_]" -
 # launch-skip: 3 warm-up steps.  Per step (512 device-resident images = 2 path groups and 2 transform sub-batches of 256):
 # k1_walk launches 4 times (per group: the windowed instantiation, then the bulk one), k3/k5 14 times (per sub-batch the 7
 # level launches; the tail kernel has its own name), everything else twice -- the captures land on the timed step's first launches
-for spec in k1_walk:12:2 k1_bitmaps:6:1 k1_coop_all:6:1 k2_perm:6:1 k4_select:6:1 k3_dwt_level:42:1 k5_idwt_level:48:1 k3_dwt_tail:6:1 k0_regions_fast:6:1 k0_count:6:1; do
+for spec in k1_walk:12:2 k1_bitmaps:6:1 kq_slots:6:1 k1_coop_all:6:1 k2_perm:6:1 k4_select:6:1 k3_dwt_level:42:1 k5_idwt_level:48:1 k3_dwt_tail:6:1 k0_regions_fast:6:1 k0_count:6:1; do
   IFS=: read k skip cnt <<< "$spec"
   ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c $cnt -o $T/prof_${k}_$tag \
       python bench.py $ARGS > gpurun_out/ncu_full_${k}_$tag.log 2>&1
