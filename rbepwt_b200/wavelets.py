@@ -49,7 +49,7 @@ def filter_bank(wavelet):
         try:
             import pywt  # optional: the reference's own source of filter banks
             return tuple(np.ascontiguousarray(f, dtype=np.float64) for f in pywt.Wavelet(wavelet).filter_bank)
-        except ImportError:
+        except (ImportError, AttributeError):  # absent, or a stand-in module without Wavelet (oracle/ref_harness.py)
             pass
         if name in TABLES:
             bank = _from_lowpass(*TABLES[name])

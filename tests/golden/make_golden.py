@@ -128,15 +128,59 @@ def make_perc(only, force):
         print("%-28s kept %d" % (name, np.count_nonzero(flat)), flush=True)
 
 
+def roi_cases():
+    """Roi.compute_dual_roi_coeffs (rbepwt.py:1718-1789): fixtures in tests/golden/roi/.  Label values are not 0..R-1 in
+    one case: the reference matches `regionsidx` against the keys of its region dict, which are region indices (ranks of
+    first appearance), not label values -- indices beyond R select nothing."""
+    c = []
+    lab = synth.voronoi_labels(16, 16, 6, seed=1)
+    c.append(("roi16_haar_l3", synth.piecewise_smooth_image(lab, seed=1), lab, 3, "haar", True, [0, 1], 0.5, 0.1))
+    lab = synth.voronoi_labels(32, 32, 9, seed=3)
+    img = synth.piecewise_smooth_image(lab, seed=3)
+    c.append(("roi32_haar_l5", img, lab, 5, "haar", True, [2, 3, 5], 1.0, 0.0))
+    c.append(("roi32_haar_l10_all", img, lab, 10, "haar", True, [4], 0.3, 0.05))
+    c.append(("roi32_bior44_l6", img, lab, 6, "bior4.4", True, [0, 7, 8], 0.25, 0.02))
+    c.append(("roi32_cheb_sparse_labels", img, lab * 7 + 3, 6, "haar", False, [3, 24, 59], 0.6, 0.0))
+    return c
+
+
+def make_roi(only, force):
+    import contextlib
+    import io
+
+    ref = ref_harness.load_reference()
+    os.makedirs(os.path.join(HERE, "roi"), exist_ok=True)
+    for name, img, lab, levels, wav, euclid, regs, pin, pout in roi_cases():
+        if only and name not in only:
+            continue
+        path = os.path.join(HERE, "roi", name + ".npz")
+        if os.path.exists(path) and not force:
+            continue
+        im = ref_harness.make_image(img, lab)
+        with contextlib.redirect_stdout(io.StringIO()):
+            im.encode_rbepwt(levels, wav, euclidean_distance=euclid)
+            nin, nout = ref.Roi(im).compute_dual_roi_coeffs(regs, pin, pout)
+            flat = np.asarray(im.rbepwt.flat_wavelet(), dtype=np.float64).copy()
+            im.decode_rbepwt()
+        np.savez_compressed(path, img=img, labels=lab, levels=levels, wavelet=wav, euclidean_distance=euclid,
+                            regions=np.asarray(regs, dtype=np.int32), perc_in=pin, perc_out=pout, nin=nin, nout=nout,
+                            thresholded=flat, decoded=np.asarray(im.decoded_img, dtype=np.float64), psnr=float(im.psnr()))
+        print("%-28s nin %d nout %d kept %d" % (name, nin, nout, np.count_nonzero(flat)), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", nargs="*")
     ap.add_argument("--big", action="store_true")
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--perc", action="store_true", help="the threshold_by_percentage fixtures (tests/golden/perc/)")
+    ap.add_argument("--roi", action="store_true", help="the region-of-interest thresholding fixtures (tests/golden/roi/)")
     args = ap.parse_args()
     if args.perc:
         make_perc(args.only, args.force)
+        return
+    if args.roi:
+        make_roi(args.only, args.force)
         return
     for case in cases(args.big):
         name, img, lab, levels, wav, ptype, euclid, k = case[:8]

@@ -379,3 +379,43 @@ def test_dwt2_baseline_vs_oracle(tmp_path):
         c.dwt2_encode(np.zeros((1, 32, 64)), 2, "haar")
     with pytest.raises(Exception):
         c.threshold_by_percentage(0.5)  # regions do not exist for this encoding
+
+
+def test_roi_thresholding_vs_reference():
+    """Roi.compute_dual_roi_coeffs / compute_roi_coeffs through the facade (rbepwt.py:1712-1789) against the fixtures the
+    unmodified reference produced (tests/golden/roi): counts, surviving coefficients, decoded image, PSNR."""
+    import glob
+    import os
+
+    import rbepwt_b200 as rbepwt
+    from conftest import GOLDEN_DIR
+
+    files = sorted(glob.glob(os.path.join(GOLDEN_DIR, "roi", "*.npz")))
+    assert len(files) >= 5
+    for f in files:
+        z = np.load(f)
+        im = rbepwt.Image()
+        im.read_array(z["img"])
+        im.set_labels(z["labels"])
+        im.encode_rbepwt(int(z["levels"]), str(z["wavelet"]), euclidean_distance=bool(z["euclidean_distance"]))
+        roi = rbepwt.Roi(im)
+        nin, nout = roi.compute_dual_roi_coeffs([int(r) for r in z["regions"]], float(z["perc_in"]), float(z["perc_out"]))
+        assert (nin, nout) == (int(z["nin"]), int(z["nout"])), f
+        got, want = im.rbepwt.flat_wavelet(), z["thresholded"]
+        np.testing.assert_array_equal(got != 0, want != 0, err_msg=f)
+        assert np.max(np.abs(got - want)) <= 1e-9 * np.max(np.abs(want))
+        assert im.nonzero_coefs() == int(np.count_nonzero(want))
+        im.decode_rbepwt()
+        assert np.max(np.abs(im.decoded_img - z["decoded"])) <= 1e-9 * 255
+        assert abs(im.psnr() - float(z["psnr"])) < 5e-7
+    # threshold=False only counts; compute_roi_coeffs = perc_out 0
+    im = rbepwt.Image()
+    im.read_array(z["img"])
+    im.set_labels(z["labels"])
+    im.encode_rbepwt(int(z["levels"]), str(z["wavelet"]), euclidean_distance=bool(z["euclidean_distance"]))
+    before = im.nonzero_coefs()
+    n = rbepwt.Roi(im).compute_roi_coeffs([0], 1, threshold=False)
+    assert n > 0 and im.nonzero_coefs() == before
+    assert rbepwt.Roi(im).find_intersecting_regions((0, 0, 3, 3)) == set(int(v) for v in np.unique(z["labels"][:4, :4]))
+    with pytest.raises(Exception, match="between 0 and 1"):
+        rbepwt.Roi(im).compute_dual_roi_coeffs([0], 2.0, 0.0)

@@ -84,3 +84,46 @@ def test_oracle_dwt2_baseline():
     np.testing.assert_allclose(pywt_port.wavedec2(x, "db3", 1)[0], aa, atol=1e-12 * 255)
     dec, nz, mags = pywt_port.dwt2_baseline(x, 3, "db3", 40)
     assert nz == 40 and len(mags) == 40 and dec.shape == x.shape
+
+
+def _roi_fixtures():
+    import glob
+    import os
+
+    from conftest import GOLDEN_DIR
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "roi", "*.npz")))
+
+
+def test_roi_select_reproduces_reference():
+    """Region-of-interest thresholding (Roi.compute_dual_roi_coeffs, rbepwt.py:1718-1789): the host-side selection
+    (rbepwt_b200/roi.py, numpy) on the oracle's paths and coefficients against what the unmodified reference kept
+    (tests/golden/roi/*.npz, tests/golden/make_golden.py --roi): counts and the set of surviving coefficients."""
+    import rbepwt_b200 as rb
+    from rbepwt_b200.roi import global_perm, roi_select
+
+    files = _roi_fixtures()
+    assert len(files) >= 5
+    for f in files:
+        z = np.load(f)
+        img, lab, L = z["img"], z["labels"], int(z["levels"])
+        out = c_oracle.run(img, lab, L, rb.filter_bank(str(z["wavelet"])), "easypath", bool(z["euclidean_distance"]))
+        N = img.size
+        # `regions` are region indices (rank of first appearance), whatever the label values are
+        off = out["roff"][1]
+        in_mask = np.zeros(N, dtype=bool)
+        for r in set(int(x) for x in z["regions"]):
+            if r < off.size - 1:
+                in_mask[off[r]:off[r + 1]] = True
+        flat = out["coefs"].copy()
+        det_off = {lev: N - (N >> (lev - 1)) for lev in range(1, L + 2)}
+        details = {lev: flat[det_off[lev]:det_off[lev + 1]] for lev in range(1, L + 1)}
+        perms = {lev: global_perm(out["perm"][lev], out["roff"][lev]) for lev in range(2, L + 1)}
+        keep, nin, nout = roi_select(details, in_mask, perms, float(z["perc_in"]), float(z["perc_out"]))
+        assert (nin, nout) == (int(z["nin"]), int(z["nout"])), f
+        for lev in range(1, L + 1):
+            details[lev][~keep[lev]] = 0.0  # views into flat
+        want = z["thresholded"]
+        np.testing.assert_array_equal(flat != 0, want != 0, err_msg=f)
+        assert np.max(np.abs(flat - want)) <= 1e-9 * np.max(np.abs(want)), f
+    with pytest.raises(Exception, match="between 0 and 1"):
+        roi_select({1: np.zeros(2)}, np.zeros(4, dtype=bool), {}, 1.5, 0.0)
