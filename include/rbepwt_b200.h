@@ -96,6 +96,16 @@ int rbepwt_encode(rbepwt_ctx *ctx, const double *img, const int32_t *labels, int
 #define RBEPWT_OPT_COOP_LIMIT 4
 int rbepwt_set_option(rbepwt_ctx *ctx, int option, int64_t value);
 
+/* Image.segment(method='felzenszwalb', scale, sigma, min_size)                rbepwt.py:220-245, 779-785
+ * The label map the path starts from, when the caller has none: Felzenszwalb-Huttenlocher graph segmentation as
+ * scikit-image's felzenszwalb() computes it for a 2-D image.  HOST code and host pointers (no context, no GPU): like the
+ * reference's, it runs once per image before the accelerated path.  img: float64 [H][W] as scikit-image's
+ * img_as_float64 would deliver it (a uint8 image divided by 255; a float image as it is); labels: int32 [H][W] out,
+ * numbered in order of first appearance; *nlabels (may be NULL): their count.  Parity with scikit-image is unpinned
+ * (it is not available to test against): csrc/segment.hpp states what is restated. */
+int rbepwt_felzenszwalb(const double *img, int H, int W, double scale, double sigma, int min_size, int32_t *labels,
+                        int32_t *nlabels);
+
 /* Rbepwt.threshold_coefs(ncoefs), per image                                 rbepwt.py:2081-2112
  * k <= 0 or k >= H*W keeps everything (reference quirk).  Ties at the k-th magnitude are
  * unpinned in the reference; here the highest flat index survives. */

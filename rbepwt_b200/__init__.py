@@ -10,8 +10,9 @@ hand-written sm_100a CUDA kernels behind the C ABI in include/rbepwt_b200.h; the
 from .box import BoxCodec  # noqa: F401
 from .codec import BatchCodec, encode_threshold_decode, path_mode  # noqa: F401
 from .roi import Roi  # noqa: F401
+from .image import felzenszwalb_labels  # noqa: F401
 from .image import Dwt, Image, Rbepwt, Segmentation, full_decode, ispowerof2, psnr  # noqa: F401
 from .wavelets import filter_bank, wavelist  # noqa: F401
 
-__all__ = ["Image", "Rbepwt", "Dwt", "Roi", "Segmentation", "BatchCodec", "BoxCodec", "encode_threshold_decode", "full_decode",
+__all__ = ["Image", "Rbepwt", "Dwt", "Roi", "felzenszwalb_labels", "Segmentation", "BatchCodec", "BoxCodec", "encode_threshold_decode", "full_decode",
            "psnr", "ispowerof2", "filter_bank", "wavelist", "path_mode"]

@@ -17,7 +17,7 @@ T_NAMES = ["h2d", "regions", "paths", "dwt", "select", "idwt", "d2h", "paths_big
 
 EXPORTS = [
     "rbepwt_create", "rbepwt_destroy", "rbepwt_last_error", "rbepwt_sync", "rbepwt_set_wavelet",
-    "rbepwt_encode", "rbepwt_threshold", "rbepwt_threshold_percentage", "rbepwt_decode", "rbepwt_transcode", "rbepwt_transcode_ex", "rbepwt_set_option",
+    "rbepwt_felzenszwalb", "rbepwt_encode", "rbepwt_threshold", "rbepwt_threshold_percentage", "rbepwt_decode", "rbepwt_transcode", "rbepwt_transcode_ex", "rbepwt_set_option",
     "rbepwt_full_decode", "rbepwt_dwt2_encode", "rbepwt_psnr",
     "rbepwt_nonzero_coefs", "rbepwt_get_coefs", "rbepwt_set_coefs", "rbepwt_region_count",
     "rbepwt_region_offsets", "rbepwt_region_labels", "rbepwt_get_paths", "rbepwt_get_perm",
@@ -59,6 +59,7 @@ def lib():
     L.rbepwt_transcode.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i64, vp, u32]
     L.rbepwt_transcode_ex.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i64, vp, i32, vp, vp, vp, u32]
     L.rbepwt_set_option.argtypes = [vp, i32, i64]
+    L.rbepwt_felzenszwalb.argtypes = [vp, i32, i32, ctypes.c_double, ctypes.c_double, i32, vp, vp]
     L.rbepwt_full_decode.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, u32]
     L.rbepwt_psnr.argtypes = [vp, vp, vp, i32, i64, vp, u32]
     L.rbepwt_nonzero_coefs.argtypes = [vp, vp]

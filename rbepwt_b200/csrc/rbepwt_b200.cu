@@ -18,6 +18,7 @@
 #include "paths.cuh"
 #include "perm.cuh"
 #include "regions.cuh"
+#include "segment.hpp"
 #include "select.cuh"
 #include "walk.cuh"
 
@@ -1566,6 +1567,20 @@ int rbepwt_get_stage_launches(rbepwt_ctx *c, int64_t *launches, int n) {
 }
 
 int64_t rbepwt_launch_count(rbepwt_ctx *c) { return c ? c->launches : 0; }
+
+int rbepwt_felzenszwalb(const double *img, int H, int W, double scale, double sigma, int min_size, int32_t *labels,
+                        int32_t *nlabels) {
+  if (!img || !labels) return fail(RBEPWT_E_ARG, "img and labels must not be NULL");
+  if (H < 1 || W < 1 || (long long)H * W > (1ll << 29)) return fail(RBEPWT_E_ARG, "image shape out of range");
+  if (!(scale >= 0.0) || !(sigma >= 0.0) || min_size < 0) return fail(RBEPWT_E_ARG, "scale, sigma and min_size must be non-negative");
+  try {
+    const int n = felzenszwalb(img, H, W, scale, sigma, min_size, labels);
+    if (nlabels) *nlabels = n;
+  } catch (const std::exception &e) {
+    return fail(RBEPWT_E_CUDA, "felzenszwalb: %s", e.what());
+  }
+  return RBEPWT_OK;
+}
 
 #ifdef WK_STATS  // debug build only (tools/wk_stats.py): warp trips and lane units by kind of k1_walk
 int rbepwt_debug_wk_stats(rbepwt_ctx *c, unsigned long long *out, int reset) {

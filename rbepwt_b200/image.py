@@ -65,6 +65,34 @@ def _release_codec(codec):
         codec.close()
 
 
+def felzenszwalb_labels(img, scale=1.0, sigma=0.8, min_size=20):
+    """skimage.segmentation.felzenszwalb for a 2-D image through the library (rbepwt_felzenszwalb, csrc/segment.hpp):
+    int32 label map numbered in order of first appearance.  A uint8 image is scaled to [0, 1] first, as scikit-image's
+    img_as_float64 does; other integer types are not accepted (their scaling rules differ), floats pass as they are."""
+    import ctypes
+
+    from . import _capi
+
+    a = np.asarray(img)
+    if a.ndim != 2:
+        raise ValueError("a 2-D (grayscale) image is required")
+    if a.dtype == np.uint8:
+        a = a.astype(np.float64) / 255.0
+    elif a.dtype.kind == "f":
+        a = a.astype(np.float64)
+    elif a.dtype == np.bool_:
+        a = a.astype(np.float64)
+    else:
+        raise TypeError("felzenszwalb_labels takes uint8 or floating-point images")
+    a = np.ascontiguousarray(a)
+    lab = np.empty(a.shape, dtype=np.int32)
+    n = ctypes.c_int32()
+    _capi.check(_capi.lib().rbepwt_felzenszwalb(a.ctypes.data_as(ctypes.c_void_p), a.shape[0], a.shape[1], float(scale),
+                                                float(sigma), int(min_size), lab.ctypes.data_as(ctypes.c_void_p),
+                                                ctypes.byref(n)))
+    return lab
+
+
 class Segmentation:
     """Holder of an externally produced label map (rbepwt.py:770-848).  Region order = first
     appearance of the label in a row-major scan; computed on the GPU at encode time (K0)."""
@@ -559,16 +587,17 @@ class Image:
         self.shape = self.img.shape
 
     def segment(self, method="felzenszwalb", **args):
-        """Label maps are an INPUT of the B200 path; this only forwards to scikit-image when present."""
+        """Image.segment (rbepwt.py:220-245).  method='felzenszwalb' (779-785): scikit-image's own function when it is
+        installed -- the reference's dependency --, else the library's restatement of it (csrc/segment.hpp,
+        rbepwt_felzenszwalb: host code, parity with scikit-image unpinned).  Other label maps: set_labels()."""
         if method != "felzenszwalb":
-            raise NotImplementedError("only method='felzenszwalb' (via scikit-image) or set_labels()")
+            raise NotImplementedError("only method='felzenszwalb' or set_labels() / load_mat_segmentation()")
+        scale, sigma, min_size = args.get("scale", 200), args.get("sigma", 2), args.get("min_size", 10)
         try:
             from skimage.segmentation import felzenszwalb
+            lab = felzenszwalb(self.img, scale=float(scale), sigma=float(sigma), min_size=int(min_size))
         except ImportError:
-            raise ImportError("scikit-image is not installed: supply the label map with Image.set_labels(label_img) "
-                              "or Image.load_mat_segmentation()")
-        scale, sigma, min_size = args.get("scale", 200), args.get("sigma", 2), args.get("min_size", 10)
-        lab = felzenszwalb(self.img, scale=float(scale), sigma=float(sigma), min_size=int(min_size))
+            lab = felzenszwalb_labels(self.img, scale, sigma, min_size)
         self.set_labels(lab, "felzenszwalb")
         self.felz_scale, self.felz_sigma, self.felz_min_size = scale, sigma, min_size
 
