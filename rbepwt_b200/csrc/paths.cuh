@@ -4,14 +4,14 @@
 // rotate 78-82), the start-point rule of Region.__init_dict_and_extreme_values__ (1020-1036) and
 // the point bookkeeping of RegionCollection.reduce / Region.reduce_points (1563-1584, 1349-1375).
 //
-// This file: the warp-per-region form -- one warp owns one region and walks its greedy path, the
-// lanes share the rows of the search window (find_next_geo: euclid, integer keys; find_next: chebyshev
-// and EPWT, the reference's fp64 expressions).  It serves the LONG chains: regions of >= TPR_COOP_MIN
-// pixels, regions whose bounding-box bitmap is too large for a shared-memory arena, every region of a
-// small group (latency matters, not throughput), and the EPWT mode (one region per image, values read
-// per candidate).  The bulk -- hundreds of thousands of small regions per batch -- is walked thread per
-// region by walk.cuh.  The unvisited points are a bitmap over the region's bounding box (shared
-// memory; global scratch for boxes too large).
+// This file: the warp-per-region searches -- one warp owns one region, the lanes share the rows of the search window
+// (find_next_geo: euclid, integer keys; find_next: chebyshev and EPWT, the reference's fp64 expressions;
+// find_next_grad: gradpath) -- and the walker built on them (run_path / region_pyramid), which now serves gradpath and
+// the chebyshev mode's oversized regions.  The euclidean mode's whole-warp walker (oversized regions, the largest
+// regions of a group, every region of a small group) and EPWT keep the bitmap window in registers (regwin.cuh) and
+// come here only for the searches beyond half-width 8 (euclid) / 2 (EPWT).  The bulk -- hundreds of thousands of
+// small regions per batch -- is walked thread per region by walk.cuh.  The unvisited points are a bitmap over the
+// region's bounding box (shared memory; global scratch for boxes too large).
 //
 // Step rule (exactly the reference's, restated order-independently):
 //   candidates = unvisited points of the region inside the smallest square of half-width
