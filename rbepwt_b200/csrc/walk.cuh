@@ -547,53 +547,36 @@ __device__ __forceinline__ void wk_geometry(const PathParams &P, int g, int &r0,
 }
 
 // Cooperative build of ONE region's slot of an arena image (all arguments warp-uniform): the level-1 bitmap in plane 0
-// (one ballot per bitmap word, lanes = columns) and zeros in the rest of the slot.  dst = the slot's first word.
+// and zeros in the rest of the slot.  dst = the slot's first word.  Word column by word column, 32 bitmap rows at a
+// time: lane = column for the loads and ballots, lane = row for the result, which leaves as one store per 32 rows; per
+// row an add, a load, a compare, a ballot and a select.  The rows and columns of the bounding box lie inside the image;
+// the margin rows / columns stay zero.
 __device__ __forceinline__ void wk_build_one(const PathParams &P, uint32_t *dst, int img_r, int label_r, int r0_r, int c0_r,
                                              int h_r, int w_r, int ws_r, int slot_r) {
   const int lane = (int)lane_id(), logW = P.logW;
-  const int32_t *lab = P.labels + (size_t)img_r * P.N;
-  const int words_r = h_r * ws_r;
-  if (ws_r == 1 && h_r <= 32) {
-    // the common shape (one word per row, at most 32 rows): lane = column for the loads and ballots, lane = row for
-    // the result, which leaves as ONE coalesced store; per row an add, a load, a compare, a ballot and a select.
-    // The rows and columns of the bounding box lie inside the image; the margin rows / columns stay zero.
-    const bool cok = lane >= WK_PAD && lane < w_r - WK_PAD;
-    const int32_t *p = lab + ((r0_r + WK_PAD) << logW) + c0_r + lane;
-    const int nrows = h_r - 2 * WK_PAD;
-    uint32_t mine = 0u;
-    for (int i0 = 0; i0 < nrows; i0 += 8) {  // eight independent label loads in flight per lane
-      int lv[8];
+  const int32_t *lab = P.labels + (size_t)img_r * P.N + ((r0_r + WK_PAD) << logW) + c0_r;  // first row of the bounding box
+  const int nrows = h_r - 2 * WK_PAD;
+  for (int wd = 0; wd < ws_r; wd++) {
+    const int col = (wd << 5) + lane;
+    const bool cok = col >= WK_PAD && col < w_r - WK_PAD;
+    const int32_t *p = lab + col;
+    for (int rb = 0; rb < h_r; rb += 32) {  // bitmap rows rb .. rb + 31 = bounding-box rows rb - WK_PAD ..
+      const int i_lo = max(rb - WK_PAD, 0), i_hi = min(rb + 32 - WK_PAD, nrows);
+      uint32_t mine = 0u;
+      for (int i0 = i_lo; i0 < i_hi; i0 += 8) {  // eight independent label loads in flight per lane
+        int lv[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) lv[u] = (cok && i0 + u < nrows) ? p[(size_t)(i0 + u) << logW] : ~label_r;
+        for (int u = 0; u < 8; u++) lv[u] = (cok && i0 + u < i_hi) ? p[(size_t)(i0 + u) << logW] : ~label_r;
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const unsigned bits = __ballot_sync(FULL_MASK, lv[u] == label_r);
-        mine = lane == i0 + u + WK_PAD ? bits : mine;
+        for (int u = 0; u < 8; u++) {
+          const unsigned bits = __ballot_sync(FULL_MASK, lv[u] == label_r);
+          mine = lane == i0 + u + WK_PAD - rb ? bits : mine;
+        }
       }
-    }
-    for (int q = lane; q < slot_r; q += 32) dst[q] = q < h_r ? mine : 0u;
-    return;
-  }
-  for (int wi = 0; wi < words_r; wi += 8) {  // eight independent label loads in flight per lane
-    int lv[8];
-    bool inb[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const int w_ = wi + u;
-      const int i = ws_r == 1 ? w_ : w_ / ws_r;
-      const int col = ((w_ - i * ws_r) << 5) + lane;
-      // the margin rows / columns hold no pixel of the region (they lie outside its bounding box)
-      inb[u] = w_ < words_r && i >= WK_PAD && i < h_r - WK_PAD && col >= WK_PAD && col < w_r - WK_PAD &&
-               (unsigned)(r0_r + i) < (unsigned)P.H && (unsigned)(c0_r + col) < (unsigned)P.W;
-      lv[u] = inb[u] ? lab[((r0_r + i) << logW) + c0_r + col] : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const unsigned bits = __ballot_sync(FULL_MASK, inb[u] && lv[u] == label_r);
-      if (lane == 0 && wi + u < words_r) dst[wi + u] = bits;
+      if (rb + lane < h_r) dst[(rb + lane) * ws_r + wd] = mine;
     }
   }
-  for (int q = words_r + lane; q < slot_r; q += 32) dst[q] = 0u;
+  for (int q = h_r * ws_r + lane; q < slot_r; q += 32) dst[q] = 0u;
 }
 
 // One chunk's arena image: lane r holds region r's geometry and its word offset `base` in `dst`; `slot` = its slot words.
